@@ -1,0 +1,285 @@
+// Native C ABI (include/gliclass_b200.h).  Every entry point catches C++ exceptions and turns
+// them into an error code + thread-local message, as a C caller (the reference's model.c) expects.
+#include <cuda_bf16.h>
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "gliclass_b200.h"
+#include "kernels.h"
+#include "model_weights.h"
+
+struct glc_model {
+  glc::Model* m;
+  int weight_dtype;
+};
+struct glc_onnx {
+  glc::ModelWeights w;
+  std::vector<std::string> roles;
+};
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+void fill_info(const glc::ModelConfig& c, glc_info* o) {
+  memset(o, 0, sizeof(*o));
+  o->vocab = c.vocab; o->hidden = c.hidden; o->layers = c.layers; o->heads = c.heads; o->inter = c.inter;
+  o->head_hidden = c.head_hidden; o->buckets = c.buckets; o->max_rel_pos = c.max_rel_pos; o->ln_eps = c.ln_eps;
+  o->class_token = c.class_token;
+}
+}  // namespace
+
+extern "C" {
+
+const char* glc_last_error(void) { return g_err.c_str(); }
+
+int glc_device_count(void) { return glc::usable_device_count(); }
+
+glc_model* glc_load(const char* onnx_path, const glc_opts* opts) {
+  try {
+    if (!onnx_path) { fail(GLC_ERR_ARG, "glc_load: null path"); return nullptr; }
+    std::vector<int> devices;
+    int max_tokens = 0;
+    int dtype = GLC_DTYPE_BF16;
+    if (opts && opts->struct_size >= sizeof(glc_opts)) {
+      for (int i = 0; i < opts->num_devices && i < 8; ++i) devices.push_back(opts->device_ids[i]);
+      max_tokens = opts->max_tokens;
+      dtype = opts->weight_dtype;
+    }
+    if (dtype != GLC_DTYPE_BF16) { fail(GLC_ERR_ARG, "glc_load: only GLC_DTYPE_BF16 weights are implemented"); return nullptr; }
+    if (devices.empty()) {
+      // GLC_DEVICES="0,1,2" or "all"; default: device 0
+      const char* env = getenv("GLC_DEVICES");
+      if (env && *env) {
+        if (!strcmp(env, "all")) {
+          int n = 0;
+          cudaGetDeviceCount(&n);
+          for (int d = 0; d < n; ++d) devices.push_back(d);
+        } else {
+          std::stringstream ss(env);
+          std::string tok;
+          while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
+        }
+      }
+      if (devices.empty()) devices.push_back(0);
+    }
+    if (glc::usable_device_count() == 0) {
+      fail(GLC_ERR_CUDA, "glc_load: no usable sm_100 CUDA device (this engine has no CPU fallback)");
+      return nullptr;
+    }
+    if (const char* mt = getenv("GLC_MAX_TOKENS")) if (max_tokens <= 0) max_tokens = atoi(mt);
+    glc_model* h = new glc_model;
+    h->m = new glc::Model(onnx_path, devices, max_tokens);
+    h->weight_dtype = dtype;
+    return h;
+  } catch (const std::exception& e) {
+    fail(GLC_ERR, std::string("glc_load: ") + e.what());
+    return nullptr;
+  }
+}
+
+void glc_free(glc_model* m) {
+  if (!m) return;
+  try { delete m->m; } catch (...) {}
+  delete m;
+}
+
+int glc_model_info(const glc_model* m, glc_info* out) {
+  if (!m || !out) return fail(GLC_ERR_ARG, "glc_model_info: null argument");
+  fill_info(m->m->cfg(), out);
+  out->num_devices = m->m->num_devices();
+  out->weight_dtype = m->weight_dtype;
+  return GLC_OK;
+}
+
+int glc_num_classes(const glc_model* m, const int64_t* input_ids, int B, int S) {
+  if (!m || (!input_ids && B * S > 0) || B < 0 || S < 0) return fail(GLC_ERR_ARG, "glc_num_classes: bad argument");
+  return m->m->num_classes(input_ids, B, S);
+}
+
+int glc_run(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S, float* logits_out,
+            size_t logits_capacity, int* C_out) {
+  try {
+    if (!m || B < 0 || S < 0) return fail(GLC_ERR_ARG, "glc_run: bad argument");
+    if (B * S > 0 && (!input_ids || !attention_mask)) return fail(GLC_ERR_ARG, "glc_run: null input");
+    const int C = m->m->num_classes(input_ids, B, S);
+    if (C_out) *C_out = C;
+    if ((size_t)B * C > logits_capacity) return fail(GLC_ERR_CAPACITY, "glc_run: logits buffer too small");
+    if (B == 0 || S == 0 || C == 0) return GLC_OK;
+    if (!logits_out) return fail(GLC_ERR_ARG, "glc_run: null output");
+    m->m->run(input_ids, attention_mask, B, S, C, logits_out);
+    return GLC_OK;
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_run: ") + e.what());
+  }
+}
+
+int glc_run_device(glc_model* m, int slot, const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C,
+                   float* d_logits, int async) {
+  try {
+    if (!m || slot < 0 || slot >= m->m->num_devices() || B < 0 || S < 0 || C < 0)
+      return fail(GLC_ERR_ARG, "glc_run_device: bad argument");
+    glc::DeviceModel& d = m->m->dev(slot);
+    std::lock_guard<std::mutex> lk(d.mu);
+    cudaSetDevice(d.device());
+    d.forward(d_ids, d_mask, B, S, C, d_logits);
+    if (!async) {
+      cudaError_t e = cudaStreamSynchronize(d.stream());
+      if (e != cudaSuccess) return fail(GLC_ERR_CUDA, std::string("glc_run_device: ") + cudaGetErrorString(e));
+    }
+    return GLC_OK;
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_run_device: ") + e.what());
+  }
+}
+
+int glc_sync(glc_model* m, int slot) {
+  if (!m || slot < 0 || slot >= m->m->num_devices()) return fail(GLC_ERR_ARG, "glc_sync: bad argument");
+  cudaSetDevice(m->m->dev(slot).device());
+  cudaError_t e = cudaStreamSynchronize(m->m->dev(slot).stream());
+  if (e != cudaSuccess) return fail(GLC_ERR_CUDA, std::string("glc_sync: ") + cudaGetErrorString(e));
+  return GLC_OK;
+}
+
+void* glc_stream(glc_model* m, int slot) {
+  if (!m || slot < 0 || slot >= m->m->num_devices()) return nullptr;
+  return (void*)m->m->dev(slot).stream();
+}
+
+uint64_t glc_launch_count(const glc_model* m) { return m ? m->m->launches() : 0; }
+
+int64_t glc_debug_fetch(glc_model* m, int slot, const char* name, float* out, size_t capacity) {
+  try {
+    if (!m || !name || slot < 0 || slot >= m->m->num_devices()) return fail(GLC_ERR_ARG, "glc_debug_fetch: bad argument");
+    return m->m->dev(slot).debug_fetch(name, out, capacity);
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_debug_fetch: ") + e.what());
+  }
+}
+
+// reference src/postprocessor.c:14-16 (sigmoid), :93-95 (strict >), :119-128 (argmax from 0 / -1)
+int glc_decide(const float* logits, int B, int C, float threshold, uint8_t* out_mask, int32_t* out_argmax, float* out_prob) {
+  if (B < 0 || C < 0 || (!logits && B * C > 0)) return fail(GLC_ERR_ARG, "glc_decide: bad argument");
+  for (int i = 0; i < B; ++i) {
+    float max_prob = 0.0f;
+    int max_idx = -1;
+    for (int j = 0; j < C; ++j) {
+      const float prob = 1.0f / (1.0f + expf(-logits[(size_t)i * C + j]));
+      if (out_prob) out_prob[(size_t)i * C + j] = prob;
+      if (out_mask) out_mask[(size_t)i * C + j] = prob > threshold ? 1 : 0;
+      if (prob > max_prob) { max_prob = prob; max_idx = j; }
+    }
+    if (out_argmax) out_argmax[i] = max_idx;
+  }
+  return GLC_OK;
+}
+
+// ---- host-only inspection --------------------------------------------------------------------
+
+glc_onnx* glc_onnx_open(const char* path) {
+  try {
+    if (!path) { fail(GLC_ERR_ARG, "glc_onnx_open: null path"); return nullptr; }
+    glc_onnx* h = new glc_onnx;
+    try {
+      glc::load_model_weights(path, &h->w);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    for (auto& kv : h->w.t) h->roles.push_back(kv.first);
+    return h;
+  } catch (const std::exception& e) {
+    fail(GLC_ERR, std::string("glc_onnx_open: ") + e.what());
+    return nullptr;
+  }
+}
+void glc_onnx_close(glc_onnx* h) { delete h; }
+int glc_onnx_info(const glc_onnx* h, glc_info* out) {
+  if (!h || !out) return fail(GLC_ERR_ARG, "glc_onnx_info: null argument");
+  fill_info(h->w.cfg, out);
+  return GLC_OK;
+}
+int glc_onnx_tensor(const glc_onnx* h, const char* role, const float** data, int64_t dims[4]) {
+  if (!h || !role || !data || !dims) return fail(GLC_ERR_ARG, "glc_onnx_tensor: null argument");
+  auto it = h->w.t.find(role);
+  if (it == h->w.t.end()) return fail(GLC_ERR_ARG, std::string("glc_onnx_tensor: unknown role ") + role);
+  const glc::HostTensor& t = it->second;
+  if (t.dims.size() > 4) return fail(GLC_ERR, "glc_onnx_tensor: rank > 4");
+  for (size_t i = 0; i < t.dims.size(); ++i) dims[i] = t.dims[i];
+  *data = t.data.data();
+  return (int)t.dims.size();
+}
+int glc_onnx_num_roles(const glc_onnx* h) { return h ? (int)h->roles.size() : 0; }
+const char* glc_onnx_role_name(const glc_onnx* h, int i) {
+  if (!h || i < 0 || i >= (int)h->roles.size()) return nullptr;
+  return h->roles[i].c_str();
+}
+int glc_rel_index_table(int S, int buckets, int max_pos, int32_t* out) {
+  if (S <= 0 || buckets <= 1 || max_pos <= 1 || !out) return fail(GLC_ERR_ARG, "glc_rel_index_table: bad argument");
+  glc::rel_index_table(S, buckets, max_pos, out);
+  return GLC_OK;
+}
+
+// ---- single-kernel entry points --------------------------------------------------------------
+
+static int num_sms_current() {
+  int dev = 0, n = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
+static int wrap(const char* what, cudaError_t e) {
+  if (e == cudaSuccess) return GLC_OK;
+  return fail(GLC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define GLC_TRY(tag, expr)                                        \
+  try {                                                           \
+    return wrap(tag, (expr));                                     \
+  } catch (const std::exception& e) {                             \
+    return fail(GLC_ERR_CUDA, std::string(tag) + ": " + e.what()); \
+  }
+
+int glc_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N,
+                int K, int act, int out_f32, void* stream) {
+  GLC_TRY("glc_op_gemm", glc::gemm_bf16(A, lda, W, ldw, bias, C, ldc, M, N, K, act, out_f32 != 0, num_sms_current(),
+                                        (cudaStream_t)stream));
+}
+int glc_op_embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, const float* gamma, const float* beta, float eps,
+                    void* y, int M, int H, int vocab, void* stream) {
+  GLC_TRY("glc_op_embed_ln", glc::embed_ln(ids, mask, emb, gamma, beta, eps, y, M, H, vocab, (cudaStream_t)stream));
+}
+int glc_op_residual_ln(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y, int M, int H,
+                       void* stream) {
+  GLC_TRY("glc_op_residual_ln", glc::residual_ln(x, r, gamma, beta, eps, y, M, H, (cudaStream_t)stream));
+}
+int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, void* stream) {
+  GLC_TRY("glc_op_mask_prep", glc::mask_prep(mask, bits, kv_len, B, S, (cudaStream_t)stream));
+}
+int glc_op_attention(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
+                     const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads, int buckets,
+                     int naive, void* stream) {
+  if (naive) {
+    GLC_TRY("glc_op_attention(naive)", glc::attention_naive(qkv, pos_k, pos_q, ld_pos, rel_idx, mask_bits, ctx, B, S, heads,
+                                                             buckets, (cudaStream_t)stream));
+  }
+  GLC_TRY("glc_op_attention", glc::attention_fused(qkv, pos_k, pos_q, ld_pos, rel_idx, mask_bits, kv_len, ctx, B, S, heads,
+                                                   buckets, num_sms_current(), (cudaStream_t)stream));
+}
+int glc_op_head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S, int H,
+                       int C, void* stream) {
+  GLC_TRY("glc_op_head_gather", glc::head_gather(h, ids, class_token, pooled, cls, B, S, H, C, (cudaStream_t)stream));
+}
+int glc_op_head_score(const float* t, const float* k, float* logits, float* probs, uint8_t* decisions, float threshold, int B,
+                      int C, int Hh, void* stream) {
+  GLC_TRY("glc_op_head_score", glc::head_score(t, k, logits, probs, decisions, threshold, B, C, Hh, (cudaStream_t)stream));
+}
+
+}  // extern "C"

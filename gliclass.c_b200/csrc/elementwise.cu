@@ -1,0 +1,305 @@
+// HBM-bound kernels of the hot path: K1 embedding gather + LayerNorm + mask, K4 residual +
+// LayerNorm, attention-mask bit packing, K5a <<LABEL>> pooling and K5b dot scorer (+sigmoid /
+// threshold).  One warp per row, 128-bit loads/stores, fp32 statistics via warp shuffles.
+//
+// Arithmetic restated from transformers' modeling_deberta_v2.py (T:) and SURVEY.md App. B:
+//   K1  T:520-564   e = LN(word_emb[ids]) * mask           (no position / token-type term in v3)
+//   K4  T:49-53, T:408-412   y = LN(dense_out + residual)  (eps 1e-7, biased variance)
+//   K5  App. B      cls[b,c] = h[b,pos_c]; pooled = h[b,0]; logit = <t_b, k_bc>
+#include <cuda_bf16.h>
+
+#include <type_traits>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace glc {
+namespace {
+
+constexpr int ROWS_PER_BLOCK = 8;   // 8 warps / block, one row per warp
+constexpr int MAXC = 8;             // up to 8 chunks of 8 elements per lane -> H <= 2048
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+
+// LN over a row held as NC chunks of 8 floats per lane; writes bf16, scaled by `post`.
+template <int NC>
+__device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, float eps, float post,
+                                         __nv_bfloat16* __restrict__ out) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if ((lane + 32 * c) * 8 < H) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s += v[c][i];
+    }
+  const float mean = warp_sum(s) / (float)H;
+  float q = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if ((lane + 32 * c) * 8 < H) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float d = v[c][i] - mean;
+        q += d * d;
+      }
+    }
+  const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int e0 = (lane + 32 * c) * 8;
+    if (e0 < H) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e0));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e0 + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + e0));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + e0 + 4));
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y[i] = ((v[c][i] - mean) * rstd * g[i] + b[i]) * post;
+      uint4 o;
+      o.x = ptx::pack_bf16(y[0], y[1]);
+      o.y = ptx::pack_bf16(y[2], y[3]);
+      o.z = ptx::pack_bf16(y[4], y[5]);
+      o.w = ptx::pack_bf16(y[6], y[7]);
+      *reinterpret_cast<uint4*>(out + e0) = o;
+    }
+  }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                const __nv_bfloat16* __restrict__ emb, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int M, int H, int vocab) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  int64_t id = ids[row];
+  if (id < 0 || id >= vocab) id = 0;   // ORT's Gather would fail; clamp to [PAD] instead of reading out of bounds
+  const float post = mask[row] != 0 ? 1.0f : 0.0f;
+  const __nv_bfloat16* src = emb + id * (int64_t)H;
+  float v[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int e0 = (lane + 32 * c) * 8;
+    if (e0 < H) unpack8(__ldg(reinterpret_cast<const uint4*>(src + e0)), v[c]);
+  }
+  ln_store<NC>(v, lane, H, gamma, beta, eps, post, y + (int64_t)row * H);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+residual_ln_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ r,
+                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                   __nv_bfloat16* __restrict__ y, int M, int H) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const __nv_bfloat16* xs = x + (int64_t)row * H;
+  const __nv_bfloat16* rs = r ? r + (int64_t)row * H : nullptr;
+  float v[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int e0 = (lane + 32 * c) * 8;
+    if (e0 < H) {
+      unpack8(*reinterpret_cast<const uint4*>(xs + e0), v[c]);
+      if (rs) {
+        float t[8];
+        unpack8(*reinterpret_cast<const uint4*>(rs + e0), t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+      }
+    }
+  }
+  ln_store<NC>(v, lane, H, gamma, beta, eps, 1.0f, y + (int64_t)row * H);
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+ln_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+              __nv_bfloat16* __restrict__ y, int M, int H) {
+  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const float* xs = x + (int64_t)row * H;
+  float v[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int e0 = (lane + 32 * c) * 8;
+    if (e0 < H) {
+      const float4 a = *reinterpret_cast<const float4*>(xs + e0);
+      const float4 b = *reinterpret_cast<const float4*>(xs + e0 + 4);
+      v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+      v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+    }
+  }
+  ln_store<NC>(v, lane, H, gamma, beta, eps, 1.0f, y + (int64_t)row * H);
+}
+
+// one warp per batch row: 32 mask words at a time via ballot
+__global__ void mask_prep_kernel(const int64_t* __restrict__ mask, uint32_t* __restrict__ bits,
+                                 int32_t* __restrict__ kv_len, int B, int S) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  const int words = (S + 31) / 32;
+  int last = 0;
+  for (int w = 0; w < words; ++w) {
+    const int j = w * 32 + lane;
+    const bool v = (j < S) && (mask[(int64_t)b * S + j] != 0);
+    const uint32_t m = __ballot_sync(0xffffffffu, v);
+    if (lane == 0) bits[(int64_t)b * words + w] = m;
+    if (m) last = w * 32 + (32 - __clz(m));
+  }
+  if (lane == 0) kv_len[b] = last;
+}
+
+// one warp per batch row scans for <<LABEL>> tokens; then every lane copies rows with 128-bit loads
+__global__ void __launch_bounds__(128)
+head_gather_kernel(const __nv_bfloat16* __restrict__ h, const int64_t* __restrict__ ids, int64_t class_token,
+                   __nv_bfloat16* __restrict__ pooled, __nv_bfloat16* __restrict__ cls, int B, int S, int H, int C) {
+  extern __shared__ int pos_s[];   // [C] per block (one batch row per block)
+  const int b = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0) {
+    int count = 0;
+    for (int j0 = 0; j0 < S; j0 += 32) {
+      const int j = j0 + lane;
+      const bool hit = (j < S) && (ids[(int64_t)b * S + j] == class_token);
+      const uint32_t m = __ballot_sync(0xffffffffu, hit);
+      if (hit) {
+        const int c = count + __popc(m & ((1u << lane) - 1u));
+        if (c < C) pos_s[c] = j;
+      }
+      count += __popc(m);
+    }
+    for (int c = count + lane; c < C; c += 32) pos_s[c] = -1;
+  }
+  __syncthreads();
+  const int vec = H / 8;
+  // row 0 of the output block is the pooled (first-token) row, rows 1..C the class rows
+  for (int r = warp; r <= C; r += (blockDim.x >> 5)) {
+    const int p = (r == 0) ? 0 : pos_s[r - 1];
+    __nv_bfloat16* dst = (r == 0) ? pooled + (int64_t)b * H : cls + ((int64_t)b * C + (r - 1)) * H;
+    const __nv_bfloat16* src = h + ((int64_t)b * S + (p < 0 ? 0 : p)) * H;
+    for (int i = lane; i < vec; i += 32) {
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (p >= 0) u = *reinterpret_cast<const uint4*>(src + i * 8);
+      *reinterpret_cast<uint4*>(dst + i * 8) = u;
+    }
+  }
+}
+
+// one warp per (b,c): fp32 dot over Hh, then sigmoid / strict threshold (postprocessor.c:14-16,93-95)
+__global__ void __launch_bounds__(256)
+head_score_kernel(const float* __restrict__ t, const float* __restrict__ k, float* __restrict__ logits,
+                  float* __restrict__ probs, uint8_t* __restrict__ decisions, float threshold, int B, int C, int Hh) {
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (idx >= B * C) return;
+  const int b = idx / C;
+  const float4* tv = reinterpret_cast<const float4*>(t + (int64_t)b * Hh);
+  const float4* kv = reinterpret_cast<const float4*>(k + (int64_t)idx * Hh);
+  float s = 0.f;
+  for (int i = lane; i < Hh / 4; i += 32) {
+    const float4 a = tv[i], c = kv[i];
+    s = fmaf(a.x, c.x, s); s = fmaf(a.y, c.y, s); s = fmaf(a.z, c.z, s); s = fmaf(a.w, c.w, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    logits[idx] = s;
+    const float p = 1.0f / (1.0f + expf(-s));
+    if (probs) probs[idx] = p;
+    if (decisions) decisions[idx] = p > threshold ? 1 : 0;
+  }
+}
+
+template <typename F>
+cudaError_t dispatch_nc(int H, F&& f) {
+  if (H % 8 != 0 || H > 256 * MAXC) return cudaErrorInvalidValue;
+  const int nc = (H + 255) / 256;
+  switch (nc) {
+    case 1: return f(std::integral_constant<int, 1>{});
+    case 2: return f(std::integral_constant<int, 2>{});
+    case 3: return f(std::integral_constant<int, 3>{});
+    case 4: return f(std::integral_constant<int, 4>{});
+    case 5: case 6: return f(std::integral_constant<int, 6>{});
+    default: return f(std::integral_constant<int, 8>{});
+  }
+}
+
+}  // namespace
+
+cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, const float* gamma, const float* beta,
+                     float eps, void* y, int M, int H, int vocab, cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  return dispatch_nc(H, [&](auto nc) {
+    constexpr int NC = decltype(nc)::value;
+    embed_ln_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
+        ids, mask, (const __nv_bfloat16*)emb, gamma, beta, eps, (__nv_bfloat16*)y, M, H, vocab);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y, int M,
+                        int H, cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  return dispatch_nc(H, [&](auto nc) {
+    constexpr int NC = decltype(nc)::value;
+    residual_ln_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)r, gamma, beta, eps, (__nv_bfloat16*)y, M, H);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t ln_f32_to_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y, int M, int H,
+                           cudaStream_t stream) {
+  if (M <= 0) return cudaSuccess;
+  return dispatch_nc(H, [&](auto nc) {
+    constexpr int NC = decltype(nc)::value;
+    ln_f32_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
+        x, gamma, beta, eps, (__nv_bfloat16*)y, M, H);
+    return cudaGetLastError();
+  });
+}
+
+cudaError_t mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  mask_prep_kernel<<<(B + 3) / 4, 128, 0, stream>>>(mask, bits, kv_len, B, S);
+  return cudaGetLastError();
+}
+
+cudaError_t head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S,
+                        int H, int C, cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  if (H % 8 != 0) return cudaErrorInvalidValue;
+  head_gather_kernel<<<B, 128, (size_t)(C > 0 ? C : 1) * sizeof(int), stream>>>(
+      (const __nv_bfloat16*)h, ids, class_token, (__nv_bfloat16*)pooled, (__nv_bfloat16*)cls, B, S, H, C);
+  return cudaGetLastError();
+}
+
+cudaError_t head_score(const float* t, const float* k, float* logits, float* probs, uint8_t* decisions, float threshold,
+                       int B, int C, int Hh, cudaStream_t stream) {
+  if (B * C <= 0) return cudaSuccess;
+  if (Hh % 4 != 0) return cudaErrorInvalidValue;
+  head_score_kernel<<<(B * C + 7) / 8, 256, 0, stream>>>(t, k, logits, probs, decisions, threshold, B, C, Hh);
+  return cudaGetLastError();
+}
+
+}  // namespace glc

@@ -1,0 +1,343 @@
+// See engine.h.  Forward = what ORT executes per Run for the reference (src/model.c:173-182),
+// as a fixed kernel sequence:
+//   K1 embed+LN+mask -> L x { K2 QKV GEMM -> K3 fused disentangled attention -> K2 out-proj ->
+//   K4 +res LN -> K2 FFN1(+GELU) -> K2 FFN2 -> K4 +res LN } -> K5a label pooling -> K2 projectors ->
+//   K5b dot scorer.
+#include "engine.h"
+
+#include <cuda_bf16.h>
+
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <thread>
+
+#include "kernels.h"
+
+namespace glc {
+
+#define GLC_CUDA(expr)                                                                                  \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr);    \
+  } while (0)
+
+namespace {
+
+inline uint16_t f32_to_bf16(float f) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
+  u += 0x7fffu + ((u >> 16) & 1u);                                            // round to nearest even
+  return (uint16_t)(u >> 16);
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+int usable_device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int d = 0; d < n; ++d) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, d) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+void* DeviceModel::dalloc(size_t bytes) {
+  void* p = nullptr;
+  GLC_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+  return p;
+}
+
+void DeviceModel::upload_f32(float** dst, const HostTensor& t) {
+  *dst = (float*)dalloc(t.data.size() * 4);
+  perm_allocs_.push_back(*dst);
+  GLC_CUDA(cudaMemcpyAsync(*dst, t.data.data(), t.data.size() * 4, cudaMemcpyHostToDevice, stream_));
+}
+
+void DeviceModel::upload_bf16(void** dst, const float* src, size_t n) {
+  std::vector<uint16_t> h(n);
+  for (size_t i = 0; i < n; ++i) h[i] = f32_to_bf16(src[i]);
+  *dst = dalloc(n * 2);
+  perm_allocs_.push_back(*dst);
+  GLC_CUDA(cudaMemcpy(*dst, h.data(), n * 2, cudaMemcpyHostToDevice));
+}
+
+DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : device_(device), cfg_(w.cfg) {
+  GLC_CUDA(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  GLC_CUDA(cudaGetDeviceProperties(&prop, device_));
+  if (prop.major != 10)
+    throw std::runtime_error("device " + std::to_string(device_) + " (" + prop.name + ", sm_" + std::to_string(prop.major) +
+                             std::to_string(prop.minor) + ") is not sm_100: this engine has no fallback path");
+  num_sms_ = prop.multiProcessorCount;
+  if (cfg_.hidden / cfg_.heads != 64)
+    throw std::runtime_error("attention kernel requires head dim 64 (got " + std::to_string(cfg_.hidden / cfg_.heads) + ")");
+  if (max_tokens > 0) max_tokens_ = max_tokens;
+  const char* dk = getenv("GLC_DEBUG_KEEP");
+  debug_keep_ = dk && dk[0] == '1';
+  GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+
+  const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
+  const HostTensor& we = w.at("emb.word");
+  upload_bf16(&word_emb_, we.data.data(), we.data.size());
+  upload_f32(&emb_g_, w.at("emb.ln.g"));
+  upload_f32(&emb_b_, w.at("emb.ln.b"));
+
+  // LN(rel_embeddings) once (T:597-601: input independent)
+  float *rel_f32 = nullptr, *rel_g = nullptr, *rel_b = nullptr;
+  upload_f32(&rel_f32, w.at("rel.emb"));
+  upload_f32(&rel_g, w.at("rel.ln.g"));
+  upload_f32(&rel_b, w.at("rel.ln.b"));
+  void* rel_ln = dalloc((size_t)R * H * 2);
+  perm_allocs_.push_back(rel_ln);
+  GLC_CUDA(ln_f32_to_bf16(rel_f32, rel_g, rel_b, cfg_.ln_eps, rel_ln, R, H, stream_));
+  ++launches_;
+
+  layers_.resize(cfg_.layers);
+  std::vector<float> cat((size_t)3 * H * H), bcat((size_t)3 * H);
+  for (int l = 0; l < cfg_.layers; ++l) {
+    DeviceLayer& d = layers_[l];
+    const std::string r = "layer." + std::to_string(l);
+    const char* names[3] = {".q", ".k", ".v"};
+    for (int j = 0; j < 3; ++j) {
+      memcpy(cat.data() + (size_t)j * H * H, w.at(r + names[j] + ".w").data.data(), (size_t)H * H * 4);
+      memcpy(bcat.data() + (size_t)j * H, w.at(r + names[j] + ".b").data.data(), (size_t)H * 4);
+    }
+    upload_bf16(&d.wqkv, cat.data(), cat.size());
+    HostTensor hb;
+    hb.data = bcat;
+    upload_f32(&d.bqkv, hb);
+    GLC_CUDA(cudaStreamSynchronize(stream_));   // hb is a temporary
+    upload_bf16(&d.wo, w.at(r + ".o.w").data.data(), (size_t)H * H);
+    upload_f32(&d.bo, w.at(r + ".o.b"));
+    upload_f32(&d.ln1g, w.at(r + ".ln1.g"));
+    upload_f32(&d.ln1b, w.at(r + ".ln1.b"));
+    upload_bf16(&d.w1, w.at(r + ".ffn1.w").data.data(), (size_t)I * H);
+    upload_f32(&d.b1, w.at(r + ".ffn1.b"));
+    upload_bf16(&d.w2, w.at(r + ".ffn2.w").data.data(), (size_t)H * I);
+    upload_f32(&d.b2, w.at(r + ".ffn2.b"));
+    upload_f32(&d.ln2g, w.at(r + ".ln2.g"));
+    upload_f32(&d.ln2b, w.at(r + ".ln2.b"));
+    // position projections with the shared content weights (T:296-302, share_att_key), hoisted
+    // out of the per-Run graph: pos_qk[:, 0:H] = query_proj(rel), pos_qk[:, H:2H] = key_proj(rel)
+    d.pos_qk = dalloc((size_t)R * 2 * H * 2);
+    perm_allocs_.push_back(d.pos_qk);
+    GLC_CUDA(gemm_bf16(rel_ln, H, d.wqkv, H, d.bqkv, d.pos_qk, 2 * H, R, 2 * H, H, 0, false, num_sms_, stream_));
+    ++launches_;
+  }
+  upload_bf16(&t1w_, w.at("text.1.w").data.data(), (size_t)Hh * H);
+  upload_f32(&t1b_, w.at("text.1.b"));
+  upload_bf16(&t2w_, w.at("text.2.w").data.data(), (size_t)Hh * Hh);
+  upload_f32(&t2b_, w.at("text.2.b"));
+  upload_bf16(&c1w_, w.at("cls.1.w").data.data(), (size_t)Hh * H);
+  upload_f32(&c1b_, w.at("cls.1.b"));
+  upload_bf16(&c2w_, w.at("cls.2.w").data.data(), (size_t)Hh * Hh);
+  upload_f32(&c2b_, w.at("cls.2.b"));
+  GLC_CUDA(cudaStreamSynchronize(stream_));
+}
+
+DeviceModel::~DeviceModel() {
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (void* p : ws_allocs_) cudaFree(p);
+  for (void* p : perm_allocs_) cudaFree(p);
+  for (auto& kv : rel_tables_) cudaFree(kv.second);
+  for (auto& kv : debug_) cudaFree(kv.second.ptr);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+const int32_t* DeviceModel::rel_table(int S) {
+  const int Spad = round_up(S, 128);
+  auto it = rel_tables_.find(Spad);
+  if (it != rel_tables_.end()) return it->second;
+  std::vector<int32_t> h((size_t)2 * Spad - 1);
+  rel_index_table(Spad, cfg_.buckets, cfg_.max_rel_pos, h.data());
+  int32_t* d = (int32_t*)dalloc(h.size() * 4);
+  GLC_CUDA(cudaMemcpy(d, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  rel_tables_[Spad] = d;
+  return d;
+}
+
+void DeviceModel::ensure_workspace(int tokens, int B, int C) {
+  const int rows = B * (C > 0 ? C : 1);
+  if (tokens <= ws_tokens_ && B <= ws_B_ && rows <= ws_rows_) return;
+  GLC_CUDA(cudaStreamSynchronize(stream_));
+  for (void* p : ws_allocs_) cudaFree(p);
+  ws_allocs_.clear();
+  ws_tokens_ = tokens > ws_tokens_ ? tokens : ws_tokens_;
+  ws_B_ = B > ws_B_ ? B : ws_B_;
+  ws_rows_ = rows > ws_rows_ ? rows : ws_rows_;
+  const size_t M = (size_t)ws_tokens_, H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
+  auto A = [&](size_t bytes) { void* p = dalloc(bytes); ws_allocs_.push_back(p); return p; };
+  ids_ = (int64_t*)A(M * 8);
+  mask_ = (int64_t*)A(M * 8);
+  x_ = A(M * H * 2);
+  x1_ = A(M * H * 2);
+  qkv_ = A(M * 3 * H * 2);
+  ctx_ = A(M * H * 2);
+  tmp_ = A(M * H * 2);
+  ffn_ = A(M * I * 2);
+  mask_bits_ = (uint32_t*)A(((M + 31) / 32 + (size_t)ws_B_) * 4);
+  kv_len_ = (int32_t*)A((size_t)ws_B_ * 4);
+  pooled_ = A((size_t)ws_B_ * H * 2);
+  cls_ = A((size_t)ws_rows_ * H * 2);
+  tmid_ = A((size_t)ws_B_ * Hh * 2);
+  cmid_ = A((size_t)ws_rows_ * Hh * 2);
+  tvec_ = (float*)A((size_t)ws_B_ * Hh * 4);
+  kvec_ = (float*)A((size_t)ws_rows_ * Hh * 4);
+  logits_ = (float*)A((size_t)ws_rows_ * 4);
+}
+
+void DeviceModel::keep(const char* name, const void* src, size_t count) {
+  if (!debug_keep_) return;
+  DebugBuf& d = debug_[name];
+  if (d.count < count) {
+    if (d.ptr) cudaFree(d.ptr);
+    d.ptr = dalloc(count * 2);
+  }
+  d.count = count;
+  GLC_CUDA(cudaMemcpyAsync(d.ptr, src, count * 2, cudaMemcpyDeviceToDevice, stream_));
+}
+
+int64_t DeviceModel::debug_fetch(const std::string& name, float* out, size_t capacity) {
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = debug_.find(name);
+  if (it == debug_.end()) return -1;
+  const size_t n = it->second.count;
+  if (n > capacity) return -(int64_t)n;
+  cudaSetDevice(device_);
+  std::vector<uint16_t> h(n);
+  GLC_CUDA(cudaStreamSynchronize(stream_));
+  GLC_CUDA(cudaMemcpy(h.data(), it->second.ptr, n * 2, cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t u = (uint32_t)h[i] << 16;
+    memcpy(&out[i], &u, 4);
+  }
+  return (int64_t)n;
+}
+
+void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits) {
+  const int H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
+  const int M = B * S;
+  if (M <= 0) return;
+  if (d_ids != ids_) ensure_workspace(M, B, C);   // run_host already sized it
+  const int32_t* rel = rel_table(S);
+  cudaStream_t st = stream_;
+  uint64_t n = 0;
+
+  GLC_CUDA(mask_prep(d_mask, mask_bits_, kv_len_, B, S, st)); ++n;
+  GLC_CUDA(embed_ln(d_ids, d_mask, word_emb_, emb_g_, emb_b_, cfg_.ln_eps, x_, M, H, cfg_.vocab, st)); ++n;
+  keep("emb", x_, (size_t)M * H);
+  for (int l = 0; l < cfg_.layers; ++l) {
+    const DeviceLayer& d = layers_[l];
+    GLC_CUDA(gemm_bf16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st)); ++n;
+    if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
+    const __nv_bfloat16* pq = (const __nv_bfloat16*)d.pos_qk;
+    GLC_CUDA(attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, cfg_.buckets,
+                             num_sms_, st)); ++n;
+    if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
+    GLC_CUDA(gemm_bf16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st)); ++n;
+    GLC_CUDA(residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st)); ++n;
+    GLC_CUDA(gemm_bf16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_bf16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st)); ++n;
+    GLC_CUDA(residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st)); ++n;
+    if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
+  }
+  if (C > 0) {
+    GLC_CUDA(head_gather(x_, d_ids, cfg_.class_token, pooled_, cls_, B, S, H, C, st)); ++n;
+    GLC_CUDA(gemm_bf16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, 1, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_bf16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_bf16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_bf16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st)); ++n;
+    GLC_CUDA(head_score(tvec_, kvec_, d_logits, nullptr, nullptr, 0.5f, B, C, Hh, st)); ++n;
+  }
+  launches_ += n;
+}
+
+void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits) {
+  if (B <= 0 || S <= 0) return;
+  std::lock_guard<std::mutex> lk(mu);
+  GLC_CUDA(cudaSetDevice(device_));
+  int rows_mb = max_tokens_ / S;
+  if (rows_mb < 1) rows_mb = 1;
+  if (rows_mb > B) rows_mb = B;
+  ensure_workspace(rows_mb * S, rows_mb, C);
+  for (int r0 = 0; r0 < B; r0 += rows_mb) {
+    const int nb = (B - r0 < rows_mb) ? (B - r0) : rows_mb;
+    const size_t bytes = (size_t)nb * S * 8;
+    GLC_CUDA(cudaMemcpyAsync(ids_, ids + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
+    GLC_CUDA(cudaMemcpyAsync(mask_, mask + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
+    forward(ids_, mask_, nb, S, C, logits_);
+    if (C > 0)
+      GLC_CUDA(cudaMemcpyAsync(logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+    if (r0 + rows_mb < B) GLC_CUDA(cudaStreamSynchronize(stream_));   // workspace reuse
+  }
+  GLC_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// ---------------------------------------------------------------------------------------------
+
+Model::Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens) {
+  ModelWeights w;
+  load_model_weights(onnx_path, &w);
+  cfg_ = w.cfg;
+  if (devices.empty()) throw std::runtime_error("no CUDA device selected");
+  for (int d : devices) devs_.emplace_back(new DeviceModel(d, w, max_tokens));
+}
+
+int Model::num_classes(const int64_t* ids, int B, int S) const {
+  int C = 0;
+  for (int b = 0; b < B; ++b) {
+    int n = 0;
+    const int64_t* row = ids + (size_t)b * S;
+    for (int j = 0; j < S; ++j) n += (row[j] == cfg_.class_token);
+    if (n > C) C = n;
+  }
+  return C;
+}
+
+uint64_t Model::launches() const {
+  uint64_t n = 0;
+  for (auto& d : devs_) n += d->launches();
+  return n;
+}
+
+void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits) {
+  const int G = (int)devs_.size();
+  if (G == 1 || B < 2 * G) {
+    // small call (the reference's BATCH_SIZE=8 Run): whole batch on one device, round robin
+    // across concurrent callers (the OpenMP loop of main.c:141-150)
+    const int slot = (int)(rr_.fetch_add(1) % (uint32_t)G);
+    devs_[slot]->run_host(ids, mask, B, S, C, logits);
+    return;
+  }
+  // large call: contiguous row shards, one host thread per device, host gather into `logits`
+  const int per = (B + G - 1) / G;
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(G);
+  for (int g = 0; g < G; ++g) {
+    const int r0 = g * per;
+    const int nb = (r0 >= B) ? 0 : ((B - r0 < per) ? B - r0 : per);
+    if (nb == 0) continue;
+    auto work = [&, g, r0, nb]() {
+      try {
+        devs_[g]->run_host(ids + (size_t)r0 * S, mask + (size_t)r0 * S, nb, S, C, logits + (size_t)r0 * C);
+      } catch (...) {
+        err[g] = std::current_exception();
+      }
+    };
+    if (g == G - 1 || r0 + per >= B) { work(); break; }
+    th.emplace_back(work);
+  }
+  for (auto& t : th) t.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
+
+}  // namespace glc

@@ -1,0 +1,108 @@
+// Engine: per-GPU replica of the model (bf16 weights + precomputed position projections), a
+// workspace, one stream, and the forward pass as a fixed sequence of the K1..K5 kernels.  A
+// Model owns one DeviceModel per GPU and shards the rows of a batch across them (SURVEY.md §8e:
+// batch rows are independent, no collective; the only cross-GPU traffic is the host gather of
+// [rows, C] fp32 logits).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "model_weights.h"
+
+namespace glc {
+
+struct DeviceLayer {
+  void* wqkv = nullptr;   // bf16 [3H,H]  (Wq | Wk | Wv rows)
+  float* bqkv = nullptr;  // [3H]
+  void* wo = nullptr;     // bf16 [H,H]
+  float* bo = nullptr;
+  float *ln1g = nullptr, *ln1b = nullptr;
+  void* w1 = nullptr;     // bf16 [I,H]
+  float* b1 = nullptr;
+  void* w2 = nullptr;     // bf16 [H,I]
+  float* b2 = nullptr;
+  float *ln2g = nullptr, *ln2b = nullptr;
+  void* pos_qk = nullptr; // bf16 [2*buckets, 2H]: cols [0,H) = query_proj(rel), [H,2H) = key_proj(rel)
+};
+
+struct DebugBuf { void* ptr = nullptr; size_t count = 0; };
+
+class DeviceModel {
+ public:
+  DeviceModel(int device, const ModelWeights& w, int max_tokens);
+  ~DeviceModel();
+  DeviceModel(const DeviceModel&) = delete;
+
+  // device-resident inputs; logits fp32 [B,C] on device.  Enqueues on stream(); no sync.
+  void forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits);
+  // host buffers: rows [0,B) of ids/mask, writes logits rows [0,B) (width C); micro-batches by
+  // max_tokens; synchronises before returning.  Serialised per device by `mu`.
+  void run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits);
+
+  int device() const { return device_; }
+  cudaStream_t stream() const { return stream_; }
+  uint64_t launches() const { return launches_.load(); }
+  int64_t debug_fetch(const std::string& name, float* out, size_t capacity);
+  std::mutex mu;
+
+ private:
+  void ensure_workspace(int tokens, int B, int C);
+  const int32_t* rel_table(int S);
+  void* dalloc(size_t bytes);
+  void upload_f32(float** dst, const HostTensor& t);
+  void upload_bf16(void** dst, const float* src, size_t n);
+  void keep(const char* name, const void* src_bf16, size_t count);
+
+  int device_ = 0;
+  int num_sms_ = 148;
+  cudaStream_t stream_ = nullptr;
+  ModelConfig cfg_;
+  int max_tokens_ = 65536;
+  bool debug_keep_ = false;
+  std::atomic<uint64_t> launches_{0};
+
+  // weights
+  void* word_emb_ = nullptr;
+  float *emb_g_ = nullptr, *emb_b_ = nullptr;
+  std::vector<DeviceLayer> layers_;
+  void *t1w_ = nullptr, *t2w_ = nullptr, *c1w_ = nullptr, *c2w_ = nullptr;
+  float *t1b_ = nullptr, *t2b_ = nullptr, *c1b_ = nullptr, *c2b_ = nullptr;
+  std::map<int, int32_t*> rel_tables_;   // keyed by Spad
+
+  // workspace
+  int ws_tokens_ = 0, ws_B_ = 0, ws_rows_ = 0;
+  int64_t *ids_ = nullptr, *mask_ = nullptr;
+  void *x_ = nullptr, *x1_ = nullptr, *qkv_ = nullptr, *ctx_ = nullptr, *tmp_ = nullptr, *ffn_ = nullptr;
+  uint32_t* mask_bits_ = nullptr;
+  int32_t* kv_len_ = nullptr;
+  void *pooled_ = nullptr, *cls_ = nullptr, *tmid_ = nullptr, *cmid_ = nullptr;
+  float *tvec_ = nullptr, *kvec_ = nullptr, *logits_ = nullptr;
+  std::vector<void*> ws_allocs_, perm_allocs_;
+  std::map<std::string, DebugBuf> debug_;
+};
+
+class Model {
+ public:
+  Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens);
+  int num_classes(const int64_t* ids, int B, int S) const;
+  void run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits);
+  const ModelConfig& cfg() const { return cfg_; }
+  int num_devices() const { return (int)devs_.size(); }
+  DeviceModel& dev(int slot) { return *devs_[slot]; }
+  uint64_t launches() const;
+
+ private:
+  ModelConfig cfg_;
+  std::vector<std::unique_ptr<DeviceModel>> devs_;
+  std::atomic<uint32_t> rr_{0};
+};
+
+int usable_device_count();   // sm_100 devices; 0 when there is no driver / GPU
+
+}  // namespace glc

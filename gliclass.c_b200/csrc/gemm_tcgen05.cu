@@ -1,0 +1,270 @@
+// K2 — dense projection GEMM for sm_100a:  C[M,N] = act(A[M,K] · W[N,K]^T + bias[N])
+//
+// Replaces the MatMul+Add(+Erf-GELU) groups ORT executes for query/key/value_proj,
+// attention.output.dense, intermediate.dense and output.dense (arithmetic
+// T:231-233, T:49-53, T:393-396, T:408-412 of transformers' modeling_deberta_v2.py), and the
+// GLiClass projector Linears.
+//
+// Design (one CTA per SM, persistent over 128 x BN output tiles):
+//   warp 0   : TMA producer   — cp.async.bulk.tensor 2D, 128B swizzle, BK = 64 per stage
+//   warp 1   : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage,
+//                               fp32 accumulators in TMEM, double buffered (2 x BN columns)
+//   warps 2-5: epilogue       — tcgen05.ld 32x32b -> +bias -> (erf-GELU) -> bf16/fp32 -> global
+// Pipelines: smem ring full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), all mbarrier.
+// Ragged M/N/K are handled by TMA out-of-bounds zero fill on loads and predication on stores.
+#include <cuda_bf16.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+#include "tma_desc.h"
+
+namespace glc {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int STAGES = (BN == 256) ? 4 : 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // +1024: manual alignment slack
+  static constexpr uint32_t TMEM_COLS = 2 * BN;
+};
+
+// erf-GELU, 0.5 x (1 + erf(x / sqrt 2)).  erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), two
+// MUFU ops (rcp, ex2) + ~10 FMA: cheap enough to hide under the MMA of the next tile.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = __expf(-z * z);
+  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float erf_v = copysignf(erf_abs, x);
+  return 0.5f * x * (1.0f + erf_v);
+}
+
+template <int BN, int ACT, bool OUT_F32>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                         const float* __restrict__ bias, void* __restrict__ Cout, int64_t ldc, int M, int N, int K) {
+  using Cfg = GemmCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_w);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 4);   // one arrive per epilogue warp
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + BM - 1) / BM;
+  const int num_n = (N + BN - 1) / BN;
+  const int num_k = (K + BK - 1) / BK;
+  const int tiles = num_m * num_n;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int m0 = (tile / num_n) * BM;
+        const int n0 = (tile % num_n) * BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&empty[s], ph ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          ptx::tma_load_2d(sa, &tm_a, &full[s], kb * BK, m0);
+          ptx::tma_load_2d(sa + Cfg::A_BYTES, &tm_w, &full[s], kb * BK, n0);
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN);
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_ph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a_base + k * 32), ptx::smem_desc_sw128(b_base + k * 32), idesc,
+                            (uint32_t)((kb | k) != 0));
+          }
+          ptx::mma_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        ptx::mma_commit(&tfull[acc]);   // accumulator complete
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3;   // TMEM lane quarter this warp may read
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM;
+      const int n0 = (tile % num_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      ptx::mbar_wait(&tfull[acc], acc_ph);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
+        ptx::tmem_ld_wait();
+        const int n = n0 + c * 32;
+        if (n >= N) continue;   // warp-uniform
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (bias != nullptr) {
+          if (n + 32 <= N) {
+            const float4* b4 = reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldg(b4 + j);
+              v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(bias + n + j);
+          }
+        }
+        if (ACT == 1) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (row < M) {
+          if (OUT_F32) {
+            float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + n;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (n + 4 * j + 4 <= N) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + (int64_t)row * ldc + n;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (n + 8 * j + 8 <= N) {
+                uint4 o;
+                o.x = ptx::pack_bf16(v[8 * j + 0], v[8 * j + 1]);
+                o.y = ptx::pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+                o.z = ptx::pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+                o.w = ptx::pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                reinterpret_cast<uint4*>(dst)[j] = o;
+              }
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int BN, int ACT, bool OUT_F32>
+cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                        int M, int N, int K, int num_sms, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t sa[1] = {(uint64_t)lda * 2};
+  uint32_t ba[2] = {BK, BM};
+  uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
+  uint64_t sw[1] = {(uint64_t)ldw * 2};
+  uint32_t bw[2] = {BK, BN};
+  CUtensorMap tm_a = make_tmap_bf16(A, 2, da, sa, ba);
+  CUtensorMap tm_w = make_tmap_bf16(W, 2, dw, sw, bw);
+  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_F32>;
+  static bool attr_set[64] = {};   // per template instantiation, per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, bias, C, ldc, M, N, K);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
+                      int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return cudaErrorInvalidValue;
+  if ((lda % 8) || (ldw % 8) || (K % 8) || (N % 8) || (ldc % (out_f32 ? 4 : 8))) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15)
+    return cudaErrorInvalidValue;
+  // 128x256 tiles when that still fills the machine; otherwise 128x128 (more tiles, less tail)
+  const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
+  const bool wide = (N % 256 == 0) && tiles256 >= num_sms;
+  if (out_f32) {
+    if (act == 0) return launch_gemm<128, 0, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+  }
+  if (wide) {
+    if (act == 0) return launch_gemm<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    return launch_gemm<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+  }
+  if (act == 0) return launch_gemm<128, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+  return launch_gemm<128, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+}
+
+}  // namespace glc

@@ -1,0 +1,270 @@
+// ONNX graph -> role-named fp32 host tensors.  Roles:
+//   emb.word [V,H]  emb.ln.g/b [H]  rel.emb [2*buckets,H]  rel.ln.g/b [H]
+//   layer.<l>.{q,k,v,o}.w [H,H]  .b [H]   layer.<l>.ln1.g/b
+//   layer.<l>.ffn1.w [I,H] .b [I]  layer.<l>.ffn2.w [H,I] .b [H]  layer.<l>.ln2.g/b
+//   text.1.w [Hh,H] text.1.b  text.2.w [Hh,Hh] text.2.b   cls.1.* cls.2.*  (FeaturesProjector x2)
+// Naming facts relied on (verified on a real torch export):
+//   * 3-D-input nn.Linear -> MatMul(x, anonymous [in,out] initializer) + Add(named bias)
+//   * 2-D-input nn.Linear -> Gemm(x, W[out,in], b) with transB=1
+//   * node names carry module scope: .../encoder/layer.<l>/attention/self/query_proj/MatMul
+//   * identical tensors are deduplicated into Identity aliases (resolved by OnnxGraph::resolve)
+#include "model_weights.h"
+
+#include <cmath>
+#include <cstring>
+#include <stdexcept>
+
+#include "onnx_reader.h"
+
+namespace glc {
+namespace {
+
+bool ends_with(const std::string& s, const std::string& suf) {
+  return s.size() >= suf.size() && s.compare(s.size() - suf.size(), suf.size(), suf) == 0;
+}
+
+const OnnxNode* find_node(const OnnxGraph& g, const std::string& suffix, const char* op = nullptr) {
+  for (auto& n : g.nodes)
+    if (ends_with(n.name, suffix) && (!op || n.op_type == op)) return &n;
+  return nullptr;
+}
+
+HostTensor to_host(const OnnxTensor& t) {
+  HostTensor h;
+  h.dims = t.dims;
+  h.data.resize((size_t)t.numel());
+  tensor_to_float(t, h.data.data());
+  return h;
+}
+
+HostTensor transpose2d(const HostTensor& a) {
+  HostTensor o;
+  int64_t r = a.dims[0], c = a.dims[1];
+  o.dims = {c, r};
+  o.data.resize(a.data.size());
+  for (int64_t i = 0; i < r; ++i)
+    for (int64_t j = 0; j < c; ++j) o.data[(size_t)(j * r + i)] = a.data[(size_t)(i * c + j)];
+  return o;
+}
+
+// scope e.g. "/layer.0/attention/self/query_proj"
+void load_linear(const OnnxGraph& g, const std::string& scope, const std::string& role, ModelWeights* out) {
+  const OnnxNode* mm = find_node(g, scope + "/MatMul", "MatMul");
+  if (mm) {
+    if (mm->inputs.size() != 2) throw std::runtime_error("onnx: MatMul arity at " + mm->name);
+    const OnnxTensor* w = g.resolve(mm->inputs[1]);
+    if (!w || w->dims.size() != 2) throw std::runtime_error("onnx: no constant 2-D weight at " + mm->name);
+    out->t[role + ".w"] = transpose2d(to_host(*w));   // [in,out] -> [out,in]
+    const OnnxNode* add = find_node(g, scope + "/Add", "Add");
+    if (!add) throw std::runtime_error("onnx: no bias Add after " + mm->name);
+    const OnnxTensor* b = nullptr;
+    for (auto& in : add->inputs) { b = g.resolve(in); if (b) break; }
+    if (!b) throw std::runtime_error("onnx: no constant bias at " + add->name);
+    out->t[role + ".b"] = to_host(*b);
+    return;
+  }
+  const OnnxNode* gm = find_node(g, scope + "/Gemm", "Gemm");
+  if (gm) {
+    if (gm->inputs.size() < 2) throw std::runtime_error("onnx: Gemm arity at " + gm->name);
+    const OnnxTensor* w = g.resolve(gm->inputs[1]);
+    if (!w || w->dims.size() != 2) throw std::runtime_error("onnx: no constant 2-D weight at " + gm->name);
+    const OnnxAttr* tb = gm->attr("transB");
+    const OnnxAttr* ta = gm->attr("transA");
+    const OnnxAttr* al = gm->attr("alpha");
+    const OnnxAttr* be = gm->attr("beta");
+    if ((ta && ta->i != 0) || (al && al->f != 1.0f) || (be && be->f != 1.0f))
+      throw std::runtime_error("onnx: unsupported Gemm attributes at " + gm->name);
+    HostTensor hw = to_host(*w);
+    out->t[role + ".w"] = (tb && tb->i == 1) ? hw : transpose2d(hw);
+    HostTensor hb;
+    if (gm->inputs.size() >= 3) {
+      const OnnxTensor* b = g.resolve(gm->inputs[2]);
+      if (!b) throw std::runtime_error("onnx: non-constant Gemm bias at " + gm->name);
+      hb = to_host(*b);
+    } else {
+      hb.dims = {out->t[role + ".w"].dims[0]};
+      hb.data.assign((size_t)hb.dims[0], 0.f);
+    }
+    out->t[role + ".b"] = hb;
+    return;
+  }
+  throw std::runtime_error("onnx: no MatMul/Gemm node for scope " + scope);
+}
+
+// decomposed opset-14 LayerNorm: .../LayerNorm/Mul(x, gamma), .../LayerNorm/Add_1(x, beta)
+void load_layernorm(const OnnxGraph& g, const std::string& scope, const std::string& role, int64_t H,
+                    ModelWeights* out) {
+  auto pick = [&](const char* leaf, const char* op) -> HostTensor {
+    const OnnxNode* n = find_node(g, scope + "/LayerNorm/" + leaf, op);
+    if (!n) throw std::runtime_error("onnx: no " + scope + "/LayerNorm/" + leaf);
+    for (auto& in : n->inputs) {
+      const OnnxTensor* t = g.resolve(in);
+      if (t && t->numel() == H) return to_host(*t);
+    }
+    throw std::runtime_error("onnx: no constant [H] operand at " + n->name);
+  };
+  out->t[role + ".g"] = pick("Mul", "Mul");
+  out->t[role + ".b"] = pick("Add_1", "Add");
+}
+
+const OnnxTensor* find_named(const OnnxGraph& g, const std::string& suffix) {
+  for (auto& t : g.initializers)
+    if (ends_with(t.name, suffix)) return &t;
+  for (auto& n : g.nodes)
+    if (n.op_type == "Identity" && n.outputs.size() == 1 && ends_with(n.outputs[0], suffix))
+      return g.resolve(n.outputs[0]);
+  return nullptr;
+}
+
+}  // namespace
+
+const HostTensor& ModelWeights::at(const std::string& role) const {
+  auto it = t.find(role);
+  if (it == t.end()) throw std::runtime_error("weights: missing role " + role);
+  return it->second;
+}
+
+void load_model_weights(const std::string& path, ModelWeights* out) {
+  OnnxGraph g;
+  g.load(path);
+  if (g.input_names.size() < 2 || g.input_names[0] != "input_ids" || g.input_names[1] != "attention_mask")
+    throw std::runtime_error("onnx: expected graph inputs (input_ids, attention_mask)");
+  ModelConfig& c = out->cfg;
+
+  // ---- embeddings
+  const OnnxTensor* we = find_named(g, "embeddings.word_embeddings.weight");
+  if (!we || we->dims.size() != 2) throw std::runtime_error("onnx: word_embeddings.weight not found");
+  c.vocab = (int)we->dims[0];
+  c.hidden = (int)we->dims[1];
+  out->t["emb.word"] = to_host(*we);
+  load_layernorm(g, "/embeddings", "emb.ln", c.hidden, out);
+  const OnnxTensor* re = find_named(g, "encoder.rel_embeddings.weight");
+  if (!re || re->dims.size() != 2 || re->dims[1] != c.hidden)
+    throw std::runtime_error("onnx: encoder.rel_embeddings.weight not found (relative_attention model expected)");
+  c.buckets = (int)(re->dims[0] / 2);
+  out->t["rel.emb"] = to_host(*re);
+  load_layernorm(g, "/encoder", "rel.ln", c.hidden, out);
+
+  // ---- layers
+  int L = 0;
+  while (find_node(g, "/layer." + std::to_string(L) + "/attention/self/query_proj/MatMul")) ++L;
+  if (L == 0) throw std::runtime_error("onnx: no encoder layers found (node names without module scopes?)");
+  c.layers = L;
+  for (int l = 0; l < L; ++l) {
+    std::string s = "/layer." + std::to_string(l), r = "layer." + std::to_string(l);
+    load_linear(g, s + "/attention/self/query_proj", r + ".q", out);
+    load_linear(g, s + "/attention/self/key_proj", r + ".k", out);
+    load_linear(g, s + "/attention/self/value_proj", r + ".v", out);
+    load_linear(g, s + "/attention/output/dense", r + ".o", out);
+    load_layernorm(g, s + "/attention/output", r + ".ln1", c.hidden, out);
+    load_linear(g, s + "/intermediate/dense", r + ".ffn1", out);
+    load_linear(g, s + "/output/dense", r + ".ffn2", out);
+    load_layernorm(g, s + "/output", r + ".ln2", c.hidden, out);
+    // share_att_key: the position projections must reuse the content projections
+    const OnnxNode* pq = find_node(g, s + "/attention/self/query_proj_1/MatMul", "MatMul");
+    const OnnxNode* cq = find_node(g, s + "/attention/self/query_proj/MatMul", "MatMul");
+    if (!pq) throw std::runtime_error("onnx: layer " + std::to_string(l) + " has no query_proj_1 (share_att_key p2c|c2p model expected)");
+    if (g.resolve(pq->inputs[1]) != g.resolve(cq->inputs[1])) {
+      // not an alias: accept only if values are identical
+      const OnnxTensor* a = g.resolve(pq->inputs[1]);
+      const OnnxTensor* b = g.resolve(cq->inputs[1]);
+      if (!a || !b || a->numel() != b->numel() || !a->raw || !b->raw || memcmp(a->raw, b->raw, a->raw_bytes) != 0)
+        throw std::runtime_error("onnx: separate pos_query_proj weights are not supported (share_att_key=false)");
+    }
+  }
+  c.inter = (int)out->at("layer.0.ffn1.w").dims[0];
+
+  // ---- heads: Concat(batch, seq, Constant(heads), Constant(-1)) feeding the first Reshape
+  c.heads = 0;
+  for (auto& n : g.nodes) {
+    if (n.op_type != "Concat" || n.inputs.size() != 4) continue;
+    if (n.name.find("/layer.0/attention/self/") == std::string::npos) continue;
+    int64_t hv = 0, last = 0;
+    if (g.scalar_int(n.inputs[2], &hv) && g.scalar_int(n.inputs[3], &last) && last == -1 && hv > 0) {
+      c.heads = (int)hv;
+      break;
+    }
+  }
+  if (c.heads == 0) c.heads = c.hidden / 64;   // d = 64 in every DeBERTa-v3 size
+  if (c.hidden % c.heads != 0) throw std::runtime_error("onnx: hidden not divisible by heads");
+
+  // ---- LayerNorm eps: Constant added to the variance in the embeddings LN
+  if (const OnnxNode* n = find_node(g, "/embeddings/LayerNorm/Add", "Add")) {
+    float e;
+    for (auto& in : n->inputs)
+      if (g.scalar_float(in, &e) && e > 0.f && e < 1e-2f) c.ln_eps = e;
+  }
+
+  // ---- log-bucket constants: Div(abs_pos, mid) -> Log -> Div(., log((max_pos-1)/mid))
+  for (auto& n : g.nodes) {
+    if (n.op_type != "Log") continue;
+    float mid = 0.f, lg = 0.f;
+    auto pit = g.producer_of.find(n.inputs[0]);
+    if (pit != g.producer_of.end() && g.nodes[pit->second].op_type == "Div" &&
+        g.scalar_float(g.nodes[pit->second].inputs[1], &mid) && mid > 0.f) {
+      for (auto& m : g.nodes)
+        if (m.op_type == "Div" && m.inputs.size() == 2 && m.inputs[0] == n.outputs[0] &&
+            g.scalar_float(m.inputs[1], &lg) && lg > 0.f) {
+          int mp = (int)std::lround(std::exp((double)lg) * mid) + 1;
+          if ((int)std::lround(mid) * 2 == c.buckets && mp > 1) c.max_rel_pos = mp;
+        }
+    }
+    break;
+  }
+
+  // ---- class token id: Equal(input_ids, Constant)
+  for (auto& n : g.nodes) {
+    if (n.op_type != "Equal" || n.inputs.size() != 2) continue;
+    int64_t v;
+    if (n.inputs[0] == "input_ids" && g.scalar_int(n.inputs[1], &v)) { c.class_token = v; break; }
+    if (n.inputs[1] == "input_ids" && g.scalar_int(n.inputs[0], &v)) { c.class_token = v; break; }
+  }
+  if (c.class_token < 0) throw std::runtime_error("onnx: Equal(input_ids, class_token_index) not found");
+
+  // ---- head
+  load_linear(g, "/text_projector/linear_1", "text.1", out);
+  load_linear(g, "/text_projector/linear_2", "text.2", out);
+  load_linear(g, "/classes_projector/linear_1", "cls.1", out);
+  load_linear(g, "/classes_projector/linear_2", "cls.2", out);
+  c.head_hidden = (int)out->at("text.2.w").dims[0];
+  bool has_einsum = false;
+  for (auto& n : g.nodes) if (n.op_type == "Einsum") has_einsum = true;
+  if (!has_einsum) throw std::runtime_error("onnx: dot scorer (Einsum) not found; only scorer_type='simple' is supported");
+
+  // ---- shape checks
+  auto expect = [&](const std::string& role, std::vector<int64_t> d) {
+    if (out->at(role).dims != d) throw std::runtime_error("weights: unexpected shape for " + role);
+  };
+  int64_t H = c.hidden, I = c.inter, Hh = c.head_hidden;
+  for (int l = 0; l < L; ++l) {
+    std::string r = "layer." + std::to_string(l);
+    for (const char* p : {".q", ".k", ".v", ".o"}) { expect(r + p + ".w", {H, H}); expect(r + p + ".b", {H}); }
+    expect(r + ".ffn1.w", {I, H}); expect(r + ".ffn1.b", {I});
+    expect(r + ".ffn2.w", {H, I}); expect(r + ".ffn2.b", {H});
+  }
+  expect("text.1.w", {Hh, H}); expect("text.2.w", {Hh, Hh});
+  expect("cls.1.w", {Hh, H}); expect("cls.2.w", {Hh, Hh});
+}
+
+void rel_index_table(int S, int buckets, int max_pos, int32_t* out) {
+  // make_log_bucket_position in fp32, as traced (T:57-69): mid = buckets/2
+  const int mid = buckets / 2;
+  const float denom = logf((float)(max_pos - 1) / (float)mid);
+  for (int delta = -(S - 1); delta <= S - 1; ++delta) {
+    int sign = (delta > 0) - (delta < 0);
+    int abs_pos = (delta < mid && delta > -mid) ? (mid - 1) : (delta < 0 ? -delta : delta);
+    int bucket;
+    if (abs_pos <= mid) {
+      bucket = delta;
+    } else {
+      float lp = ceilf(logf((float)abs_pos / (float)mid) / denom * (float)(mid - 1)) + (float)mid;
+      bucket = (int)lp * sign;
+    }
+    int idx = bucket + buckets;
+    if (idx < 0) idx = 0;
+    if (idx > 2 * buckets - 1) idx = 2 * buckets - 1;
+    out[delta + S - 1] = idx;
+  }
+}
+
+}  // namespace glc

@@ -1,0 +1,43 @@
+// Role mapping: ONNX graph -> named fp32 host tensors of the GLiClass uni-encoder
+// (DeBERTa-v3 backbone + projector/dot-scorer head).  This is the "weights" half of what ORT's
+// CreateSession does for the reference (src/model.c:269); the graph structure itself is not
+// executed — the engine hard-codes the architecture.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace glc {
+
+struct HostTensor {
+  std::vector<int64_t> dims;
+  std::vector<float> data;
+};
+
+struct ModelConfig {
+  int vocab = 0, hidden = 0, layers = 0, heads = 0, inter = 0;
+  int head_hidden = 0;          // projector width
+  int buckets = 256;            // position_buckets (= att_span); rel table has 2*buckets rows
+  int max_rel_pos = 512;        // max_position in make_log_bucket_position
+  float ln_eps = 1e-7f;
+  int64_t class_token = -1;     // <<LABEL>> id: Constant feeding Equal(input_ids, .)
+};
+
+// Linear weights are stored [out, in] row-major (torch Linear layout == the K-major "B"
+// operand of the tcgen05 GEMM); ONNX MatMul initializers ([in, out]) are transposed on load.
+struct ModelWeights {
+  ModelConfig cfg;
+  std::map<std::string, HostTensor> t;   // role -> tensor, roles listed in model_weights.cc
+  const HostTensor& at(const std::string& role) const;
+  bool has(const std::string& role) const { return t.count(role) != 0; }
+};
+
+// throws std::runtime_error with a precise message when a role cannot be found
+void load_model_weights(const std::string& onnx_path, ModelWeights* out);
+
+// idx[delta + S - 1] = clamp(bucket(delta) + buckets, 0, 2*buckets-1), delta in (-S, S)
+// (HF make_log_bucket_position / build_relative_position)
+void rel_index_table(int S, int buckets, int max_pos, int32_t* out /* 2S-1 */);
+
+}  // namespace glc

@@ -1,0 +1,137 @@
+/* gliclass_b200.h — native C ABI of the B200 GLiClass engine (libgliclass_b200.so).
+ *
+ * This is the drop-in boundary for the one hot path GLiClass.c hands to ONNX Runtime:
+ *   reference src/model.c:217-281  create_ort_session -> g_ort->CreateSession   => glc_load
+ *   reference src/model.c:122-207  run_inference      -> g_ort->Run             => glc_run
+ *   reference main.c:186           g_ort->ReleaseSession                        => glc_free
+ * The ORT-named entry points the unchanged reference sources link against live in
+ * include/onnxruntime_c_api.h (same library); they are thin wrappers over the functions below.
+ *
+ * Plain pointers and sizes only.  All functions are thread-safe unless noted.  On failure they
+ * return NULL / a negative code and glc_last_error() (thread-local) describes why.  There is no
+ * CPU fallback: glc_load fails when no sm_100 device is usable.
+ */
+#ifndef GLICLASS_B200_H
+#define GLICLASS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GLC_API __attribute__((visibility("default")))
+
+typedef struct glc_model glc_model;   /* a loaded model replicated on 1..8 GPUs */
+typedef struct glc_onnx glc_onnx;     /* host-only parse of a model.onnx (no GPU needed) */
+
+enum { GLC_OK = 0, GLC_ERR = -1, GLC_ERR_ARG = -2, GLC_ERR_CUDA = -3, GLC_ERR_CAPACITY = -4 };
+enum { GLC_DTYPE_BF16 = 0, GLC_DTYPE_FP8_E4M3 = 1 };
+
+typedef struct glc_opts {
+  uint32_t struct_size;      /* = sizeof(glc_opts) */
+  int32_t num_devices;       /* 0 = GLC_DEVICES env or device 0 only */
+  int32_t device_ids[8];
+  int32_t weight_dtype;      /* GLC_DTYPE_*; activations are always bf16, accumulation fp32 */
+  int32_t max_tokens;        /* micro-batch cap in tokens per device launch (0 = default 65536) */
+  int32_t num_heads;         /* 0 = infer from graph */
+  int32_t reserved[8];
+} glc_opts;
+
+typedef struct glc_info {
+  int32_t vocab, hidden, layers, heads, inter, head_hidden, buckets, max_rel_pos;
+  float ln_eps;
+  int64_t class_token;
+  int32_t num_devices;
+  int32_t weight_dtype;
+} glc_info;
+
+GLC_API const char* glc_last_error(void);
+GLC_API int glc_device_count(void);          /* usable sm_100 devices; 0 when none (never fails) */
+
+/* ---- the hot path ------------------------------------------------------------------------ */
+
+/* Parse model.onnx, upload weights (bf16; pos-projection tables precomputed per layer). */
+GLC_API glc_model* glc_load(const char* onnx_path, const glc_opts* opts /* may be NULL */);
+GLC_API void glc_free(glc_model* m);
+GLC_API int glc_model_info(const glc_model* m, glc_info* out);
+
+/* C = max over rows of the number of <<LABEL>> tokens (output width of the reference graph). */
+GLC_API int glc_num_classes(const glc_model* m, const int64_t* input_ids, int B, int S);
+
+/* One forward.  HOST buffers: input_ids / attention_mask int64 [B,S] row-major (the layout
+ * reference flatten_int_array, src/model.c:17-29, produces); logits_out fp32 [B,C] row-major,
+ * C returned through C_out.  logits_capacity is in floats; GLC_ERR_CAPACITY if B*C exceeds it.
+ * Rows are sharded across the model's devices; the call returns when logits_out is complete. */
+GLC_API int glc_run(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
+                    float* logits_out, size_t logits_capacity, int* C_out);
+
+/* Same forward with inputs/outputs already resident on `device` (kernel-only timing, parity
+ * tests).  d_logits fp32 [B,C] device memory with C = num_classes (caller computes it with
+ * glc_num_classes on the host copy).  Runs on the engine's stream for that device and
+ * synchronises it before returning unless `async` is non-zero. */
+GLC_API int glc_run_device(glc_model* m, int device_slot, const int64_t* d_input_ids,
+                           const int64_t* d_attention_mask, int B, int S, int C, float* d_logits, int async);
+GLC_API int glc_sync(glc_model* m, int device_slot);
+/* CUDA stream (cudaStream_t) the engine launches on for a device slot, for event timing. */
+GLC_API void* glc_stream(glc_model* m, int device_slot);
+/* kernels launched by this model since load (all devices) — bench.py's gpu_launches */
+GLC_API uint64_t glc_launch_count(const glc_model* m);
+/* copy a named intermediate of the last forward on device_slot to host as fp32.
+ * names: "emb", "qkv0", "ctx0", "h<l>" .  Returns element count or <0. */
+GLC_API int64_t glc_debug_fetch(glc_model* m, int device_slot, const char* name, float* out, size_t capacity);
+
+/* ---- fused decision epilogue (reference src/postprocessor.c:85-150) ------------------------ */
+/* multi-label: out_mask[b*C+c] = sigmoid(logit) > threshold (strict); single-label: out_argmax[b]
+ * = argmax_c sigmoid(logit) with the reference's initial max_prob = 0 / max_idx = -1. */
+GLC_API int glc_decide(const float* logits, int B, int C, float threshold, uint8_t* out_mask /*nullable*/,
+                       int32_t* out_argmax /*nullable*/, float* out_prob /*nullable [B,C]*/);
+
+/* ---- host-only model inspection (tests; no GPU needed) ------------------------------------- */
+GLC_API glc_onnx* glc_onnx_open(const char* onnx_path);
+GLC_API void glc_onnx_close(glc_onnx* h);
+GLC_API int glc_onnx_info(const glc_onnx* h, glc_info* out);
+/* role-named tensor ("layer.3.q.w", "emb.word", ... see csrc/model_weights.cc); Linear weights
+ * are [out,in].  Returns ndim (<=4) or <0; *data stays valid until glc_onnx_close. */
+GLC_API int glc_onnx_tensor(const glc_onnx* h, const char* role, const float** data, int64_t dims[4]);
+GLC_API int glc_onnx_num_roles(const glc_onnx* h);
+GLC_API const char* glc_onnx_role_name(const glc_onnx* h, int i);
+/* idx[delta+S-1] = clamp(bucket(delta)+buckets, 0, 2*buckets-1): the single c2p/p2c index table */
+GLC_API int glc_rel_index_table(int S, int buckets, int max_pos, int32_t* out /* 2S-1 */);
+
+/* ---- single-kernel entry points on device pointers (parity tests, ncu captures) ------------- */
+/* All take a cudaStream_t as void* (NULL = default stream), launch on the CURRENT device and
+ * return after launch (no sync).  These are the K1..K5 kernels of the forward (csrc/kernels.h). */
+
+/* K2: C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); bf16 operands, fp32 accumulate in TMEM
+ * (tcgen05 + TMA).  act: 0 none, 1 erf-GELU.  out_f32: C is fp32 instead of bf16.  ld* in elements. */
+GLC_API int glc_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                        int M, int N, int K, int act, int out_f32, void* stream);
+/* K1: y[m,:] = (LN(word_emb[ids[m],:]) * gamma + beta) * (mask[m] != 0) */
+GLC_API int glc_op_embed_ln(const int64_t* ids, const int64_t* mask, const void* word_emb_bf16, const float* gamma,
+                            const float* beta, float eps, void* y_bf16, int M, int H, int vocab, void* stream);
+/* K4: y = LN(x + r) * gamma + beta (bf16 in/out, fp32 statistics); r may be NULL */
+GLC_API int glc_op_residual_ln(const void* x_bf16, const void* r_bf16, const float* gamma, const float* beta,
+                               float eps, void* y_bf16, int M, int H, void* stream);
+/* attention-mask packing: bits[b][w] bit j = mask[b][32w+j] != 0; kv_len[b] = 1 + last valid key */
+GLC_API int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, void* stream);
+/* K3: fused disentangled attention for one layer.  qkv bf16 [B*S,3H] (Q|K|V); pos_k / pos_q bf16
+ * [2*buckets][ld_pos] row-major (head h at columns h*64..); rel_idx int32 [2*Spad-1] built with
+ * glc_rel_index_table(Spad) where Spad = S rounded up to 128; mask_bits/kv_len from
+ * glc_op_mask_prep; ctx bf16 [B*S,H].  naive != 0 runs the slow CUDA-core restatement instead
+ * (tests only). */
+GLC_API int glc_op_attention(const void* qkv_bf16, const void* pos_k_bf16, const void* pos_q_bf16, int64_t ld_pos,
+                             const int32_t* rel_idx, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_bf16,
+                             int B, int S, int heads, int buckets, int naive, void* stream);
+/* K5a: pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] for the c-th <<LABEL>> token, else 0 */
+GLC_API int glc_op_head_gather(const void* h_bf16, const int64_t* ids, int64_t class_token, void* pooled_bf16,
+                               void* cls_bf16, int B, int S, int H, int C, void* stream);
+/* K5b: logits[b,c] = <t[b,:], k[b,c,:]>; optional probs = sigmoid(logit), decisions = probs > threshold */
+GLC_API int glc_op_head_score(const float* t, const float* k, float* logits, float* probs, uint8_t* decisions,
+                              float threshold, int B, int C, int Hh, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GLICLASS_B200_H */

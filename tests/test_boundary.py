@@ -1,0 +1,156 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads and exports every symbol the headers
+declare, the ONNX reader recovers exactly the oracle's weights and config from a file exported
+with the reference's own export call, the rel-pos table / decision helpers agree with the
+oracle, and the ORT shim behaves like the API the unchanged reference sources call."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+
+
+def _declared(header):
+    src = open(os.path.join(ROOT, "include", header)).read()
+    return sorted(set(re.findall(r"\b(glc_[a-z0-9_]+|Ort[A-Za-z_]+)\s*\(", src)) - {"glc_opts", "glc_info"})
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = ctypes.CDLL(pkg.LIB_PATH)
+    names = [n for n in _declared("gliclass_b200.h") if n.startswith("glc_")]
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/gliclass_b200.h but not exported"
+    for n in ("OrtGetApiBase", "OrtSessionOptionsAppendExecutionProvider_CUDA"):
+        assert hasattr(L, n)
+    # and the python binding covers them all
+    assert set(names) <= set(pkg._SIGS)
+
+
+def test_onnx_reader_recovers_oracle_weights(pkg, orc, golden_onnx):
+    cfg = orc.make_config("tiny")
+    w = orc.init_weights(cfg, 0)
+    f = pkg.OnnxFile(golden_onnx)
+    i = f.info
+    assert (i["vocab"], i["hidden"], i["layers"], i["heads"], i["inter"]) == (1027, 128, 2, 2, 512)
+    assert i["head_hidden"] == 128 and i["buckets"] == 256 and i["max_rel_pos"] == 512
+    assert i["class_token"] == cfg.class_token_index
+    assert abs(i["ln_eps"] - 1e-7) < 1e-12
+    E = orc.ENC
+    expect = {"emb.word": E + "embeddings.word_embeddings.weight", "emb.ln.g": E + "embeddings.LayerNorm.weight",
+              "emb.ln.b": E + "embeddings.LayerNorm.bias", "rel.emb": E + "encoder.rel_embeddings.weight",
+              "rel.ln.g": E + "encoder.LayerNorm.weight", "rel.ln.b": E + "encoder.LayerNorm.bias"}
+    for l in range(cfg.num_layers):
+        p = f"{E}encoder.layer.{l}."
+        for r, n in (("q", "attention.self.query_proj"), ("k", "attention.self.key_proj"), ("v", "attention.self.value_proj"),
+                     ("o", "attention.output.dense"), ("ffn1", "intermediate.dense"), ("ffn2", "output.dense")):
+            expect[f"layer.{l}.{r}.w"] = p + n + ".weight"       # [out,in], as torch stores it
+            expect[f"layer.{l}.{r}.b"] = p + n + ".bias"
+        for r, n in (("ln1", "attention.output.LayerNorm"), ("ln2", "output.LayerNorm")):
+            expect[f"layer.{l}.{r}.g"] = p + n + ".weight"
+            expect[f"layer.{l}.{r}.b"] = p + n + ".bias"
+    for r, n in (("text", "text_projector"), ("cls", "classes_projector")):
+        for k in (1, 2):
+            expect[f"{r}.{k}.w"] = f"model.{n}.linear_{k}.weight"
+            expect[f"{r}.{k}.b"] = f"model.{n}.linear_{k}.bias"
+    assert sorted(f.roles()) == sorted(expect)
+    for role, name in expect.items():
+        got = f.tensor(role)
+        ref = w[name].numpy()
+        assert got.shape == ref.shape, role
+        assert np.array_equal(got, ref), role      # bit exact: fp32 in, fp32 out
+    f.close()
+
+
+def test_onnx_reader_resolves_dedup_aliases(pkg, orc, tmp_path):
+    # HF-default-style degenerate init: identical biases / gammas collapse into Identity aliases
+    # in torch's exporter; the reader must still resolve every role.
+    import torch
+    cfg = orc.make_config("tiny")
+    w = orc.init_weights(cfg, 3)
+    for k in w:
+        if k.endswith(".bias"):
+            w[k] = torch.zeros_like(w[k])
+        elif "LayerNorm.weight" in k:
+            w[k] = torch.ones_like(w[k])
+    path = str(tmp_path / "dedup.onnx")
+    orc.export_onnx(orc.build_hf_module(cfg, w), cfg, path)
+    f = pkg.OnnxFile(path)
+    assert np.array_equal(f.tensor("layer.1.ln2.g"), np.ones(128, np.float32))
+    assert np.array_equal(f.tensor("layer.0.k.b"), np.zeros(128, np.float32))
+    assert np.array_equal(f.tensor("layer.1.ffn2.w"), w[orc.ENC + "encoder.layer.1.output.dense.weight"].numpy())
+    f.close()
+
+
+def test_onnx_reader_errors_are_loud(pkg, tmp_path):
+    with pytest.raises(pkg.GlcError, match="cannot open"):
+        pkg.OnnxFile(str(tmp_path / "nope.onnx"))
+    bad = tmp_path / "bad.onnx"
+    bad.write_bytes(b"\x0a\xff\xff\xff\xff\xff\xff\xff\xff\xff\xff\x01garbage")
+    with pytest.raises(pkg.GlcError):
+        pkg.OnnxFile(str(bad))
+    trunc = tmp_path / "trunc.onnx"
+    trunc.write_bytes(open(os.path.join(GOLDEN, "model.onnx"), "rb").read()[:100000])
+    with pytest.raises(pkg.GlcError):
+        pkg.OnnxFile(str(trunc))
+
+
+@pytest.mark.parametrize("S", [1, 37, 128, 512, 700, 1024, 2048])
+def test_rel_index_table_bit_exact(pkg, orc, S):
+    cfg = orc.make_config("tiny")
+    assert np.array_equal(pkg.rel_index_table(S, 256, 512), orc.rel_index_table(S, cfg).astype(np.int32))
+
+
+def test_decide_matches_oracle(pkg, orc):
+    rng = np.random.default_rng(0)
+    lg = (rng.standard_normal((64, 10)) * 3).astype(np.float32)
+    lg[0, :3] = [0.0, np.float32(1e-8), -np.float32(1e-8)]
+    lg[1] = -np.inf
+    m, a, p = pkg.decide(lg, 0.5)
+    assert np.array_equal(m, orc.decisions_multilabel(lg, 0.5))
+    assert np.array_equal(a, orc.decisions_singlelabel(lg))
+    assert a[1] == -1
+    assert np.allclose(p, orc.sigmoid32(lg), atol=1e-7)
+
+
+def test_no_cpu_fallback(pkg, golden_onnx):
+    """On a box without a B200 the product path must fail loudly, never compute on the CPU."""
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.GlcError, match="no usable sm_100|no CPU fallback"):
+        pkg.Session(golden_onnx)
+
+
+def test_product_path_never_imports_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "gliclass.c_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cc", ".h", ".cuh")):
+                src = open(os.path.join(dirpath, fn), errors="ignore").read()
+                assert "oracle" not in src.lower() or fn == "Makefile", f"{fn} mentions the oracle"
+
+
+def test_ort_shim_host_behaviour(pkg, golden_onnx, tmp_path):
+    exe = str(tmp_path / "shim_host_test")
+    subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-O1", "-Wall", "-Werror",
+                    "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "shim_host_test.c"),
+                    "-o", exe, "-L" + os.path.dirname(pkg.LIB_PATH), "-lgliclass_b200",
+                    "-Wl,-rpath," + os.path.dirname(pkg.LIB_PATH)], check=True)
+    r = subprocess.run([exe, golden_onnx], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "OK" in r.stdout and "missing-file:" in r.stdout
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/main.c"), reason="reference sources not present")
+def test_unchanged_reference_sources_link_against_shim(pkg):
+    """main.c, model.c, postprocessor.c, parallel_processor.c compile and link
+    UNCHANGED against include/onnxruntime_c_api.h + libgliclass_b200.so."""
+    subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=True, capture_output=True)
+    exe = os.path.join(ROOT, "oracle", "_ref", "gliclass_ref_main")
+    assert os.path.exists(exe)
+    syms = subprocess.run(["nm", "-u", exe], capture_output=True, text=True).stdout
+    assert "OrtGetApiBase" in syms
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert "Usage:" in r.stdout
