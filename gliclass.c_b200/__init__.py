@@ -136,7 +136,8 @@ def prepare_input_tensors(input_ids, attention_mask):
 class Session:
     """reference create_ort_session (src/model.c:217-281) + run_inference (src/model.c:122-207)."""
 
-    def __init__(self, model_path: str, devices: Optional[Sequence[int]] = None, max_tokens: int = 0):
+    def __init__(self, model_path: str, devices: Optional[Sequence[int]] = None, max_tokens: int = 0,
+                 weight_dtype: str = "default"):
         L = lib()
         o = glc_opts()
         o.struct_size = C.sizeof(glc_opts)
@@ -145,6 +146,7 @@ class Session:
             for k, d in enumerate(devices):
                 o.device_ids[k] = int(d)
         o.max_tokens = int(max_tokens)
+        o.weight_dtype = {"default": 0, "fp16": 1, "bf16": 2, "fp8": 3}[weight_dtype]
         self._h = L.glc_load(os.fsencode(model_path), C.byref(o))
         if not self._h:
             raise GlcError(f"create session failed: {last_error()}")

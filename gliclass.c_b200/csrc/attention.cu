@@ -19,10 +19,9 @@
 //             PV  = P . V_t            [128 x 64]        cols 448..511
 //   warps 2-9  softmax: 256 threads; thread = (row i, 32-key half g).  Stage C2P/P2C' TMEM->fp16
 //           smem, gather both biases per score element, online softmax in registers (max shared
-//           between the two halves through smem), P -> bf16 swizzled smem tile for the PV MMA,
+//           between the two halves through smem), P -> fp16 swizzled smem tile for the PV MMA,
 //           O accumulated in registers with the usual rescale.
 // Synchronisation is mbarrier based; every wait is bounded (ptx::mbar_wait traps on timeout).
-#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -67,7 +66,7 @@ struct AttnParams {
   int rel_center;
   const uint32_t* mask_bits; // [B][ceil(S/32)]
   const int32_t* kv_len;     // [B]
-  __nv_bfloat16* ctx;        // [B*S, H]
+  __half* ctx;        // [B*S, H]
   int B, S, heads, H;
   float scale_log2;          // log2(e) / sqrt(3*d)
 };
@@ -166,8 +165,8 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       const uint32_t sP = ptx::smem_u32(smem + OFF_P);
       const uint32_t sPK = ptx::smem_u32(smem + OFF_PK);
       const uint32_t sPQ = ptx::smem_u32(smem + OFF_PQ);
-      constexpr uint32_t idesc_n64 = ptx::idesc_bf16(128, 64);
-      constexpr uint32_t idesc_pv = ptx::idesc_bf16(128, 64, 0, 1);   // B (=V) is MN-major
+      constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
+      constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
       ptx::mbar_wait(q_full, 0);
       for (int t = 0; t <= T; ++t) {
         if (t < T) {
@@ -182,7 +181,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
           ptx::mbar_wait(pos_full, t & 1);
           if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);
           ptx::tc_fence_after();
-          const uint32_t idesc_c2p = ptx::idesc_bf16(128, npad);
+          const uint32_t idesc_c2p = ptx::idesc_f16(128, npad);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ss(tmem + TM_C2P, ptx::smem_desc_sw128(sQ + k * 32), ptx::smem_desc_sw128(sPK + k * 32), idesc_c2p,
@@ -341,10 +340,10 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
         for (int v = 0; v < 4; ++v) {
           uint4 o4;
-          o4.x = ptx::pack_bf16(s[8 * v + 0], s[8 * v + 1]);
-          o4.y = ptx::pack_bf16(s[8 * v + 2], s[8 * v + 3]);
-          o4.z = ptx::pack_bf16(s[8 * v + 4], s[8 * v + 5]);
-          o4.w = ptx::pack_bf16(s[8 * v + 6], s[8 * v + 7]);
+          o4.x = ptx::pack_f16(s[8 * v + 0], s[8 * v + 1]);
+          o4.y = ptx::pack_f16(s[8 * v + 2], s[8 * v + 3]);
+          o4.z = ptx::pack_f16(s[8 * v + 4], s[8 * v + 5]);
+          o4.w = ptx::pack_f16(s[8 * v + 6], s[8 * v + 7]);
           *reinterpret_cast<uint4*>(prow + (((4 * g + v) ^ (i & 7)) << 4)) = o4;
         }
       }
@@ -370,14 +369,14 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
     const int row = q0 + i;
     if (row < p.S) {
-      __nv_bfloat16* dst = p.ctx + ((int64_t)b * p.S + row) * p.H + head * D + g * 32;
+      __half* dst = p.ctx + ((int64_t)b * p.S + row) * p.H + head * D + g * 32;
 #pragma unroll
       for (int v = 0; v < 4; ++v) {
         uint4 o4;
-        o4.x = ptx::pack_bf16(o[8 * v + 0] * inv, o[8 * v + 1] * inv);
-        o4.y = ptx::pack_bf16(o[8 * v + 2] * inv, o[8 * v + 3] * inv);
-        o4.z = ptx::pack_bf16(o[8 * v + 4] * inv, o[8 * v + 5] * inv);
-        o4.w = ptx::pack_bf16(o[8 * v + 6] * inv, o[8 * v + 7] * inv);
+        o4.x = ptx::pack_f16(o[8 * v + 0] * inv, o[8 * v + 1] * inv);
+        o4.y = ptx::pack_f16(o[8 * v + 2] * inv, o[8 * v + 3] * inv);
+        o4.z = ptx::pack_f16(o[8 * v + 4] * inv, o[8 * v + 5] * inv);
+        o4.w = ptx::pack_f16(o[8 * v + 6] * inv, o[8 * v + 7] * inv);
         reinterpret_cast<uint4*>(dst)[v] = o4;
       }
     }
@@ -392,12 +391,12 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 }
 
 // ---------------------------------------------------------------------------------------------
-// slow restatement (CUDA cores, fp32 math on the same bf16 inputs): one warp per (b, h, i)
+// slow restatement (CUDA cores, fp32 math on the same fp16 inputs): one warp per (b, h, i)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-attention_naive_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat16* __restrict__ pos_k,
-                       const __nv_bfloat16* __restrict__ pos_q, const int32_t* __restrict__ rel_idx, int rel_center,
-                       const uint32_t* __restrict__ mask_bits, __nv_bfloat16* __restrict__ ctx, int B, int S, int heads,
+attention_naive_kernel(const __half* __restrict__ qkv, const __half* __restrict__ pos_k,
+                       const __half* __restrict__ pos_q, const int32_t* __restrict__ rel_idx, int rel_center,
+                       const uint32_t* __restrict__ mask_bits, __half* __restrict__ ctx, int B, int S, int heads,
                        int ld_pos, float inv_scale) {
   const int H = heads * D;
   const int gw = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -407,33 +406,33 @@ attention_naive_kernel(const __nv_bfloat16* __restrict__ qkv, const __nv_bfloat1
   const int h = (gw / S) % heads;
   const int b = gw / (S * heads);
   const int words = (S + 31) >> 5;
-  const __nv_bfloat16* qrow = qkv + ((int64_t)b * S + i) * 3 * H + h * D;
-  const float q0 = __bfloat162float(qrow[lane]), q1 = __bfloat162float(qrow[lane + 32]);
+  const __half* qrow = qkv + ((int64_t)b * S + i) * 3 * H + h * D;
+  const float q0 = __half2float(qrow[lane]), q1 = __half2float(qrow[lane + 32]);
   float m = -CUDART_INF_F, l = 0.f, a0 = 0.f, a1 = 0.f;
   for (int j = 0; j < S; ++j) {
     if (!((mask_bits[(int64_t)b * words + (j >> 5)] >> (j & 31)) & 1u)) continue;
-    const __nv_bfloat16* krow = qkv + ((int64_t)b * S + j) * 3 * H + H + h * D;
-    const __nv_bfloat16* vrow = krow + H;
+    const __half* krow = qkv + ((int64_t)b * S + j) * 3 * H + H + h * D;
+    const __half* vrow = krow + H;
     const int idx = rel_idx[rel_center + i - j];
-    const __nv_bfloat16* pk = pos_k + (int64_t)idx * ld_pos + h * D;
-    const __nv_bfloat16* pq = pos_q + (int64_t)idx * ld_pos + h * D;
-    const float k0 = __bfloat162float(krow[lane]), k1 = __bfloat162float(krow[lane + 32]);
-    float s = q0 * k0 + q1 * k1 + q0 * __bfloat162float(pk[lane]) + q1 * __bfloat162float(pk[lane + 32]) +
-              k0 * __bfloat162float(pq[lane]) + k1 * __bfloat162float(pq[lane + 32]);
+    const __half* pk = pos_k + (int64_t)idx * ld_pos + h * D;
+    const __half* pq = pos_q + (int64_t)idx * ld_pos + h * D;
+    const float k0 = __half2float(krow[lane]), k1 = __half2float(krow[lane + 32]);
+    float s = q0 * k0 + q1 * k1 + q0 * __half2float(pk[lane]) + q1 * __half2float(pk[lane + 32]) +
+              k0 * __half2float(pq[lane]) + k1 * __half2float(pq[lane + 32]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     s *= inv_scale;
     const float mn = fmaxf(m, s);
     const float al = __expf(m - mn), pe = __expf(s - mn);
     l = l * al + pe;
-    a0 = a0 * al + pe * __bfloat162float(vrow[lane]);
-    a1 = a1 * al + pe * __bfloat162float(vrow[lane + 32]);
+    a0 = a0 * al + pe * __half2float(vrow[lane]);
+    a1 = a1 * al + pe * __half2float(vrow[lane + 32]);
     m = mn;
   }
   const float inv = l > 0.f ? 1.f / l : 0.f;
-  __nv_bfloat16* dst = ctx + ((int64_t)b * S + i) * H + h * D;
-  dst[lane] = __float2bfloat16(a0 * inv);
-  dst[lane + 32] = __float2bfloat16(a1 * inv);
+  __half* dst = ctx + ((int64_t)b * S + i) * H + h * D;
+  dst[lane] = __float2half_rn(a0 * inv);
+  dst[lane + 32] = __float2half_rn(a1 * inv);
 }
 
 }  // namespace
@@ -455,9 +454,9 @@ cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_
   uint64_t dp[3] = {64, (uint64_t)R, (uint64_t)heads};
   uint64_t sp[2] = {(uint64_t)ld_pos * 2, 128};
   uint32_t bp[3] = {64, 64, 1};
-  CUtensorMap tm_qkv = make_tmap_bf16(qkv, 3, dq, sq, bq);
-  CUtensorMap tm_pk = make_tmap_bf16(pos_k, 3, dp, sp, bp);
-  CUtensorMap tm_pq = make_tmap_bf16(pos_q, 3, dp, sp, bp);
+  CUtensorMap tm_qkv = make_tmap_16b(qkv, 3, dq, sq, bq);
+  CUtensorMap tm_pk = make_tmap_16b(pos_k, 3, dp, sp, bp);
+  CUtensorMap tm_pq = make_tmap_16b(pos_q, 3, dp, sp, bp);
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -471,7 +470,7 @@ cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_
   p.rel_center = Spad - 1;
   p.mask_bits = mask_bits;
   p.kv_len = kv_len;
-  p.ctx = (__nv_bfloat16*)ctx;
+  p.ctx = (__half*)ctx;
   p.B = B; p.S = S; p.heads = heads; p.H = H;
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
   dim3 grid((S + QT - 1) / QT, heads, B);
@@ -486,8 +485,8 @@ cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_
   const int Spad = ((S + QT - 1) / QT) * QT;
   const int rows = B * heads * S;
   attention_naive_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(
-      (const __nv_bfloat16*)qkv, (const __nv_bfloat16*)pos_k, (const __nv_bfloat16*)pos_q, rel_idx, Spad - 1, mask_bits,
-      (__nv_bfloat16*)ctx, B, S, heads, (int)ld_pos, 1.0f / sqrtf(3.0f * D));
+      (const __half*)qkv, (const __half*)pos_k, (const __half*)pos_q, rel_idx, Spad - 1, mask_bits,
+      (__half*)ctx, B, S, heads, (int)ld_pos, 1.0f / sqrtf(3.0f * D));
   return cudaGetLastError();
 }
 

@@ -1,6 +1,6 @@
 // Native C ABI (include/gliclass_b200.h).  Every entry point catches C++ exceptions and turns
 // them into an error code + thread-local message, as a C caller (the reference's model.c) expects.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cmath>
 #include <cstdlib>
@@ -48,13 +48,19 @@ glc_model* glc_load(const char* onnx_path, const glc_opts* opts) {
     if (!onnx_path) { fail(GLC_ERR_ARG, "glc_load: null path"); return nullptr; }
     std::vector<int> devices;
     int max_tokens = 0;
-    int dtype = GLC_DTYPE_BF16;
+    int dtype = GLC_DTYPE_FP16;
+
     if (opts && opts->struct_size >= sizeof(glc_opts)) {
       for (int i = 0; i < opts->num_devices && i < 8; ++i) devices.push_back(opts->device_ids[i]);
       max_tokens = opts->max_tokens;
-      dtype = opts->weight_dtype;
+      if (opts->weight_dtype != GLC_DTYPE_DEFAULT) dtype = opts->weight_dtype;
     }
-    if (dtype != GLC_DTYPE_BF16) { fail(GLC_ERR_ARG, "glc_load: only GLC_DTYPE_BF16 weights are implemented"); return nullptr; }
+    if (dtype != GLC_DTYPE_FP16) {
+      fail(GLC_ERR_ARG,
+           "glc_load: only GLC_DTYPE_FP16 storage is implemented (bf16 cannot meet the 2e-2 parity bar and tcgen05 "
+           "kind::f16 rejects fp16 x bf16 operands; FP8 block-scaled weights are future work)");
+      return nullptr;
+    }
     if (devices.empty()) {
       // GLC_DEVICES="0,1,2" or "all"; default: device 0
       const char* env = getenv("GLC_DEVICES");
@@ -249,8 +255,8 @@ static int wrap(const char* what, cudaError_t e) {
 
 int glc_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N,
                 int K, int act, int out_f32, void* stream) {
-  GLC_TRY("glc_op_gemm", glc::gemm_bf16(A, lda, W, ldw, bias, C, ldc, M, N, K, act, out_f32 != 0, num_sms_current(),
-                                        (cudaStream_t)stream));
+  GLC_TRY("glc_op_gemm", glc::gemm_f16(A, lda, W, ldw, bias, C, ldc, M, N, K, act, out_f32 != 0, num_sms_current(),
+                                       (cudaStream_t)stream));
 }
 int glc_op_embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, const float* gamma, const float* beta, float eps,
                     void* y, int M, int H, int vocab, void* stream) {

@@ -6,7 +6,7 @@
 //   K1  T:520-564   e = LN(word_emb[ids]) * mask           (no position / token-type term in v3)
 //   K4  T:49-53, T:408-412   y = LN(dense_out + residual)  (eps 1e-7, biased variance)
 //   K5  App. B      cls[b,c] = h[b,pos_c]; pooled = h[b,0]; logit = <t_b, k_bc>
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <type_traits>
 
@@ -26,20 +26,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+  const __half2* p = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(p[i]);
+    const float2 t = __half22float2(p[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
 }
 
-// LN over a row held as NC chunks of 8 floats per lane; writes bf16, scaled by `post`.
+// LN over a row held as NC chunks of 8 floats per lane; writes fp16, scaled by `post`.
 template <int NC>
 __device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, const float* __restrict__ gamma,
                                          const float* __restrict__ beta, float eps, float post,
-                                         __nv_bfloat16* __restrict__ out) {
+                                         __half* __restrict__ out) {
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < NC; ++c)
@@ -73,10 +73,10 @@ __device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, con
 #pragma unroll
       for (int i = 0; i < 8; ++i) y[i] = ((v[c][i] - mean) * rstd * g[i] + b[i]) * post;
       uint4 o;
-      o.x = ptx::pack_bf16(y[0], y[1]);
-      o.y = ptx::pack_bf16(y[2], y[3]);
-      o.z = ptx::pack_bf16(y[4], y[5]);
-      o.w = ptx::pack_bf16(y[6], y[7]);
+      o.x = ptx::pack_f16(y[0], y[1]);
+      o.y = ptx::pack_f16(y[2], y[3]);
+      o.z = ptx::pack_f16(y[4], y[5]);
+      o.w = ptx::pack_f16(y[6], y[7]);
       *reinterpret_cast<uint4*>(out + e0) = o;
     }
   }
@@ -85,15 +85,15 @@ __device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, con
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
-                const __nv_bfloat16* __restrict__ emb, const float* __restrict__ gamma,
-                const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ y, int M, int H, int vocab) {
+                const __half* __restrict__ emb, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H, int vocab) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   int64_t id = ids[row];
   if (id < 0 || id >= vocab) id = 0;   // ORT's Gather would fail; clamp to [PAD] instead of reading out of bounds
   const float post = mask[row] != 0 ? 1.0f : 0.0f;
-  const __nv_bfloat16* src = emb + id * (int64_t)H;
+  const __half* src = emb + id * (int64_t)H;
   float v[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -105,14 +105,14 @@ embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mas
 
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
-residual_ln_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ r,
+residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   __nv_bfloat16* __restrict__ y, int M, int H) {
+                   __half* __restrict__ y, int M, int H) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
-  const __nv_bfloat16* xs = x + (int64_t)row * H;
-  const __nv_bfloat16* rs = r ? r + (int64_t)row * H : nullptr;
+  const __half* xs = x + (int64_t)row * H;
+  const __half* rs = r ? r + (int64_t)row * H : nullptr;
   float v[NC][8];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
@@ -133,7 +133,7 @@ residual_ln_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __r
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 ln_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-              __nv_bfloat16* __restrict__ y, int M, int H) {
+              __half* __restrict__ y, int M, int H) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
@@ -172,8 +172,8 @@ __global__ void mask_prep_kernel(const int64_t* __restrict__ mask, uint32_t* __r
 
 // one warp per batch row scans for <<LABEL>> tokens; then every lane copies rows with 128-bit loads
 __global__ void __launch_bounds__(128)
-head_gather_kernel(const __nv_bfloat16* __restrict__ h, const int64_t* __restrict__ ids, int64_t class_token,
-                   __nv_bfloat16* __restrict__ pooled, __nv_bfloat16* __restrict__ cls, int B, int S, int H, int C) {
+head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids, int64_t class_token,
+                   __half* __restrict__ pooled, __half* __restrict__ cls, int B, int S, int H, int C) {
   extern __shared__ int pos_s[];   // [C] per block (one batch row per block)
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -196,8 +196,8 @@ head_gather_kernel(const __nv_bfloat16* __restrict__ h, const int64_t* __restric
   // row 0 of the output block is the pooled (first-token) row, rows 1..C the class rows
   for (int r = warp; r <= C; r += (blockDim.x >> 5)) {
     const int p = (r == 0) ? 0 : pos_s[r - 1];
-    __nv_bfloat16* dst = (r == 0) ? pooled + (int64_t)b * H : cls + ((int64_t)b * C + (r - 1)) * H;
-    const __nv_bfloat16* src = h + ((int64_t)b * S + (p < 0 ? 0 : p)) * H;
+    __half* dst = (r == 0) ? pooled + (int64_t)b * H : cls + ((int64_t)b * C + (r - 1)) * H;
+    const __half* src = h + ((int64_t)b * S + (p < 0 ? 0 : p)) * H;
     for (int i = lane; i < vec; i += 32) {
       uint4 u = make_uint4(0u, 0u, 0u, 0u);
       if (p >= 0) u = *reinterpret_cast<const uint4*>(src + i * 8);
@@ -252,7 +252,7 @@ cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, c
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
     embed_ln_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
-        ids, mask, (const __nv_bfloat16*)emb, gamma, beta, eps, (__nv_bfloat16*)y, M, H, vocab);
+        ids, mask, (const __half*)emb, gamma, beta, eps, (__half*)y, M, H, vocab);
     return cudaGetLastError();
   });
 }
@@ -263,18 +263,18 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
     residual_ln_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)r, gamma, beta, eps, (__nv_bfloat16*)y, M, H);
+        (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H);
     return cudaGetLastError();
   });
 }
 
-cudaError_t ln_f32_to_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y, int M, int H,
+cudaError_t ln_f32_to_f16(const float* x, const float* gamma, const float* beta, float eps, void* y, int M, int H,
                            cudaStream_t stream) {
   if (M <= 0) return cudaSuccess;
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
     ln_f32_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
-        x, gamma, beta, eps, (__nv_bfloat16*)y, M, H);
+        x, gamma, beta, eps, (__half*)y, M, H);
     return cudaGetLastError();
   });
 }
@@ -290,7 +290,7 @@ cudaError_t head_gather(const void* h, const int64_t* ids, int64_t class_token, 
   if (B <= 0) return cudaSuccess;
   if (H % 8 != 0) return cudaErrorInvalidValue;
   head_gather_kernel<<<B, 128, (size_t)(C > 0 ? C : 1) * sizeof(int), stream>>>(
-      (const __nv_bfloat16*)h, ids, class_token, (__nv_bfloat16*)pooled, (__nv_bfloat16*)cls, B, S, H, C);
+      (const __half*)h, ids, class_token, (__half*)pooled, (__half*)cls, B, S, H, C);
   return cudaGetLastError();
 }
 

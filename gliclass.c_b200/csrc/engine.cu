@@ -5,7 +5,7 @@
 //   K5b dot scorer.
 #include "engine.h"
 
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstdlib>
 #include <cstring>
@@ -25,12 +25,40 @@ namespace glc {
 
 namespace {
 
-inline uint16_t f32_to_bf16(float f) {
-  uint32_t u;
-  memcpy(&u, &f, 4);
-  if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);   // NaN
-  u += 0x7fffu + ((u >> 16) & 1u);                                            // round to nearest even
-  return (uint16_t)(u >> 16);
+// fp32 -> fp16, round to nearest even, saturating to +-65504 (weights of this family are O(1))
+inline uint16_t f32_to_f16(float f) {
+  uint32_t x;
+  memcpy(&x, &f, 4);
+  const uint32_t sign = (x >> 16) & 0x8000u;
+  x &= 0x7fffffffu;
+  if (x > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);          // NaN
+  if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);         // >= 65520 (or inf) -> 65504
+  if (x < 0x33000001u) return (uint16_t)sign;                      // < 2^-25 -> 0
+  int e = (int)(x >> 23) - 127;
+  uint32_t m = (x & 0x7fffffu) | 0x800000u;
+  int shift = (e < -14) ? (13 + (-14 - e)) : 13;
+  uint32_t half_m = m >> shift;
+  const uint32_t rem = m & ((1u << shift) - 1u), halfway = 1u << (shift - 1);
+  if (rem > halfway || (rem == halfway && (half_m & 1u))) ++half_m;
+  uint32_t h = (e < -14) ? half_m : (((uint32_t)(e + 15) << 10) + (half_m - 0x400u));
+  return (uint16_t)(sign | h);
+}
+
+inline float f16_to_f32(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16;
+  uint32_t e = (h >> 10) & 0x1fu, m = h & 0x3ffu, u;
+  if (e == 0) {
+    if (m == 0) u = sign;
+    else {
+      int k = 0;
+      while (!(m & 0x400u)) { m <<= 1; ++k; }
+      u = sign | ((uint32_t)(127 - 15 - k + 1) << 23) | ((m & 0x3ffu) << 13);
+    }
+  } else if (e == 31) u = sign | 0x7f800000u | (m << 13);
+  else u = sign | ((e + 112u) << 23) | (m << 13);
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
 }
 
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
@@ -60,9 +88,9 @@ void DeviceModel::upload_f32(float** dst, const HostTensor& t) {
   GLC_CUDA(cudaMemcpyAsync(*dst, t.data.data(), t.data.size() * 4, cudaMemcpyHostToDevice, stream_));
 }
 
-void DeviceModel::upload_bf16(void** dst, const float* src, size_t n) {
+void DeviceModel::upload_w16(void** dst, const float* src, size_t n) {
   std::vector<uint16_t> h(n);
-  for (size_t i = 0; i < n; ++i) h[i] = f32_to_bf16(src[i]);
+  for (size_t i = 0; i < n; ++i) h[i] = f32_to_f16(src[i]);
   *dst = dalloc(n * 2);
   perm_allocs_.push_back(*dst);
   GLC_CUDA(cudaMemcpy(*dst, h.data(), n * 2, cudaMemcpyHostToDevice));
@@ -85,7 +113,7 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
 
   const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
   const HostTensor& we = w.at("emb.word");
-  upload_bf16(&word_emb_, we.data.data(), we.data.size());
+  upload_w16(&word_emb_, we.data.data(), we.data.size());
   upload_f32(&emb_g_, w.at("emb.ln.g"));
   upload_f32(&emb_b_, w.at("emb.ln.b"));
 
@@ -96,7 +124,7 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   upload_f32(&rel_b, w.at("rel.ln.b"));
   void* rel_ln = dalloc((size_t)R * H * 2);
   perm_allocs_.push_back(rel_ln);
-  GLC_CUDA(ln_f32_to_bf16(rel_f32, rel_g, rel_b, cfg_.ln_eps, rel_ln, R, H, stream_));
+  GLC_CUDA(ln_f32_to_f16(rel_f32, rel_g, rel_b, cfg_.ln_eps, rel_ln, R, H, stream_));
   ++launches_;
 
   layers_.resize(cfg_.layers);
@@ -109,18 +137,18 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
       memcpy(cat.data() + (size_t)j * H * H, w.at(r + names[j] + ".w").data.data(), (size_t)H * H * 4);
       memcpy(bcat.data() + (size_t)j * H, w.at(r + names[j] + ".b").data.data(), (size_t)H * 4);
     }
-    upload_bf16(&d.wqkv, cat.data(), cat.size());
+    upload_w16(&d.wqkv, cat.data(), cat.size());
     HostTensor hb;
     hb.data = bcat;
     upload_f32(&d.bqkv, hb);
     GLC_CUDA(cudaStreamSynchronize(stream_));   // hb is a temporary
-    upload_bf16(&d.wo, w.at(r + ".o.w").data.data(), (size_t)H * H);
+    upload_w16(&d.wo, w.at(r + ".o.w").data.data(), (size_t)H * H);
     upload_f32(&d.bo, w.at(r + ".o.b"));
     upload_f32(&d.ln1g, w.at(r + ".ln1.g"));
     upload_f32(&d.ln1b, w.at(r + ".ln1.b"));
-    upload_bf16(&d.w1, w.at(r + ".ffn1.w").data.data(), (size_t)I * H);
+    upload_w16(&d.w1, w.at(r + ".ffn1.w").data.data(), (size_t)I * H);
     upload_f32(&d.b1, w.at(r + ".ffn1.b"));
-    upload_bf16(&d.w2, w.at(r + ".ffn2.w").data.data(), (size_t)H * I);
+    upload_w16(&d.w2, w.at(r + ".ffn2.w").data.data(), (size_t)H * I);
     upload_f32(&d.b2, w.at(r + ".ffn2.b"));
     upload_f32(&d.ln2g, w.at(r + ".ln2.g"));
     upload_f32(&d.ln2b, w.at(r + ".ln2.b"));
@@ -128,16 +156,16 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
     // out of the per-Run graph: pos_qk[:, 0:H] = query_proj(rel), pos_qk[:, H:2H] = key_proj(rel)
     d.pos_qk = dalloc((size_t)R * 2 * H * 2);
     perm_allocs_.push_back(d.pos_qk);
-    GLC_CUDA(gemm_bf16(rel_ln, H, d.wqkv, H, d.bqkv, d.pos_qk, 2 * H, R, 2 * H, H, 0, false, num_sms_, stream_));
+    GLC_CUDA(gemm_f16(rel_ln, H, d.wqkv, H, d.bqkv, d.pos_qk, 2 * H, R, 2 * H, H, 0, false, num_sms_, stream_));
     ++launches_;
   }
-  upload_bf16(&t1w_, w.at("text.1.w").data.data(), (size_t)Hh * H);
+  upload_w16(&t1w_, w.at("text.1.w").data.data(), (size_t)Hh * H);
   upload_f32(&t1b_, w.at("text.1.b"));
-  upload_bf16(&t2w_, w.at("text.2.w").data.data(), (size_t)Hh * Hh);
+  upload_w16(&t2w_, w.at("text.2.w").data.data(), (size_t)Hh * Hh);
   upload_f32(&t2b_, w.at("text.2.b"));
-  upload_bf16(&c1w_, w.at("cls.1.w").data.data(), (size_t)Hh * H);
+  upload_w16(&c1w_, w.at("cls.1.w").data.data(), (size_t)Hh * H);
   upload_f32(&c1b_, w.at("cls.1.b"));
-  upload_bf16(&c2w_, w.at("cls.2.w").data.data(), (size_t)Hh * Hh);
+  upload_w16(&c2w_, w.at("cls.2.w").data.data(), (size_t)Hh * Hh);
   upload_f32(&c2b_, w.at("cls.2.b"));
   GLC_CUDA(cudaStreamSynchronize(stream_));
 }
@@ -216,8 +244,7 @@ int64_t DeviceModel::debug_fetch(const std::string& name, float* out, size_t cap
   GLC_CUDA(cudaStreamSynchronize(stream_));
   GLC_CUDA(cudaMemcpy(h.data(), it->second.ptr, n * 2, cudaMemcpyDeviceToHost));
   for (size_t i = 0; i < n; ++i) {
-    uint32_t u = (uint32_t)h[i] << 16;
-    memcpy(&out[i], &u, 4);
+    out[i] = f16_to_f32(h[i]);
   }
   return (int64_t)n;
 }
@@ -236,25 +263,25 @@ void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, in
   keep("emb", x_, (size_t)M * H);
   for (int l = 0; l < cfg_.layers; ++l) {
     const DeviceLayer& d = layers_[l];
-    GLC_CUDA(gemm_bf16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st)); ++n;
     if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
-    const __nv_bfloat16* pq = (const __nv_bfloat16*)d.pos_qk;
+    const __half* pq = (const __half*)d.pos_qk;
     GLC_CUDA(attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, cfg_.buckets,
                              num_sms_, st)); ++n;
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
-    GLC_CUDA(gemm_bf16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st)); ++n;
     GLC_CUDA(residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st)); ++n;
-    GLC_CUDA(gemm_bf16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_bf16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st)); ++n;
     GLC_CUDA(residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st)); ++n;
     if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
   }
   if (C > 0) {
     GLC_CUDA(head_gather(x_, d_ids, cfg_.class_token, pooled_, cls_, B, S, H, C, st)); ++n;
-    GLC_CUDA(gemm_bf16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, 1, false, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_bf16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_bf16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_bf16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, 1, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st)); ++n;
+    GLC_CUDA(gemm_f16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st)); ++n;
     GLC_CUDA(head_score(tvec_, kvec_, d_logits, nullptr, nullptr, 0.5f, B, C, Hh, st)); ++n;
   }
   launches_ += n;

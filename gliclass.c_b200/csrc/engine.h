@@ -1,4 +1,4 @@
-// Engine: per-GPU replica of the model (bf16 weights + precomputed position projections), a
+// Engine: per-GPU replica of the model (fp16 weights + precomputed position projections), a
 // workspace, one stream, and the forward pass as a fixed sequence of the K1..K5 kernels.  A
 // Model owns one DeviceModel per GPU and shards the rows of a batch across them (SURVEY.md §8e:
 // batch rows are independent, no collective; the only cross-GPU traffic is the host gather of
@@ -18,17 +18,17 @@
 namespace glc {
 
 struct DeviceLayer {
-  void* wqkv = nullptr;   // bf16 [3H,H]  (Wq | Wk | Wv rows)
+  void* wqkv = nullptr;   // fp16 [3H,H]  (Wq | Wk | Wv rows)
   float* bqkv = nullptr;  // [3H]
-  void* wo = nullptr;     // bf16 [H,H]
+  void* wo = nullptr;     // fp16 [H,H]
   float* bo = nullptr;
   float *ln1g = nullptr, *ln1b = nullptr;
-  void* w1 = nullptr;     // bf16 [I,H]
+  void* w1 = nullptr;     // fp16 [I,H]
   float* b1 = nullptr;
-  void* w2 = nullptr;     // bf16 [H,I]
+  void* w2 = nullptr;     // fp16 [H,I]
   float* b2 = nullptr;
   float *ln2g = nullptr, *ln2b = nullptr;
-  void* pos_qk = nullptr; // bf16 [2*buckets, 2H]: cols [0,H) = query_proj(rel), [H,2H) = key_proj(rel)
+  void* pos_qk = nullptr; // fp16 [2*buckets, 2H]: cols [0,H) = query_proj(rel), [H,2H) = key_proj(rel)
 };
 
 struct DebugBuf { void* ptr = nullptr; size_t count = 0; };
@@ -56,8 +56,8 @@ class DeviceModel {
   const int32_t* rel_table(int S);
   void* dalloc(size_t bytes);
   void upload_f32(float** dst, const HostTensor& t);
-  void upload_bf16(void** dst, const float* src, size_t n);
-  void keep(const char* name, const void* src_bf16, size_t count);
+  void upload_w16(void** dst, const float* src, size_t n);
+  void keep(const char* name, const void* src_f16, size_t count);
 
   int device_ = 0;
   int num_sms_ = 148;

@@ -1,4 +1,6 @@
 // K2 — dense projection GEMM for sm_100a:  C[M,N] = act(A[M,K] · W[N,K]^T + bias[N])
+// A fp16, W fp16, fp32 accumulation, C fp16 (or fp32).  (tcgen05 kind::f16 needs A and B in the
+// same 16-bit format: an fp16 x bf16 descriptor raises an illegal-instruction fault on B200.)
 //
 // Replaces the MatMul+Add(+Erf-GELU) groups ORT executes for query/key/value_proj,
 // attention.output.dense, intermediate.dense and output.dense (arithmetic
@@ -9,10 +11,10 @@
 //   warp 0   : TMA producer   — cp.async.bulk.tensor 2D, 128B swizzle, BK = 64 per stage
 //   warp 1   : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage,
 //                               fp32 accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2-5: epilogue       — tcgen05.ld 32x32b -> +bias -> (erf-GELU) -> bf16/fp32 -> global
+//   warps 2-5: epilogue       — tcgen05.ld 32x32b -> +bias -> (erf-GELU) -> fp16/fp32 -> global
 // Pipelines: smem ring full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), all mbarrier.
 // Ragged M/N/K are handled by TMA out-of-bounds zero fill on loads and predication on stores.
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "kernels.h"
 #include "ptx.cuh"
@@ -54,7 +56,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 template <int BN, int ACT, bool OUT_F32>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const float* __restrict__ bias, void* __restrict__ Cout, int64_t ldc, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -113,7 +115,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_bf16(BM, BN);
+      constexpr uint32_t idesc = ptx::idesc_f16(BM, BN);
       int s = 0;
       uint32_t ph = 0;
       int acc = 0;
@@ -186,15 +188,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_
             for (int j = 0; j < 8; ++j)
               if (n + 4 * j + 4 <= N) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           } else {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(Cout) + (int64_t)row * ldc + n;
+            __half* dst = reinterpret_cast<__half*>(Cout) + (int64_t)row * ldc + n;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               if (n + 8 * j + 8 <= N) {
                 uint4 o;
-                o.x = ptx::pack_bf16(v[8 * j + 0], v[8 * j + 1]);
-                o.y = ptx::pack_bf16(v[8 * j + 2], v[8 * j + 3]);
-                o.z = ptx::pack_bf16(v[8 * j + 4], v[8 * j + 5]);
-                o.w = ptx::pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+                o.x = ptx::pack_f16(v[8 * j + 0], v[8 * j + 1]);
+                o.y = ptx::pack_f16(v[8 * j + 2], v[8 * j + 3]);
+                o.z = ptx::pack_f16(v[8 * j + 4], v[8 * j + 5]);
+                o.w = ptx::pack_f16(v[8 * j + 6], v[8 * j + 7]);
                 reinterpret_cast<uint4*>(dst)[j] = o;
               }
             }
@@ -227,9 +229,9 @@ cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, 
   uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
   uint64_t sw[1] = {(uint64_t)ldw * 2};
   uint32_t bw[2] = {BK, BN};
-  CUtensorMap tm_a = make_tmap_bf16(A, 2, da, sa, ba);
-  CUtensorMap tm_w = make_tmap_bf16(W, 2, dw, sw, bw);
-  auto kern = gemm_bf16_tcgen05_kernel<BN, ACT, OUT_F32>;
+  CUtensorMap tm_a = make_tmap_16b(A, 2, da, sa, ba);
+  CUtensorMap tm_w = make_tmap_16b(W, 2, dw, sw, bw);
+  auto kern = gemm_f16_tcgen05_kernel<BN, ACT, OUT_F32>;
   static bool attr_set[64] = {};   // per template instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
@@ -246,8 +248,8 @@ cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, 
 
 }  // namespace
 
-cudaError_t gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
-                      int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream) {
+cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
+                     int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaErrorInvalidValue;
   if ((lda % 8) || (ldw % 8) || (K % 8) || (N % 8) || (ldc % (out_f32 ? 4 : 8))) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15)

@@ -6,27 +6,31 @@
 
 namespace glc {
 
-// K2: C[M,N] = act(A[M,K] W[N,K]^T + bias); bf16 operands, fp32 accumulate; C bf16 or fp32.
-cudaError_t gemm_bf16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
-                      int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream);
+// Storage convention: activations and weights are fp16, every accumulation / statistic is fp32.
+// fp16 rather than bf16 because bf16's 8-bit mantissa cannot meet the 2e-2 logit parity bar on
+// this model family (DESIGN.md "Numerics").
+//
+// K2: C[M,N] = act(A[M,K] W[N,K]^T + bias); A, W fp16, fp32 accumulate; C fp16 or fp32.
+cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
+                     int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream);
 
 // K1: y[m,:] = LN(word_emb[ids[m],:]) * gamma + beta, times mask[m]   (T:520-564)
-cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* word_emb_bf16, const float* gamma,
-                     const float* beta, float eps, void* y_bf16, int M, int H, int vocab, cudaStream_t stream);
+cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* word_emb_f16, const float* gamma,
+                     const float* beta, float eps, void* y_f16, int M, int H, int vocab, cudaStream_t stream);
 
 // K4: y = LN(x + r) * gamma + beta   (T:49-53, T:408-412); r may be null (plain LN).
-cudaError_t residual_ln(const void* x_bf16, const void* r_bf16, const float* gamma, const float* beta, float eps,
-                        void* y_bf16, int M, int H, cudaStream_t stream);
-// plain LN on fp32 rows -> bf16 (load-time LN of rel_embeddings, T:597-601)
-cudaError_t ln_f32_to_bf16(const float* x, const float* gamma, const float* beta, float eps, void* y_bf16, int M, int H,
+cudaError_t residual_ln(const void* x_f16, const void* r_f16, const float* gamma, const float* beta, float eps,
+                        void* y_f16, int M, int H, cudaStream_t stream);
+// plain LN on fp32 rows -> fp16 (load-time LN of rel_embeddings, T:597-601)
+cudaError_t ln_f32_to_f16(const float* x, const float* gamma, const float* beta, float eps, void* y_f16, int M, int H,
                            cudaStream_t stream);
 
 // key-validity words for attention: bits[b][w] bit j = mask[b][32w+j] != 0 ; kv_len[b] = 1 + last valid key
 cudaError_t mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, cudaStream_t stream);
 
-// K3: fused disentangled attention (T:229-345).  qkv bf16 [B*S,3H] (Q | K | V, head-major
-// inside each third); pos_k/pos_q bf16 [2*buckets][ld_pos] row-major (head h = columns h*64..);
-// rel_idx int32 [2*Spad-1] with Spad = S rounded up to 128; ctx bf16 [B*S,H].
+// K3: fused disentangled attention (T:229-345).  qkv fp16 [B*S,3H] (Q | K | V, head-major
+// inside each third); pos_k/pos_q fp16 [2*buckets][ld_pos] row-major (head h = columns h*64..);
+// rel_idx int32 [2*Spad-1] with Spad = S rounded up to 128; ctx fp16 [B*S,H].
 cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
                             const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                             int buckets, int num_sms, cudaStream_t stream);
@@ -36,7 +40,7 @@ cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_
                             cudaStream_t stream);
 
 // K5a: <<LABEL>>-token pooling.  pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] or 0  
-cudaError_t head_gather(const void* h_bf16, const int64_t* ids, int64_t class_token, void* pooled_bf16, void* cls_bf16,
+cudaError_t head_gather(const void* h_f16, const int64_t* ids, int64_t class_token, void* pooled_f16, void* cls_f16,
                         int B, int S, int H, int C, cudaStream_t stream);
 // K5b: logits[b,c] = <t[b,:], k[b,c,:]> (+ optional sigmoid / threshold decisions)
 cudaError_t head_score(const float* t, const float* k, float* logits, float* probs, uint8_t* decisions, float threshold,

@@ -157,11 +157,14 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t sbo
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B and fp32 D.
-// bits: [4,6) D fmt (1 = f32) | [7,10) A fmt (1 = bf16) | [10,13) B fmt | 15 A major | 16 B major
-// (0 = K-major, 1 = MN-major) | [17,23) N>>3 | [24,29) M>>4
-__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+// Instruction descriptor for kind::f16 with 16-bit A/B and fp32 D.
+// bits: [4,6) D fmt (1 = f32) | [7,10) A fmt (0 = f16, 1 = bf16) | [10,13) B fmt | 15 A major |
+// 16 B major (0 = K-major, 1 = MN-major) | [17,23) N>>3 | [24,29) M>>4
+constexpr uint32_t FMT_F16 = 0, FMT_BF16 = 1;
+__host__ __device__ constexpr uint32_t idesc_f16(uint32_t M, uint32_t N, uint32_t a_mn_major = 0, uint32_t b_mn_major = 0,
+                                                 uint32_t a_fmt = FMT_F16, uint32_t b_fmt = FMT_F16) {
+  return (1u << 4) | (a_fmt << 7) | (b_fmt << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
+         ((M >> 4) << 24);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -179,9 +182,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// two fp32 -> packed fp16x2, round to nearest, saturating to +-65504 instead of overflowing to inf
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
-  __half2 v = __floats2half2_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 }  // namespace ptx
