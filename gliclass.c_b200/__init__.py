@@ -63,6 +63,8 @@ _SIGS = {
     "glc_sync": (_i, [_vp, _i]),
     "glc_stream": (_vp, [_vp, _i]),
     "glc_launch_count": (C.c_uint64, [_vp]),
+    "glc_profile_enable": (_i, [_vp, _i, _i]),
+    "glc_profile_collect": (_i, [_vp, _i, _vp, _vp, _i]),
     "glc_debug_fetch": (_i64, [_vp, _i, C.c_char_p, _vp, C.c_size_t]),
     "glc_decide": (_i, [_vp, _i, _i, _f, _vp, _vp, _vp]),
     "glc_onnx_open": (_vp, [C.c_char_p]),
@@ -206,6 +208,21 @@ class Session:
 
     def launch_count(self) -> int:
         return int(lib().glc_launch_count(self._h))
+
+    PROFILE_CATEGORIES = ("embed", "gemm_qkv", "attention", "gemm_out", "residual_ln", "gemm_ffn1", "gemm_ffn2",
+                          "head_gemm", "head_misc")
+
+    def profile_enable(self, on: bool, slot: int = 0) -> None:
+        _check(lib().glc_profile_enable(self._h, slot, 1 if on else 0), "glc_profile_enable")
+
+    def profile_collect(self, slot: int = 0) -> dict:
+        """{category: (total_ms, launches)} accumulated since the last collect."""
+        ms = np.zeros(16, dtype=np.float64)
+        n = np.zeros(16, dtype=np.uint64)
+        k = lib().glc_profile_collect(self._h, slot, ms.ctypes.data, n.ctypes.data, 16)
+        if k < 0:
+            raise GlcError(last_error())
+        return {c: (float(ms[i]), int(n[i])) for i, c in enumerate(self.PROFILE_CATEGORIES[:k])}
 
     def debug_fetch(self, name: str, count: int, slot: int = 0) -> np.ndarray:
         out = np.empty(count, dtype=np.float32)

@@ -162,6 +162,23 @@ void* glc_stream(glc_model* m, int slot) {
 
 uint64_t glc_launch_count(const glc_model* m) { return m ? m->m->launches() : 0; }
 
+int glc_profile_enable(glc_model* m, int slot, int on) {
+  if (!m || slot < 0 || slot >= m->m->num_devices()) return fail(GLC_ERR_ARG, "glc_profile_enable: bad argument");
+  m->m->dev(slot).profile_enable(on != 0);
+  return GLC_OK;
+}
+
+int glc_profile_collect(glc_model* m, int slot, double* ms, uint64_t* n, int capacity) {
+  try {
+    if (!m || !ms || !n || slot < 0 || slot >= m->m->num_devices() || capacity < (int)glc::KC_COUNT)
+      return fail(GLC_ERR_ARG, "glc_profile_collect: bad argument");
+    m->m->dev(slot).profile_collect(ms, n);
+    return (int)glc::KC_COUNT;
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_profile_collect: ") + e.what());
+  }
+}
+
 int64_t glc_debug_fetch(glc_model* m, int slot, const char* name, float* out, size_t capacity) {
   try {
     if (!m || !name || slot < 0 || slot >= m->m->num_devices()) return fail(GLC_ERR_ARG, "glc_debug_fetch: bad argument");

@@ -177,6 +177,8 @@ DeviceModel::~DeviceModel() {
   for (void* p : perm_allocs_) cudaFree(p);
   for (auto& kv : rel_tables_) cudaFree(kv.second);
   for (auto& kv : debug_) cudaFree(kv.second.ptr);
+  for (auto& r : prof_recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (auto e : prof_pool_) cudaEventDestroy(e);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -249,6 +251,63 @@ int64_t DeviceModel::debug_fetch(const std::string& name, float* out, size_t cap
   return (int64_t)n;
 }
 
+cudaEvent_t DeviceModel::prof_event() {
+  if (!prof_pool_.empty()) {
+    cudaEvent_t e = prof_pool_.back();
+    prof_pool_.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  GLC_CUDA(cudaEventCreate(&e));
+  return e;
+}
+
+void DeviceModel::profile_enable(bool on) {
+  std::lock_guard<std::mutex> lk(mu);
+  prof_on_ = on;
+}
+
+void DeviceModel::profile_collect(double* ms, uint64_t* n) {
+  std::lock_guard<std::mutex> lk(mu);
+  cudaSetDevice(device_);
+  GLC_CUDA(cudaStreamSynchronize(stream_));
+  for (auto& r : prof_recs_) {
+    float t = 0.f;
+    GLC_CUDA(cudaEventElapsedTime(&t, r.a, r.b));
+    ms[r.cat] += t;
+    n[r.cat] += 1;
+    prof_pool_.push_back(r.a);
+    prof_pool_.push_back(r.b);
+  }
+  prof_recs_.clear();
+}
+
+// brackets one launch with events when profiling is on
+struct ProfScope {
+  DeviceModel* d;
+  int cat;
+  cudaEvent_t a = nullptr;
+  ProfScope(DeviceModel* dm, int c) : d(dm), cat(c) {
+    if (d->prof_on_) {
+      a = d->prof_event();
+      cudaEventRecord(a, d->stream_);
+    }
+  }
+  ~ProfScope() {
+    if (a) {
+      cudaEvent_t b = d->prof_event();
+      cudaEventRecord(b, d->stream_);
+      d->prof_recs_.push_back({cat, a, b});
+    }
+  }
+};
+#define GLC_LAUNCH(cat, expr)      \
+  do {                             \
+    ProfScope _ps(this, cat);      \
+    GLC_CUDA(expr);                \
+    ++n;                           \
+  } while (0)
+
 void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits) {
   const int H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
   const int M = B * S;
@@ -258,31 +317,31 @@ void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, in
   cudaStream_t st = stream_;
   uint64_t n = 0;
 
-  GLC_CUDA(mask_prep(d_mask, mask_bits_, kv_len_, B, S, st)); ++n;
-  GLC_CUDA(embed_ln(d_ids, d_mask, word_emb_, emb_g_, emb_b_, cfg_.ln_eps, x_, M, H, cfg_.vocab, st)); ++n;
+  GLC_LAUNCH(KC_EMBED, mask_prep(d_mask, mask_bits_, kv_len_, B, S, st));
+  GLC_LAUNCH(KC_EMBED, embed_ln(d_ids, d_mask, word_emb_, emb_g_, emb_b_, cfg_.ln_eps, x_, M, H, cfg_.vocab, st));
   keep("emb", x_, (size_t)M * H);
   for (int l = 0; l < cfg_.layers; ++l) {
     const DeviceLayer& d = layers_[l];
-    GLC_CUDA(gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st)); ++n;
+    GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st));
     if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
     const __half* pq = (const __half*)d.pos_qk;
-    GLC_CUDA(attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, cfg_.buckets,
-                             num_sms_, st)); ++n;
+    GLC_LAUNCH(KC_ATTN, attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads,
+                                        cfg_.buckets, num_sms_, st));
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
-    GLC_CUDA(gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st)); ++n;
-    GLC_CUDA(residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st)); ++n;
-    GLC_CUDA(gemm_f16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_f16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st)); ++n;
-    GLC_CUDA(residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st)); ++n;
+    GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st));
+    GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));
+    GLC_LAUNCH(KC_GEMM_FFN1, gemm_f16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st));
+    GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st));
+    GLC_LAUNCH(KC_LN, residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st));
     if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
   }
   if (C > 0) {
-    GLC_CUDA(head_gather(x_, d_ids, cfg_.class_token, pooled_, cls_, B, S, H, C, st)); ++n;
-    GLC_CUDA(gemm_f16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, 1, false, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_f16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st)); ++n;
-    GLC_CUDA(gemm_f16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st)); ++n;
-    GLC_CUDA(head_score(tvec_, kvec_, d_logits, nullptr, nullptr, 0.5f, B, C, Hh, st)); ++n;
+    GLC_LAUNCH(KC_HEAD_MISC, head_gather(x_, d_ids, cfg_.class_token, pooled_, cls_, B, S, H, C, st));
+    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, 1, false, num_sms_, st));
+    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st));
+    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st));
+    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st));
+    GLC_LAUNCH(KC_HEAD_MISC, head_score(tvec_, kvec_, d_logits, nullptr, nullptr, 0.5f, B, C, Hh, st));
   }
   launches_ += n;
 }

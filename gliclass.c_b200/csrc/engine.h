@@ -33,6 +33,9 @@ struct DeviceLayer {
 
 struct DebugBuf { void* ptr = nullptr; size_t count = 0; };
 
+// kernel categories for the in-stream profiler (CUDA events around every launch)
+enum KernelCat { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTN, KC_GEMM_OUT, KC_LN, KC_GEMM_FFN1, KC_GEMM_FFN2, KC_HEAD_GEMM, KC_HEAD_MISC, KC_COUNT };
+
 class DeviceModel {
  public:
   DeviceModel(int device, const ModelWeights& w, int max_tokens);
@@ -49,6 +52,10 @@ class DeviceModel {
   cudaStream_t stream() const { return stream_; }
   uint64_t launches() const { return launches_.load(); }
   int64_t debug_fetch(const std::string& name, float* out, size_t capacity);
+  // profiler: when enabled every launch is bracketed by CUDA events on stream(); collect() syncs
+  // the stream, adds the elapsed times per category into ms[KC_COUNT] / n[KC_COUNT] and resets.
+  void profile_enable(bool on);
+  void profile_collect(double* ms, uint64_t* n);
   std::mutex mu;
 
  private:
@@ -85,6 +92,13 @@ class DeviceModel {
   float *tvec_ = nullptr, *kvec_ = nullptr, *logits_ = nullptr;
   std::vector<void*> ws_allocs_, perm_allocs_;
   std::map<std::string, DebugBuf> debug_;
+  // profiler state
+  struct ProfRec { int cat; cudaEvent_t a, b; };
+  bool prof_on_ = false;
+  std::vector<ProfRec> prof_recs_;
+  std::vector<cudaEvent_t> prof_pool_;
+  cudaEvent_t prof_event();
+  friend struct ProfScope;
 };
 
 class Model {

@@ -80,6 +80,14 @@ GLC_API int glc_sync(glc_model* m, int device_slot);
 GLC_API void* glc_stream(glc_model* m, int device_slot);
 /* kernels launched by this model since load (all devices) — bench.py's gpu_launches */
 GLC_API uint64_t glc_launch_count(const glc_model* m);
+/* In-stream profiler: when enabled, every kernel launch of glc_run / glc_run_device on that slot is
+ * bracketed by CUDA events on the engine stream.  glc_profile_collect synchronises the stream and
+ * ADDS the elapsed milliseconds / launch counts per category into ms[] / n[] (capacity >= 9),
+ * returning the number of categories:
+ *   0 embed+mask  1 QKV GEMM  2 attention  3 out-proj GEMM  4 residual+LN  5 FFN1 GEMM(+GELU)
+ *   6 FFN2 GEMM   7 head projector GEMMs   8 head gather/score */
+GLC_API int glc_profile_enable(glc_model* m, int device_slot, int on);
+GLC_API int glc_profile_collect(glc_model* m, int device_slot, double* ms, uint64_t* n, int capacity);
 /* copy a named intermediate of the last forward on device_slot to host as fp32.
  * names: "emb", "qkv0", "ctx0", "h<l>" .  Returns element count or <0. */
 GLC_API int64_t glc_debug_fetch(glc_model* m, int device_slot, const char* name, float* out, size_t capacity);

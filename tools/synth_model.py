@@ -1,0 +1,275 @@
+"""Synthetic workload builder: random-init GLiClass checkpoints of the named architectures exported
+to model.onnx with the reference's own export call, and synthetic token batches.
+
+This is the offline stand-in for the reference's model tooling (ONNX_CONVERTING/convert_to_onnx.py,
+which downloads a trained checkpoint — impossible here: no network, no `gliclass` package) and for
+its host-side tokenisation (src/preprocessor.c + src/tokenizer.c), producing the SAME file format
+and tensor layouts the engine consumes.  It contains no forward arithmetic: the CPU oracle lives in
+oracle/gliclass_oracle.py and imports the definitions below.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, asdict
+
+import torch
+import torch.nn.functional as F
+
+# --------------------------------------------------------------------------------------------
+# architecture table (HF microsoft/deberta-v3-{small,base,large})
+# --------------------------------------------------------------------------------------------
+
+
+@dataclass
+class ArchConfig:
+    name: str
+    vocab_size: int
+    hidden_size: int
+    num_layers: int
+    num_heads: int
+    intermediate_size: int
+    position_buckets: int = 256
+    max_relative_positions: int = 512      # config value -1 -> max_position_embeddings (T:158-160)
+    layer_norm_eps: float = 1e-7
+    class_token_index: int = 128001        # <<LABEL>>
+    sep_token_index: int = 128002          # <<SEP>>
+    head_hidden_size: int = 0              # GLiClass config.hidden_size; 0 -> same as encoder
+
+    def __post_init__(self):
+        if self.head_hidden_size == 0:
+            self.head_hidden_size = self.hidden_size
+
+    @property
+    def head_dim(self) -> int:
+        return self.hidden_size // self.num_heads
+
+
+ARCHS = {
+    # unit-test scale; two heads of d=64 so the real kernels (d=64 only) run it
+    "tiny": dict(vocab_size=1027, hidden_size=128, num_layers=2, num_heads=2, intermediate_size=512,
+                 class_token_index=1025, sep_token_index=1026),
+    "mini": dict(vocab_size=2051, hidden_size=256, num_layers=3, num_heads=4, intermediate_size=1024,
+                 class_token_index=2049, sep_token_index=2050),
+    "small": dict(vocab_size=128003, hidden_size=768, num_layers=6, num_heads=12, intermediate_size=3072),
+    "base": dict(vocab_size=128003, hidden_size=768, num_layers=12, num_heads=12, intermediate_size=3072),
+    "large": dict(vocab_size=128003, hidden_size=1024, num_layers=24, num_heads=16, intermediate_size=4096),
+}
+
+
+def make_config(arch: str, **over) -> ArchConfig:
+    d = dict(ARCHS[arch])
+    d.update(over)
+    return ArchConfig(name=arch, **d)
+
+
+# --------------------------------------------------------------------------------------------
+# deterministic non-degenerate init (every tensor random so that dedup in the
+# exporter cannot merge them and bias / gamma bugs are observable)
+# --------------------------------------------------------------------------------------------
+
+ENC = "model.encoder_model."
+
+
+def init_weights(cfg: ArchConfig, seed: int = 0) -> dict[str, torch.Tensor]:
+    """Fan-in scaled Gaussian init, every tensor random.
+
+    Scales are chosen so that the random model behaves like a trained one where it matters for
+    parity: attention scores have std ~2 (peaked softmax, so rel-pos bias errors are visible), the
+    attention / FFN branches are comparable to the residual, and logits are O(1) and straddle the
+    sigmoid threshold (HF's default std=0.02 gives three identical logits).  Larger
+    gains (q/k 1.8, v/o/ffn 1.4) put a random net in a chaotic regime where even rounding the
+    WEIGHTS to 16 bits moves logits by several 1e-2 (scripts/emulate_precision.py, DESIGN.md
+    "Numerics"); that says nothing about a kernel, so the fixtures stay out of it.
+    """
+    g = torch.Generator().manual_seed(seed)
+    H, I, Hh = cfg.hidden_size, cfg.intermediate_size, cfg.head_hidden_size
+
+    def n(*shape, std=0.05, mean=0.0):
+        return (torch.randn(*shape, generator=g) * std + mean).float()
+
+    w: dict[str, torch.Tensor] = {}
+    w[ENC + "embeddings.word_embeddings.weight"] = n(cfg.vocab_size, H, std=0.5)
+    w[ENC + "embeddings.LayerNorm.weight"] = n(H, std=0.1, mean=1.0)
+    w[ENC + "embeddings.LayerNorm.bias"] = n(H, std=0.02)
+    w[ENC + "encoder.rel_embeddings.weight"] = n(2 * cfg.position_buckets, H, std=0.5)
+    w[ENC + "encoder.LayerNorm.weight"] = n(H, std=0.1, mean=1.0)
+    w[ENC + "encoder.LayerNorm.bias"] = n(H, std=0.02)
+    for l in range(cfg.num_layers):
+        p = f"{ENC}encoder.layer.{l}."
+        for nm, s in (("query_proj", 1.4), ("key_proj", 1.4), ("value_proj", 1.0)):
+            w[p + f"attention.self.{nm}.weight"] = n(H, H, std=s / math.sqrt(H))
+            w[p + f"attention.self.{nm}.bias"] = n(H, std=0.02)
+        w[p + "attention.output.dense.weight"] = n(H, H, std=1.0 / math.sqrt(H))
+        w[p + "attention.output.dense.bias"] = n(H, std=0.02)
+        w[p + "attention.output.LayerNorm.weight"] = n(H, std=0.1, mean=1.0)
+        w[p + "attention.output.LayerNorm.bias"] = n(H, std=0.02)
+        w[p + "intermediate.dense.weight"] = n(I, H, std=1.0 / math.sqrt(H))
+        w[p + "intermediate.dense.bias"] = n(I, std=0.02)
+        w[p + "output.dense.weight"] = n(H, I, std=0.7 / math.sqrt(I))
+        w[p + "output.dense.bias"] = n(H, std=0.02)
+        w[p + "output.LayerNorm.weight"] = n(H, std=0.1, mean=1.0)
+        w[p + "output.LayerNorm.bias"] = n(H, std=0.02)
+    # head: two FeaturesProjectors (Linear-GELU-Linear); linear_2 scaled for O(1) logits.
+    s2 = 1.2 / math.sqrt(Hh) / (Hh ** 0.25)
+    for pj in ("text_projector", "classes_projector"):
+        w[f"model.{pj}.linear_1.weight"] = n(Hh, H, std=1.4 / math.sqrt(H))
+        w[f"model.{pj}.linear_1.bias"] = n(Hh, std=0.02)
+        w[f"model.{pj}.linear_2.weight"] = n(Hh, Hh, std=s2)
+        w[f"model.{pj}.linear_2.bias"] = n(Hh, std=0.02)
+    return w
+
+
+# --------------------------------------------------------------------------------------------
+# synthetic inputs (layout of reference src/preprocessor.c:96-108 with
+# prompt_first=false and src/tokenizer.c:44-84 pad-to-longest, pad id 0 / mask 0)
+# --------------------------------------------------------------------------------------------
+
+
+def synth_inputs(cfg: ArchConfig, B: int, S: int, n_labels, seed: int, ragged: bool = False,
+                 min_frac: float = 0.25):
+    """Returns (input_ids, attention_mask) int64 [B,S].
+
+    n_labels: int or list of per-row label counts.  Row layout: [CLS]=1, text tokens uniform in
+    [3, text_hi), then per label <<LABEL>> + 2 tokens, then <<SEP>>, then [SEP]=2; if ragged the row
+    length is uniform in [S*min_frac, S] and the tail is padded with id 0 / mask 0.
+    """
+    g = torch.Generator().manual_seed(seed)
+    text_hi = min(cfg.class_token_index, 128000)
+    if isinstance(n_labels, int):
+        n_labels = [n_labels] * B
+    ids = torch.zeros(B, S, dtype=torch.long)
+    mask = torch.zeros(B, S, dtype=torch.long)
+    for b in range(B):
+        nl = n_labels[b]
+        tail = 3 * nl + 2
+        L = S
+        if ragged:
+            lo = max(int(S * min_frac), tail + 2)
+            L = int(torch.randint(lo, S + 1, (1,), generator=g).item())
+        row = torch.randint(3, text_hi, (L,), generator=g)
+        row[0] = 1
+        p = L - tail
+        for c in range(nl):
+            row[p + 3 * c] = cfg.class_token_index
+        row[L - 2] = cfg.sep_token_index
+        row[L - 1] = 2
+        ids[b, :L] = row
+        mask[b, :L] = 1
+    return ids, mask
+
+
+# --------------------------------------------------------------------------------------------
+# the traced module + export (reference ONNX_CONVERTING/convert_to_onnx.py:62-79)
+# --------------------------------------------------------------------------------------------
+
+
+def build_hf_module(cfg: ArchConfig, w: dict):
+    """GLiClassModel-shaped nn.Module around transformers.DebertaV2Model, loaded with `w`.
+
+    Attribute names mirror the gliclass package (model.encoder_model / text_projector /
+    classes_projector) so exported node / initializer names carry the same scopes.
+    """
+    from transformers import DebertaV2Config, DebertaV2Model
+    import torch.nn as nn
+
+    hf_cfg = DebertaV2Config(
+        vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_layers,
+        num_attention_heads=cfg.num_heads, intermediate_size=cfg.intermediate_size, hidden_act="gelu",
+        relative_attention=True, position_buckets=cfg.position_buckets, norm_rel_ebd="layer_norm",
+        share_att_key=True, pos_att_type=["p2c", "c2p"], position_biased_input=False, type_vocab_size=0,
+        max_relative_positions=-1, max_position_embeddings=cfg.max_relative_positions,
+        layer_norm_eps=cfg.layer_norm_eps, hidden_dropout_prob=0.0, attention_probs_dropout_prob=0.0,
+        pad_token_id=0)
+
+    class FeaturesProjector(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear_1 = nn.Linear(cfg.hidden_size, cfg.head_hidden_size)
+            self.linear_2 = nn.Linear(cfg.head_hidden_size, cfg.head_hidden_size)
+
+        def forward(self, t):
+            return self.linear_2(F.gelu(self.linear_1(t)))
+
+    class UniEncoder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder_model = DebertaV2Model(hf_cfg)
+            self.text_projector = FeaturesProjector()
+            self.classes_projector = FeaturesProjector()
+
+        def forward(self, input_ids, attention_mask):
+            hs = self.encoder_model(input_ids, attention_mask=attention_mask)[0]
+            B, S, D = hs.shape
+            class_token_mask = input_ids == cfg.class_token_index
+            num_class_tokens = torch.sum(class_token_mask, dim=-1, keepdim=True)
+            max_c = num_class_tokens.max()
+            ar = torch.arange(max_c, dtype=attention_mask.dtype).unsqueeze(0).expand(B, -1)
+            batch_idx, target_idx = torch.where(ar < num_class_tokens)
+            bi_cls, pos_cls = torch.where(class_token_mask)
+            cls = torch.zeros(B, max_c, D, dtype=hs.dtype)
+            cls[batch_idx, target_idx] = hs[bi_cls, pos_cls]
+            pooled = self.text_projector(hs[:, 0, :])
+            cls = self.classes_projector(cls)
+            return torch.einsum("BD,BCD->BC", pooled, cls)
+
+    class GLiClassModel(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = UniEncoder()
+
+        def forward(self, input_ids, attention_mask):
+            return self.model(input_ids, attention_mask)
+
+    m = GLiClassModel().eval()
+    sd = m.state_dict()
+    missing = [k for k in sd if k not in w and "position_ids" not in k]
+    assert not missing, missing
+    m.load_state_dict({k: v for k, v in w.items()}, strict=False)
+    return m
+
+
+def export_onnx(module, cfg: ArchConfig, path: str, S: int = 24, n_labels: int = 3) -> None:
+    """The reference's export call (convert_to_onnx.py:62-79), opset 14, legacy TorchScript path.
+
+    The final onnxscript-function splice needs the `onnx` package (absent here); it is a no-op for
+    this graph, so it is bypassed.
+    """
+    import warnings
+    from torch.onnx._internal.torchscript_exporter import onnx_proto_utils
+
+    onnx_proto_utils._add_onnxscript_fn = lambda model_bytes, custom_opsets: model_bytes
+    ids, mask = synth_inputs(cfg, 2, S, [n_labels, max(1, n_labels - 1)], seed=7, ragged=True, min_frac=0.7)
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        torch.onnx.export(
+            module, (ids, mask), path,
+            input_names=["input_ids", "attention_mask"], output_names=["logits"],
+            dynamic_axes={"input_ids": {0: "batch_size", 1: "sequence_length"},
+                          "attention_mask": {0: "batch_size", 1: "sequence_length"},
+                          "logits": {0: "position", 1: "batch_size"}},
+            opset_version=14, dynamo=False)
+
+
+def make_model_file(arch: str, path: str, seed: int = 0, **over):
+    """weights -> HF module -> model.onnx at `path`.  Returns (cfg, weights)."""
+    cfg = make_config(arch, **over)
+    w = init_weights(cfg, seed)
+    if not os.path.exists(path):
+        m = build_hf_module(cfg, w)
+        tmp = path + ".tmp%d" % os.getpid()
+        export_onnx(m, cfg, tmp)
+        os.replace(tmp, path)
+    return cfg, w
+
+
+def flops_per_text(cfg: ArchConfig, S: int, C: int) -> float:
+    """Algorithmic FLOPs per text: pos projections hoisted and excluded."""
+    L, H, R = cfg.num_layers, cfg.hidden_size, 2 * cfg.position_buckets
+    Hh = cfg.head_hidden_size
+    return L * (24.0 * S * H * H + 4.0 * S * S * H + 4.0 * S * R * H) + (1 + C) * (2.0 * H * Hh + 2.0 * Hh * Hh) + 2.0 * C * Hh
+
+
+def config_dict(cfg: ArchConfig) -> dict:
+    return asdict(cfg)
