@@ -52,7 +52,8 @@ constexpr int OFF_C2P = OFF_P + 16384;            // 128 x 464 B
 constexpr int OFF_P2C = OFF_C2P + QT * C2P_PITCH * 2;      // 192 x 132 B
 constexpr int OFF_XMAX = OFF_P2C + WMAX * P2C_PITCH * 2;   // 2 x 2 x 128 floats
 constexpr int OFF_LUT = OFF_XMAX + 2048;          // uint16[LUT_MAX]
-constexpr int OFF_BAR = OFF_LUT + ((LUT_MAX * 2 + 15) / 16) * 16;
+constexpr int OFF_MASK = OFF_LUT + ((LUT_MAX * 2 + 15) / 16) * 16;   // uint32[68]: key-validity words of this batch row
+constexpr int OFF_BAR = OFF_MASK + 68 * 4;
 constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
 
 // TMEM columns
@@ -68,6 +69,7 @@ struct AttnParams {
   const int32_t* kv_len;     // [B]
   __half* ctx;        // [B*S, H]
   int B, S, heads, H;
+  int buckets;               // position_buckets: idx(delta) = delta + buckets exactly for |delta| <= buckets/2
   float scale_log2;          // log2(e) / sqrt(3*d)
 };
 
@@ -82,7 +84,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_pk,
                        const __grid_constant__ CUtensorMap tm_pq, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B-swizzle atoms) by pointer arithmetic on the __shared__ symbol: an
+  // integer round-trip would turn every later access into a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
   uint64_t* kv_full = bars + 1;      // [2]
@@ -232,6 +236,8 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const int d_lo = q0 - (T * KT - 1);
     const int n_lut = T * KT + QT - 1;
     for (int e = threadIdx.x - 64; e < n_lut; e += 256) lut[e] = (uint16_t)__ldg(p.rel_idx + p.rel_center + d_lo + e);
+    uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
+    if (threadIdx.x - 64 < 68) kmask[threadIdx.x - 64] = (threadIdx.x - 64 < words) ? __ldg(p.mask_bits + (int64_t)b * words + (threadIdx.x - 64)) : 0u;
     ptx::named_bar_sync(1, 256);
 
     float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
@@ -242,10 +248,12 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
-      int c0, w;
-      slice_bounds(p, q0, k0, c0, w);
+      const int dmin = q0 - k0 - (KT - 1), dmax = q0 + (QT - 1) - k0;
+      const int c0 = lut[dmin - d_lo];
+      const int w = lut[dmax - d_lo] - c0 + 1;
       const int npad = (w + 15) & ~15;
       const int nblk = (w > 128) ? 2 : 1;
+      const bool linear = (dmin >= -(p.buckets >> 1)) && (dmax <= (p.buckets >> 1));   // idx = delta + buckets
 
       ptx::mbar_wait(mma1_full, t & 1);
       ptx::tc_fence_after();
@@ -281,7 +289,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       if (lane == 0) ptx::mbar_arrive(bias_free);
       ptx::named_bar_sync(1, 256);   // staged biases visible to all softmax threads
 
-      // ---- scores for (row i, keys k0+32g .. +32)
+      // ---- scores for (row i, keys k0+32g .. +32): S + c2p[i][idx] + p2c[idx][j]
       float s[32];
       {
         uint32_t r[32];
@@ -291,19 +299,34 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(r[jj]);
       }
       const int kb = k0 + g * 32;
-      const uint32_t kbits = (kb < p.S) ? __ldg(p.mask_bits + (int64_t)b * words + (kb >> 5)) : 0u;
-      const uint16_t* lut_i = lut + (q0 + i - kb - d_lo);          // index by -jj
-      const __half* c2p_i = c2p_s + i * C2P_PITCH - c0;
-      const __half* p2c_g = p2c_s + g * 32 - c0 * P2C_PITCH;
-      float mloc = -CUDART_INF_F;
+      if (linear) {
+        // every delta of this tile is in the linear bucket region: slice row = delta - dmin, so both
+        // gathers are affine in jj (immediate offsets, no LUT)
+        const int rel0 = i + (KT - 1) - g * 32;                               // slice row for jj = 0
+        const __half* c2p_i = c2p_s + i * C2P_PITCH + rel0;
+        const __half* p2c_i = p2c_s + rel0 * P2C_PITCH + g * 32;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const int c = lut_i[-jj];
-        const float bias = __half2float(c2p_i[c]) + __half2float(p2c_g[c * P2C_PITCH + jj]);
-        const float v = ((kbits >> jj) & 1u) ? s[jj] + bias : -CUDART_INF_F;
-        s[jj] = v;
-        mloc = fmaxf(mloc, v);
+        for (int jj = 0; jj < 32; ++jj)
+          s[jj] += __half2float(__hadd(c2p_i[-jj], p2c_i[-jj * (P2C_PITCH - 1)]));
+      } else {
+        const uint16_t* lut_i = lut + (q0 + i - kb - d_lo);                   // indexed by -jj
+        const __half* c2p_i = c2p_s + i * C2P_PITCH - c0;
+        const __half* p2c_g = p2c_s + g * 32 - c0 * P2C_PITCH;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) {
+          const int c = lut_i[-jj];
+          s[jj] += __half2float(__hadd(c2p_i[c], p2c_g[c * P2C_PITCH + jj]));
+        }
       }
+      const uint32_t kbits = kmask[kb >> 5];
+      if (kbits != 0xffffffffu) {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj)
+          if (!((kbits >> jj) & 1u)) s[jj] = -CUDART_INF_F;
+      }
+      float mloc = s[0];
+#pragma unroll
+      for (int jj = 1; jj < 32; ++jj) mloc = fmaxf(mloc, s[jj]);
       // ---- row max shared between the two key halves
       xmax[((t & 1) * 2 + g) * 128 + i] = mloc;
       ptx::named_bar_sync(2, 256);
@@ -472,6 +495,7 @@ cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_
   p.kv_len = kv_len;
   p.ctx = (__half*)ctx;
   p.B = B; p.S = S; p.heads = heads; p.H = H;
+  p.buckets = buckets;
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
   dim3 grid((S + QT - 1) / QT, heads, B);
   attention_fused_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, tm_pk, tm_pq, p);

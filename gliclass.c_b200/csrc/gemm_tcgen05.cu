@@ -11,7 +11,10 @@
 //   warp 0   : TMA producer   — cp.async.bulk.tensor 2D, 128B swizzle, BK = 64 per stage
 //   warp 1   : MMA issuer     — tcgen05.mma.cta_group::1.kind::f16, M=128, N=BN, K=16 x4 per stage,
 //                               fp32 accumulators in TMEM, double buffered (2 x BN columns)
-//   warps 2-5: epilogue       — tcgen05.ld 32x32b -> +bias -> (erf-GELU) -> fp16/fp32 -> global
+//   warps 2.. : epilogue      — EPI groups of 4 warps (one warp per TMEM lane quarter); group g takes
+//                               the 32-column chunks c = g, g+EPI, ...: tcgen05.ld 32x32b -> +bias ->
+//                               (erf-GELU) -> fp16/fp32 -> global.  EPI = 4 for the GELU variant (the
+//                               epilogue, not the MMA, bounds FFN1 otherwise), 2 for the rest.
 // Pipelines: smem ring full/empty (TMA <-> MMA) and TMEM full/empty (MMA <-> epilogue), all mbarrier.
 // Ragged M/N/K are handled by TMA out-of-bounds zero fill on loads and predication on stores.
 #include <cuda_fp16.h>
@@ -25,7 +28,11 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;
+template <int ACT>
+struct EpiCfg {
+  static constexpr int GROUPS = (ACT == 1) ? 4 : 2;        // epilogue warp groups (4 warps each)
+  static constexpr int THREADS = 64 + 128 * GROUPS;
+};
 
 template <int BN>
 struct GemmCfg {
@@ -38,29 +45,32 @@ struct GemmCfg {
   static constexpr uint32_t TMEM_COLS = 2 * BN;
 };
 
-// erf-GELU, 0.5 x (1 + erf(x / sqrt 2)).  erf by Abramowitz-Stegun 7.1.26 (|err| < 1.5e-7), two
-// MUFU ops (rcp, ex2) + ~10 FMA: cheap enough to hide under the MMA of the next tile.
+// erf-GELU: x * Phi(x), Phi(x) = 0.5 erfc(-x / sqrt 2).  With z = |x| / sqrt 2 and
+// h = 0.5 * poly(t) * exp(-z^2), t = 1 / (1 + p z)  (Abramowitz-Stegun 7.1.26, |err| < 1.5e-7):
+// Phi(x) = h for x < 0 and 1 - h for x >= 0.  Two MUFU ops (rcp, ex2) + ~11 FP32 ops per element.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  float p = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  p = fmaf(p, t, 0.5f * 1.421413741f);
+  p = fmaf(p, t, 0.5f * -0.284496736f);
+  p = fmaf(p, t, 0.5f * 0.254829592f);
   p *= t;
-  const float e = __expf(-z * z);
-  const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
-  return 0.5f * x * (1.0f + erf_v);
+  const float e = ptx::ex2(x * x * -0.72134752044448170f);   // exp(-x^2/2) = 2^(-x^2 * log2(e)/2)
+  const float h = p * e;
+  return x * (x < 0.f ? h : 1.0f - h);
 }
 
 template <int BN, int ACT, bool OUT_F32>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const float* __restrict__ bias, void* __restrict__ Cout, int64_t ldc, int M, int N, int K) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment (128B-swizzle atoms) by pointer arithmetic on the __shared__ symbol: an
+  // integer round-trip would turn every later access into a generic LD/ST instead of LDS/STS
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + Cfg::STAGES;
@@ -80,7 +90,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tfull[a], 1);
-      ptx::mbar_init(&tempty[a], 4);   // one arrive per epilogue warp
+      ptx::mbar_init(&tempty[a], 4 * EpiCfg<ACT>::GROUPS);   // one arrive per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -145,6 +155,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     __syncwarp();
   } else {
     const int q = warp & 3;   // TMEM lane quarter this warp may read
+    const int grp = (warp - 2) >> 2;
     int acc = 0;
     uint32_t acc_ph = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -155,7 +166,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
         uint32_t r[32];
         ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
         ptx::tmem_ld_wait();
@@ -242,7 +253,7 @@ cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, bias, C, ldc, M, N, K);
+  kern<<<grid, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, bias, C, ldc, M, N, K);
   return cudaGetLastError();
 }
 

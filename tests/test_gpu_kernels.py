@@ -239,7 +239,7 @@ def test_attention_fused(pkg, dev, B, S, heads, lens):
     v = mask.bool()
     got, want = ctx[v], ref[v]
     d = (got.float() - want.float()).abs()
-    if d.max().item() > 6e-3 or torch.isnan(got.float()).any():
+    if d.max().item() > 1e-2 or torch.isnan(got.float()).any():
         # localise: per (batch, head, 128-row query tile) error map
         H = heads * 64
         full = (ctx.float() - ref.float()).abs().nan_to_num(99.0) * mask[..., None].float()
@@ -250,9 +250,9 @@ def test_attention_fused(pkg, dev, B, S, heads, lens):
                     row.append(f"{full[b, q0:q0 + 128, h * 64:(h + 1) * 64].max().item():.3f}")
                 print(f"   b{b} h{h} per-q-tile max err: {row}")
         # first bad row: show which columns
-        bad = torch.nonzero(full.max(-1).values > 6e-3)
+        bad = torch.nonzero(full.max(-1).values > 1e-2)
         print("   first bad (b,row):", bad[:10].tolist())
-    _report(f"attn-fused B{B} S{S} h{heads}", got, want, 6e-3, 6e-3)
+    _report(f"attn-fused B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
 
 
 def test_attention_fused_softmax_peaked(pkg, dev):
