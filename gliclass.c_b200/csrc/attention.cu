@@ -25,6 +25,10 @@
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tma_desc.h"
@@ -35,26 +39,36 @@ namespace {
 constexpr int QT = 128;            // queries per CTA
 constexpr int KT = 64;             // keys per tile
 constexpr int D = 64;              // head dim
+constexpr int G = 4;               // key groups per tile: softmax thread = (query row, 16-key group)
+constexpr int E = KT / G;          // scores per softmax thread per tile
+constexpr int SM_WARPS = 4 * G;    // 4 TMEM lane quarters x G groups
+constexpr int SM_THREADS = 32 * SM_WARPS;
 constexpr int WMAX = 192;          // max slice rows (191 needed)
-constexpr int ATT_THREADS = 320;
-constexpr int C2P_PITCH = 232;     // halves; 116 words = 20 mod 32 -> conflict-free 128-bit row stores, near conflict-free diagonal gathers
+constexpr int ATT_THREADS = 64 + SM_THREADS;
+constexpr int C2P_PITCH = 120;     // halves; a 32-row warp quarter touches <= 7 16-column chunks of the slice (band-packed);
+                                   // 60 words = 28 mod 32 -> conflict-free 128-bit row stores
 constexpr int P2C_PITCH = 66;      // halves; 33 words -> conflict-free
 constexpr int LUT_MAX = 2048 + 128 + 64;
+constexpr int TMAX = 2048 / KT;    // key tiles at the reference MAX_LENGTH
 
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int OFF_Q = 0;                          // 128 x 128 B
 constexpr int OFF_K = OFF_Q + 16384;              // 2 x 8 KB
 constexpr int OFF_V = OFF_K + 16384;              // 2 x 8 KB
-constexpr int OFF_PK = OFF_V + 16384;             // 192 x 128 B
-constexpr int OFF_PQ = OFF_PK + 24576;            // 256 x 128 B (two M=128 blocks)
-constexpr int OFF_P = OFF_PQ + 32768;             // 128 x 128 B
-constexpr int OFF_C2P = OFF_P + 16384;            // 128 x 464 B
+constexpr int POS_BYTES = WMAX * 128;             // one 192-row slice
+constexpr int OFF_PK = OFF_V + 16384;             // 2 x 192 x 128 B
+constexpr int OFF_PQ = OFF_PK + 2 * POS_BYTES;    // 2 x 192 x 128 B; the second M=128 block of a slice reads 64 rows past
+                                                  // its end (next buffer / P tile): never-indexed accumulator rows
+constexpr int OFF_P = OFF_PQ + 2 * POS_BYTES;     // 128 x 128 B
+constexpr int OFF_C2P = OFF_P + 16384;            // 128 x 240 B
 constexpr int OFF_P2C = OFF_C2P + QT * C2P_PITCH * 2;      // 192 x 132 B
-constexpr int OFF_XMAX = OFF_P2C + WMAX * P2C_PITCH * 2;   // 2 x 2 x 128 floats
-constexpr int OFF_LUT = OFF_XMAX + 2048;          // uint16[LUT_MAX]
+constexpr int OFF_XMAX = OFF_P2C + WMAX * P2C_PITCH * 2;   // G x 128 floats
+constexpr int OFF_LUT = OFF_XMAX + G * QT * 4;    // uint16[LUT_MAX]
 constexpr int OFF_MASK = OFF_LUT + ((LUT_MAX * 2 + 15) / 16) * 16;   // uint32[68]: key-validity words of this batch row
-constexpr int OFF_BAR = OFF_MASK + 68 * 4;
+constexpr int OFF_TILE = OFF_MASK + 68 * 4;       // uint32[TMAX]: per key tile (slice start c0 | slice rows w << 16)
+constexpr int OFF_BAR = OFF_TILE + TMAX * 4;
 constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
+static_assert(ATT_SMEM <= 227 * 1024, "attention smem budget");
 
 // TMEM columns
 constexpr uint32_t TM_S = 0;       // 2 x 64
@@ -71,15 +85,30 @@ struct AttnParams {
   int B, S, heads, H;
   int buckets;               // position_buckets: idx(delta) = delta + buckets exactly for |delta| <= buckets/2
   float scale_log2;          // log2(e) / sqrt(3*d)
+  int flags;                 // TRACE instantiation only: developer what-if switches (results become wrong)
+  long long* trace;          // TRACE instantiation only: [2 roles][TMAX][8] clock64 stamps of CTA (1,0,0)
 };
 
-__device__ __forceinline__ void slice_bounds(const AttnParams& p, int q0, int k0, int& c0, int& w) {
-  const int dmin = q0 - k0 - (KT - 1);
-  const int dmax = q0 + (QT - 1) - k0;
-  c0 = __ldg(p.rel_idx + p.rel_center + dmin);
-  w = __ldg(p.rel_idx + p.rel_center + dmax) - c0 + 1;
+#define GLC_TRACE(role, tile, slot)                                                               \
+  do {                                                                                            \
+    if (TRACE && p.trace && (threadIdx.x & 31) == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)                         \
+      p.trace[((role) * TMAX + (tile)) * 8 + (slot)] = clock64();                                 \
+  } while (0)
+
+// 16 fp32 accumulator columns -> 16 halves -> two 128-bit shared stores
+__device__ __forceinline__ void pack16_store(const uint32_t (&r)[16], uint4* dst) {
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    uint4 o4;
+    o4.x = ptx::pack_f16(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1]));
+    o4.y = ptx::pack_f16(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]));
+    o4.z = ptx::pack_f16(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]));
+    o4.w = ptx::pack_f16(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]));
+    dst[v] = o4;
+  }
 }
 
+template <bool TRACE>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_pk,
                        const __grid_constant__ CUtensorMap tm_pq, const AttnParams p) {
@@ -89,15 +118,20 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;      // [2]
-  uint64_t* kv_empty = bars + 3;     // [2]
-  uint64_t* pos_full = bars + 5;
-  uint64_t* pos_empty = bars + 6;
-  uint64_t* mma1_full = bars + 7;    // bias + QK accumulators of tile t ready
-  uint64_t* bias_free = bars + 8;    // softmax warps have drained the bias TMEM of tile t
-  uint64_t* p_full = bars + 9;       // P tile written
-  uint64_t* pv_full = bars + 10;     // PV accumulator ready
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  // two operand rings, each two deep, freed at different moments of a tile:
+  //   A = K_t + posK/posQ slices (read by the S / C2P / P2C' MMAs)   B = V_t (read by the PV MMA)
+  uint64_t* a_full = bars + 1;       // [2]
+  uint64_t* a_empty = bars + 3;      // [2]
+  uint64_t* b_full = bars + 5;       // [2]
+  uint64_t* b_empty = bars + 7;      // [2]
+  uint64_t* mma1_full = bars + 9;    // bias + QK accumulators of tile t ready
+  uint64_t* bias_free = bars + 10;   // softmax warps have drained the bias TMEM of tile t
+  uint64_t* p_full = bars + 11;      // P tile written
+  uint64_t* pv_full = bars + 12;     // PV accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint16_t* lut = reinterpret_cast<uint16_t*>(smem + OFF_LUT);
+  uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
+  uint32_t* tile_cw = reinterpret_cast<uint32_t*>(smem + OFF_TILE);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -122,16 +156,39 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     ptx::prefetch_tensormap(&tm_pk);
     ptx::prefetch_tensormap(&tm_pq);
     ptx::mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&kv_full[s], 1); ptx::mbar_init(&kv_empty[s], 1); }
-    ptx::mbar_init(pos_full, 1);
-    ptx::mbar_init(pos_empty, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
     ptx::mbar_init(mma1_full, 1);
-    ptx::mbar_init(bias_free, 8);
-    ptx::mbar_init(p_full, 8);
+    ptx::mbar_init(bias_free, SM_WARPS);
+    ptx::mbar_init(p_full, SM_WARPS);
     ptx::mbar_init(pv_full, 1);
     ptx::fence_barrier_init();
+    // Q and the first V tile do not depend on the tables built below: start them now
+    ptx::mbar_arrive_expect_tx(q_full, QT * 128);
+    ptx::tma_load_3d(smem + OFF_Q, &tm_qkv, q_full, head * D, q0, b);
+    ptx::tma_load_3d(smem + OFF_Q + 8192, &tm_qkv, q_full, head * D, q0 + 64, b);
+    ptx::mbar_arrive_expect_tx(&b_full[0], KT * 128);
+    ptx::tma_load_3d(smem + OFF_V, &tm_qkv, &b_full[0], 2 * p.H + head * D, 0, b);
   }
   if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+
+  // relative-position LUT for every delta this CTA can see: delta in [q0 - (T*64-1), q0+127];
+  // per key tile the slice [c0, c0+w) of the position tables its deltas index; key-validity words
+  const int d_lo = q0 - (T * KT - 1);
+  {
+    const int n_lut = T * KT + QT - 1;
+    const int32_t* rel = p.rel_idx + p.rel_center + d_lo;
+    for (int e = threadIdx.x; e < n_lut; e += ATT_THREADS) lut[e] = (uint16_t)__ldg(rel + e);
+    if (threadIdx.x < T) {
+      const int k0 = threadIdx.x * KT;
+      const int c0 = __ldg(p.rel_idx + p.rel_center + q0 - k0 - (KT - 1));
+      const int c1 = __ldg(p.rel_idx + p.rel_center + q0 + (QT - 1) - k0);
+      tile_cw[threadIdx.x] = (uint32_t)c0 | ((uint32_t)(c1 - c0 + 1) << 16);
+    }
+    const int words = (p.S + 31) >> 5;
+    const int e = threadIdx.x - 64;
+    if (e >= 0 && e < 68) kmask[e] = (e < words) ? __ldg(p.mask_bits + (int64_t)b * words + e) : 0u;
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -140,205 +197,241 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      ptx::mbar_arrive_expect_tx(q_full, QT * 128);
-      ptx::tma_load_3d(smem + OFF_Q, &tm_qkv, q_full, head * D, q0, b);
-      ptx::tma_load_3d(smem + OFF_Q + 8192, &tm_qkv, q_full, head * D, q0 + 64, b);
-      for (int t = 0; t < T; ++t) {
-        const int st = t & 1;
-        const int k0 = t * KT;
-        ptx::mbar_wait(&kv_empty[st], ((t >> 1) & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * KT * 128);
-        ptx::tma_load_3d(smem + OFF_K + st * 8192, &tm_qkv, &kv_full[st], p.H + head * D, k0, b);
-        ptx::tma_load_3d(smem + OFF_V + st * 8192, &tm_qkv, &kv_full[st], 2 * p.H + head * D, k0, b);
-        int c0, w;
-        slice_bounds(p, q0, k0, c0, w);
-        const int nbox = (w + 63) >> 6;
-        ptx::mbar_wait(pos_empty, (t & 1) ^ 1);
-        ptx::mbar_arrive_expect_tx(pos_full, (uint32_t)(2 * nbox * 64 * 128));
-        for (int x = 0; x < nbox; ++x) {
-          ptx::tma_load_3d(smem + OFF_PK + x * 8192, &tm_pk, pos_full, 0, c0 + x * 64, head);
-          ptx::tma_load_3d(smem + OFF_PQ + x * 8192, &tm_pq, pos_full, 0, c0 + x * 64, head);
+      // ring A: K_x and the position slices of tile x; free once the bias MMAs of tile x-2 retired
+      auto load_a = [&](int x) {
+        const uint32_t cw = tile_cw[x];
+        const int c0 = (int)(cw & 0xffffu), w = (int)(cw >> 16);
+        const int nbox = (TRACE && (p.flags & 16)) ? 1 : ((w + 63) >> 6);
+        const int st = x & 1;
+        ptx::mbar_wait(&a_empty[st], ((x >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&a_full[st], (uint32_t)((1 + 2 * nbox) * 64 * 128));
+        ptx::tma_load_3d(smem + OFF_K + st * 8192, &tm_qkv, &a_full[st], p.H + head * D, x * KT, b);
+        for (int bx = 0; bx < nbox; ++bx) {
+          ptx::tma_load_3d(smem + OFF_PK + st * POS_BYTES + bx * 8192, &tm_pk, &a_full[st], 0, c0 + bx * 64, head);
+          ptx::tma_load_3d(smem + OFF_PQ + st * POS_BYTES + bx * 8192, &tm_pq, &a_full[st], 0, c0 + bx * 64, head);
         }
+      };
+      // ring B: V_x; free once the PV MMA of tile x-2 retired
+      auto load_b = [&](int x) {
+        const int st = x & 1;
+        ptx::mbar_wait(&b_empty[st], ((x >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&b_full[st], KT * 128);
+        ptx::tma_load_3d(smem + OFF_V + st * 8192, &tm_qkv, &b_full[st], 2 * p.H + head * D, x * KT, b);
+      };
+      // issue order = order in which the buffers come free: bias(t) retires before PV(t-1)
+      load_a(0);
+      if (T > 1) load_a(1);
+      for (int t = 0; t < T; ++t) {
+        if (t + 2 < T) load_a(t + 2);
+        if (t + 1 < T) load_b(t + 1);
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      const uint32_t sQ = ptx::smem_u32(smem + OFF_Q);
-      const uint32_t sP = ptx::smem_u32(smem + OFF_P);
-      const uint32_t sPK = ptx::smem_u32(smem + OFF_PK);
-      const uint32_t sPQ = ptx::smem_u32(smem + OFF_PQ);
-      constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
-      constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
-      ptx::mbar_wait(q_full, 0);
-      for (int t = 0; t <= T; ++t) {
-        if (t < T) {
-          const int st = t & 1;
-          const int k0 = t * KT;
-          int c0, w;
-          slice_bounds(p, q0, k0, c0, w);
-          const uint32_t npad = (uint32_t)((w + 15) & ~15);
-          const int nblk = (w > 128) ? 2 : 1;
-          const uint32_t sK = ptx::smem_u32(smem + OFF_K + st * 8192);
-          ptx::mbar_wait(&kv_full[st], (t >> 1) & 1);
-          ptx::mbar_wait(pos_full, t & 1);
-          if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);
-          ptx::tc_fence_after();
+    // All 32 lanes walk the (warp-uniform) loop and wait on the barriers; one elected lane issues the
+    // tcgen05 instructions.  Issuing from inside `if (lane == 0)` makes the compiler wrap every UTCHMMA
+    // in an R2UR + ELECT retry loop (~100 cycles per instruction).
+    const uint32_t sQ = ptx::smem_u32(smem + OFF_Q);
+    const uint32_t sP = ptx::smem_u32(smem + OFF_P);
+    constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
+    constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
+    const uint64_t dQ = ptx::smem_desc_sw128(sQ);
+    const uint64_t dP = ptx::smem_desc_sw128(sP);
+    ptx::mbar_wait(q_full, 0);
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        const int st = t & 1;
+        const uint32_t cw = tile_cw[t];
+        const int w = (int)(cw >> 16);
+        const uint32_t npad = (uint32_t)((w + 15) & ~15);
+        const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
+        const uint64_t dPK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_PK + st * POS_BYTES));
+        const uint64_t dPQ = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_PQ + st * POS_BYTES));
+        GLC_TRACE(1, t, 0);
+        ptx::mbar_wait(&a_full[st], (t >> 1) & 1);
+        ptx::tc_fence_after();
+        GLC_TRACE(1, t, 1);
+        // S first: it only needs K_t (its TMEM buffer was drained two tiles ago)
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // +2 in the descriptor = +32 bytes = 16 halves along K
+            ptx::mma_f16_ss(tmem + TM_S + (uint32_t)(st * 64), dQ + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+        }
+        __syncwarp();
+        GLC_TRACE(1, t, 2);
+        if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);
+        ptx::tc_fence_after();
+        GLC_TRACE(1, t, 3);
+        if (ptx::elect_one()) {
           const uint32_t idesc_c2p = ptx::idesc_f16(128, npad);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ss(tmem + TM_C2P, ptx::smem_desc_sw128(sQ + k * 32), ptx::smem_desc_sw128(sPK + k * 32), idesc_c2p,
-                            (uint32_t)(k != 0));
-          for (int blk = 0; blk < nblk; ++blk) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              ptx::mma_f16_ss(tmem + TM_P2C + blk * 64, ptx::smem_desc_sw128(sPQ + blk * 16384 + k * 32),
-                              ptx::smem_desc_sw128(sK + k * 32), idesc_n64, (uint32_t)(k != 0));
-          }
-          ptx::mma_commit(pos_empty);   // pos slices consumed once the MMAs above retire
+            ptx::mma_f16_ss(tmem + TM_C2P, dQ + 2 * k, dPK + 2 * k, idesc_c2p, (uint32_t)(k != 0));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ss(tmem + TM_S + (uint32_t)(st * 64), ptx::smem_desc_sw128(sQ + k * 32),
-                            ptx::smem_desc_sw128(sK + k * 32), idesc_n64, (uint32_t)(k != 0));
+            ptx::mma_f16_ss(tmem + TM_P2C, dPQ + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+          if (w > 128) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)   // second M=128 block of the slice: +16384 bytes = +1024 in the descriptor
+              ptx::mma_f16_ss(tmem + TM_P2C + 64, dPQ + 1024 + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+          }
+          ptx::mma_commit(&a_empty[st]);   // K_t and the slices are consumed once the MMAs above retire
           ptx::mma_commit(mma1_full);
         }
-        if (t > 0) {
-          const int tp = t - 1;
-          const int st = tp & 1;
-          const uint32_t sV = ptx::smem_u32(smem + OFF_V + st * 8192);
-          ptx::mbar_wait(p_full, tp & 1);
-          ptx::tc_fence_after();
+        __syncwarp();
+        GLC_TRACE(1, t, 4);
+      }
+      if (t > 0) {
+        const int tp = t - 1;
+        const int st = tp & 1;
+        const uint64_t dV = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_V + st * 8192));
+        ptx::mbar_wait(&b_full[st], (tp >> 1) & 1);
+        ptx::mbar_wait(p_full, tp & 1);
+        ptx::tc_fence_after();
+        GLC_TRACE(1, tp, 5);
+        if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ss(tmem + TM_PV, ptx::smem_desc_sw128(sP + k * 32), ptx::smem_desc_sw128(sV + k * 2048), idesc_pv,
-                            (uint32_t)(k != 0));
-          ptx::mma_commit(&kv_empty[st]);
+          for (int k = 0; k < 4; ++k)   // V is MN-major: 16 keys further = +2048 bytes = +128 in the descriptor
+            ptx::mma_f16_ss(tmem + TM_PV, dP + 2 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0));
+          ptx::mma_commit(&b_empty[st]);
           ptx::mma_commit(pv_full);
         }
+        __syncwarp();
       }
     }
-    __syncwarp();
   } else {
     // ------------------------------------------------------------------ softmax warps
-    const int sw = warp - 2;          // 0..7
-    const int g = sw >> 2;            // key half of the tile: keys [32g, 32g+32)
+    const int sw = warp - 2;          // 0..SM_WARPS-1
+    const int g = sw >> 2;            // key group of the tile: keys [E*g, E*g+E)
     const int qd = warp & 3;          // TMEM lane quarter
     const int i = qd * 32 + lane;     // row in the query tile
     const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
     __half* c2p_s = reinterpret_cast<__half*>(smem + OFF_C2P);
     __half* p2c_s = reinterpret_cast<__half*>(smem + OFF_P2C);
     float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
-    uint16_t* lut = reinterpret_cast<uint16_t*>(smem + OFF_LUT);
-    const int words = (p.S + 31) >> 5;
-
-    // relative-position LUT for every delta this CTA can see: delta in [q0 - (T*64-1), q0+127]
-    const int d_lo = q0 - (T * KT - 1);
-    const int n_lut = T * KT + QT - 1;
-    for (int e = threadIdx.x - 64; e < n_lut; e += 256) lut[e] = (uint16_t)__ldg(p.rel_idx + p.rel_center + d_lo + e);
-    uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
-    if (threadIdx.x - 64 < 68) kmask[threadIdx.x - 64] = (threadIdx.x - 64 < words) ? __ldg(p.mask_bits + (int64_t)b * words + (threadIdx.x - 64)) : 0u;
-    ptx::named_bar_sync(1, 256);
+    const uint32_t s_c2p = ptx::smem_u32(c2p_s), s_p2c = ptx::smem_u32(p2c_s), s_lut = ptx::smem_u32(lut);
 
     float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
-    float o[32];
+    float o[E];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) o[k] = 0.f;
+    for (int k = 0; k < E; ++k) o[k] = 0.f;
     const float sc = p.scale_log2;
+    const int half_b = p.buckets >> 1;
 
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
       const int dmin = q0 - k0 - (KT - 1), dmax = q0 + (QT - 1) - k0;
-      const int c0 = lut[dmin - d_lo];
-      const int w = lut[dmax - d_lo] - c0 + 1;
-      const int npad = (w + 15) & ~15;
-      const int nblk = (w > 128) ? 2 : 1;
-      const bool linear = (dmin >= -(p.buckets >> 1)) && (dmax <= (p.buckets >> 1));   // idx = delta + buckets
+      const uint32_t cw = tile_cw[t];
+      const int c0 = (int)(cw & 0xffffu), w = (int)(cw >> 16);
+      const bool linear = (dmin >= -half_b) && (dmax <= half_b);   // idx = delta + buckets
 
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 0);
       ptx::mbar_wait(mma1_full, t & 1);
       ptx::tc_fence_after();
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 1);
 
-      // ---- stage C2P (row i, 32-column chunks ch = g, g+2, g+4) as fp16
-      for (int ch = g; ch * 32 < npad; ch += 2) {
-        uint32_t r[32];
-        ptx::tmem_ld_x32(t_lane + TM_C2P + (uint32_t)(ch * 32), r);
-        ptx::tmem_ld_wait();
-        uint4* dst = reinterpret_cast<uint4*>(c2p_s + i * C2P_PITCH + ch * 32);
+      // ---- stage C2P as fp16, band-packed: the 32 rows of this warp quarter only index slice columns
+      //      [lo, hi] (<= 95 wide), i.e. 16-column chunks u_lo..u_hi (<= 7); group g takes u_lo+g, u_lo+g+G
+      const int dq = q0 + qd * 32 - k0 - d_lo;   // LUT position of (first row of the quarter, key k0)
+      const int u_lo = ((int)lut[dq - (KT - 1)] - c0) >> 4;
+      const int u_hi = ((int)lut[dq + 31] - c0) >> 4;
+      {
+        uint4* dst = reinterpret_cast<uint4*>(c2p_s + i * C2P_PITCH + g * 16);
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint4 o4;
-          o4.x = ptx::pack_f16(__uint_as_float(r[8 * v + 0]), __uint_as_float(r[8 * v + 1]));
-          o4.y = ptx::pack_f16(__uint_as_float(r[8 * v + 2]), __uint_as_float(r[8 * v + 3]));
-          o4.z = ptx::pack_f16(__uint_as_float(r[8 * v + 4]), __uint_as_float(r[8 * v + 5]));
-          o4.w = ptx::pack_f16(__uint_as_float(r[8 * v + 6]), __uint_as_float(r[8 * v + 7]));
-          dst[v] = o4;
+        for (int u = 0; u < 2; ++u) {
+          const int ch = u_lo + g + u * G;
+          if (ch <= u_hi && !(TRACE && (p.flags & 2))) {   // warp-uniform
+            uint32_t ra[16];
+            ptx::tmem_ld_x16(t_lane + TM_C2P + (uint32_t)(ch * 16), ra);
+            ptx::tmem_ld_wait();
+            pack16_store(ra, dst + 2 * G * u);
+          }
         }
       }
-      // ---- stage P2C' (slice row c = blk*128 + i, keys [32g, 32g+32)) as fp16
-      for (int blk = 0; blk < nblk; ++blk) {
-        if (blk == 1 && qd >= 2) break;   // rows 192..255 are never indexed (warp-uniform)
-        uint32_t r[32];
-        ptx::tmem_ld_x32(t_lane + TM_P2C + (uint32_t)(blk * 64 + g * 32), r);
+      // ---- stage P2C' (slice row c = blk*128 + i, keys [E*g, E*g+E)) as fp16
+      {
+        uint32_t ra[16], rb[16];
+        const bool two = (w > 128) && (qd < 2);   // rows 192..255 are never indexed (warp-uniform)
+        if (!(TRACE && (p.flags & 4)))
+        ptx::tmem_ld_x16(t_lane + TM_P2C + (uint32_t)(g * E), ra);
+        if (two) ptx::tmem_ld_x16(t_lane + TM_P2C + (uint32_t)(64 + g * E), rb);
         ptx::tmem_ld_wait();
-        uint32_t* dst = reinterpret_cast<uint32_t*>(p2c_s + (blk * 128 + i) * P2C_PITCH + g * 32);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(p2c_s + i * P2C_PITCH + g * E);
+        if (!(TRACE && (p.flags & 4)))
 #pragma unroll
-        for (int v = 0; v < 16; ++v) dst[v] = ptx::pack_f16(__uint_as_float(r[2 * v]), __uint_as_float(r[2 * v + 1]));
+        for (int v = 0; v < 8; ++v) dst[v] = ptx::pack_f16(__uint_as_float(ra[2 * v]), __uint_as_float(ra[2 * v + 1]));
+        if (two) {
+          uint32_t* dst2 = dst + 128 * P2C_PITCH / 2;
+#pragma unroll
+          for (int v = 0; v < 8; ++v) dst2[v] = ptx::pack_f16(__uint_as_float(rb[2 * v]), __uint_as_float(rb[2 * v + 1]));
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bias_free);
-      ptx::named_bar_sync(1, 256);   // staged biases visible to all softmax threads
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 2);
+      ptx::named_bar_sync(1, SM_THREADS);   // staged biases visible to all softmax threads
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 3);
 
-      // ---- scores for (row i, keys k0+32g .. +32): S + c2p[i][idx] + p2c[idx][j]
-      float s[32];
+      // ---- scores for (row i, keys k0+E*g .. +E): S + c2p[i][idx] + p2c[idx][j]
+      float s[E];
       {
-        uint32_t r[32];
-        ptx::tmem_ld_x32(t_lane + TM_S + (uint32_t)((t & 1) * 64 + g * 32), r);
+        uint32_t r[16];
+        ptx::tmem_ld_x16(t_lane + TM_S + (uint32_t)((t & 1) * 64 + g * E), r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) s[jj] = __uint_as_float(r[jj]);
+        for (int jj = 0; jj < E; ++jj) s[jj] = __uint_as_float(r[jj]);
       }
-      const int kb = k0 + g * 32;
-      if (linear) {
+      const int kb = k0 + g * E;
+      if (TRACE && (p.flags & 1)) {
+      } else if (linear) {
         // every delta of this tile is in the linear bucket region: slice row = delta - dmin, so both
         // gathers are affine in jj (immediate offsets, no LUT)
-        const int rel0 = i + (KT - 1) - g * 32;                               // slice row for jj = 0
-        const __half* c2p_i = c2p_s + i * C2P_PITCH + rel0;
-        const __half* p2c_i = p2c_s + rel0 * P2C_PITCH + g * 32;
+        const int rel0 = i + (KT - 1) - g * E;                               // slice row for jj = 0
+        const uint32_t a1 = s_c2p + 2u * (uint32_t)(i * C2P_PITCH + rel0 - u_lo * 16);
+        const uint32_t a2 = s_p2c + 2u * (uint32_t)(rel0 * P2C_PITCH + g * E);
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
-          s[jj] += __half2float(__hadd(c2p_i[-jj], p2c_i[-jj * (P2C_PITCH - 1)]));
+        for (int jj = 0; jj < E; ++jj)
+          s[jj] += __half2float(__hadd(ptx::lds_f16(a1 - 2u * jj), ptx::lds_f16(a2 - 2u * jj * (P2C_PITCH - 1))));
       } else {
-        const uint16_t* lut_i = lut + (q0 + i - kb - d_lo);                   // indexed by -jj
-        const __half* c2p_i = c2p_s + i * C2P_PITCH - c0;
-        const __half* p2c_g = p2c_s + g * 32 - c0 * P2C_PITCH;
+        // byte addresses by hand (one multiply-add per gather): the compiler otherwise spends six
+        // integer instructions per element on index -> address conversion
+        const uint32_t al = s_lut + 2u * (uint32_t)(q0 + i - kb - d_lo);                 // LUT entry of jj = 0
+        uint32_t a1 = s_c2p + 2u * (uint32_t)(i * C2P_PITCH - c0 - u_lo * 16);           // + 2 c
+        uint32_t a2 = s_p2c + 2u * (uint32_t)(g * E - c0 * P2C_PITCH);                   // + 132 c + 2 jj
+        asm volatile("" : "+r"(a1), "+r"(a2));   // opaque: keep the folded bases, one IMAD per gather
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int c = lut_i[-jj];
-          s[jj] += __half2float(__hadd(c2p_i[c], p2c_g[c * P2C_PITCH + jj]));
+        for (int jj = 0; jj < E; ++jj) {
+          const uint32_t c = ptx::lds_u16(al - 2u * jj);
+          s[jj] += __half2float(__hadd(ptx::lds_f16(a1 + 2u * c), ptx::lds_f16(a2 + (2u * P2C_PITCH) * c + 2u * jj)));
         }
       }
-      const uint32_t kbits = kmask[kb >> 5];
-      if (kbits != 0xffffffffu) {
+      const uint32_t kbits = (kmask[kb >> 5] >> (kb & 31)) & ((1u << E) - 1u);
+      if (kbits != ((1u << E) - 1u)) {
 #pragma unroll
-        for (int jj = 0; jj < 32; ++jj)
+        for (int jj = 0; jj < E; ++jj)
           if (!((kbits >> jj) & 1u)) s[jj] = -CUDART_INF_F;
       }
       float mloc = s[0];
 #pragma unroll
-      for (int jj = 1; jj < 32; ++jj) mloc = fmaxf(mloc, s[jj]);
-      // ---- row max shared between the two key halves
-      xmax[((t & 1) * 2 + g) * 128 + i] = mloc;
-      ptx::named_bar_sync(2, 256);
-      const float mo = xmax[((t & 1) * 2 + (g ^ 1)) * 128 + i];
-      const float m_new = fmaxf(m_run, fmaxf(mloc, mo));
+      for (int jj = 1; jj < E; ++jj) mloc = fmaxf(mloc, s[jj]);
+      // ---- row max shared between the key groups (the barrier of the next tile's staging orders
+      //      these reads before the next writes)
+      xmax[g * QT + i] = mloc;
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 4);
+      ptx::named_bar_sync(2 + qd, 32 * G);   // only the G warps of this lane quarter share rows
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 5);
+      float m_new = m_run;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) m_new = fmaxf(m_new, xmax[gg * QT + i]);
       const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
       const float alpha = ptx::ex2((m_run - m_use) * sc);
       const float neg_ms = -m_use * sc;
       float psum = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < 32; ++jj) {
-        const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
+      for (int jj = 0; jj < E; ++jj) {
+        const float e = (TRACE && (p.flags & 8)) ? fmaf(s[jj], sc, neg_ms) : ptx::ex2(fmaf(s[jj], sc, neg_ms));
         s[jj] = e;
         psum += e;
       }
@@ -346,55 +439,60 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       m_run = m_new;
 
       // ---- fold in PV of the previous tile (also guarantees the P buffer is free again)
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 6);
       if (t > 0) {
         ptx::mbar_wait(pv_full, (t - 1) & 1);
         ptx::tc_fence_after();
-        uint32_t r[32];
-        ptx::tmem_ld_x32(t_lane + TM_PV + (uint32_t)(g * 32), r);
+        uint32_t r[16];
+        ptx::tmem_ld_x16(t_lane + TM_PV + (uint32_t)(g * E), r);
         ptx::tmem_ld_wait();
 #pragma unroll
-        for (int k = 0; k < 32; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
+        for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
       }
       alpha_prev = alpha;
 
-      // ---- P tile: row i, 16-byte chunks 4g..4g+3, 128-byte swizzle
+      // ---- P tile: row i, 16-byte chunks 2g, 2g+1, 128-byte swizzle
       {
         uint8_t* prow = smem + OFF_P + (i >> 3) * 1024 + (i & 7) * 128;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
+        for (int v = 0; v < E / 8; ++v) {
           uint4 o4;
           o4.x = ptx::pack_f16(s[8 * v + 0], s[8 * v + 1]);
           o4.y = ptx::pack_f16(s[8 * v + 2], s[8 * v + 3]);
           o4.z = ptx::pack_f16(s[8 * v + 4], s[8 * v + 5]);
           o4.w = ptx::pack_f16(s[8 * v + 6], s[8 * v + 7]);
-          *reinterpret_cast<uint4*>(prow + (((4 * g + v) ^ (i & 7)) << 4)) = o4;
+          *reinterpret_cast<uint4*>(prow + ((((E / 8) * g + v) ^ (i & 7)) << 4)) = o4;
         }
       }
       ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
+      if (sw == 0 && lane == 0) GLC_TRACE(0, t, 7);
     }
 
     // ---- last PV, normalise, write ctx
     ptx::mbar_wait(pv_full, (T - 1) & 1);
     ptx::tc_fence_after();
     {
-      uint32_t r[32];
-      ptx::tmem_ld_x32(t_lane + TM_PV + (uint32_t)(g * 32), r);
+      uint32_t r[16];
+      ptx::tmem_ld_x16(t_lane + TM_PV + (uint32_t)(g * E), r);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < 32; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
+      for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
     }
-    xmax[g * 128 + i] = l_run;   // reuse the exchange buffer for the row sums
-    ptx::named_bar_sync(2, 256);
-    const float l_tot = l_run + xmax[(g ^ 1) * 128 + i];
+    ptx::named_bar_sync(2 + qd, 32 * G);  // the quarter is past its last row-max read
+    xmax[g * QT + i] = l_run;             // reuse the exchange buffer for the row sums
+    ptx::named_bar_sync(2 + qd, 32 * G);
+    float l_tot = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg) l_tot += xmax[gg * QT + i];
     const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
     const int row = q0 + i;
     if (row < p.S) {
-      __half* dst = p.ctx + ((int64_t)b * p.S + row) * p.H + head * D + g * 32;
+      __half* dst = p.ctx + ((int64_t)b * p.S + row) * p.H + head * D + g * E;
 #pragma unroll
-      for (int v = 0; v < 4; ++v) {
+      for (int v = 0; v < E / 8; ++v) {
         uint4 o4;
         o4.x = ptx::pack_f16(o[8 * v + 0] * inv, o[8 * v + 1] * inv);
         o4.y = ptx::pack_f16(o[8 * v + 2] * inv, o[8 * v + 3] * inv);
@@ -484,7 +582,9 @@ cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(attention_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
@@ -497,8 +597,37 @@ cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_
   p.B = B; p.S = S; p.heads = heads; p.H = H;
   p.buckets = buckets;
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
+  p.trace = nullptr;
+  p.flags = 0;
   dim3 grid((S + QT - 1) / QT, heads, B);
-  attention_fused_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, tm_pk, tm_pq, p);
+  // developer aid: GLC_ATTN_TRACE=<file> dumps per-tile clock64 stamps of CTA (1,0,0) (synchronous)
+  if (const char* fl = getenv("GLC_ATTN_FLAGS")) p.flags = atoi(fl);
+  if (getenv("GLC_ATTN_FLAGS") && !getenv("GLC_ATTN_TRACE")) {
+    attention_fused_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, tm_pk, tm_pq, p);
+    return cudaGetLastError();
+  }
+  if (const char* tf = getenv("GLC_ATTN_TRACE")) {
+    const size_t n = 2 * TMAX * 8;
+    if (cudaMalloc(&p.trace, n * sizeof(long long)) != cudaSuccess) return cudaGetLastError();
+    cudaMemsetAsync(p.trace, 0, n * sizeof(long long), stream);
+    attention_fused_kernel<true><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, tm_pk, tm_pq, p);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    std::vector<long long> h(n);
+    cudaMemcpy(h.data(), p.trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    if (FILE* f = fopen(tf, "w")) {
+      for (int role = 0; role < 2; ++role)
+        for (int t = 0; t < TMAX; ++t) {
+          if (!h[(role * TMAX + t) * 8 + 1]) continue;
+          fprintf(f, "%s t=%d", role ? "mma" : "smx", t);
+          for (int k = 0; k < 8; ++k) fprintf(f, " %lld", h[(role * TMAX + t) * 8 + k] - h[1]);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+    return e;
+  }
+  attention_fused_kernel<false><<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, tm_pk, tm_pq, p);
   return cudaGetLastError();
 }
 

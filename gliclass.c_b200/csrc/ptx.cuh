@@ -48,14 +48,16 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (sticky CUDA error), never as a hang
-// that would hold the GPU until an external timeout.
+// that would hold the GPU until an external timeout.  try_wait suspends the thread for a
+// hardware-defined interval, so the spin count (no clock reads in the loop) bounds seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+    if (++spins > (1u << 26)) {
+#ifdef GLC_DEBUG_BARRIERS
       printf("glc: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x, smem_u32(bar), parity);
+#endif
       __trap();
     }
   }
@@ -176,6 +178,23 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// shared-memory scalar loads at a 32-bit shared address (ptxas folds constant offsets into the LDS)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return v;
+}
+__device__ __forceinline__ __half lds_f16(uint32_t saddr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(saddr));
+  return __ushort_as_half(v);
+}
+// two exponentials per MUFU op: 2^x on a packed fp16 pair
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
