@@ -19,6 +19,8 @@
 // Ragged M/N/K are handled by TMA out-of-bounds zero fill on loads and predication on stores.
 #include <cuda_fp16.h>
 
+#include <cstdlib>
+
 #include "kernels.h"
 #include "ptx.cuh"
 #include "tma_desc.h"
@@ -60,6 +62,122 @@ __device__ __forceinline__ float gelu_erf(float x) {
   const float e = ptx::ex2(x * x * -0.72134752044448170f);   // exp(-x^2/2) = 2^(-x^2 * log2(e)/2)
   const float h = p * e;
   return x * (x < 0.f ? h : 1.0f - h);
+}
+
+// Epilogue of one accumulator tile for one warp: TMEM lanes of this warp's quarter (t_row), the
+// 32-column chunks c = grp, grp+GROUPS, ...: tcgen05.ld -> +bias -> (erf-GELU) -> fp16/fp32 -> global.
+template <int BN, int ACT, bool OUT_F32>
+__device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, int row, const float* __restrict__ bias,
+                                              void* __restrict__ Cout, int64_t ldc, int M, int N) {
+#pragma unroll 1
+  for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
+  uint32_t r[32];
+  ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
+  ptx::tmem_ld_wait();
+  const int n = n0 + c * 32;
+  if (n >= N) continue;   // warp-uniform
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (bias != nullptr) {
+    if (n + 32 <= N) {
+      const float4* b4 = reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 bb = __ldg(b4 + j);
+        v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(bias + n + j);
+    }
+  }
+  if (ACT == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (row < M) {
+    if (OUT_F32) {
+      float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + n;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (n + 4 * j + 4 <= N) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    } else {
+      __half* dst = reinterpret_cast<__half*>(Cout) + (int64_t)row * ldc + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (n + 8 * j + 8 <= N) {
+          uint4 o;
+          o.x = ptx::pack_f16(v[8 * j + 0], v[8 * j + 1]);
+          o.y = ptx::pack_f16(v[8 * j + 2], v[8 * j + 3]);
+          o.z = ptx::pack_f16(v[8 * j + 4], v[8 * j + 5]);
+          o.w = ptx::pack_f16(v[8 * j + 6], v[8 * j + 7]);
+          reinterpret_cast<uint4*>(dst)[j] = o;
+        }
+      }
+    }
+  }
+}
+}
+
+// fp16 epilogue through shared memory + TMA store.  A warp's direct stores put 32 different rows in
+// every STG (32 L1 line visits per instruction: the epilogue then outlasts a K=768 tile's MMAs); here
+// the 32 x 32 chunk is written once to a 64B-swizzled staging buffer and stored by one bulk tensor copy.
+//   stage: this warp's NBUF x 2 KB staging buffers (1024-byte aligned); row0: first tile row of the warp
+template <int BN, int ACT, int NBUF>
+__device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
+                                                  const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int N) {
+#pragma unroll 1
+  for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
+    uint32_t r[32];
+    ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
+    ptx::tmem_ld_wait();
+    const int n = n0 + c * 32;
+    if (n >= N) continue;   // warp-uniform
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (bias != nullptr) {
+      if (n + 32 <= N) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(bias + n + j);
+      }
+    }
+    if (ACT == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+    // the bulk store that last read this staging buffer must have finished reading it
+    if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
+    __syncwarp();
+    uint8_t* sb = stage + buf * 2048;
+    // row = lane, 64 bytes per row; 64B swizzle: 16-byte chunk j lands at j ^ ((row >> 1) & 3)
+    uint8_t* srow = sb + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = ptx::pack_f16(v[8 * j + 0], v[8 * j + 1]);
+      o.y = ptx::pack_f16(v[8 * j + 2], v[8 * j + 3]);
+      o.z = ptx::pack_f16(v[8 * j + 4], v[8 * j + 5]);
+      o.w = ptx::pack_f16(v[8 * j + 6], v[8 * j + 7]);
+      *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = o;
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tm_c, sb, n, row0);   // rows >= M and columns >= N are clipped by the tensor map
+      ptx::bulk_commit_group();
+    }
+    buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+  }
 }
 
 template <int BN, int ACT, bool OUT_F32>
@@ -105,54 +223,57 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   const int num_k = (K + BK - 1) / BK;
   const int tiles = num_m * num_n;
 
+  // Producer and MMA warps run their loops warp-uniformly (all lanes wait on the barriers) and elect
+  // one lane per issue: tcgen05 / TMA instructions issued from inside `if (lane == 0)` get wrapped by
+  // the compiler in an R2UR + ELECT retry loop that costs ~100 cycles per instruction.
   if (warp == 0) {
-    if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int m0 = (tile / num_n) * BM;
-        const int n0 = (tile % num_n) * BN;
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&empty[s], ph ^ 1);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      const int m0 = (tile / num_n) * BM;
+      const int n0 = (tile % num_n) * BN;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        if (ptx::elect_one()) {
           ptx::mbar_arrive_expect_tx(&full[s], Cfg::STAGE_BYTES);
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
           ptx::tma_load_2d(sa, &tm_a, &full[s], kb * BK, m0);
           ptx::tma_load_2d(sa + Cfg::A_BYTES, &tm_w, &full[s], kb * BK, n0);
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
         }
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
     }
-    __syncwarp();
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = ptx::idesc_f16(BM, BN);
-      int s = 0;
-      uint32_t ph = 0;
-      int acc = 0;
-      uint32_t acc_ph = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&tempty[acc], acc_ph ^ 1);
+    constexpr uint32_t idesc = ptx::idesc_f16(BM, BN);
+    const uint64_t desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem));
+    int s = 0;
+    uint32_t ph = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+      ptx::mbar_wait(&tempty[acc], acc_ph ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&full[s], ph);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_k; ++kb) {
-          ptx::mbar_wait(&full[s], ph);
-          ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(smem + s * Cfg::STAGE_BYTES);
-          const uint32_t b_base = a_base + Cfg::A_BYTES;
+        if (ptx::elect_one()) {
+          // descriptor address field is in 16-byte units: stage s starts s*STAGE_BYTES/16 further
+          const uint64_t da = desc0 + (uint64_t)(s * (Cfg::STAGE_BYTES >> 4));
+          const uint64_t db = da + (Cfg::A_BYTES >> 4);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            ptx::mma_f16_ss(d_tmem, ptx::smem_desc_sw128(a_base + k * 32), ptx::smem_desc_sw128(b_base + k * 32), idesc,
-                            (uint32_t)((kb | k) != 0));
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            ptx::mma_f16_ss(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
           ptx::mma_commit(&empty[s]);   // frees the smem stage once these MMAs have read it
-          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+          if (kb == num_k - 1) ptx::mma_commit(&tfull[acc]);   // accumulator complete
         }
-        ptx::mma_commit(&tfull[acc]);   // accumulator complete
-        acc ^= 1;
-        if (acc == 0) acc_ph ^= 1;
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
     }
-    __syncwarp();
   } else {
     const int q = warp & 3;   // TMEM lane quarter this warp may read
     const int grp = (warp - 2) >> 2;
@@ -165,55 +286,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
-        uint32_t r[32];
-        ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
-        ptx::tmem_ld_wait();
-        const int n = n0 + c * 32;
-        if (n >= N) continue;   // warp-uniform
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (bias != nullptr) {
-          if (n + 32 <= N) {
-            const float4* b4 = reinterpret_cast<const float4*>(bias + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = __ldg(b4 + j);
-              v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(bias + n + j);
-          }
-        }
-        if (ACT == 1) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (row < M) {
-          if (OUT_F32) {
-            float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + n;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (n + 4 * j + 4 <= N) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-            __half* dst = reinterpret_cast<__half*>(Cout) + (int64_t)row * ldc + n;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (n + 8 * j + 8 <= N) {
-                uint4 o;
-                o.x = ptx::pack_f16(v[8 * j + 0], v[8 * j + 1]);
-                o.y = ptx::pack_f16(v[8 * j + 2], v[8 * j + 3]);
-                o.z = ptx::pack_f16(v[8 * j + 4], v[8 * j + 5]);
-                o.w = ptx::pack_f16(v[8 * j + 6], v[8 * j + 7]);
-                reinterpret_cast<uint4*>(dst)[j] = o;
-              }
-            }
-          }
-        }
-      }
+      epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -228,6 +301,198 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
     ptx::tc_fence_after();
     ptx::tmem_dealloc<Cfg::TMEM_COLS>(tmem_base);
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant: 256 x 256 output tile per cluster of two CTAs (tcgen05 cta_group::2).
+// Each CTA stages its own 128 rows of A and ITS HALF (128 N-rows) of the W tile, so a k-block costs
+// 32 KB of L2->SM traffic per SM instead of 48 KB and the smem ring is six deep instead of four:
+// the single-CTA kernel keeps the tensor pipe only 45-60 % busy because operand delivery, not the
+// MMA, paces it.  The leader CTA (cluster rank 0) issues the MMAs for both; every CTA runs its own
+// TMA producer and its own epilogue on its 128 TMEM lanes.
+//   full[s]   (leader's copy)  <- transaction bytes of both CTAs' loads of stage s
+//   empty[s]  (both copies)    <- multicast tcgen05.commit: the stage may be refilled
+//   tfull[a]  (both copies)    <- multicast tcgen05.commit: accumulator a complete
+//   tempty[a] (leader's copy)  <- epilogue warps of both CTAs
+// ---------------------------------------------------------------------------------------------
+struct Gemm2Cfg {
+  static constexpr int BN = 256;            // cluster tile N; per CTA B half = 128 rows
+  static constexpr int STAGES = 6;
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = 128 * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int EPI_BYTES = 32768;   // TMA-store staging: 2 KB buffers, split over the epilogue warps
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
+  static constexpr uint32_t TMEM_COLS = 512;   // two 256-column accumulators
+};
+
+template <int ACT, bool OUT_F32>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
+gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                     const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias, void* __restrict__ Cout,
+                     int64_t ldc, int M, int N, int K) {
+  using Cfg = Gemm2Cfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* epi_stage = smem + Cfg::STAGES * Cfg::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + Cfg::EPI_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + Cfg::STAGES;
+  uint64_t* tfull = bars + 2 * Cfg::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = (rank == 0);
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tm_a);
+    ptx::prefetch_tensormap(&tm_w);
+    if (!OUT_F32) ptx::prefetch_tensormap(&tm_c);
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1);
+      ptx::mbar_init(&tempty[a], 2 * 4 * EpiCfg<ACT>::GROUPS);   // epilogue warps of both CTAs
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_2cta<Cfg::TMEM_COLS>(tmem_slot);
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // barrier inits and the TMEM allocation of both CTAs are visible
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);
+  const int num_n = (N + BN - 1) / BN;
+  const int num_k = (K + BK - 1) / BK;
+  const int tiles = num_m * num_n;
+  const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+
+  if (warp == 0) {
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = cl; tile < tiles; tile += ncl) {
+      const int m0 = (tile / num_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile % num_n) * BN + (int)rank * 128;
+      for (int kb = 0; kb < num_k; ++kb) {
+        ptx::mbar_wait(&empty[s], ph ^ 1);
+        if (ptx::elect_one()) {
+          if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
+          const uint32_t fb = ptx::smem_u32(&full[s]) & ptx::PEER_BIT_MASK;   // the leader's barrier
+          uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
+          ptx::tma_load_2d_2cta(sa, &tm_a, fb, kb * BK, m0);
+          ptx::tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_w, fb, kb * BK, n0);
+        }
+        __syncwarp();
+        if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (leader) {
+      constexpr uint32_t idesc = ptx::idesc_f16(2 * BM, BN);
+      const uint64_t desc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem));
+      int s = 0;
+      uint32_t ph = 0;
+      int acc = 0;
+      uint32_t acc_ph = 0;
+      for (int tile = cl; tile < tiles; tile += ncl) {
+        ptx::mbar_wait(&tempty[acc], acc_ph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_k; ++kb) {
+          ptx::mbar_wait(&full[s], ph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t da = desc0 + (uint64_t)(s * (Cfg::STAGE_BYTES >> 4));
+            const uint64_t db = da + (Cfg::A_BYTES >> 4);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              ptx::mma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            ptx::mma_commit_2cta_mc(&empty[s], 3);
+            if (kb == num_k - 1) ptx::mma_commit_2cta_mc(&tfull[acc], 3);
+          }
+          __syncwarp();
+          if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
+        }
+        acc ^= 1;
+        if (acc == 0) acc_ph ^= 1;
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
+    constexpr int NBUF = Cfg::EPI_BYTES / (4 * EpiCfg<ACT>::GROUPS) / 2048;   // staging buffers per epilogue warp
+    uint8_t* my_stage = epi_stage + (warp - 2) * (NBUF * 2048);
+    int sbuf = 0;
+    int acc = 0;
+    uint32_t acc_ph = 0;
+    for (int tile = cl; tile < tiles; tile += ncl) {
+      const int m0 = (tile / num_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (tile % num_n) * BN;
+      const int row = m0 + q * 32 + lane;
+      ptx::mbar_wait(&tfull[acc], acc_ph);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
+      if (OUT_F32)
+        epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
+      else
+        epilogue_tile_tma<BN, ACT, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, N);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tempty[acc]) & ptx::PEER_BIT_MASK);
+      acc ^= 1;
+      if (acc == 0) acc_ph ^= 1;
+    }
+    if (!OUT_F32 && lane == 0) ptx::bulk_wait_group_read<0>();   // staging smem must outlive its readers
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();   // nobody leaves (or frees TMEM) while the peer may still signal or read
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_2cta<Cfg::TMEM_COLS>(tmem_base);
+  }
+}
+
+template <int ACT, bool OUT_F32>
+cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                             int M, int N, int K, int num_sms, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t sa[1] = {(uint64_t)lda * 2};
+  uint32_t ba[2] = {BK, BM};
+  uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
+  uint64_t sw[1] = {(uint64_t)ldw * 2};
+  uint32_t bw[2] = {BK, 128};
+  CUtensorMap tm_a = make_tmap_16b(A, 2, da, sa, ba);
+  CUtensorMap tm_w = make_tmap_16b(W, 2, dw, sw, bw);
+  CUtensorMap tm_c = tm_a;   // unused by the fp32-output instantiation
+  if (!OUT_F32) {
+    uint64_t dc[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t sc[1] = {(uint64_t)ldc * 2};
+    uint32_t bc[2] = {32, 32};
+    tm_c = make_tmap_16b(C, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
+  }
+  auto kern = gemm_f16_2cta_kernel<ACT, OUT_F32>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + Cfg::BN - 1) / Cfg::BN);
+  const int max_cl = num_sms / 2;
+  const int ncl = tiles < max_cl ? tiles : max_cl;
+  kern<<<2 * ncl, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, tm_c, bias, C, ldc, M, N, K);
+  return cudaGetLastError();
 }
 
 template <int BN, int ACT, bool OUT_F32>
@@ -271,6 +536,13 @@ cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, con
   if (out_f32) {
     if (act == 0) return launch_gemm<128, 0, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
     return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+  }
+  // CTA pairs (256 x 256 cluster tiles) whenever they fill the machine
+  const int tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
+  static const bool no_pairs = getenv("GLC_GEMM_NO_PAIRS") != nullptr;
+  if (!no_pairs && tiles2 >= num_sms / 2 && N >= 256) {
+    if (act == 0) return launch_gemm_2cta<0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    return launch_gemm_2cta<1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
   }
   if (wide) {
     if (act == 0) return launch_gemm<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);

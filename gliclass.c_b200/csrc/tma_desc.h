@@ -31,7 +31,7 @@ inline EncodeTiledFn get_encode_tiled() {
 // (128 bytes; data is moved verbatim, so one UINT16 map serves fp16 and bf16) for the 128-byte swizzle used by every tcgen05 operand in this engine.
 // dims/box are innermost-first; strides_bytes has rank-1 entries (dims 1..rank-1).
 inline CUtensorMap make_tmap_16b(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                                  const uint32_t* box, bool swizzle128 = true) {
+                                  const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   CUtensorMap m;
   cuuint64_t gdims[5];
   cuuint64_t gstr[5];
@@ -41,7 +41,7 @@ inline CUtensorMap make_tmap_16b(const void* base, int rank, const uint64_t* dim
   for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
   CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT16, (cuuint32_t)rank, const_cast<void*>(base), gdims,
                                   gstr, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                                  swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  swizzle,
                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed, CUresult=" + std::to_string((int)r));
   return m;
