@@ -71,7 +71,9 @@ constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
 static_assert(ATT_SMEM <= 227 * 1024, "attention smem budget");
 
 // TMEM columns
-constexpr uint32_t TM_S = 0;       // 2 x 64
+constexpr uint32_t TM_S = 0;       // 64
+constexpr uint32_t TM_Q = 64;      // 32: the Q tile as fp16 pairs (A operand of the S and C2P MMAs)
+constexpr uint32_t TM_P = 96;      // 32: the P tile as fp16 pairs (A operand of the PV MMA)
 constexpr uint32_t TM_C2P = 128;   // 192
 constexpr uint32_t TM_P2C = 320;   // 2 x 64
 constexpr uint32_t TM_PV = 448;    // 64
@@ -128,6 +130,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   uint64_t* bias_free = bars + 10;   // softmax warps have drained the bias TMEM of tile t
   uint64_t* p_full = bars + 11;      // P tile written
   uint64_t* pv_full = bars + 12;     // PV accumulator ready
+  uint64_t* qt_full = bars + 13;     // Q tile copied into TMEM
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   uint16_t* lut = reinterpret_cast<uint16_t*>(smem + OFF_LUT);
   uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
@@ -162,6 +165,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     ptx::mbar_init(bias_free, SM_WARPS);
     ptx::mbar_init(p_full, SM_WARPS);
     ptx::mbar_init(pv_full, 1);
+    ptx::mbar_init(qt_full, SM_WARPS);
     ptx::fence_barrier_init();
     // Q and the first V tile do not depend on the tables built below: start them now
     ptx::mbar_arrive_expect_tx(q_full, QT * 128);
@@ -232,13 +236,10 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     // All 32 lanes walk the (warp-uniform) loop and wait on the barriers; one elected lane issues the
     // tcgen05 instructions.  Issuing from inside `if (lane == 0)` makes the compiler wrap every UTCHMMA
     // in an R2UR + ELECT retry loop (~100 cycles per instruction).
-    const uint32_t sQ = ptx::smem_u32(smem + OFF_Q);
-    const uint32_t sP = ptx::smem_u32(smem + OFF_P);
     constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
     constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
-    const uint64_t dQ = ptx::smem_desc_sw128(sQ);
-    const uint64_t dP = ptx::smem_desc_sw128(sP);
-    ptx::mbar_wait(q_full, 0);
+    ptx::mbar_wait(qt_full, 0);
+    ptx::tc_fence_after();
     for (int t = 0; t <= T; ++t) {
       if (t < T) {
         const int st = t & 1;
@@ -252,22 +253,19 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         ptx::mbar_wait(&a_full[st], (t >> 1) & 1);
         ptx::tc_fence_after();
         GLC_TRACE(1, t, 1);
-        // S first: it only needs K_t (its TMEM buffer was drained two tiles ago)
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // +2 in the descriptor = +32 bytes = 16 halves along K
-            ptx::mma_f16_ss(tmem + TM_S + (uint32_t)(st * 64), dQ + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
-        }
-        __syncwarp();
         GLC_TRACE(1, t, 2);
-        if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);
+        if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);   // S, C2P and P2C' accumulators drained
         ptx::tc_fence_after();
         GLC_TRACE(1, t, 3);
         if (ptx::elect_one()) {
           const uint32_t idesc_c2p = ptx::idesc_f16(128, npad);
+          // A = Q from TMEM: 16 halves along K = 8 columns per step
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ss(tmem + TM_C2P, dQ + 2 * k, dPK + 2 * k, idesc_c2p, (uint32_t)(k != 0));
+            ptx::mma_f16_ts(tmem + TM_S, tmem + TM_Q + 8 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ts(tmem + TM_C2P, tmem + TM_Q + 8 * k, dPK + 2 * k, idesc_c2p, (uint32_t)(k != 0));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ss(tmem + TM_P2C, dPQ + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
@@ -293,7 +291,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // V is MN-major: 16 keys further = +2048 bytes = +128 in the descriptor
-            ptx::mma_f16_ss(tmem + TM_PV, dP + 2 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0));
+            ptx::mma_f16_ts(tmem + TM_PV, tmem + TM_P + 8 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0));
           ptx::mma_commit(&b_empty[st]);
           ptx::mma_commit(pv_full);
         }
@@ -311,6 +309,20 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     __half* p2c_s = reinterpret_cast<__half*>(smem + OFF_P2C);
     float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
     const uint32_t s_c2p = ptx::smem_u32(c2p_s), s_p2c = ptx::smem_u32(p2c_s), s_lut = ptx::smem_u32(lut);
+
+    // ---- Q tile -> TMEM once (row i, halves [16g, 16g+16) = 16-byte chunks 2g, 2g+1 of the swizzled row)
+    ptx::mbar_wait(q_full, 0);
+    {
+      const uint8_t* qrow = smem + OFF_Q + (i >> 3) * 1024 + (i & 7) * 128;
+      const uint4 lo = *reinterpret_cast<const uint4*>(qrow + (((2 * g) ^ (i & 7)) << 4));
+      const uint4 hi = *reinterpret_cast<const uint4*>(qrow + (((2 * g + 1) ^ (i & 7)) << 4));
+      const uint32_t qr[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+      ptx::tmem_st_x8(t_lane + TM_Q + (uint32_t)(8 * g), qr);
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(qt_full);
+    }
 
     float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
     float o[E];
@@ -330,6 +342,16 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       ptx::mbar_wait(mma1_full, t & 1);
       ptx::tc_fence_after();
       if (sw == 0 && lane == 0) GLC_TRACE(0, t, 1);
+      // ---- S for (row i, keys k0+E*g .. +E) first: the single S accumulator is released together with
+      //      the bias accumulators
+      float s[E];
+      {
+        uint32_t r[16];
+        ptx::tmem_ld_x16(t_lane + TM_S + (uint32_t)(g * E), r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < E; ++jj) s[jj] = __uint_as_float(r[jj]);
+      }
 
       // ---- stage C2P as fp16, band-packed: the 32 rows of this warp quarter only index slice columns
       //      [lo, hi] (<= 95 wide), i.e. 16-column chunks u_lo..u_hi (<= 7); group g takes u_lo+g, u_lo+g+G
@@ -374,15 +396,7 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       ptx::named_bar_sync(1, SM_THREADS);   // staged biases visible to all softmax threads
       if (sw == 0 && lane == 0) GLC_TRACE(0, t, 3);
 
-      // ---- scores for (row i, keys k0+E*g .. +E): S + c2p[i][idx] + p2c[idx][j]
-      float s[E];
-      {
-        uint32_t r[16];
-        ptx::tmem_ld_x16(t_lane + TM_S + (uint32_t)((t & 1) * 64 + g * E), r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int jj = 0; jj < E; ++jj) s[jj] = __uint_as_float(r[jj]);
-      }
+      // ---- scores: S + c2p[i][idx] + p2c[idx][j]
       const int kb = k0 + g * E;
       if (TRACE && (p.flags & 1)) {
       } else if (linear) {
@@ -451,20 +465,14 @@ attention_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       }
       alpha_prev = alpha;
 
-      // ---- P tile: row i, 16-byte chunks 2g, 2g+1, 128-byte swizzle
+      // ---- P tile -> TMEM: row i, fp16 pairs at columns 8g .. 8g+7 (PV of tile t-1 has retired: pv_full)
       {
-        uint8_t* prow = smem + OFF_P + (i >> 3) * 1024 + (i & 7) * 128;
+        uint32_t pr[E / 2];
 #pragma unroll
-        for (int v = 0; v < E / 8; ++v) {
-          uint4 o4;
-          o4.x = ptx::pack_f16(s[8 * v + 0], s[8 * v + 1]);
-          o4.y = ptx::pack_f16(s[8 * v + 2], s[8 * v + 3]);
-          o4.z = ptx::pack_f16(s[8 * v + 4], s[8 * v + 5]);
-          o4.w = ptx::pack_f16(s[8 * v + 6], s[8 * v + 7]);
-          *reinterpret_cast<uint4*>(prow + ((((E / 8) * g + v) ^ (i & 7)) << 4)) = o4;
-        }
+        for (int v = 0; v < E / 2; ++v) pr[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
+        ptx::tmem_st_x8(t_lane + TM_P + (uint32_t)(8 * g), pr);
+        ptx::tmem_st_wait();
       }
-      ptx::fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);

@@ -203,10 +203,21 @@ def test_unchanged_reference_binary_end_to_end(pkg, orc, tmp_path):
     labels = ["format", "Model", "tool", "necessity", "cat"]
     (work / "data.json").write_text(json.dumps({"texts": texts, "labels": [labels], "same_labels": True,
                                                 "classification_type": "multi-label"}))
-    r = subprocess.run([exe, "data.json", "false"], cwd=work, capture_output=True, text=True, timeout=300,
-                       env={**os.environ, "OMP_NUM_THREADS": "4"})
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
-    assert "DONE: create_ort_session" in r.stdout and "Execution time" in r.stdout
+    # The reference prints from inside its OpenMP post-processing loop (parallel_processor.c:73-89), so
+    # with several threads the per-text blocks of different batches interleave on stdout.  Decisions
+    # are therefore parsed from a single-threaded run; a 4-thread run (concurrent Run calls on one
+    # session, main.c:141-149) must print the same multiset of lines.
+    def run_ref(threads):
+        rr = subprocess.run([exe, "data.json", "false"], cwd=work, capture_output=True, text=True, timeout=300,
+                            env={**os.environ, "OMP_NUM_THREADS": str(threads)})
+        assert rr.returncode == 0, rr.stdout[-2000:] + rr.stderr[-2000:]
+        assert "DONE: create_ort_session" in rr.stdout and "Execution time" in rr.stdout
+        return rr
+
+    r = run_ref(1)
+    r4 = run_ref(4)
+    keep = lambda out: sorted(ln for ln in out.splitlines() if ln.startswith("Text_") or ln.startswith("  Text_"))  # noqa: E731
+    assert keep(r4.stdout) == keep(r.stdout), "concurrent Run calls changed the printed decisions"
     # parse "  Text_<i> Label: <label>, Score: <p>" lines, grouped under "Text_<i>: <text>:" headers
     got = {}
     cur = None
