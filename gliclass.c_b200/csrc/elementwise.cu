@@ -8,6 +8,7 @@
 //   K5  App. B      cls[b,c] = h[b,pos_c]; pooled = h[b,0]; logit = <t_b, k_bc>
 #include <cuda_fp16.h>
 
+#include <cstdlib>
 #include <type_traits>
 
 #include "kernels.h"
@@ -25,6 +26,15 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// read-once 128-bit load that does not linger in L1
+__device__ __forceinline__ uint4 ld_stream(const __half* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   const __half2* p = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
@@ -35,10 +45,31 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
+// gamma / beta of this lane's chunks, fetched up front so that their (L2) latency overlaps the row loads
+template <int NC>
+struct LnParams {
+  float g[NC][8], b[NC][8];
+  __device__ __forceinline__ void load(int lane, int H, const float* __restrict__ gamma, const float* __restrict__ beta) {
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int e0 = (lane + 32 * c) * 8;
+      if (e0 < H) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e0));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e0 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + e0));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + e0 + 4));
+        g[c][0] = g0.x; g[c][1] = g0.y; g[c][2] = g0.z; g[c][3] = g0.w;
+        g[c][4] = g1.x; g[c][5] = g1.y; g[c][6] = g1.z; g[c][7] = g1.w;
+        b[c][0] = b0.x; b[c][1] = b0.y; b[c][2] = b0.z; b[c][3] = b0.w;
+        b[c][4] = b1.x; b[c][5] = b1.y; b[c][6] = b1.z; b[c][7] = b1.w;
+      }
+    }
+  }
+};
+
 // LN over a row held as NC chunks of 8 floats per lane; writes fp16, scaled by `post`.
 template <int NC>
-__device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, float eps, float post,
+__device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, const LnParams<NC>& gb, float eps, float post,
                                          __half* __restrict__ out) {
   float s = 0.f;
 #pragma unroll
@@ -63,15 +94,9 @@ __device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, con
   for (int c = 0; c < NC; ++c) {
     const int e0 = (lane + 32 * c) * 8;
     if (e0 < H) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + e0));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + e0 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + e0));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + e0 + 4));
-      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float y[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = ((v[c][i] - mean) * rstd * g[i] + b[i]) * post;
+      for (int i = 0; i < 8; ++i) y[i] = ((v[c][i] - mean) * rstd * gb.g[c][i] + gb.b[c][i]) * post;
       uint4 o;
       o.x = ptx::pack_f16(y[0], y[1]);
       o.y = ptx::pack_f16(y[2], y[3]);
@@ -94,40 +119,69 @@ embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mas
   if (id < 0 || id >= vocab) id = 0;   // ORT's Gather would fail; clamp to [PAD] instead of reading out of bounds
   const float post = mask[row] != 0 ? 1.0f : 0.0f;
   const __half* src = emb + id * (int64_t)H;
-  float v[NC][8];
+  uint4 raw[NC];
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int e0 = (lane + 32 * c) * 8;
-    if (e0 < H) unpack8(__ldg(reinterpret_cast<const uint4*>(src + e0)), v[c]);
+    if (e0 < H) raw[c] = __ldg(reinterpret_cast<const uint4*>(src + e0));
   }
-  ln_store<NC>(v, lane, H, gamma, beta, eps, post, y + (int64_t)row * H);
+  LnParams<NC> gb;
+  gb.load(lane, H, gamma, beta);
+  float v[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if ((lane + 32 * c) * 8 < H) unpack8(raw[c], v[c]);
+  ln_store<NC>(v, lane, H, gb, eps, post, y + (int64_t)row * H);
 }
 
+// Each warp walks rows (row = global warp id, += total warps): gamma / beta stay in registers and the
+// loads of the next row are issued before the statistics of the current one (two rows in flight).
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                    __half* __restrict__ y, int M, int H) {
-  const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * ROWS_PER_BLOCK;
+  int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   if (row >= M) return;
-  const __half* xs = x + (int64_t)row * H;
-  const __half* rs = r ? r + (int64_t)row * H : nullptr;
-  float v[NC][8];
+  uint4 xa[NC], ra[NC];
+  auto fetch = [&](int rw) {
+    const __half* xs = x + (int64_t)rw * H;
+    const __half* rs = r + (int64_t)rw * H;
 #pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    const int e0 = (lane + 32 * c) * 8;
-    if (e0 < H) {
-      unpack8(*reinterpret_cast<const uint4*>(xs + e0), v[c]);
-      if (rs) {
-        float t[8];
-        unpack8(*reinterpret_cast<const uint4*>(rs + e0), t);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+    for (int c = 0; c < NC; ++c) {
+      const int e0 = (lane + 32 * c) * 8;
+      if (e0 < H) {
+        xa[c] = ld_stream(xs + e0);
+        if (r) ra[c] = ld_stream(rs + e0);
       }
     }
+  };
+  fetch(row);
+  LnParams<NC> gb;
+  gb.load(lane, H, gamma, beta);
+  while (true) {
+    float v[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      if ((lane + 32 * c) * 8 < H) {
+        unpack8(xa[c], v[c]);
+        if (r) {
+          float t[8];
+          unpack8(ra[c], t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+        }
+      }
+    }
+    const int cur = row;
+    row += stride;
+    const bool more = row < M;   // warp-uniform
+    if (more) fetch(row);
+    ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)cur * H);
+    if (!more) break;
   }
-  ln_store<NC>(v, lane, H, gamma, beta, eps, 1.0f, y + (int64_t)row * H);
 }
 
 template <int NC>
@@ -149,7 +203,9 @@ ln_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
       v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
     }
   }
-  ln_store<NC>(v, lane, H, gamma, beta, eps, 1.0f, y + (int64_t)row * H);
+  LnParams<NC> gb;
+  gb.load(lane, H, gamma, beta);
+  ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)row * H);
 }
 
 // one warp per batch row: 32 mask words at a time via ballot
@@ -230,6 +286,18 @@ head_score_kernel(const float* __restrict__ t, const float* __restrict__ k, floa
   }
 }
 
+inline int ln_grid_cap() {
+  static int cap = 0;
+  if (!cap) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const char* e = getenv("GLC_LN_BLOCKS_PER_SM");
+    cap = sms * (e ? atoi(e) : 4);
+  }
+  return cap;
+}
+
 template <typename F>
 cudaError_t dispatch_nc(int H, F&& f) {
   if (H % 8 != 0 || H > 256 * MAXC) return cudaErrorInvalidValue;
@@ -262,7 +330,10 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
   if (M <= 0) return cudaSuccess;
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
-    residual_ln_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
+    int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+    const int cap = ln_grid_cap();   // a few resident blocks per SM, each warp walking several rows
+    if (blocks > cap) blocks = cap;
+    residual_ln_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, 0, stream>>>(
         (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H);
     return cudaGetLastError();
   });
