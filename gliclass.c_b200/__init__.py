@@ -59,6 +59,7 @@ _SIGS = {
     "glc_model_info": (_i, [_vp, C.POINTER(glc_info)]),
     "glc_num_classes": (_i, [_vp, _vp, _i, _i]),
     "glc_run": (_i, [_vp, _vp, _vp, _i, _i, _vp, C.c_size_t, C.POINTER(_i)]),
+    "glc_run_decisions": (_i, [_vp, _vp, _vp, _i, _i, _f, _vp, _vp, _vp, C.c_size_t, C.POINTER(_i)]),
     "glc_run_device": (_i, [_vp, _i, _vp, _vp, _i, _i, _i, _vp, _i]),
     "glc_sync": (_i, [_vp, _i]),
     "glc_stream": (_vp, [_vp, _i]),
@@ -183,6 +184,22 @@ class Session:
         cc = C.c_int(0)
         _check(L.glc_run(self._h, ids.ctypes.data, mask.ctypes.data, B, S, out.ctypes.data, out.size, C.byref(cc)), "glc_run")
         return out.reshape(B, cc.value) if out.size == B * cc.value else out.ravel()[: B * cc.value].reshape(B, cc.value)
+
+    def run_decisions(self, input_ids: np.ndarray, attention_mask: np.ndarray, threshold: float = 0.5):
+        """run_inference + the reference's post-processing arithmetic (src/postprocessor.c:14-16,93-95)
+        fused into the scorer kernel: returns (logits, probs, decisions[bool]) each [B, C]."""
+        ids = np.ascontiguousarray(input_ids, dtype=np.int64)
+        mask = np.ascontiguousarray(attention_mask, dtype=np.int64)
+        B, S = ids.shape
+        L = lib()
+        ncls = max(0, L.glc_num_classes(self._h, ids.ctypes.data, B, S))
+        lg = np.empty((B, ncls), dtype=np.float32)
+        pr = np.empty((B, ncls), dtype=np.float32)
+        de = np.zeros((B, ncls), dtype=np.uint8)
+        cc = C.c_int(0)
+        _check(L.glc_run_decisions(self._h, ids.ctypes.data, mask.ctypes.data, B, S, threshold, lg.ctypes.data, pr.ctypes.data,
+                                   de.ctypes.data, lg.size, C.byref(cc)), "glc_run_decisions")
+        return lg, pr, de.astype(bool)
 
     def run_pinned(self, ids_ptr: int, mask_ptr: int, B: int, S: int, out_ptr: int, out_capacity: int) -> int:
         """Same call on raw host pointers (pinned buffers in bench.py's e2e leg). Returns C."""

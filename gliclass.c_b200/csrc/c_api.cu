@@ -128,6 +128,27 @@ int glc_run(glc_model* m, const int64_t* input_ids, const int64_t* attention_mas
   }
 }
 
+int glc_run_decisions(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S, float threshold,
+                      float* logits_out, float* probs_out, uint8_t* decisions_out, size_t capacity, int* C_out) {
+  try {
+    if (!m || B < 0 || S < 0) return fail(GLC_ERR_ARG, "glc_run_decisions: bad argument");
+    if (B * S > 0 && (!input_ids || !attention_mask)) return fail(GLC_ERR_ARG, "glc_run_decisions: null input");
+    const int C = m->m->num_classes(input_ids, B, S);
+    if (C_out) *C_out = C;
+    if ((size_t)B * C > capacity) return fail(GLC_ERR_CAPACITY, "glc_run_decisions: output buffers too small");
+    if (B == 0 || S == 0 || C == 0) return GLC_OK;
+    if (!logits_out && !probs_out && !decisions_out) return fail(GLC_ERR_ARG, "glc_run_decisions: no output requested");
+    glc::DecisionOut d;
+    d.probs = probs_out;
+    d.decisions = decisions_out;
+    d.threshold = threshold;
+    m->m->run(input_ids, attention_mask, B, S, C, logits_out, &d);
+    return GLC_OK;
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_run_decisions: ") + e.what());
+  }
+}
+
 int glc_run_device(glc_model* m, int slot, const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C,
                    float* d_logits, int async) {
   try {

@@ -222,6 +222,8 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   tvec_ = (float*)A((size_t)ws_B_ * Hh * 4);
   kvec_ = (float*)A((size_t)ws_rows_ * Hh * 4);
   logits_ = (float*)A((size_t)ws_rows_ * 4);
+  probs_ = (float*)A((size_t)ws_rows_ * 4);
+  decisions_ = (uint8_t*)A((size_t)ws_rows_);
 }
 
 void DeviceModel::keep(const char* name, const void* src, size_t count) {
@@ -308,7 +310,8 @@ struct ProfScope {
     ++n;                           \
   } while (0)
 
-void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits) {
+void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
+                          uint8_t* d_decisions, float threshold) {
   const int H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
   const int M = B * S;
   if (M <= 0) return;
@@ -341,12 +344,13 @@ void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, in
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st));
-    GLC_LAUNCH(KC_HEAD_MISC, head_score(tvec_, kvec_, d_logits, nullptr, nullptr, 0.5f, B, C, Hh, st));
+    GLC_LAUNCH(KC_HEAD_MISC, head_score(tvec_, kvec_, d_logits, d_probs, d_decisions, threshold, B, C, Hh, st));
   }
   launches_ += n;
 }
 
-void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits) {
+void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,
+                           const DecisionOut* dec) {
   if (B <= 0 || S <= 0) return;
   std::lock_guard<std::mutex> lk(mu);
   GLC_CUDA(cudaSetDevice(device_));
@@ -359,9 +363,17 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
     const size_t bytes = (size_t)nb * S * 8;
     GLC_CUDA(cudaMemcpyAsync(ids_, ids + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
     GLC_CUDA(cudaMemcpyAsync(mask_, mask + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
-    forward(ids_, mask_, nb, S, C, logits_);
-    if (C > 0)
-      GLC_CUDA(cudaMemcpyAsync(logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+    const bool want_p = dec && dec->probs, want_d = dec && dec->decisions;
+    forward(ids_, mask_, nb, S, C, logits_, want_p ? probs_ : nullptr, want_d ? decisions_ : nullptr,
+            dec ? dec->threshold : 0.5f);
+    if (C > 0) {
+      if (logits)
+        GLC_CUDA(cudaMemcpyAsync(logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+      if (want_p)
+        GLC_CUDA(cudaMemcpyAsync(dec->probs + (size_t)r0 * C, probs_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+      if (want_d)
+        GLC_CUDA(cudaMemcpyAsync(dec->decisions + (size_t)r0 * C, decisions_, (size_t)nb * C, cudaMemcpyDeviceToHost, stream_));
+    }
     if (r0 + rows_mb < B) GLC_CUDA(cudaStreamSynchronize(stream_));   // workspace reuse
   }
   GLC_CUDA(cudaStreamSynchronize(stream_));
@@ -394,13 +406,13 @@ uint64_t Model::launches() const {
   return n;
 }
 
-void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits) {
+void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits, const DecisionOut* dec) {
   const int G = (int)devs_.size();
   if (G == 1 || B < 2 * G) {
     // small call (the reference's BATCH_SIZE=8 Run): whole batch on one device, round robin
     // across concurrent callers (the OpenMP loop of main.c:141-150)
     const int slot = (int)(rr_.fetch_add(1) % (uint32_t)G);
-    devs_[slot]->run_host(ids, mask, B, S, C, logits);
+    devs_[slot]->run_host(ids, mask, B, S, C, logits, dec);
     return;
   }
   // large call: contiguous row shards, one host thread per device, host gather into `logits`
@@ -413,7 +425,14 @@ void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, fl
     if (nb == 0) continue;
     auto work = [&, g, r0, nb]() {
       try {
-        devs_[g]->run_host(ids + (size_t)r0 * S, mask + (size_t)r0 * S, nb, S, C, logits + (size_t)r0 * C);
+        DecisionOut sub;
+        if (dec) {
+          sub.threshold = dec->threshold;
+          sub.probs = dec->probs ? dec->probs + (size_t)r0 * C : nullptr;
+          sub.decisions = dec->decisions ? dec->decisions + (size_t)r0 * C : nullptr;
+        }
+        devs_[g]->run_host(ids + (size_t)r0 * S, mask + (size_t)r0 * S, nb, S, C, logits ? logits + (size_t)r0 * C : nullptr,
+                           dec ? &sub : nullptr);
       } catch (...) {
         err[g] = std::current_exception();
       }

@@ -33,6 +33,13 @@ struct DeviceLayer {
 
 struct DebugBuf { void* ptr = nullptr; size_t count = 0; };
 
+// optional fused decision epilogue (reference src/postprocessor.c:85-150): host destinations, any may be null
+struct DecisionOut {
+  float* probs = nullptr;        // [B,C] sigmoid(logit)
+  uint8_t* decisions = nullptr;  // [B,C] prob > threshold (strict)
+  float threshold = 0.5f;
+};
+
 // kernel categories for the in-stream profiler (CUDA events around every launch)
 enum KernelCat { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTN, KC_GEMM_OUT, KC_LN, KC_GEMM_FFN1, KC_GEMM_FFN2, KC_HEAD_GEMM, KC_HEAD_MISC, KC_COUNT };
 
@@ -43,10 +50,12 @@ class DeviceModel {
   DeviceModel(const DeviceModel&) = delete;
 
   // device-resident inputs; logits fp32 [B,C] on device.  Enqueues on stream(); no sync.
-  void forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits);
+  void forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs = nullptr,
+               uint8_t* d_decisions = nullptr, float threshold = 0.5f);
   // host buffers: rows [0,B) of ids/mask, writes logits rows [0,B) (width C); micro-batches by
   // max_tokens; synchronises before returning.  Serialised per device by `mu`.
-  void run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits);
+  void run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,
+                const DecisionOut* dec = nullptr);
 
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
@@ -89,7 +98,8 @@ class DeviceModel {
   uint32_t* mask_bits_ = nullptr;
   int32_t* kv_len_ = nullptr;
   void *pooled_ = nullptr, *cls_ = nullptr, *tmid_ = nullptr, *cmid_ = nullptr;
-  float *tvec_ = nullptr, *kvec_ = nullptr, *logits_ = nullptr;
+  float *tvec_ = nullptr, *kvec_ = nullptr, *logits_ = nullptr, *probs_ = nullptr;
+  uint8_t* decisions_ = nullptr;
   std::vector<void*> ws_allocs_, perm_allocs_;
   std::map<std::string, DebugBuf> debug_;
   // profiler state
@@ -105,7 +115,7 @@ class Model {
  public:
   Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens);
   int num_classes(const int64_t* ids, int B, int S) const;
-  void run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits);
+  void run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits, const DecisionOut* dec = nullptr);
   const ModelConfig& cfg() const { return cfg_; }
   int num_devices() const { return (int)devs_.size(); }
   DeviceModel& dev(int slot) { return *devs_[slot]; }

@@ -69,6 +69,15 @@ GLC_API int glc_num_classes(const glc_model* m, const int64_t* input_ids, int B,
 GLC_API int glc_run(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
                     float* logits_out, size_t logits_capacity, int* C_out);
 
+/* glc_run with the decision epilogue of reference src/postprocessor.c:14-16,93-95 fused into the
+ * scorer kernel on the GPU: probs_out [B,C] = 1/(1+expf(-logit)), decisions_out [B,C] (uint8) =
+ * prob > threshold (strict).  Any of the three outputs may be NULL; `capacity` is in elements and
+ * applies to each non-NULL buffer.  Zero-padded classes (c >= the row's label count) are scored
+ * like the reference scores them (postprocessor.c prints them as "[Unknown]"). */
+GLC_API int glc_run_decisions(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
+                              float threshold, float* logits_out /*nullable*/, float* probs_out /*nullable*/,
+                              uint8_t* decisions_out /*nullable*/, size_t capacity, int* C_out);
+
 /* Same forward with inputs/outputs already resident on `device` (kernel-only timing, parity
  * tests).  d_logits fp32 [B,C] device memory with C = num_classes (caller computes it with
  * glc_num_classes on the host copy).  Runs on the engine's stream for that device and

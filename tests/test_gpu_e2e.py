@@ -3,6 +3,7 @@ reference's run_inference makes) against the fp32 CPU oracle.  Bar (BASELINE.jso
 |dlogit| <= 2e-2 and identical sigmoid>THRESHOLD decisions outside a +-1e-2 band.  The engine
 stores weights/activations in fp16 (fp32 accumulation) because bf16 storage cannot meet that bar
 (DESIGN.md "Numerics"); bf16 / fp8 storage requests are rejected."""
+import ctypes
 import json
 import os
 import subprocess
@@ -109,6 +110,32 @@ def test_device_resident_path_matches_host_path(pkg, orc, tiny_session, golden):
     assert np.array_equal(out.cpu().numpy(), host)    # same kernels, same order: bit identical
 
 
+def test_fused_decision_epilogue_matches_reference_postprocessing(pkg, orc, tiny_session, golden):
+    """glc_run_decisions: sigmoid + strict `> THRESHOLD` computed in the scorer kernel (reference
+    src/postprocessor.c:14-16,93-95) vs the host restatement glc_decide and vs the oracle."""
+    for case in ("full", "ragged", "long"):
+        ids, mask = golden[f"{case}.input_ids"], golden[f"{case}.attention_mask"]
+        logits = tiny_session.run_inference(ids, mask)
+        lg, pr, de = tiny_session.run_decisions(ids, mask, THRESHOLD)
+        assert np.array_equal(lg, logits)                               # same forward, bit identical
+        m_host, _, p_host = pkg.decide(logits, THRESHOLD)
+        assert np.abs(pr - p_host).max() < 2e-6                         # expf on device vs host libm
+        away = np.abs(p_host - THRESHOLD) > 1e-5
+        assert np.array_equal(de[away], m_host[away])
+        p_ref = orc.sigmoid32(golden[f"{case}.logits"])
+        band = np.abs(p_ref - THRESHOLD) > BAND
+        assert np.array_equal(de[band], (p_ref > THRESHOLD)[band])      # decision parity outside the band
+    # only decisions requested (logits / probs NULL)
+    ids, mask = golden["full.input_ids"], golden["full.attention_mask"]
+    de2 = np.zeros(ids.shape[0] * 8, dtype=np.uint8)
+    cc = ctypes.c_int(0)
+    rc = pkg.lib().glc_run_decisions(tiny_session._h, ids.ctypes.data, mask.ctypes.data, ids.shape[0], ids.shape[1],
+                                     THRESHOLD, None, None, de2.ctypes.data, de2.size, ctypes.byref(cc))
+    assert rc == 0, pkg.last_error()
+    _, _, de_full = tiny_session.run_decisions(ids, mask, THRESHOLD)
+    assert np.array_equal(de2[: ids.shape[0] * cc.value].reshape(ids.shape[0], cc.value).astype(bool), de_full)
+
+
 def test_micro_batching_is_transparent(pkg, orc, golden_onnx, golden):
     """max_tokens smaller than the batch forces several device launches; rows are independent,
     so results must be bit-identical to the single-launch run"""
@@ -174,6 +201,31 @@ def test_base_arch_sample_rows(pkg, orc, model_cache):
     # are not guaranteed, so compare within a tight tolerance)
     alone = sess.run_inference(ids[rows].numpy(), mask[rows].numpy())
     assert np.abs(alone - out[rows]).max() < 5e-3
+    sess.close()
+
+
+def test_large_arch_and_reranker_shape_sample_rows(pkg, orc, model_cache):
+    """BASELINE.json configs[2] architecture (DeBERTa-v3-large 24L/1024/16 heads) at seq 1024 with 50
+    labels, and configs[3]'s shape (seq 1024, 100 labels, micro-batched): the GPU runs every row, the
+    CPU oracle checks one sampled row of each (rows are independent)."""
+    path = os.path.join(model_cache, "large.onnx")
+    cfg, w = orc.make_model_file("large", path, seed=0)
+    sess = pkg.Session(path, max_tokens=4096)          # 6 rows x 1024 tokens -> two device launches
+    assert sess.info["layers"] == 24 and sess.info["hidden"] == 1024 and sess.info["heads"] == 16
+    ids, mask = orc.synth_inputs(cfg, 6, 1024, 50, seed=1236, ragged=True, min_frac=0.6)
+    out = sess.run_inference(ids.numpy(), mask.numpy())
+    assert out.shape == (6, 50) and np.isfinite(out).all()
+    ref = orc.forward_restated(w, cfg, ids[4:5], mask[4:5]).numpy()
+    _check_logits("large/S1024/50 labels row 4", out[4:5], ref, orc)
+    sess.close()
+    path = os.path.join(model_cache, "base.onnx")
+    cfg, w = orc.make_model_file("base", path, seed=0)
+    sess = pkg.Session(path, max_tokens=8192)
+    ids, mask = orc.synth_inputs(cfg, 20, 1024, 100, seed=1237)
+    out = sess.run_inference(ids.numpy(), mask.numpy())
+    assert out.shape == (20, 100) and np.isfinite(out).all()
+    ref = orc.forward_restated(w, cfg, ids[13:14], mask[13:14]).numpy()
+    _check_logits("base/S1024/100 labels row 13", out[13:14], ref, orc)
     sess.close()
 
 
