@@ -33,6 +33,9 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 ARCH, BATCH, SEQ, LABELS = "base", 64, 512, 10
 WORKLOAD = "gliclass-base-v1.0 arch (DeBERTa-v3-base 12L/768), batch 64/GPU, seq 512, 10 labels, random-init ONNX"
 METRIC = "texts/sec gliclass-base seq512 10 labels"
+# ncu --set full capture of the four GEMM launches of one layer (profiles/r1c_kernels_ncu.md):
+# QKV 154.0, out-proj 61.8, FFN1 204.3, FFN2 243.0 MB of DRAM traffic -> mean per launch
+NCU_GEMM_TRAFFIC_MB = 165.8
 
 
 def model_path(arch: str) -> str:
@@ -216,17 +219,19 @@ def main():
     def step_e2e():
         sess.run_pinned(h_ids.data_ptr(), h_mask.data_ptr(), B, S, h_logits.data_ptr(), h_logits.numel())
 
-    # ---- warm-up, then the kernel-only timed region with per-launch events + clock sampling
+    # ---- warm-up, then the kernel-only timed region (K steps, clocks sampled), then the same K steps
+    #      again with CUDA events around every launch for the per-kernel roofline numbers
     for _ in range(args.warmup):
         step_dev()
     sess.sync()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    sess.profile_enable(True)
-    sess.profile_collect()
     l0 = sess.launch_count()
     ms_dev = timed(step_dev, args.steps)
     launches = sess.launch_count() - l0
+    sess.profile_enable(True)
+    sess.profile_collect()
+    ms_prof = timed(step_dev, args.steps)
     prof = sess.profile_collect()
     sess.profile_enable(False)
     # ---- end-to-end through the host-buffer call
@@ -274,10 +279,13 @@ def main():
         "e2e": {"value": e2e, "unit": "texts/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": int(2 * B * S * 8), "d2h_bytes_per_step": int(B * C * 4)},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_f16_tcgen05_kernel (QKV, out-proj, FFN1+GELU, FFN2)", "achieved": achieved,
-                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None, "traffic": None,
+        "roofline": {"bound": "tensor", "kernel": "gemm_f16_2cta_kernel (QKV, out-proj, FFN1+GELU, FFN2)", "achieved": achieved,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
+                     "traffic": NCU_GEMM_TRAFFIC_MB * 1e6 if (args.arch, B, S) == (ARCH, BATCH, SEQ) else None,
+                     "traffic_note": "dram__bytes_read+write per launch, mean over the four GEMM shapes, from profiles/r1c_kernels_ncu.md",
                      "peak_source": peak_src, "launches_timed": int(gemm_n),
-                     "share_of_step": gemm_ms / ms_dev if ms_dev else None},
+                     "share_of_step": gemm_ms / ms_prof if ms_prof else None,
+                     "timed_over": f"{args.steps} steps re-run with CUDA events around every launch ({ms_prof / args.steps:.3f} ms/step)"},
         "kernels": kernels,
         "clocks": sampler.summary(),
     }
