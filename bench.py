@@ -238,6 +238,22 @@ def main():
     for _ in range(3):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
+    # ---- BASELINE.json's second number: p50 latency of one batch-8 Run (8 texts x 512 tokens) through the
+    #      host-buffer call, one call at a time (H2D + forward + D2H + sync inside each sample)
+    lat = None
+    if rank == 0:
+        ids8, mask8 = SM.synth_inputs(cfg, 8, S, NL, seed=4321)
+        p_ids8, p_mask8 = ids8.pin_memory(), mask8.pin_memory()
+        out8 = torch.empty(8, C).pin_memory()
+        samples = []
+        for k in range(60):
+            t0 = time.perf_counter()
+            sess.run_pinned(p_ids8.data_ptr(), p_mask8.data_ptr(), 8, S, out8.data_ptr(), out8.numel())
+            if k >= 10:
+                samples.append((time.perf_counter() - t0) * 1e3)
+        samples.sort()
+        lat = {"p50_ms": samples[len(samples) // 2], "p90_ms": samples[int(len(samples) * 0.9)], "batch": 8, "seq_len": S,
+               "samples": len(samples), "how": "wall clock around glc_run (pinned host buffers, synchronous), after 10 warm-up calls"}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -287,6 +303,7 @@ def main():
                      "share_of_step": gemm_ms / ms_prof if ms_prof else None,
                      "timed_over": f"{args.steps} steps re-run with CUDA events around every launch ({ms_prof / args.steps:.3f} ms/step)"},
         "kernels": kernels,
+        "latency_batch8": lat,
         "clocks": sampler.summary(),
     }
     if rank == 0:

@@ -109,6 +109,7 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   if (max_tokens > 0) max_tokens_ = max_tokens;
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
+  graphs_on_ = getenv("GLC_NO_GRAPHS") == nullptr;
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
   const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
@@ -170,9 +171,16 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   GLC_CUDA(cudaStreamSynchronize(stream_));
 }
 
+void DeviceModel::drop_graphs() {
+  for (auto& kv : graphs_)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  graphs_.clear();
+}
+
 DeviceModel::~DeviceModel() {
   cudaSetDevice(device_);
   if (stream_) cudaStreamSynchronize(stream_);
+  drop_graphs();
   for (void* p : ws_allocs_) cudaFree(p);
   for (void* p : perm_allocs_) cudaFree(p);
   for (auto& kv : rel_tables_) cudaFree(kv.second);
@@ -198,6 +206,7 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   const int rows = B * (C > 0 ? C : 1);
   if (tokens <= ws_tokens_ && B <= ws_B_ && rows <= ws_rows_) return;
   GLC_CUDA(cudaStreamSynchronize(stream_));
+  drop_graphs();   // they captured the old workspace pointers
   for (void* p : ws_allocs_) cudaFree(p);
   ws_allocs_.clear();
   ws_tokens_ = tokens > ws_tokens_ ? tokens : ws_tokens_;
@@ -312,10 +321,54 @@ struct ProfScope {
 
 void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
                           uint8_t* d_decisions, float threshold) {
+  if (B * S <= 0) return;
+  if (d_ids != ids_) ensure_workspace(B * S, B, C);   // run_host already sized it
+  if (!graphs_on_ || prof_on_ || debug_keep_) {
+    forward_eager(d_ids, d_mask, B, S, C, d_logits, d_probs, d_decisions, threshold);
+    return;
+  }
+  uint32_t thr;
+  memcpy(&thr, &threshold, 4);
+  const GraphKey key{B, S, C, d_ids, d_mask, d_logits, d_probs, d_decisions, thr};
+  GraphEntry& e = graphs_[key];
+  if (e.exec) {
+    GLC_CUDA(cudaGraphLaunch(e.exec, stream_));
+    launches_ += e.launches;
+    return;
+  }
+  if (e.seen++ == 0) {   // first sight of this shape: run eagerly (one-time attribute / table set-up is not capturable)
+    forward_eager(d_ids, d_mask, B, S, C, d_logits, d_probs, d_decisions, threshold);
+    return;
+  }
+  if (graphs_.size() > 64) {   // unbounded variety of shapes (pad-to-longest batches): stop caching new ones
+    graphs_.erase(key);
+    forward_eager(d_ids, d_mask, B, S, C, d_logits, d_probs, d_decisions, threshold);
+    return;
+  }
+  const uint64_t before = launches_.load();
+  GLC_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+  cudaGraph_t g = nullptr;
+  try {
+    forward_eager(d_ids, d_mask, B, S, C, d_logits, d_probs, d_decisions, threshold);
+  } catch (...) {
+    cudaStreamEndCapture(stream_, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  GLC_CUDA(cudaStreamEndCapture(stream_, &g));
+  e.launches = launches_.load() - before;
+  cudaGraphExec_t exec = nullptr;
+  cudaError_t ie = cudaGraphInstantiate(&exec, g, 0);
+  cudaGraphDestroy(g);
+  if (ie != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
+  e.exec = exec;
+  GLC_CUDA(cudaGraphLaunch(e.exec, stream_));
+}
+
+void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits,
+                                float* d_probs, uint8_t* d_decisions, float threshold) {
   const int H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
   const int M = B * S;
-  if (M <= 0) return;
-  if (d_ids != ids_) ensure_workspace(M, B, C);   // run_host already sized it
   const int32_t* rel = rel_table(S);
   cudaStream_t st = stream_;
   uint64_t n = 0;

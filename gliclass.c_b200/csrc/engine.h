@@ -11,6 +11,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "model_weights.h"
@@ -69,6 +70,8 @@ class DeviceModel {
 
  private:
   void ensure_workspace(int tokens, int B, int C);
+  void forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
+                     uint8_t* d_decisions, float threshold);
   const int32_t* rel_table(int S);
   void* dalloc(size_t bytes);
   void upload_f32(float** dst, const HostTensor& t);
@@ -102,6 +105,21 @@ class DeviceModel {
   uint8_t* decisions_ = nullptr;
   std::vector<void*> ws_allocs_, perm_allocs_;
   std::map<std::string, DebugBuf> debug_;
+  // CUDA graphs of the forward, one per (shape, buffer set): the kernel sequence of a forward is fixed,
+  // so replaying it removes ~100 launches of CPU work per Run (what a batch-8 Run is bound by)
+  struct GraphKey {
+    int B, S, C;
+    const void *ids, *mask, *logits, *probs, *dec;
+    uint32_t thr;
+    bool operator<(const GraphKey& o) const {
+      return std::tie(B, S, C, ids, mask, logits, probs, dec, thr) <
+             std::tie(o.B, o.S, o.C, o.ids, o.mask, o.logits, o.probs, o.dec, o.thr);
+    }
+  };
+  struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; uint64_t launches = 0; };
+  std::map<GraphKey, GraphEntry> graphs_;
+  bool graphs_on_ = true;
+  void drop_graphs();
   // profiler state
   struct ProfRec { int cat; cudaEvent_t a, b; };
   bool prof_on_ = false;
