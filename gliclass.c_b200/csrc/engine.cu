@@ -7,6 +7,8 @@
 
 #include <cuda_fp16.h>
 
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
@@ -405,6 +407,9 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
 void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,
                            const DecisionOut* dec) {
   if (B <= 0 || S <= 0) return;
+  static const bool timing = getenv("GLC_TIMING") != nullptr;
+  auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t0 = timing ? now() : 0;
   std::lock_guard<std::mutex> lk(mu);
   GLC_CUDA(cudaSetDevice(device_));
   int rows_mb = max_tokens_ / S;
@@ -429,7 +434,9 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
     }
     if (r0 + rows_mb < B) GLC_CUDA(cudaStreamSynchronize(stream_));   // workspace reuse
   }
+  const double t1 = timing ? now() : 0;
   GLC_CUDA(cudaStreamSynchronize(stream_));
+  if (timing) fprintf(stderr, "glc run_host B=%d S=%d: enqueue %.1f us, wait %.1f us\n", B, S, t1 - t0, now() - t1);
 }
 
 // ---------------------------------------------------------------------------------------------
