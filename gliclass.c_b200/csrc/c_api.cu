@@ -317,6 +317,30 @@ int glc_op_attention(const void* qkv, const void* pos_k, const void* pos_q, int6
   GLC_TRY("glc_op_attention", glc::attention_fused(qkv, pos_k, pos_q, ld_pos, rel_idx, mask_bits, kv_len, ctx, B, S, heads,
                                                    buckets, num_sms_current(), (cudaStream_t)stream));
 }
+int glc_op_expand_pos(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst, int cols,
+                      void* stream) {
+  try {
+    const int ER = glc::expanded_pos_rows();
+    std::vector<int32_t> h(ER);
+    glc::expanded_pos_index(buckets, max_pos, h.data());
+    int32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, (size_t)ER * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = glc::expand_pos_table(pos_f16, ld_src, d, out_f16, ld_dst, cols, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (d) cudaFree(d);
+    if (e != cudaSuccess) return fail(GLC_ERR_CUDA, std::string("glc_op_expand_pos: ") + cudaGetErrorString(e));
+    return GLC_OK;
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_op_expand_pos: ") + e.what());
+  }
+}
+int glc_expanded_pos_rows(void) { return glc::expanded_pos_rows(); }
+int glc_op_attention_toeplitz(const void* qkv, const void* exp_k, const void* exp_q, int64_t ld_exp, const uint32_t* mask_bits,
+                              const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
+  GLC_TRY("glc_op_attention_toeplitz",
+          glc::attention_toeplitz(qkv, exp_k, exp_q, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
+}
 int glc_op_head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S, int H,
                        int C, void* stream) {
   GLC_TRY("glc_op_head_gather", glc::head_gather(h, ids, class_token, pooled, cls, B, S, H, C, (cudaStream_t)stream));

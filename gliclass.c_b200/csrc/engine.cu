@@ -112,6 +112,8 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
   graphs_on_ = getenv("GLC_NO_GRAPHS") == nullptr;
+  const char* al = getenv("GLC_ATTN_LEGACY");
+  attn_legacy_ = al && al[0] == '1';
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
   const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
@@ -129,6 +131,17 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   perm_allocs_.push_back(rel_ln);
   GLC_CUDA(ln_f32_to_f16(rel_f32, rel_g, rel_b, cfg_.ln_eps, rel_ln, R, H, stream_));
   ++launches_;
+
+  // index of the delta-expanded position tables (attention_toeplitz.cu): row rho <- pos_qk[idx(2047 - rho)]
+  const int ER = expanded_pos_rows();
+  int32_t* d_exp_idx = nullptr;
+  {
+    std::vector<int32_t> h(ER);
+    expanded_pos_index(cfg_.buckets, cfg_.max_rel_pos, h.data());
+    d_exp_idx = (int32_t*)dalloc((size_t)ER * 4);
+    perm_allocs_.push_back(d_exp_idx);
+    GLC_CUDA(cudaMemcpy(d_exp_idx, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice));
+  }
 
   layers_.resize(cfg_.layers);
   std::vector<float> cat((size_t)3 * H * H), bcat((size_t)3 * H);
@@ -160,6 +173,10 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
     d.pos_qk = dalloc((size_t)R * 2 * H * 2);
     perm_allocs_.push_back(d.pos_qk);
     GLC_CUDA(gemm_f16(rel_ln, H, d.wqkv, H, d.bqkv, d.pos_qk, 2 * H, R, 2 * H, H, 0, false, num_sms_, stream_));
+    ++launches_;
+    d.pos_exp = dalloc((size_t)ER * 2 * H * 2);
+    perm_allocs_.push_back(d.pos_exp);
+    GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx, d.pos_exp, 2 * H, 2 * H, stream_));
     ++launches_;
   }
   upload_w16(&t1w_, w.at("text.1.w").data.data(), (size_t)Hh * H);
@@ -383,8 +400,13 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st));
     if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
     const __half* pq = (const __half*)d.pos_qk;
-    GLC_LAUNCH(KC_ATTN, attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads,
-                                        cfg_.buckets, num_sms_, st));
+    if (attn_legacy_) {
+      GLC_LAUNCH(KC_ATTN, attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads,
+                                          cfg_.buckets, num_sms_, st));
+    } else {
+      const __half* pe = (const __half*)d.pos_exp;
+      GLC_LAUNCH(KC_ATTN, attention_toeplitz(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
+    }
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
     GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st));
     GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));

@@ -30,6 +30,7 @@ struct DeviceLayer {
   float* b2 = nullptr;
   float *ln2g = nullptr, *ln2b = nullptr;
   void* pos_qk = nullptr; // fp16 [2*buckets, 2H]: cols [0,H) = query_proj(rel), [H,2H) = key_proj(rel)
+  void* pos_exp = nullptr; // fp16 [expanded_pos_rows(), 2H]: pos_qk expanded to one row per delta (row rho = pos_qk[idx(2047 - rho)])
 };
 
 struct DebugBuf { void* ptr = nullptr; size_t count = 0; };
@@ -84,6 +85,7 @@ class DeviceModel {
   ModelConfig cfg_;
   int max_tokens_ = 65536;
   bool debug_keep_ = false;
+  bool attn_legacy_ = false;   // GLC_ATTN_LEGACY=1: first-generation attention kernel (A/B comparisons)
   std::atomic<uint64_t> launches_{0};
 
   // weights

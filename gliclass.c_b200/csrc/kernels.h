@@ -34,6 +34,16 @@ cudaError_t mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int 
 cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
                             const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                             int buckets, int num_sms, cudaStream_t stream);
+// K3, second generation (attention_toeplitz.cu): same op with the two relative-position biases added by the
+// tensor core.  exp_k / exp_q are the position tables expanded to one row per delta by expand_pos_table:
+// fp16 [expanded_pos_rows()][ld_exp], row rho = pos[idx(2047 - rho)].
+int expanded_pos_rows();
+void expanded_pos_index(int buckets, int max_pos, int32_t* out /* host, [expanded_pos_rows()] */);
+cudaError_t expand_pos_table(const void* pos_f16, int64_t ld_src, const int32_t* d_exp_index, void* out_f16, int64_t ld_dst,
+                             int cols, cudaStream_t stream);
+cudaError_t attention_toeplitz(const void* qkv, const void* exp_k, const void* exp_q, int64_t ld_exp,
+                               const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
+                               cudaStream_t stream);
 // slow CUDA-core restatement of the same op, used only by tests to localise bugs on the GPU
 cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
                             const uint32_t* mask_bits, void* ctx, int B, int S, int heads, int buckets,

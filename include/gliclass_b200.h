@@ -143,6 +143,17 @@ GLC_API int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_le
 GLC_API int glc_op_attention(const void* qkv_f16, const void* pos_k_f16, const void* pos_q_f16, int64_t ld_pos,
                              const int32_t* rel_idx, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16,
                              int B, int S, int heads, int buckets, int naive, void* stream);
+/* K3, production kernel (csrc/attention_toeplitz.cu): the same op with both relative-position biases added by
+ * the tensor core.  It reads the position tables expanded to one row per relative distance:
+ * glc_op_expand_pos writes out[rho][0:cols) = pos[idx(2047 - rho)][0:cols) for rho in [0, glc_expanded_pos_rows())
+ * (idx = glc_rel_index_table; the last row is zero) and synchronises `stream`.  exp_k / exp_q: fp16
+ * [glc_expanded_pos_rows()][ld_exp], head h at columns h*64... */
+GLC_API int glc_expanded_pos_rows(void);
+GLC_API int glc_op_expand_pos(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst,
+                              int cols, void* stream);
+GLC_API int glc_op_attention_toeplitz(const void* qkv_f16, const void* exp_k_f16, const void* exp_q_f16, int64_t ld_exp,
+                                      const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S,
+                                      int heads, void* stream);
 /* K5a: pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] for the c-th <<LABEL>> token, else 0 */
 GLC_API int glc_op_head_gather(const void* h_f16, const int64_t* ids, int64_t class_token, void* pooled_f16,
                                void* cls_f16, int B, int S, int H, int C, void* stream);

@@ -30,7 +30,18 @@ ctx = torch.zeros(B, S, H, dtype=torch.float16, device=dev)
 pos_q, pos_k = pos[:, :H], pos[:, H:]
 
 
+ER = L.glc_expanded_pos_rows()
+exp = torch.zeros(ER, 2 * H, dtype=torch.float16, device=dev)
+assert L.glc_op_expand_pos(pos.data_ptr(), 2 * H, 256, 512, exp.data_ptr(), 2 * H, 2 * H, None) == 0, pkg.last_error()
+LEGACY = os.environ.get("GLC_ATTN_LEGACY") == "1"
+
+
 def run(naive, out, nb=B):
+    if not naive and not LEGACY:
+        rc = L.glc_op_attention_toeplitz(qkv.data_ptr(), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, bits.data_ptr(),
+                                         kv.data_ptr(), out.data_ptr(), nb, S, heads, None)
+        assert rc == 0, pkg.last_error()
+        return
     rc = L.glc_op_attention(qkv.data_ptr(), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, rel.data_ptr(), bits.data_ptr(),
                             kv.data_ptr(), out.data_ptr(), nb, S, heads, 256, int(naive), None)
     assert rc == 0, pkg.last_error()

@@ -201,9 +201,20 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, naive, qk_std=1.8):
     _sync_check(pkg, L.glc_op_mask_prep(_ptr(mask), _ptr(bits), _ptr(kv), B, S, None), "mask_prep")
     ctx = torch.full((B, S, H), float("nan"), dtype=torch.float16, device=dev)
     pos_q, pos_k = pos[:, :H], pos[:, H:]
-    rc = L.glc_op_attention(_ptr(qkv), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, _ptr(rel), _ptr(bits), _ptr(kv), _ptr(ctx),
-                            B, S, heads, 256, int(naive), None)
-    _sync_check(pkg, rc, "glc_op_attention")
+    if naive == "toeplitz":
+        # production kernel: position tables expanded to one row per relative distance, biases added by the tensor core
+        ER = L.glc_expanded_pos_rows()
+        exp = torch.full((ER, 2 * H), float("nan"), dtype=torch.float16, device=dev)
+        _sync_check(pkg, L.glc_op_expand_pos(_ptr(pos), 2 * H, 256, 512, _ptr(exp), 2 * H, 2 * H, None), "expand_pos")
+        full = torch.from_numpy(pkg.rel_index_table(2048, 256, 512)).long().to(dev)    # idx[delta + 2047]
+        assert torch.equal(exp[:ER - 1], pos[full.flip(0)]) and (exp[ER - 1] == 0).all()   # row rho = pos[idx(2047 - rho)]
+        rc = L.glc_op_attention_toeplitz(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv),
+                                         _ptr(ctx), B, S, heads, None)
+        _sync_check(pkg, rc, "glc_op_attention_toeplitz")
+    else:
+        rc = L.glc_op_attention(_ptr(qkv), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, _ptr(rel), _ptr(bits), _ptr(kv),
+                                _ptr(ctx), B, S, heads, 256, int(naive), None)
+        _sync_check(pkg, rc, "glc_op_attention")
     ii = torch.arange(S, device=dev)
     idx = rel.long()[(ii[:, None] - ii[None, :]) + (Spad - 1)]
     ref = _attention_ref(qkv, pos_k.contiguous(), pos_q.contiguous(), idx, mask, heads)
@@ -231,6 +242,29 @@ def test_attention_naive_kernel(pkg, dev, B, S, heads, lens):
     ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive=True)
     v = mask.bool()
     _report(f"attn-naive B{B} S{S} h{heads}", ctx[v], ref[v], 3e-3, 3e-3)
+
+
+@pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1])])
+def test_attention_toeplitz(pkg, dev, B, S, heads, lens):
+    """production attention kernel (csrc/attention_toeplitz.cu) against the fp32 restatement"""
+    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive="toeplitz")
+    v = mask.bool()
+    got, want = ctx[v], ref[v]
+    d = (got.float() - want.float()).abs()
+    if d.max().item() > 1e-2 or torch.isnan(got.float()).any():
+        full = (ctx.float() - ref.float()).abs().nan_to_num(99.0) * mask[..., None].float()
+        for b in range(B):
+            for h in range(heads):
+                row = [f"{full[b, q0:q0 + 128, h * 64:(h + 1) * 64].max().item():.3f}" for q0 in range(0, S, 128)]
+                print(f"   b{b} h{h} per-q-tile max err: {row}")
+        bad = torch.nonzero(full.max(-1).values > 1e-2)
+        print("   first bad (b,row):", bad[:10].tolist())
+    _report(f"attn-toeplitz B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
+
+
+def test_attention_toeplitz_softmax_peaked(pkg, dev):
+    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, naive="toeplitz", qk_std=3.0)
+    _report("attn-toeplitz peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
 
 
 @pytest.mark.parametrize("B,S,heads,lens", ATT_CASES)
