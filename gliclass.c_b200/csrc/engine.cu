@@ -112,8 +112,10 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
   graphs_on_ = getenv("GLC_NO_GRAPHS") == nullptr;
-  const char* al = getenv("GLC_ATTN_LEGACY");
-  attn_legacy_ = al && al[0] == '1';
+  // production attention = attention.cu (gather kernel, 360 us/launch at C2); GLC_ATTN_TOEPLITZ=1 selects the
+  // tensor-core-bias experiment (attention_toeplitz.cu, 413 us/launch) for A/B comparisons
+  const char* al = getenv("GLC_ATTN_TOEPLITZ");
+  attn_legacy_ = !(al && al[0] == '1');
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
   const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
@@ -135,7 +137,7 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   // index of the delta-expanded position tables (attention_toeplitz.cu): row rho <- pos_qk[idx(2047 - rho)]
   const int ER = expanded_pos_rows();
   int32_t* d_exp_idx = nullptr;
-  {
+  if (!attn_legacy_) {
     std::vector<int32_t> h(ER);
     expanded_pos_index(cfg_.buckets, cfg_.max_rel_pos, h.data());
     d_exp_idx = (int32_t*)dalloc((size_t)ER * 4);
@@ -174,10 +176,12 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
     perm_allocs_.push_back(d.pos_qk);
     GLC_CUDA(gemm_f16(rel_ln, H, d.wqkv, H, d.bqkv, d.pos_qk, 2 * H, R, 2 * H, H, 0, false, num_sms_, stream_));
     ++launches_;
-    d.pos_exp = dalloc((size_t)ER * 2 * H * 2);
-    perm_allocs_.push_back(d.pos_exp);
-    GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx, d.pos_exp, 2 * H, 2 * H, stream_));
-    ++launches_;
+    if (!attn_legacy_) {
+      d.pos_exp = dalloc((size_t)ER * 2 * H * 2);
+      perm_allocs_.push_back(d.pos_exp);
+      GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx, d.pos_exp, 2 * H, 2 * H, stream_));
+      ++launches_;
+    }
   }
   upload_w16(&t1w_, w.at("text.1.w").data.data(), (size_t)Hh * H);
   upload_f32(&t1b_, w.at("text.1.b"));

@@ -85,7 +85,7 @@ class DeviceModel {
   ModelConfig cfg_;
   int max_tokens_ = 65536;
   bool debug_keep_ = false;
-  bool attn_legacy_ = false;   // GLC_ATTN_LEGACY=1: first-generation attention kernel (A/B comparisons)
+  bool attn_legacy_ = true;    // false with GLC_ATTN_TOEPLITZ=1: tensor-core-bias experiment (A/B comparisons)
   std::atomic<uint64_t> launches_{0};
 
   // weights

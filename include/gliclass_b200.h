@@ -143,7 +143,7 @@ GLC_API int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_le
 GLC_API int glc_op_attention(const void* qkv_f16, const void* pos_k_f16, const void* pos_q_f16, int64_t ld_pos,
                              const int32_t* rel_idx, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16,
                              int B, int S, int heads, int buckets, int naive, void* stream);
-/* K3, production kernel (csrc/attention_toeplitz.cu): the same op with both relative-position biases added by
+/* K3, experimental variant (csrc/attention_toeplitz.cu; engine uses it only with GLC_ATTN_TOEPLITZ=1): the same op with both relative-position biases added by
  * the tensor core.  It reads the position tables expanded to one row per relative distance:
  * glc_op_expand_pos writes out[rho][0:cols) = pos[idx(2047 - rho)][0:cols) for rho in [0, glc_expanded_pos_rows())
  * (idx = glc_rel_index_table; the last row is zero) and synchronises `stream`.  exp_k / exp_q: fp16

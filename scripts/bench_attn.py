@@ -33,7 +33,7 @@ pos_q, pos_k = pos[:, :H], pos[:, H:]
 ER = L.glc_expanded_pos_rows()
 exp = torch.zeros(ER, 2 * H, dtype=torch.float16, device=dev)
 assert L.glc_op_expand_pos(pos.data_ptr(), 2 * H, 256, 512, exp.data_ptr(), 2 * H, 2 * H, None) == 0, pkg.last_error()
-LEGACY = os.environ.get("GLC_ATTN_LEGACY") == "1"
+LEGACY = os.environ.get("GLC_ATTN_TOEPLITZ") != "1"
 
 
 def run(naive, out, nb=B):

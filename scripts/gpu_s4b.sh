@@ -5,9 +5,9 @@ timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "toeplitz" > gpu
 tail -n 30 gpurun_out/s4b_kernels.log
 if grep -q "rc=0" gpurun_out/s4b_kernels.log; then
   timeout 300 python scripts/bench_attn.py 64 512 12 20 > gpurun_out/s4b_attn.log 2>&1
-  GLC_ATTN_LEGACY=1 timeout 300 python scripts/bench_attn.py 64 512 12 20 >> gpurun_out/s4b_attn.log 2>&1
+  timeout 300 python scripts/bench_attn.py 64 512 12 20 >> gpurun_out/s4b_attn.log 2>&1
   timeout 300 python scripts/bench_attn.py 16 1024 16 10 >> gpurun_out/s4b_attn.log 2>&1
-  GLC_ATTN_LEGACY=1 timeout 300 python scripts/bench_attn.py 16 1024 16 10 >> gpurun_out/s4b_attn.log 2>&1
+  timeout 300 python scripts/bench_attn.py 16 1024 16 10 >> gpurun_out/s4b_attn.log 2>&1
   cat gpurun_out/s4b_attn.log
   timeout 900 python -m pytest tests/test_gpu_e2e.py -x -q > gpurun_out/s4b_e2e.log 2>&1; echo "rc=$?" >> gpurun_out/s4b_e2e.log
   tail -n 5 gpurun_out/s4b_e2e.log
