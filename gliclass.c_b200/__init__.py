@@ -41,7 +41,8 @@ class glc_info(C.Structure):
     _fields_ = [("vocab", C.c_int32), ("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32),
                 ("inter", C.c_int32), ("head_hidden", C.c_int32), ("buckets", C.c_int32), ("max_rel_pos", C.c_int32),
                 ("ln_eps", C.c_float), ("class_token", C.c_int64), ("num_devices", C.c_int32),
-                ("weight_dtype", C.c_int32)]
+                ("weight_dtype", C.c_int32), ("pooling", C.c_int32), ("scorer", C.c_int32),
+                ("normalize_features", C.c_int32), ("logit_scale", C.c_float)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -64,6 +65,10 @@ _SIGS = {
     "glc_sync": (_i, [_vp, _i]),
     "glc_stream": (_vp, [_vp, _i]),
     "glc_launch_count": (C.c_uint64, [_vp]),
+    "glc_submit": (_vp, [_vp, _vp, _vp, _i, _i, _vp, C.c_size_t, C.POINTER(_i)]),
+    "glc_poll": (_i, [_vp]),
+    "glc_collect": (_i, [_vp]),
+    "glc_coalesce_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "glc_profile_enable": (_i, [_vp, _i, _i]),
     "glc_profile_collect": (_i, [_vp, _i, _vp, _vp, _i]),
     "glc_debug_fetch": (_i64, [_vp, _i, C.c_char_p, _vp, C.c_size_t]),
@@ -203,6 +208,34 @@ class Session:
         _check(L.glc_run_decisions(self._h, ids.ctypes.data, mask.ctypes.data, B, S, threshold, lg.ctypes.data, pr.ctypes.data,
                                    de.ctypes.data, lg.size, C.byref(cc)), "glc_run_decisions")
         return lg, pr, de.astype(bool)
+
+    # -- asynchronous submit / collect: tokenise the next batch while this one runs
+    def submit(self, input_ids: np.ndarray, attention_mask: np.ndarray):
+        """Returns a ticket; collect(ticket) waits and returns logits [B, C]."""
+        ids = np.ascontiguousarray(input_ids, dtype=np.int64)
+        mask = np.ascontiguousarray(attention_mask, dtype=np.int64)
+        B, S = ids.shape
+        L = lib()
+        ncls = max(0, L.glc_num_classes(self._h, ids.ctypes.data, B, S))
+        out = np.empty((B, ncls), dtype=np.float32)
+        cc = C.c_int(0)
+        t = L.glc_submit(self._h, ids.ctypes.data, mask.ctypes.data, B, S, out.ctypes.data, out.size, C.byref(cc))
+        if not t:
+            raise GlcError(f"glc_submit failed: {last_error()}")
+        return (t, ids, mask, out)   # keeps the buffers alive until collect
+
+    def poll(self, ticket) -> bool:
+        return lib().glc_poll(ticket[0]) == 1
+
+    def collect(self, ticket) -> np.ndarray:
+        _check(lib().glc_collect(ticket[0]), "glc_collect")
+        return ticket[3]
+
+    def coalesce_stats(self):
+        """(merged launches, requests served by them) since load"""
+        g, r = C.c_uint64(0), C.c_uint64(0)
+        _check(lib().glc_coalesce_stats(self._h, C.byref(g), C.byref(r)), "glc_coalesce_stats")
+        return int(g.value), int(r.value)
 
     def run_pinned(self, ids_ptr: int, mask_ptr: int, B: int, S: int, out_ptr: int, out_capacity: int) -> int:
         """Same call on raw host pointers (pinned buffers in bench.py's e2e leg). Returns C."""

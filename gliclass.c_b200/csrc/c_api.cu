@@ -2,9 +2,11 @@
 // them into an error code + thread-local message, as a C caller (the reference's model.c) expects.
 #include <cuda_fp16.h>
 
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <future>
 #include <sstream>
 #include <string>
 #include <vector>
@@ -17,6 +19,11 @@
 struct glc_model {
   glc::Model* m;
   int weight_dtype;
+};
+struct glc_ticket {
+  std::future<int> fut;
+  std::string err;
+  int C = 0;
 };
 struct glc_onnx {
   glc::ModelWeights w;
@@ -34,6 +41,7 @@ void fill_info(const glc::ModelConfig& c, glc_info* o) {
   o->vocab = c.vocab; o->hidden = c.hidden; o->layers = c.layers; o->heads = c.heads; o->inter = c.inter;
   o->head_hidden = c.head_hidden; o->buckets = c.buckets; o->max_rel_pos = c.max_rel_pos; o->ln_eps = c.ln_eps;
   o->class_token = c.class_token;
+  o->pooling = c.pooling; o->scorer = c.scorer; o->normalize_features = c.normalize ? 1 : 0; o->logit_scale = c.logit_scale;
 }
 }  // namespace
 
@@ -182,6 +190,70 @@ void* glc_stream(glc_model* m, int slot) {
 }
 
 uint64_t glc_launch_count(const glc_model* m) { return m ? m->m->launches() : 0; }
+
+glc_ticket* glc_submit(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S, float* logits_out,
+                       size_t logits_capacity, int* C_out) {
+  try {
+    if (!m || B < 0 || S < 0 || (B * S > 0 && (!input_ids || !attention_mask))) {
+      fail(GLC_ERR_ARG, "glc_submit: bad argument");
+      return nullptr;
+    }
+    const int C = m->m->num_classes(input_ids, B, S);
+    if (C_out) *C_out = C;
+    if ((size_t)B * C > logits_capacity || ((size_t)B * C > 0 && !logits_out)) {
+      fail(GLC_ERR_CAPACITY, "glc_submit: logits buffer too small");
+      return nullptr;
+    }
+    glc_ticket* t = new glc_ticket;
+    t->C = C;
+    glc::Model* mm = m->m;
+    if (B == 0 || S == 0 || C == 0) {
+      std::promise<int> p;
+      p.set_value(GLC_OK);
+      t->fut = p.get_future();
+      return t;
+    }
+    // one host thread per in-flight request: it blocks in the coalescing queue / on the device like a
+    // reference OpenMP worker would block in g_ort->Run, while the submitting thread goes on tokenising
+    t->fut = std::async(std::launch::async, [mm, t, input_ids, attention_mask, B, S, C, logits_out]() -> int {
+      try {
+        mm->run(input_ids, attention_mask, B, S, C, logits_out);
+        return (int)GLC_OK;
+      } catch (const std::exception& e) {
+        t->err = std::string("glc_submit: ") + e.what();
+        return (int)GLC_ERR_CUDA;
+      }
+    });
+    return t;
+  } catch (const std::exception& e) {
+    fail(GLC_ERR, std::string("glc_submit: ") + e.what());
+    return nullptr;
+  }
+}
+
+int glc_poll(glc_ticket* t) {
+  if (!t) return fail(GLC_ERR_ARG, "glc_poll: null ticket");
+  return t->fut.wait_for(std::chrono::seconds(0)) == std::future_status::ready ? 1 : 0;
+}
+
+int glc_collect(glc_ticket* t) {
+  if (!t) return fail(GLC_ERR_ARG, "glc_collect: null ticket");
+  int rc = GLC_ERR;
+  try {
+    rc = t->fut.get();
+  } catch (const std::exception& e) {
+    t->err = std::string("glc_collect: ") + e.what();
+  }
+  if (rc != GLC_OK) g_err = t->err;
+  delete t;
+  return rc;
+}
+
+int glc_coalesce_stats(const glc_model* m, uint64_t* groups, uint64_t* requests) {
+  if (!m) return fail(GLC_ERR_ARG, "glc_coalesce_stats: null model");
+  m->m->coalesce_stats(groups, requests);
+  return GLC_OK;
+}
 
 int glc_profile_enable(glc_model* m, int slot, int on) {
   if (!m || slot < 0 || slot >= m->m->num_devices()) return fail(GLC_ERR_ARG, "glc_profile_enable: bad argument");

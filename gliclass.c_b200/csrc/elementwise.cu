@@ -228,8 +228,9 @@ __global__ void mask_prep_kernel(const int64_t* __restrict__ mask, uint32_t* __r
 
 // one warp per batch row scans for <<LABEL>> tokens; then every lane copies rows with 128-bit loads
 __global__ void __launch_bounds__(128)
-head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids, int64_t class_token,
-                   __half* __restrict__ pooled, __half* __restrict__ cls, int B, int S, int H, int C) {
+head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
+                   int64_t class_token, int pool_mode, __half* __restrict__ pooled, __half* __restrict__ cls, int B, int S,
+                   int H, int C) {
   extern __shared__ int pos_s[];   // [C] per block (one batch row per block)
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -249,9 +250,36 @@ head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids
   }
   __syncthreads();
   const int vec = H / 8;
-  // row 0 of the output block is the pooled (first-token) row, rows 1..C the class rows
-  for (int r = warp; r <= C; r += (blockDim.x >> 5)) {
-    const int p = (r == 0) ? 0 : pos_s[r - 1];
+  if (pool_mode >= 2) {
+    // masked mean / masked max over the sequence (gliclass poolings): thread = 8 columns
+    for (int i = threadIdx.x; i < vec; i += blockDim.x) {
+      float acc[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] = (pool_mode == 2) ? 0.f : -3.4028234663852886e38f;
+      int cnt = 0;
+      for (int j = 0; j < S; ++j) {
+        if (mask[(int64_t)b * S + j] == 0) continue;   // block-uniform
+        ++cnt;
+        const uint4 u = *reinterpret_cast<const uint4*>(h + ((int64_t)b * S + j) * H + i * 8);
+        const __half2* hp = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(hp[e]);
+          if (pool_mode == 2) { acc[2 * e] += f.x; acc[2 * e + 1] += f.y; }
+          else { acc[2 * e] = fmaxf(acc[2 * e], f.x); acc[2 * e + 1] = fmaxf(acc[2 * e + 1], f.y); }
+        }
+      }
+      const float inv = (pool_mode == 2) ? 1.0f / (float)cnt : 1.0f;
+      uint4 o;
+      __half2* op = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) op[e] = __floats2half2_rn(acc[2 * e] * inv, acc[2 * e + 1] * inv);
+      *reinterpret_cast<uint4*>(pooled + (int64_t)b * H + i * 8) = o;
+    }
+  }
+  // row 0 of the output block is the pooled (first / last token) row, rows 1..C the class rows
+  for (int r = (pool_mode >= 2 ? warp + 1 : warp); r <= C; r += (blockDim.x >> 5)) {
+    const int p = (r == 0) ? (pool_mode == 1 ? S - 1 : 0) : pos_s[r - 1];
     __half* dst = (r == 0) ? pooled + (int64_t)b * H : cls + ((int64_t)b * C + (r - 1)) * H;
     const __half* src = h + ((int64_t)b * S + (p < 0 ? 0 : p)) * H;
     for (int i = lane; i < vec; i += 32) {
@@ -283,6 +311,117 @@ head_score_kernel(const float* __restrict__ t, const float* __restrict__ k, floa
     const float p = 1.0f / (1.0f + expf(-s));
     if (probs) probs[idx] = p;
     if (decisions) decisions[idx] = p > threshold ? 1 : 0;
+  }
+}
+
+
+// generalised scorer tail: one warp per (b,c) row.
+//   logits[row] = scale * <t[b*t_stride ..], k[row,:]> * (normalize ? 1 / ((|t|+eps)(|k|+eps)) : 1) + bias
+// t_stride = 0 turns it into the last Linear(K -> 1) of the MLP / weighted-dot scorers (t = weight row).
+__global__ void __launch_bounds__(256)
+head_score_ex_kernel(const float* __restrict__ t, int64_t t_stride, const float* __restrict__ k, float* __restrict__ logits,
+                     float* __restrict__ probs, uint8_t* __restrict__ decisions, float threshold, int B, int C, int K,
+                     int normalize, float eps, float scale, float bias) {
+  const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (idx >= B * C) return;
+  const int b = idx / C;
+  const float4* tv = reinterpret_cast<const float4*>(t + (int64_t)b * t_stride);
+  const float4* kv = reinterpret_cast<const float4*>(k + (int64_t)idx * K);
+  float s = 0.f, tt = 0.f, kk = 0.f;
+  for (int i = lane; i < K / 4; i += 32) {
+    const float4 a = tv[i], c = kv[i];
+    s = fmaf(a.x, c.x, s); s = fmaf(a.y, c.y, s); s = fmaf(a.z, c.z, s); s = fmaf(a.w, c.w, s);
+    if (normalize) {
+      tt = fmaf(a.x, a.x, tt); tt = fmaf(a.y, a.y, tt); tt = fmaf(a.z, a.z, tt); tt = fmaf(a.w, a.w, tt);
+      kk = fmaf(c.x, c.x, kk); kk = fmaf(c.y, c.y, kk); kk = fmaf(c.z, c.z, kk); kk = fmaf(c.w, c.w, kk);
+    }
+  }
+  s = warp_sum(s);
+  if (normalize) {
+    tt = warp_sum(tt);
+    kk = warp_sum(kk);
+    s = s / ((sqrtf(tt) + eps) * (sqrtf(kk) + eps));
+  }
+  if (lane == 0) {
+    s = fmaf(s, scale, bias);
+    logits[idx] = s;
+    const float p = 1.0f / (1.0f + expf(-s));
+    if (probs) probs[idx] = p;
+    if (decisions) decisions[idx] = p > threshold ? 1 : 0;
+  }
+}
+
+// fp32 rows -> fp16 rows with optional L2 normalisation x / (|x| + eps); one warp per row.
+// Destination row r goes to dst + r * ld_dst + col0 (so the same kernel fills halves of a concat buffer);
+// src row = r / rep (rep = C broadcasts the text row of batch b to its C class rows).
+__global__ void __launch_bounds__(256)
+head_rows16_kernel(const float* __restrict__ src, int K, int rep, __half* __restrict__ dst, int64_t ld_dst, int col0, int rows,
+                   int normalize, float eps) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float4* sv = reinterpret_cast<const float4*>(src + (int64_t)(r / rep) * K);
+  float inv = 1.0f;
+  if (normalize) {
+    float q = 0.f;
+    for (int i = lane; i < K / 4; i += 32) {
+      const float4 a = sv[i];
+      q = fmaf(a.x, a.x, q); q = fmaf(a.y, a.y, q); q = fmaf(a.z, a.z, q); q = fmaf(a.w, a.w, q);
+    }
+    inv = 1.0f / (sqrtf(warp_sum(q)) + eps);
+  }
+  __half2* d = reinterpret_cast<__half2*>(dst + (int64_t)r * ld_dst + col0);
+  for (int i = lane; i < K / 4; i += 32) {
+    const float4 a = sv[i];
+    d[2 * i] = __floats2half2_rn(a.x * inv, a.y * inv);
+    d[2 * i + 1] = __floats2half2_rn(a.z * inv, a.w * inv);
+  }
+}
+
+// weighted-dot scorer combine: pt [B,2Hh], pl [B*C,2Hh] fp32 with (d, half) interleaved ->
+// cat[row] = [pt0_b | pl0_row | pt1_b * pl1_row]  fp16 [B*C, 3Hh]
+__global__ void __launch_bounds__(256)
+head_wdot_combine_kernel(const float* __restrict__ pt, const float* __restrict__ pl, __half* __restrict__ cat, int B, int C,
+                         int Hh) {
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= B * C) return;
+  const float2* tv = reinterpret_cast<const float2*>(pt + (int64_t)(r / C) * 2 * Hh);
+  const float2* lv = reinterpret_cast<const float2*>(pl + (int64_t)r * 2 * Hh);
+  __half* o = cat + (int64_t)r * 3 * Hh;
+  for (int d = lane; d < Hh; d += 32) {
+    const float2 a = tv[d], c = lv[d];
+    o[d] = __float2half_rn(a.x);
+    o[Hh + d] = __float2half_rn(c.x);
+    o[2 * Hh + d] = __float2half_rn(a.y * c.y);
+  }
+}
+
+// Reference behaviour at PADDED query rows (only observable through pooling_strategy='last' on a right-padded
+// batch): the traced graph masks scores with the outer product of the attention mask (T:603-610, T:256), so a
+// padded query row has every score at finfo.min, its softmax is exactly uniform over ALL S keys and its context
+// is the plain mean of V over the S rows of the batch.  One block per batch row; no-op for unpadded rows.
+__global__ void __launch_bounds__(256)
+pad_rows_mean_v_kernel(const __half* __restrict__ qkv, const int64_t* __restrict__ mask, __half* __restrict__ ctx, int S, int H) {
+  const int b = blockIdx.x;
+  __shared__ int any_pad;
+  if (threadIdx.x == 0) any_pad = 0;
+  __syncthreads();
+  int pad = 0;
+  for (int j = threadIdx.x; j < S; j += blockDim.x) pad |= (mask[(int64_t)b * S + j] == 0);
+  if (pad) any_pad = 1;
+  __syncthreads();
+  if (!any_pad) return;
+  for (int c = threadIdx.x; c < H / 2; c += blockDim.x) {
+    float ax = 0.f, ay = 0.f;
+    for (int j = 0; j < S; ++j) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(qkv + ((int64_t)b * S + j) * 3 * H + 2 * H + 2 * c));
+      ax += f.x; ay += f.y;
+    }
+    const __half2 m = __floats2half2_rn(ax / (float)S, ay / (float)S);
+    for (int j = 0; j < S; ++j)
+      if (mask[(int64_t)b * S + j] == 0) *reinterpret_cast<__half2*>(ctx + ((int64_t)b * S + j) * H + 2 * c) = m;
   }
 }
 
@@ -358,10 +497,47 @@ cudaError_t mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int 
 
 cudaError_t head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S,
                         int H, int C, cudaStream_t stream) {
+  return head_gather_pool(h, ids, nullptr, class_token, 0, pooled, cls, B, S, H, C, stream);
+}
+
+cudaError_t head_gather_pool(const void* h, const int64_t* ids, const int64_t* mask, int64_t class_token, int pool_mode,
+                             void* pooled, void* cls, int B, int S, int H, int C, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  if (H % 8 != 0) return cudaErrorInvalidValue;
+  if (H % 8 != 0 || pool_mode < 0 || pool_mode > 3 || (pool_mode >= 2 && !mask)) return cudaErrorInvalidValue;
   head_gather_kernel<<<B, 128, (size_t)(C > 0 ? C : 1) * sizeof(int), stream>>>(
-      (const __half*)h, ids, class_token, (__half*)pooled, (__half*)cls, B, S, H, C);
+      (const __half*)h, ids, mask, class_token, pool_mode, (__half*)pooled, (__half*)cls, B, S, H, C);
+  return cudaGetLastError();
+}
+
+cudaError_t pad_rows_mean_v(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int H, cudaStream_t stream) {
+  if (B <= 0 || S <= 0) return cudaSuccess;
+  if (H % 2) return cudaErrorInvalidValue;
+  pad_rows_mean_v_kernel<<<B, 256, 0, stream>>>((const __half*)qkv, mask, (__half*)ctx, S, H);
+  return cudaGetLastError();
+}
+
+cudaError_t head_score_ex(const float* t, int64_t t_stride, const float* k, float* logits, float* probs, uint8_t* decisions,
+                          float threshold, int B, int C, int K, bool normalize, float eps, float scale, float bias,
+                          cudaStream_t stream) {
+  if (B * C <= 0) return cudaSuccess;
+  if (K % 4 != 0 || (t_stride % 4) != 0) return cudaErrorInvalidValue;
+  head_score_ex_kernel<<<(B * C + 7) / 8, 256, 0, stream>>>(t, t_stride, k, logits, probs, decisions, threshold, B, C, K,
+                                                            normalize ? 1 : 0, eps, scale, bias);
+  return cudaGetLastError();
+}
+
+cudaError_t head_rows16(const float* src, int K, int rep, void* dst_f16, int64_t ld_dst, int col0, int rows, bool normalize,
+                        float eps, cudaStream_t stream) {
+  if (rows <= 0) return cudaSuccess;
+  if (K % 4 != 0 || rep < 1 || (ld_dst % 2) || (col0 % 2)) return cudaErrorInvalidValue;
+  head_rows16_kernel<<<(rows + 7) / 8, 256, 0, stream>>>(src, K, rep, (__half*)dst_f16, ld_dst, col0, rows, normalize ? 1 : 0,
+                                                         eps);
+  return cudaGetLastError();
+}
+
+cudaError_t head_wdot_combine(const float* pt, const float* pl, void* cat_f16, int B, int C, int Hh, cudaStream_t stream) {
+  if (B * C <= 0) return cudaSuccess;
+  head_wdot_combine_kernel<<<(B * C + 7) / 8, 256, 0, stream>>>(pt, pl, (__half*)cat_f16, B, C, Hh);
   return cudaGetLastError();
 }
 

@@ -191,6 +191,23 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   upload_f32(&c1b_, w.at("cls.1.b"));
   upload_w16(&c2w_, w.at("cls.2.w").data.data(), (size_t)Hh * Hh);
   upload_f32(&c2b_, w.at("cls.2.b"));
+  if (cfg_.scorer == SCORER_MLP) {
+    upload_w16(&m1w_, w.at("scorer.mlp.0.w").data.data(), w.at("scorer.mlp.0.w").data.size());
+    upload_f32(&m1b_, w.at("scorer.mlp.0.b"));
+    upload_w16(&m2w_, w.at("scorer.mlp.2.w").data.data(), w.at("scorer.mlp.2.w").data.size());
+    upload_f32(&m2b_, w.at("scorer.mlp.2.b"));
+    upload_f32(&last_w_, w.at("scorer.mlp.4.w"));
+    last_b_ = w.at("scorer.mlp.4.b").data.at(0);
+  } else if (cfg_.scorer == SCORER_WEIGHTED_DOT) {
+    upload_w16(&ptw_, w.at("scorer.pt.w").data.data(), w.at("scorer.pt.w").data.size());
+    upload_f32(&ptb_, w.at("scorer.pt.b"));
+    upload_w16(&plw_, w.at("scorer.pl.w").data.data(), w.at("scorer.pl.w").data.size());
+    upload_f32(&plb_, w.at("scorer.pl.b"));
+    upload_w16(&o1w_, w.at("scorer.o1.w").data.data(), w.at("scorer.o1.w").data.size());
+    upload_f32(&o1b_, w.at("scorer.o1.b"));
+    upload_f32(&last_w_, w.at("scorer.o2.w"));
+    last_b_ = w.at("scorer.o2.b").data.at(0);
+  }
   GLC_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -206,6 +223,8 @@ DeviceModel::~DeviceModel() {
   drop_graphs();
   for (void* p : ws_allocs_) cudaFree(p);
   for (void* p : perm_allocs_) cudaFree(p);
+  if (h_ids_) { cudaFreeHost(h_ids_); cudaFreeHost(h_mask_); }
+  if (h_logits_) { cudaFreeHost(h_logits_); cudaFreeHost(h_probs_); cudaFreeHost(h_dec_); }
   for (auto& kv : rel_tables_) cudaFree(kv.second);
   for (auto& kv : debug_) cudaFree(kv.second.ptr);
   for (auto& r : prof_recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -256,6 +275,18 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   logits_ = (float*)A((size_t)ws_rows_ * 4);
   probs_ = (float*)A((size_t)ws_rows_ * 4);
   decisions_ = (uint8_t*)A((size_t)ws_rows_);
+  if (cfg_.scorer == SCORER_MLP) {
+    cat16_ = A((size_t)ws_rows_ * 2 * Hh * 2);
+    s1_ = A((size_t)ws_rows_ * cfg_.mlp1 * 2);
+    s2_ = (float*)A((size_t)ws_rows_ * cfg_.mlp2 * 4);
+  } else if (cfg_.scorer == SCORER_WEIGHTED_DOT) {
+    t16_ = A((size_t)ws_B_ * Hh * 2);
+    k16_ = A((size_t)ws_rows_ * Hh * 2);
+    pt_ = (float*)A((size_t)ws_B_ * 2 * Hh * 4);
+    pl_ = (float*)A((size_t)ws_rows_ * 2 * Hh * 4);
+    cat16_ = A((size_t)ws_rows_ * 3 * Hh * 2);
+    s2_ = (float*)A((size_t)ws_rows_ * 4 * Hh * 4);
+  }
 }
 
 void DeviceModel::keep(const char* name, const void* src, size_t count) {
@@ -343,10 +374,10 @@ struct ProfScope {
   } while (0)
 
 void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
-                          uint8_t* d_decisions, float threshold) {
+                          uint8_t* d_decisions, float threshold, bool cacheable) {
   if (B * S <= 0) return;
   if (d_ids != ids_) ensure_workspace(B * S, B, C);   // run_host already sized it
-  if (!graphs_on_ || prof_on_ || debug_keep_) {
+  if (!graphs_on_ || prof_on_ || debug_keep_ || !cacheable) {
     forward_eager(d_ids, d_mask, B, S, C, d_logits, d_probs, d_decisions, threshold);
     return;
   }
@@ -411,6 +442,7 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
       const __half* pe = (const __half*)d.pos_exp;
       GLC_LAUNCH(KC_ATTN, attention_toeplitz(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
     }
+    if (cfg_.pooling == POOL_LAST) GLC_LAUNCH(KC_ATTN, pad_rows_mean_v(qkv_, d_mask, ctx_, B, S, H, st));
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
     GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st));
     GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));
@@ -420,18 +452,43 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
   }
   if (C > 0) {
-    GLC_LAUNCH(KC_HEAD_MISC, head_gather(x_, d_ids, cfg_.class_token, pooled_, cls_, B, S, H, C, st));
+    GLC_LAUNCH(KC_HEAD_MISC, head_gather_pool(x_, d_ids, d_mask, cfg_.class_token, cfg_.pooling, pooled_, cls_, B, S, H, C, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, 1, false, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st));
-    GLC_LAUNCH(KC_HEAD_MISC, head_score(tvec_, kvec_, d_logits, d_probs, d_decisions, threshold, B, C, Hh, st));
+    const bool nrm = cfg_.normalize;
+    const float eps = cfg_.norm_eps, ls = nrm ? cfg_.logit_scale : 1.0f;
+    const int R = B * C;
+    if (cfg_.scorer == SCORER_DOT) {
+      GLC_LAUNCH(KC_HEAD_MISC, head_score_ex(tvec_, Hh, kvec_, d_logits, d_probs, d_decisions, threshold, B, C, Hh, nrm, eps, ls,
+                                             0.f, st));
+    } else if (cfg_.scorer == SCORER_MLP) {
+      // cat[t_b | k_bc] -> Linear-ReLU -> Linear-ReLU -> Linear(1)
+      const int m1 = cfg_.mlp1, m2 = cfg_.mlp2;
+      GLC_LAUNCH(KC_HEAD_MISC, head_rows16(tvec_, Hh, C, cat16_, 2 * Hh, 0, R, nrm, eps, st));
+      GLC_LAUNCH(KC_HEAD_MISC, head_rows16(kvec_, Hh, 1, cat16_, 2 * Hh, Hh, R, nrm, eps, st));
+      GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cat16_, 2 * Hh, m1w_, 2 * Hh, m1b_, s1_, m1, R, m1, 2 * Hh, 2, false, num_sms_, st));
+      GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(s1_, m1, m2w_, m1, m2b_, s2_, m2, R, m2, m1, 2, true, num_sms_, st));
+      GLC_LAUNCH(KC_HEAD_MISC, head_score_ex(last_w_, 0, s2_, d_logits, d_probs, d_decisions, threshold, B, C, m2, false, 0.f, ls,
+                                             last_b_ * ls, st));
+    } else {
+      // proj_text / proj_label -> (d, half) -> cat[t0 | l0 | t1*l1] -> Linear-ReLU -> Linear(1)
+      GLC_LAUNCH(KC_HEAD_MISC, head_rows16(tvec_, Hh, 1, t16_, Hh, 0, B, nrm, eps, st));
+      GLC_LAUNCH(KC_HEAD_MISC, head_rows16(kvec_, Hh, 1, k16_, Hh, 0, R, nrm, eps, st));
+      GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(t16_, Hh, ptw_, Hh, ptb_, pt_, 2 * Hh, B, 2 * Hh, Hh, 0, true, num_sms_, st));
+      GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(k16_, Hh, plw_, Hh, plb_, pl_, 2 * Hh, R, 2 * Hh, Hh, 0, true, num_sms_, st));
+      GLC_LAUNCH(KC_HEAD_MISC, head_wdot_combine(pt_, pl_, cat16_, B, C, Hh, st));
+      GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cat16_, 3 * Hh, o1w_, 3 * Hh, o1b_, s2_, 4 * Hh, R, 4 * Hh, 3 * Hh, 2, true, num_sms_, st));
+      GLC_LAUNCH(KC_HEAD_MISC, head_score_ex(last_w_, 0, s2_, d_logits, d_probs, d_decisions, threshold, B, C, 4 * Hh, false, 0.f,
+                                             ls, last_b_ * ls, st));
+    }
   }
   launches_ += n;
 }
 
 void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,
-                           const DecisionOut* dec) {
+                           const DecisionOut* dec, bool cacheable) {
   if (B <= 0 || S <= 0) return;
   static const bool timing = getenv("GLC_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -449,7 +506,7 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
     GLC_CUDA(cudaMemcpyAsync(mask_, mask + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
     const bool want_p = dec && dec->probs, want_d = dec && dec->decisions;
     forward(ids_, mask_, nb, S, C, logits_, want_p ? probs_ : nullptr, want_d ? decisions_ : nullptr,
-            dec ? dec->threshold : 0.5f);
+            dec ? dec->threshold : 0.5f, cacheable);
     if (C > 0) {
       if (logits)
         GLC_CUDA(cudaMemcpyAsync(logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
@@ -466,6 +523,120 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
 }
 
 // ---------------------------------------------------------------------------------------------
+// request coalescing (see engine.h)
+
+void DeviceModel::run_host_coalesced(HostReq& r) {
+  std::unique_lock<std::mutex> lk(qmu_);
+  queue_.push_back(&r);
+  while (!r.done) {
+    if (leader_) {
+      qcv_.wait(lk);
+      continue;
+    }
+    // device idle: lead.  Take requests from the front while the padded group fits one launch.
+    leader_ = true;
+    std::vector<HostReq*> group;
+    int rows = 0, smax = 0;
+    while (!queue_.empty()) {
+      HostReq* q = queue_.front();
+      const int ns = q->S > smax ? q->S : smax;
+      if (!group.empty()) {
+        if ((int64_t)(rows + q->B) * ns > max_tokens_) break;
+        // one threshold per launch: group only requests that agree on the decision epilogue
+        // 'last' pooling reads position S-1, padded or not: its value depends on the batch's padded length
+        if (cfg_.pooling == POOL_LAST && q->S != smax) break;
+        const DecisionOut *a = group[0]->dec, *b = q->dec;
+        if ((a != nullptr) != (b != nullptr) || (a && b && a->threshold != b->threshold)) break;
+      }
+      group.push_back(q);
+      queue_.pop_front();
+      rows += q->B;
+      smax = ns;
+    }
+    lk.unlock();
+    std::exception_ptr err;
+    try {
+      run_group(group);
+    } catch (...) {
+      err = std::current_exception();
+    }
+    lk.lock();
+    for (HostReq* q : group) { q->err = err; q->done = true; }
+    leader_ = false;
+    qcv_.notify_all();
+  }
+  lk.unlock();
+  if (r.err) std::rethrow_exception(r.err);
+}
+
+void DeviceModel::run_group(std::vector<HostReq*>& group) {
+  if (group.size() == 1) {
+    HostReq* q = group[0];
+    run_host(q->ids, q->mask, q->B, q->S, q->C, q->logits, q->dec);
+    return;
+  }
+  int rows = 0, S = 0, C = 0;
+  bool want_l = false, want_p = false, want_d = false;
+  for (HostReq* q : group) {
+    rows += q->B;
+    if (q->S > S) S = q->S;
+    if (q->C > C) C = q->C;
+    want_l |= q->logits != nullptr;
+    want_p |= q->dec && q->dec->probs;
+    want_d |= q->dec && q->dec->decisions;
+  }
+  GLC_CUDA(cudaSetDevice(device_));
+  const size_t tok = (size_t)rows * S, nout = (size_t)rows * C;
+  if (tok > h_tok_) {
+    if (h_ids_) { cudaFreeHost(h_ids_); cudaFreeHost(h_mask_); }
+    h_tok_ = tok > (size_t)max_tokens_ ? tok : (size_t)max_tokens_;
+    GLC_CUDA(cudaMallocHost((void**)&h_ids_, h_tok_ * 8));
+    GLC_CUDA(cudaMallocHost((void**)&h_mask_, h_tok_ * 8));
+  }
+  if (nout > h_rows_) {
+    if (h_logits_) { cudaFreeHost(h_logits_); cudaFreeHost(h_probs_); cudaFreeHost(h_dec_); }
+    h_rows_ = nout * 2;
+    GLC_CUDA(cudaMallocHost((void**)&h_logits_, h_rows_ * 4));
+    GLC_CUDA(cudaMallocHost((void**)&h_probs_, h_rows_ * 4));
+    GLC_CUDA(cudaMallocHost((void**)&h_dec_, h_rows_));
+  }
+  // pad every request to the group's longest sequence: id 0 / mask 0 (tokenizer.c:78-82)
+  int r0 = 0;
+  for (HostReq* q : group) {
+    for (int b = 0; b < q->B; ++b) {
+      int64_t* di = h_ids_ + (size_t)(r0 + b) * S;
+      int64_t* dm = h_mask_ + (size_t)(r0 + b) * S;
+      memcpy(di, q->ids + (size_t)b * q->S, (size_t)q->S * 8);
+      memcpy(dm, q->mask + (size_t)b * q->S, (size_t)q->S * 8);
+      if (q->S < S) {
+        memset(di + q->S, 0, (size_t)(S - q->S) * 8);
+        memset(dm + q->S, 0, (size_t)(S - q->S) * 8);
+      }
+    }
+    r0 += q->B;
+  }
+  DecisionOut d;
+  d.threshold = group[0]->dec ? group[0]->dec->threshold : 0.5f;
+  d.probs = want_p ? h_probs_ : nullptr;
+  d.decisions = want_d ? h_dec_ : nullptr;
+  run_host(h_ids_, h_mask_, rows, S, C, want_l ? h_logits_ : nullptr, (want_p || want_d) ? &d : nullptr, /*cacheable=*/false);
+  // scatter: request i gets its rows, first C_i columns (columns >= C_i only exist because another request of the
+  // group has more labels; columns in [count(b), C_i) are the zero-padded classes the reference also scores)
+  r0 = 0;
+  for (HostReq* q : group) {
+    for (int b = 0; b < q->B; ++b) {
+      const size_t src = (size_t)(r0 + b) * C, dst = (size_t)b * q->C;
+      if (q->logits) memcpy(q->logits + dst, h_logits_ + src, (size_t)q->C * 4);
+      if (q->dec && q->dec->probs) memcpy(q->dec->probs + dst, h_probs_ + src, (size_t)q->C * 4);
+      if (q->dec && q->dec->decisions) memcpy(q->dec->decisions + dst, h_dec_ + src, (size_t)q->C);
+    }
+    r0 += q->B;
+  }
+  merged_groups_ += 1;
+  merged_requests_ += group.size();
+}
+
+// ---------------------------------------------------------------------------------------------
 
 Model::Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens) {
   ModelWeights w;
@@ -473,6 +644,17 @@ Model::Model(const std::string& onnx_path, const std::vector<int>& devices, int 
   cfg_ = w.cfg;
   if (devices.empty()) throw std::runtime_error("no CUDA device selected");
   for (int d : devices) devs_.emplace_back(new DeviceModel(d, w, max_tokens));
+  const char* co = getenv("GLC_COALESCE");
+  coalesce_ = !(co && co[0] == '0');
+  coalesce_tokens_ = (max_tokens > 0 ? max_tokens : 65536) / 2;
+  if (const char* ct = getenv("GLC_COALESCE_TOKENS")) coalesce_tokens_ = atoi(ct);
+}
+
+void Model::coalesce_stats(uint64_t* groups, uint64_t* requests) const {
+  uint64_t g = 0, r = 0;
+  for (auto& d : devs_) { g += d->merged_groups(); r += d->merged_requests(); }
+  if (groups) *groups = g;
+  if (requests) *requests = r;
 }
 
 int Model::num_classes(const int64_t* ids, int B, int S) const {
@@ -498,7 +680,13 @@ void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, fl
     // small call (the reference's BATCH_SIZE=8 Run): whole batch on one device, round robin
     // across concurrent callers (the OpenMP loop of main.c:141-150)
     const int slot = (int)(rr_.fetch_add(1) % (uint32_t)G);
-    devs_[slot]->run_host(ids, mask, B, S, C, logits, dec);
+    if (coalesce_ && (int64_t)B * S <= coalesce_tokens_) {
+      DeviceModel::HostReq r;
+      r.ids = ids; r.mask = mask; r.B = B; r.S = S; r.C = C; r.logits = logits; r.dec = dec;
+      devs_[slot]->run_host_coalesced(r);
+    } else {
+      devs_[slot]->run_host(ids, mask, B, S, C, logits, dec);
+    }
     return;
   }
   // large call: contiguous row shards, one host thread per device, host gather into `logits`

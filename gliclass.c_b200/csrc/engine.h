@@ -7,6 +7,9 @@
 #include <cuda_runtime.h>
 
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <exception>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -53,11 +56,30 @@ class DeviceModel {
 
   // device-resident inputs; logits fp32 [B,C] on device.  Enqueues on stream(); no sync.
   void forward(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs = nullptr,
-               uint8_t* d_decisions = nullptr, float threshold = 0.5f);
+               uint8_t* d_decisions = nullptr, float threshold = 0.5f, bool cacheable = true);
   // host buffers: rows [0,B) of ids/mask, writes logits rows [0,B) (width C); micro-batches by
   // max_tokens; synchronises before returning.  Serialised per device by `mu`.
   void run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,
-                const DecisionOut* dec = nullptr);
+                const DecisionOut* dec = nullptr, bool cacheable = true);
+
+  // Request coalescing: the reference calls Run from its OpenMP workers with BATCH_SIZE=8
+  // batches (main.c:141-150), each far too small to fill a B200.  Concurrent callers queue here; whichever
+  // caller finds the device idle becomes the leader, takes every queued request that fits max_tokens, pads
+  // them to the longest sequence of the group (pad id 0 / mask 0, exactly what tokenizer.c:78-82 does inside
+  // a batch), runs ONE forward and scatters each request's rows [B_i, C_i] back.  A lone caller runs directly
+  // from its own buffers (no copy, no thread hand-off).
+  struct HostReq {
+    const int64_t* ids = nullptr;
+    const int64_t* mask = nullptr;
+    int B = 0, S = 0, C = 0;
+    float* logits = nullptr;
+    const DecisionOut* dec = nullptr;
+    bool done = false;
+    std::exception_ptr err;
+  };
+  void run_host_coalesced(HostReq& r);
+  uint64_t merged_groups() const { return merged_groups_.load(); }
+  uint64_t merged_requests() const { return merged_requests_.load(); }
 
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
@@ -71,6 +93,7 @@ class DeviceModel {
 
  private:
   void ensure_workspace(int tokens, int B, int C);
+  void run_group(std::vector<HostReq*>& group);
   void forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
                      uint8_t* d_decisions, float threshold);
   const int32_t* rel_table(int S);
@@ -94,6 +117,11 @@ class DeviceModel {
   std::vector<DeviceLayer> layers_;
   void *t1w_ = nullptr, *t2w_ = nullptr, *c1w_ = nullptr, *c2w_ = nullptr;
   float *t1b_ = nullptr, *t2b_ = nullptr, *c1b_ = nullptr, *c2b_ = nullptr;
+  // scorer variants: MLP (m1 -> m2 -> m3) or weighted dot (pt, pl projections; o1 -> o2)
+  void *m1w_ = nullptr, *m2w_ = nullptr, *ptw_ = nullptr, *plw_ = nullptr, *o1w_ = nullptr;
+  float *m1b_ = nullptr, *m2b_ = nullptr, *ptb_ = nullptr, *plb_ = nullptr, *o1b_ = nullptr;
+  float* last_w_ = nullptr;     // fp32 weight row of the final Linear(K -> 1)
+  float last_b_ = 0.f;
   std::map<int, int32_t*> rel_tables_;   // keyed by Spad
 
   // workspace
@@ -105,6 +133,8 @@ class DeviceModel {
   void *pooled_ = nullptr, *cls_ = nullptr, *tmid_ = nullptr, *cmid_ = nullptr;
   float *tvec_ = nullptr, *kvec_ = nullptr, *logits_ = nullptr, *probs_ = nullptr;
   uint8_t* decisions_ = nullptr;
+  void *cat16_ = nullptr, *s1_ = nullptr, *t16_ = nullptr, *k16_ = nullptr;   // scorer-variant scratch
+  float *s2_ = nullptr, *pt_ = nullptr, *pl_ = nullptr;
   std::vector<void*> ws_allocs_, perm_allocs_;
   std::map<std::string, DebugBuf> debug_;
   // CUDA graphs of the forward, one per (shape, buffer set): the kernel sequence of a forward is fixed,
@@ -122,6 +152,16 @@ class DeviceModel {
   std::map<GraphKey, GraphEntry> graphs_;
   bool graphs_on_ = true;
   void drop_graphs();
+  // coalescing queue + pinned staging of merged groups (touched only by the current leader)
+  std::mutex qmu_;
+  std::condition_variable qcv_;
+  std::deque<HostReq*> queue_;
+  bool leader_ = false;
+  int64_t *h_ids_ = nullptr, *h_mask_ = nullptr;
+  float *h_logits_ = nullptr, *h_probs_ = nullptr;
+  uint8_t* h_dec_ = nullptr;
+  size_t h_tok_ = 0, h_rows_ = 0;
+  std::atomic<uint64_t> merged_groups_{0}, merged_requests_{0};
   // profiler state
   struct ProfRec { int cat; cudaEvent_t a, b; };
   bool prof_on_ = false;
@@ -138,6 +178,7 @@ class Model {
   void run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits, const DecisionOut* dec = nullptr);
   const ModelConfig& cfg() const { return cfg_; }
   int num_devices() const { return (int)devs_.size(); }
+  void coalesce_stats(uint64_t* groups, uint64_t* requests) const;
   DeviceModel& dev(int slot) { return *devs_[slot]; }
   uint64_t launches() const;
 
@@ -145,6 +186,8 @@ class Model {
   ModelConfig cfg_;
   std::vector<std::unique_ptr<DeviceModel>> devs_;
   std::atomic<uint32_t> rr_{0};
+  bool coalesce_ = true;        // GLC_COALESCE=0 disables
+  int coalesce_tokens_ = 0;     // requests up to this many tokens go through the coalescing queue
 };
 
 int usable_device_count();   // sm_100 devices; 0 when there is no driver / GPU

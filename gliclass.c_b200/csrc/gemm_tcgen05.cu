@@ -95,6 +95,10 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
   }
+  if (ACT == 2) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
   if (row < M) {
     if (OUT_F32) {
       float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + n;
@@ -152,6 +156,10 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n
     if (ACT == 1) {
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+    }
+    if (ACT == 2) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
     // the bulk store that last read this staging buffer must have finished reading it
     if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
@@ -314,23 +322,24 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
 //   tfull[a]  (both copies)    <- multicast tcgen05.commit: accumulator a complete
 //   tempty[a] (leader's copy)  <- epilogue warps of both CTAs
 // ---------------------------------------------------------------------------------------------
+template <int BN_>
 struct Gemm2Cfg {
-  static constexpr int BN = 256;            // cluster tile N; per CTA B half = 128 rows
+  static constexpr int BN = BN_;            // cluster tile N (256, or 192 where that quantises better); per CTA B half = BN/2 rows
   static constexpr int STAGES = 6;
   static constexpr int A_BYTES = BM * BK * 2;
-  static constexpr int B_BYTES = 128 * BK * 2;
+  static constexpr int B_BYTES = (BN / 2) * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_BYTES = 32768;   // TMA-store staging: 2 KB buffers, split over the epilogue warps
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_BYTES + 256 + 1024;
-  static constexpr uint32_t TMEM_COLS = 512;   // two 256-column accumulators
+  static constexpr uint32_t TMEM_COLS = 512;   // two BN-column accumulators
 };
 
-template <int ACT, bool OUT_F32>
+template <int BN_, int ACT, bool OUT_F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
 gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                      const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias, void* __restrict__ Cout,
                      int64_t ldc, int M, int N, int K) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<BN_>;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -378,7 +387,7 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
     uint32_t ph = 0;
     for (int tile = cl; tile < tiles; tile += ncl) {
       const int m0 = (tile / num_n) * (2 * BM) + (int)rank * BM;
-      const int n0 = (tile % num_n) * BN + (int)rank * 128;
+      const int n0 = (tile % num_n) * BN + (int)rank * (BN / 2);
       for (int kb = 0; kb < num_k; ++kb) {
         ptx::mbar_wait(&empty[s], ph ^ 1);
         if (ptx::elect_one()) {
@@ -459,16 +468,16 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   }
 }
 
-template <int ACT, bool OUT_F32>
+template <int BN_, int ACT, bool OUT_F32>
 cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
                              int M, int N, int K, int num_sms, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<BN_>;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t sa[1] = {(uint64_t)lda * 2};
   uint32_t ba[2] = {BK, BM};
   uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
   uint64_t sw[1] = {(uint64_t)ldw * 2};
-  uint32_t bw[2] = {BK, 128};
+  uint32_t bw[2] = {BK, (uint32_t)(Cfg::BN / 2)};
   CUtensorMap tm_a = make_tmap_16b(A, 2, da, sa, ba);
   CUtensorMap tm_w = make_tmap_16b(W, 2, dw, sw, bw);
   CUtensorMap tm_c = tm_a;   // unused by the fp32-output instantiation
@@ -478,7 +487,7 @@ cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t 
     uint32_t bc[2] = {32, 32};
     tm_c = make_tmap_16b(C, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
   }
-  auto kern = gemm_f16_2cta_kernel<ACT, OUT_F32>;
+  auto kern = gemm_f16_2cta_kernel<BN_, ACT, OUT_F32>;
   static bool attr_set[64] = {};
   int dev = 0;
   cudaGetDevice(&dev);
@@ -532,23 +541,36 @@ cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, con
   // 128x256 tiles when that still fills the machine; otherwise 128x128 (more tiles, less tail)
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
   const bool wide = (N % 256 == 0) && tiles256 >= num_sms;
+  if (act < 0 || act > 2) return cudaErrorInvalidValue;
   if (out_f32) {
     if (act == 0) return launch_gemm<128, 0, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    if (act == 1) return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    return launch_gemm<128, 2, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
   }
   // CTA pairs (256 x 256 cluster tiles) whenever they fill the machine
   const int tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
   static const bool no_pairs = getenv("GLC_GEMM_NO_PAIRS") != nullptr;
   if (!no_pairs && tiles2 >= num_sms / 2 && N >= 256) {
-    if (act == 0) return launch_gemm_2cta<0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    return launch_gemm_2cta<1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    // 256 x 192 cluster tiles when they quantise into clearly fewer column-rounds (N = 768: 7 rounds of 192 instead of
+    // 6 of 256 per cluster, -12.5 %); a narrower tile re-reads A more often, so it has to win by > 5 %
+    static const bool no_192 = getenv("GLC_GEMM_NO_192") != nullptr;
+    const int ncl = num_sms / 2, mt = (M + 255) / 256;
+    const int64_t cost256 = (int64_t)((mt * ((N + 255) / 256) + ncl - 1) / ncl) * 256;
+    const int64_t cost192 = (int64_t)((mt * ((N + 191) / 192) + ncl - 1) / ncl) * 192;
+    if (!no_192 && act == 0 && N % 192 == 0 && cost192 * 100 < cost256 * 95)
+      return launch_gemm_2cta<192, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    if (act == 0) return launch_gemm_2cta<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    if (act == 1) return launch_gemm_2cta<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    return launch_gemm_2cta<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
   }
   if (wide) {
     if (act == 0) return launch_gemm<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    return launch_gemm<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    if (act == 1) return launch_gemm<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    return launch_gemm<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
   }
   if (act == 0) return launch_gemm<128, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-  return launch_gemm<128, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+  if (act == 1) return launch_gemm<128, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+  return launch_gemm<128, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
 }
 
 }  // namespace glc

@@ -10,7 +10,7 @@ namespace glc {
 // fp16 rather than bf16 because bf16's 8-bit mantissa cannot meet the 2e-2 logit parity bar on
 // this model family (DESIGN.md "Numerics").
 //
-// K2: C[M,N] = act(A[M,K] W[N,K]^T + bias); A, W fp16, fp32 accumulate; C fp16 or fp32.
+// K2: C[M,N] = act(A[M,K] W[N,K]^T + bias); A, W fp16, fp32 accumulate; C fp16 or fp32.  act: 0 none, 1 erf-GELU, 2 ReLU.
 cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
                      int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream);
 
@@ -49,9 +49,27 @@ cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_
                             const uint32_t* mask_bits, void* ctx, int B, int S, int heads, int buckets,
                             cudaStream_t stream);
 
+// context of padded QUERY rows as the traced graph computes it (uniform softmax over all S keys = mean of V);
+// only needed when something reads padded positions (pooling_strategy='last' on right-padded batches)
+cudaError_t pad_rows_mean_v(const void* qkv_f16, const int64_t* mask, void* ctx_f16, int B, int S, int H, cudaStream_t stream);
+
 // K5a: <<LABEL>>-token pooling.  pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] or 0  
 cudaError_t head_gather(const void* h_f16, const int64_t* ids, int64_t class_token, void* pooled_f16, void* cls_f16,
                         int B, int S, int H, int C, cudaStream_t stream);
+// K5a with the pooling strategies of the gliclass package: pool_mode 0 first token, 1 last token (h[b,S-1,:]),
+// 2 masked mean, 3 masked max over the sequence (mask required for 2/3)
+cudaError_t head_gather_pool(const void* h_f16, const int64_t* ids, const int64_t* mask, int64_t class_token, int pool_mode,
+                             void* pooled_f16, void* cls_f16, int B, int S, int H, int C, cudaStream_t stream);
+// K5b generalised: logits[b,c] = scale * <t[b*t_stride..], k[b,c,:]> / ((|t|+eps)(|k|+eps) if normalize) + bias, then the
+// sigmoid / strict-threshold epilogue.  t_stride = 0: shared weight row (last Linear(K->1) of the MLP scorers).
+cudaError_t head_score_ex(const float* t, int64_t t_stride, const float* k, float* logits, float* probs, uint8_t* decisions,
+                          float threshold, int B, int C, int K, bool normalize, float eps, float scale, float bias,
+                          cudaStream_t stream);
+// fp32 rows (row r reads src row r / rep) -> fp16 at dst[r*ld_dst + col0 ..], optional x / (|x| + eps)
+cudaError_t head_rows16(const float* src, int K, int rep, void* dst_f16, int64_t ld_dst, int col0, int rows, bool normalize,
+                        float eps, cudaStream_t stream);
+// weighted-dot scorer: cat[row] = [pt0_b | pl0_row | pt1_b * pl1_row] from (d, half)-interleaved projections
+cudaError_t head_wdot_combine(const float* pt, const float* pl, void* cat_f16, int B, int C, int Hh, cudaStream_t stream);
 // K5b: logits[b,c] = <t[b,:], k[b,c,:]> (+ optional sigmoid / threshold decisions)
 cudaError_t head_score(const float* t, const float* k, float* logits, float* probs, uint8_t* decisions, float threshold,
                        int B, int C, int Hh, cudaStream_t stream);

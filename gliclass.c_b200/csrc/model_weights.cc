@@ -3,6 +3,8 @@
 //   layer.<l>.{q,k,v,o}.w [H,H]  .b [H]   layer.<l>.ln1.g/b
 //   layer.<l>.ffn1.w [I,H] .b [I]  layer.<l>.ffn2.w [H,I] .b [H]  layer.<l>.ln2.g/b
 //   text.1.w [Hh,H] text.1.b  text.2.w [Hh,Hh] text.2.b   cls.1.* cls.2.*  (FeaturesProjector x2)
+//   scorer.mlp.{0,2,4}.w/b (MLP scorer)   scorer.pt / scorer.pl [2Hh,Hh], scorer.o1 [4Hh,3Hh], scorer.o2 [1,4Hh]
+//   (weighted-dot scorer); logit_scale is a config scalar
 // Naming facts relied on (verified on a real torch export):
 //   * 3-D-input nn.Linear -> MatMul(x, anonymous [in,out] initializer) + Add(named bias)
 //   * 2-D-input nn.Linear -> Gemm(x, W[out,in], b) with transB=1
@@ -227,9 +229,82 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
   load_linear(g, "/classes_projector/linear_1", "cls.1", out);
   load_linear(g, "/classes_projector/linear_2", "cls.2", out);
   c.head_hidden = (int)out->at("text.2.w").dims[0];
+  int64_t Hh_ = c.head_hidden;
+  // pooling strategy: whatever produces the input of text_projector.linear_1
+  {
+    const OnnxNode* l1 = find_node(g, "/text_projector/linear_1/Gemm", "Gemm");
+    if (!l1) l1 = find_node(g, "/text_projector/linear_1/MatMul", "MatMul");
+    const OnnxNode* src = nullptr;
+    if (l1) {
+      auto pit = g.producer_of.find(l1->inputs[0]);
+      if (pit != g.producer_of.end()) src = &g.nodes[pit->second];
+    }
+    if (!src) throw std::runtime_error("onnx: cannot find what feeds text_projector.linear_1");
+    int64_t gi = 0;
+    if (src->op_type == "Gather" && src->inputs.size() == 2 && g.scalar_int(src->inputs[1], &gi) && (gi == 0 || gi == -1)) {
+      c.pooling = gi == 0 ? POOL_FIRST : POOL_LAST;
+    } else if (src->op_type == "ReduceMax") {
+      c.pooling = POOL_MAX;
+    } else if (src->op_type == "Div") {
+      auto pit = g.producer_of.find(src->inputs[0]);
+      if (pit == g.producer_of.end() || g.nodes[pit->second].op_type != "ReduceSum")
+        throw std::runtime_error("onnx: unsupported pooling (Div not fed by ReduceSum) at " + src->name);
+      c.pooling = POOL_AVG;
+    } else {
+      throw std::runtime_error("onnx: unsupported pooling strategy (" + src->op_type + " at " + src->name +
+                               "); supported: first, last, avg, max");
+    }
+  }
+  // feature normalisation: ReduceL2 -> Add(eps) -> Div on both features, logits * logit_scale
+  {
+    int n_l2 = 0;
+    for (auto& n : g.nodes) {
+      if (n.op_type != "ReduceL2") continue;
+      ++n_l2;
+      for (auto& m : g.nodes) {
+        float e;
+        if (m.op_type == "Add" && m.inputs.size() == 2 && m.inputs[0] == n.outputs[0] && g.scalar_float(m.inputs[1], &e) &&
+            e >= 0.f && e < 1e-3f)
+          c.norm_eps = e;
+      }
+    }
+    const OnnxTensor* ls = find_named(g, "logit_scale");
+    if (n_l2 == 2 && ls && ls->numel() == 1) {
+      c.normalize = true;
+      tensor_to_float(*ls, &c.logit_scale);
+    } else if (n_l2 != 0 || ls) {
+      throw std::runtime_error("onnx: unrecognised feature normalisation (ReduceL2 count " + std::to_string(n_l2) + ")");
+    }
+  }
+  // scorer
   bool has_einsum = false;
   for (auto& n : g.nodes) if (n.op_type == "Einsum") has_einsum = true;
-  if (!has_einsum) throw std::runtime_error("onnx: dot scorer (Einsum) not found; only scorer_type='simple' is supported");
+  if (find_node(g, "/scorer/mlp/mlp.0/MatMul") || find_node(g, "/scorer/mlp/mlp.0/Gemm")) {
+    c.scorer = SCORER_MLP;
+    load_linear(g, "/scorer/mlp/mlp.0", "scorer.mlp.0", out);
+    load_linear(g, "/scorer/mlp/mlp.2", "scorer.mlp.2", out);
+    load_linear(g, "/scorer/mlp/mlp.4", "scorer.mlp.4", out);
+    c.mlp1 = (int)out->at("scorer.mlp.0.w").dims[0];
+    c.mlp2 = (int)out->at("scorer.mlp.2.w").dims[0];
+    if (out->at("scorer.mlp.0.w").dims[1] != 2 * Hh_ || out->at("scorer.mlp.2.w").dims[1] != c.mlp1 ||
+        out->at("scorer.mlp.4.w").dims != std::vector<int64_t>{1, (int64_t)c.mlp2} || c.mlp1 % 8 || c.mlp2 % 8)
+      throw std::runtime_error("onnx: unexpected MLP scorer shapes");
+  } else if (find_node(g, "/scorer/proj_text/MatMul") || find_node(g, "/scorer/proj_text/Gemm")) {
+    c.scorer = SCORER_WEIGHTED_DOT;
+    load_linear(g, "/scorer/proj_text", "scorer.pt", out);
+    load_linear(g, "/scorer/proj_label", "scorer.pl", out);
+    load_linear(g, "/scorer/out_mlp/out_mlp.0", "scorer.o1", out);
+    load_linear(g, "/scorer/out_mlp/out_mlp.3", "scorer.o2", out);
+    if (out->at("scorer.pt.w").dims != std::vector<int64_t>{2 * Hh_, Hh_} ||
+        out->at("scorer.pl.w").dims != std::vector<int64_t>{2 * Hh_, Hh_} ||
+        out->at("scorer.o1.w").dims != std::vector<int64_t>{4 * Hh_, 3 * Hh_} ||
+        out->at("scorer.o2.w").dims != std::vector<int64_t>{1, 4 * Hh_})
+      throw std::runtime_error("onnx: unexpected weighted-dot scorer shapes");
+  } else if (has_einsum) {
+    c.scorer = SCORER_DOT;
+  } else {
+    throw std::runtime_error("onnx: scorer not recognised (expected Einsum dot, /scorer/mlp or /scorer/proj_text)");
+  }
 
   // ---- shape checks
   auto expect = [&](const std::string& role, std::vector<int64_t> d) {

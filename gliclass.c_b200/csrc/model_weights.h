@@ -1,5 +1,5 @@
 // Role mapping: ONNX graph -> named fp32 host tensors of the GLiClass uni-encoder
-// (DeBERTa-v3 backbone + projector/dot-scorer head).  This is the "weights" half of what ORT's
+// (DeBERTa-v3 backbone + projector head with dot / MLP / weighted-dot scorer).  This is the "weights" half of what ORT's
 // CreateSession does for the reference (src/model.c:269); the graph structure itself is not
 // executed — the engine hard-codes the architecture.
 #pragma once
@@ -22,7 +22,16 @@ struct ModelConfig {
   int max_rel_pos = 512;        // max_position in make_log_bucket_position
   float ln_eps = 1e-7f;
   int64_t class_token = -1;     // <<LABEL>> id: Constant feeding Equal(input_ids, .)
+  // head variant, detected from the graph structure
+  int pooling = 0;              // POOL_*: what feeds text_projector.linear_1
+  int scorer = 0;               // SCORER_*
+  bool normalize = false;       // ReduceL2 on both features + logits * logit_scale
+  float norm_eps = 1e-8f;       // x / (|x| + eps)
+  float logit_scale = 1.0f;
+  int mlp1 = 0, mlp2 = 0;       // MLP scorer widths (cat[t,l] -> mlp1 -> mlp2 -> 1)
 };
+enum { POOL_FIRST = 0, POOL_LAST = 1, POOL_AVG = 2, POOL_MAX = 3 };
+enum { SCORER_DOT = 0, SCORER_MLP = 1, SCORER_WEIGHTED_DOT = 2 };
 
 // Linear weights are stored [out, in] row-major (torch Linear layout == the K-major "B"
 // operand of the tcgen05 GEMM); ONNX MatMul initializers ([in, out]) are transposed on load.

@@ -47,6 +47,11 @@ typedef struct glc_info {
   int64_t class_token;
   int32_t num_devices;
   int32_t weight_dtype;
+  /* head variant detected from the graph (gliclass config: pooling_strategy, scorer_type, normalize_features) */
+  int32_t pooling;             /* 0 first, 1 last, 2 avg (masked mean), 3 max (masked) */
+  int32_t scorer;              /* 0 simple (dot), 1 mlp, 2 weighted-dot */
+  int32_t normalize_features;  /* features x / (|x| + eps), logits * logit_scale */
+  float logit_scale;
 } glc_info;
 
 GLC_API const char* glc_last_error(void);
@@ -77,6 +82,23 @@ GLC_API int glc_run(glc_model* m, const int64_t* input_ids, const int64_t* atten
 GLC_API int glc_run_decisions(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
                               float threshold, float* logits_out /*nullable*/, float* probs_out /*nullable*/,
                               uint8_t* decisions_out /*nullable*/, size_t capacity, int* C_out);
+
+/* ---- asynchronous submit / collect and request coalescing --------------------
+ * The reference runs three barriered phases (main.c:116 -> 141 -> 153) and calls Run with BATCH_SIZE=8
+ * batches from its OpenMP workers; a B200 needs ~32k tokens per launch.  Two remedies, both behind the
+ * same results:
+ *  (1) coalescing, on by default (GLC_COALESCE=0 disables): concurrent glc_run / Run callers whose request
+ *      is <= GLC_COALESCE_TOKENS (default max_tokens/2) tokens are merged into one padded forward per device
+ *      and scattered back; a lone caller pays nothing.  glc_coalesce_stats counts merged launches/requests.
+ *  (2) glc_submit returns at once (C is known from the ids, so the caller can size / slice its buffer);
+ *      the inputs and logits_out must stay valid until glc_collect(ticket), which waits, frees the ticket
+ *      and returns the status.  glc_poll: 1 = finished, 0 = still running. */
+typedef struct glc_ticket glc_ticket;
+GLC_API glc_ticket* glc_submit(glc_model* m, const int64_t* input_ids, const int64_t* attention_mask, int B, int S,
+                               float* logits_out, size_t logits_capacity, int* C_out);
+GLC_API int glc_poll(glc_ticket* t);
+GLC_API int glc_collect(glc_ticket* t);
+GLC_API int glc_coalesce_stats(const glc_model* m, uint64_t* merged_launches, uint64_t* merged_requests);
 
 /* Same forward with inputs/outputs already resident on `device` (kernel-only timing, parity
  * tests).  d_logits fp32 [B,C] device memory with C = num_classes (caller computes it with
@@ -124,7 +146,7 @@ GLC_API int glc_rel_index_table(int S, int buckets, int max_pos, int32_t* out /*
  * return after launch (no sync).  These are the K1..K5 kernels of the forward (csrc/kernels.h). */
 
 /* K2: C[M,N] = act(A[M,K] * W[N,K]^T + bias[N]); A, W fp16, fp32 accumulate in TMEM (tcgen05 +
- * TMA).  act: 0 none, 1 erf-GELU.  out_f32: C is fp32 instead of fp16.  ld* in elements. */
+ * TMA).  act: 0 none, 1 erf-GELU, 2 ReLU.  out_f32: C is fp32 instead of fp16.  ld* in elements. */
 GLC_API int glc_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
                         int M, int N, int K, int act, int out_f32, void* stream);
 /* K1: y[m,:] = (LN(word_emb[ids[m],:]) * gamma + beta) * (mask[m] != 0) */

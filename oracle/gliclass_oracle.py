@@ -150,18 +150,22 @@ def forward_restated(w: dict, cfg: ArchConfig, input_ids: torch.Tensor, attentio
                 w[p + "output.LayerNorm.weight"], w[p + "output.LayerNorm.bias"], eps)
         inter[f"h{l}"] = x
 
-    logits = head_restated(w, cfg, x, input_ids)
+    logits = head_restated(w, cfg, x, input_ids, attention_mask)
     if return_intermediates:
         return logits, inter
     return logits
 
 
 @torch.no_grad()
-def head_restated(w: dict, cfg: ArchConfig, hseq: torch.Tensor, input_ids: torch.Tensor) -> torch.Tensor:
+def head_restated(w: dict, cfg: ArchConfig, hseq: torch.Tensor, input_ids: torch.Tensor,
+                  attention_mask: torch.Tensor | None = None) -> torch.Tensor:
     """GLiClass uni-encoder head (`gliclass` package, not installed -> unpinned).
 
     class rows = hidden state at each <<LABEL>> position (embed_class_token=True), zero rows for
-    c >= count(b); text = first-token pool; both through Linear-GELU-Linear; dot scorer.
+    c >= count(b); text = pooled sequence (first / last token, masked mean, masked max); both through
+    Linear-GELU-Linear; optional L2 normalisation (x / (|x| + 1e-8)) and logit_scale; scorer = dot
+    (einsum BD,BCD->BC), MLP (cat[t,l] -> 256 -> 128 -> 1, ReLU) or weighted dot (proj to (Hh,2)
+    halves, cat[t0, l0, t1*l1] -> 4Hh -> 1, ReLU).
     """
     B, S, H = hseq.shape
     m = input_ids == cfg.class_token_index
@@ -171,16 +175,46 @@ def head_restated(w: dict, cfg: ArchConfig, hseq: torch.Tensor, input_ids: torch
     for b in range(B):
         pos = torch.nonzero(m[b]).flatten()
         cls[b, : len(pos)] = hseq[b, pos]
-    pooled = hseq[:, 0, :]
+    if cfg.pooling_strategy == "first":
+        pooled = hseq[:, 0, :]
+    elif cfg.pooling_strategy == "last":
+        pooled = hseq[:, S - 1, :]
+    else:
+        am = attention_mask.to(hseq.dtype)
+        pooled = torch.zeros(B, H, dtype=hseq.dtype)
+        for b in range(B):
+            valid = hseq[b][am[b] != 0]
+            pooled[b] = valid.sum(0) / am[b].sum() if cfg.pooling_strategy == "avg" else valid.max(0)[0]
+
+    def lin(t, name):
+        return t @ w[name + ".weight"].T + w[name + ".bias"]
 
     def proj(t, name):
-        t = t @ w[f"model.{name}.linear_1.weight"].T + w[f"model.{name}.linear_1.bias"]
-        t = _gelu(t)
-        return t @ w[f"model.{name}.linear_2.weight"].T + w[f"model.{name}.linear_2.bias"]
+        return lin(_gelu(lin(t, f"model.{name}.linear_1")), f"model.{name}.linear_2")
 
     t = proj(pooled, "text_projector")          # [B,Hh]
     kcls = proj(cls, "classes_projector")       # [B,C,Hh]   (zero rows still get the biases)
-    return torch.einsum("bd,bcd->bc", t, kcls)
+    if cfg.normalize_features:
+        t = t / (torch.sqrt((t * t).sum(-1, keepdim=True)) + 1e-8)
+        kcls = kcls / (torch.sqrt((kcls * kcls).sum(-1, keepdim=True)) + 1e-8)
+    if cfg.scorer_type == "simple":
+        logits = torch.einsum("bd,bcd->bc", t, kcls)
+    elif cfg.scorer_type == "mlp":
+        cat = torch.cat([t[:, None, :].expand(B, C, -1), kcls], -1)
+        h1 = torch.relu(lin(cat, "model.scorer.mlp.0"))
+        h2 = torch.relu(lin(h1, "model.scorer.mlp.2"))
+        logits = lin(h2, "model.scorer.mlp.4")[..., 0]
+    else:
+        pt = lin(t, "model.scorer.proj_text")            # [B,2Hh], interleaved (d, half)
+        pl = lin(kcls, "model.scorer.proj_label")        # [B,C,2Hh]
+        t0, t1 = pt[:, None, 0::2].expand(B, C, -1), pt[:, None, 1::2].expand(B, C, -1)
+        l0, l1 = pl[..., 0::2], pl[..., 1::2]
+        cat = torch.cat([t0, l0, t1 * l1], -1)
+        h1 = torch.relu(lin(cat, "model.scorer.out_mlp.0"))
+        logits = lin(h1, "model.scorer.out_mlp.3")[..., 0]
+    if cfg.normalize_features:
+        logits = logits * w["model.logit_scale"]
+    return logits
 
 
 # --------------------------------------------------------------------------------------------

@@ -154,3 +154,34 @@ def test_unchanged_reference_sources_link_against_shim(pkg):
     assert "OrtGetApiBase" in syms
     r = subprocess.run([exe], capture_output=True, text=True)
     assert "Usage:" in r.stdout
+
+
+HEAD_VARIANTS = {
+    "mlp_max": dict(scorer_type="mlp", pooling_strategy="max"),
+    "wdot_avg_norm": dict(scorer_type="weighted-dot", pooling_strategy="avg", normalize_features=True),
+    "dot_last_norm": dict(pooling_strategy="last", normalize_features=True),
+}
+
+
+@pytest.mark.parametrize("variant", sorted(HEAD_VARIANTS))
+def test_onnx_reader_detects_head_variant(pkg, orc, model_cache, variant):
+    """pooling strategy / scorer type / feature normalisation are read off the graph structure (the
+    reference's onnx/config.json, convert_to_onnx.py:19-28, does not carry them) and the scorer weights
+    come back bit-exact under their roles."""
+    kw = HEAD_VARIANTS[variant]
+    cfg, w = orc.make_model_file("tiny", os.path.join(model_cache, f"tiny_{variant}.onnx"), **kw)
+    f = pkg.OnnxFile(os.path.join(model_cache, f"tiny_{variant}.onnx"))
+    i = f.info
+    assert i["pooling"] == {"first": 0, "last": 1, "avg": 2, "max": 3}[cfg.pooling_strategy]
+    assert i["scorer"] == {"simple": 0, "mlp": 1, "weighted-dot": 2}[cfg.scorer_type]
+    assert i["normalize_features"] == int(cfg.normalize_features)
+    if cfg.normalize_features:
+        assert i["logit_scale"] == np.float32(w["model.logit_scale"].item())
+    roles = {"mlp": {"scorer.mlp.0": "model.scorer.mlp.0", "scorer.mlp.2": "model.scorer.mlp.2", "scorer.mlp.4": "model.scorer.mlp.4"},
+             "weighted-dot": {"scorer.pt": "model.scorer.proj_text", "scorer.pl": "model.scorer.proj_label",
+                              "scorer.o1": "model.scorer.out_mlp.0", "scorer.o2": "model.scorer.out_mlp.3"},
+             "simple": {}}[cfg.scorer_type]
+    for role, name in roles.items():
+        assert np.array_equal(f.tensor(role + ".w"), w[name + ".weight"].numpy()), role
+        assert np.array_equal(f.tensor(role + ".b"), w[name + ".bias"].numpy()), role
+    f.close()

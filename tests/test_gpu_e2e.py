@@ -300,3 +300,94 @@ def test_unchanged_reference_binary_end_to_end(pkg, orc, tmp_path):
                 else:
                     assert lab not in got[t], f"spurious decision {lab} for text {b0 + r_i}"
     assert n_checked > 50
+
+
+@pytest.mark.parametrize("variant", ["mlp_max", "wdot_avg_norm", "dot_last_norm", "mlp_first_norm", "wdot_first"])
+def test_head_variants(pkg, orc, model_cache, variant):
+    """the other pooling strategies / scorers of the gliclass head (first|last|avg|max pooling,
+    simple|mlp|weighted-dot scorer, normalize_features + logit_scale) against the oracle, ragged batch with
+    mixed label counts, plus the fused sigmoid/threshold epilogue on the scorer's last kernel"""
+    kw = {"mlp_max": dict(scorer_type="mlp", pooling_strategy="max"),
+          "wdot_avg_norm": dict(scorer_type="weighted-dot", pooling_strategy="avg", normalize_features=True),
+          "dot_last_norm": dict(pooling_strategy="last", normalize_features=True),
+          "mlp_first_norm": dict(scorer_type="mlp", normalize_features=True),
+          "wdot_first": dict(scorer_type="weighted-dot")}[variant]
+    path = os.path.join(model_cache, f"tiny_{variant}.onnx")
+    cfg, w = orc.make_model_file("tiny", path, **kw)
+    ids, mask = orc.synth_inputs(cfg, 6, 200, [4, 2, 3, 1, 4, 5], seed=77, ragged=True)
+    ref = orc.forward_restated(w, cfg, ids, mask).numpy()
+    s = pkg.Session(path)
+    try:
+        out = s.run_inference(ids.numpy(), mask.numpy())
+        _check_logits(f"tiny/{variant}", out, ref, orc)
+        lg, pr, dec = s.run_decisions(ids.numpy(), mask.numpy(), THRESHOLD)
+        assert np.array_equal(lg, out)
+        assert np.array_equal(dec.astype(bool), orc.decisions_multilabel(lg, THRESHOLD))
+    finally:
+        s.close()
+
+
+def test_coalesced_concurrent_runs_match_sequential(pkg, orc, golden_onnx):
+    """concurrent small Runs (the reference's OpenMP loop, main.c:141-150) are merged into one
+    padded forward per device.  Every request must get exactly the rows / width it would get alone, whatever
+    it was merged with (different B, S and label counts, i.e. different C)."""
+    cfg = orc.make_config("tiny")
+    s = pkg.Session(golden_onnx)
+    try:
+        rng = np.random.default_rng(5)
+        reqs = []
+        for k in range(24):
+            B, S = int(rng.integers(1, 9)), int(rng.integers(40, 260))
+            nl = [int(x) for x in rng.integers(1, 6, size=B)]
+            ids, mask = orc.synth_inputs(cfg, B, S, nl, seed=900 + k, ragged=bool(k % 2))
+            reqs.append((ids.numpy(), mask.numpy()))
+        alone = [s.run_inference(i, m) for i, m in reqs]          # one caller at a time: never merged
+        g0, r0 = s.coalesce_stats()
+        assert (g0, r0) == (0, 0)
+        big_ids, big_mask = orc.synth_inputs(cfg, 60, 512, 4, seed=3)
+        out = [None] * len(reqs)
+        err = []
+
+        def call(k):
+            try:
+                out[k] = s.run_inference(*reqs[k])
+            except Exception as e:   # noqa: BLE001
+                err.append(e)
+
+        for _ in range(3):
+            # a long request occupies the device while the small ones pile up behind it
+            th = [threading.Thread(target=lambda: s.run_inference(big_ids.numpy(), big_mask.numpy()))]
+            th += [threading.Thread(target=call, args=(k,)) for k in range(len(reqs))]
+            for t in th:
+                t.start()
+            for t in th:
+                t.join()
+            assert not err, err
+            for k in range(len(reqs)):
+                assert out[k].shape == alone[k].shape, (k, out[k].shape, alone[k].shape)
+                d = np.abs(out[k] - alone[k]).max() if out[k].size else 0.0
+                assert d <= 1e-3, (k, d)
+        g1, r1 = s.coalesce_stats()
+        print(f"coalescing: {r1} requests served by {g1} merged launches")
+        assert g1 > 0 and r1 >= 2 * g1
+    finally:
+        s.close()
+
+
+def test_submit_collect_overlaps_and_matches(pkg, orc, golden_onnx):
+    """asynchronous API: glc_submit returns before the forward finished; glc_collect returns the same logits as
+    the synchronous call, in any collection order"""
+    cfg = orc.make_config("tiny")
+    s = pkg.Session(golden_onnx)
+    try:
+        reqs = [orc.synth_inputs(cfg, 8, 512, 4, seed=40 + k) for k in range(6)]
+        ref = [s.run_inference(i.numpy(), m.numpy()) for i, m in reqs]
+        tickets = [s.submit(i.numpy(), m.numpy()) for i, m in reqs]
+        for k in reversed(range(len(reqs))):
+            got = s.collect(tickets[k])
+            assert got.shape == ref[k].shape and np.abs(got - ref[k]).max() <= 1e-3
+        # degenerate tickets complete immediately
+        t = s.submit(np.zeros((0, 16), np.int64), np.zeros((0, 16), np.int64))
+        assert s.collect(t).shape[0] == 0
+    finally:
+        s.close()

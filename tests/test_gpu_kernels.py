@@ -65,6 +65,11 @@ GEMM_CASES = [
     (64, 768, 768, 0, True),       # head projector, fp32 out
     (640, 768, 768, 1, False),     # head projector 1 (GELU)
     (40000, 768, 768, 0, False),   # > 2 waves of 128x256 tiles -> wide path for N % 256 == 0
+    (32768, 768, 768, 0, False),   # out-proj at the bench shape: 256x192 cluster tiles (7 rounds instead of 6 x 256)
+    (32768, 768, 3072, 0, False),  # FFN2 at the bench shape, 256x192 cluster tiles
+    (1000, 256, 256, 2, False),    # ReLU epilogue (MLP scorer layer 1)
+    (1000, 128, 256, 2, True),     # ReLU epilogue, fp32 out (MLP scorer layer 2)
+    (20000, 512, 384, 2, False),   # ReLU epilogue on the CTA-pair path (weighted-dot scorer at reranker scale)
 ]
 
 
@@ -80,6 +85,8 @@ def test_gemm(pkg, dev, M, N, K, act, out_f32):
     ref = A.float() @ W.float().t() + bias
     if act == 1:
         ref = torch.nn.functional.gelu(ref)   # erf form
+    if act == 2:
+        ref = torch.relu(ref)
     if out_f32:
         _report(f"gemm {M}x{N}x{K} f32", C, ref, 2e-4, 2e-4)
     else:

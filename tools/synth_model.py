@@ -35,10 +35,17 @@ class ArchConfig:
     class_token_index: int = 128001        # <<LABEL>>
     sep_token_index: int = 128002          # <<SEP>>
     head_hidden_size: int = 0              # GLiClass config.hidden_size; 0 -> same as encoder
+    # head variants of the gliclass package (`M:` recalled, unpinned)
+    pooling_strategy: str = "first"        # first | last | avg | max
+    scorer_type: str = "simple"            # simple (dot) | weighted-dot | mlp
+    normalize_features: bool = False       # L2-normalise text / class features, logits *= logit_scale
+    mlp_hidden_size: int = 256             # MLPScorer: cat[t,l] -> 256 -> 128 -> 1
 
     def __post_init__(self):
         if self.head_hidden_size == 0:
             self.head_hidden_size = self.hidden_size
+        assert self.pooling_strategy in ("first", "last", "avg", "max"), self.pooling_strategy
+        assert self.scorer_type in ("simple", "weighted-dot", "mlp"), self.scorer_type
 
     @property
     def head_dim(self) -> int:
@@ -117,6 +124,27 @@ def init_weights(cfg: ArchConfig, seed: int = 0) -> dict[str, torch.Tensor]:
         w[f"model.{pj}.linear_1.bias"] = n(Hh, std=0.02)
         w[f"model.{pj}.linear_2.weight"] = n(Hh, Hh, std=s2)
         w[f"model.{pj}.linear_2.bias"] = n(Hh, std=0.02)
+    # head variants (drawn AFTER everything above so the default checkpoints are unchanged)
+    # feature scale entering the scorer: ~1/sqrt(Hh) per element after normalisation, else s2*sqrt(Hh)
+    fs = (1.0 / math.sqrt(Hh)) if cfg.normalize_features else (s2 * math.sqrt(Hh) * 0.8)
+    if cfg.normalize_features:
+        w["model.logit_scale"] = torch.tensor(2.6592) + n(1, std=0.05)[0]
+    if cfg.scorer_type == "mlp":
+        m1, m2 = cfg.mlp_hidden_size, cfg.mlp_hidden_size // 2
+        w["model.scorer.mlp.0.weight"] = n(m1, 2 * Hh, std=1.0 / (fs * math.sqrt(2 * Hh)))
+        w["model.scorer.mlp.0.bias"] = n(m1, std=0.05)
+        w["model.scorer.mlp.2.weight"] = n(m2, m1, std=1.6 / math.sqrt(m1))
+        w["model.scorer.mlp.2.bias"] = n(m2, std=0.05)
+        w["model.scorer.mlp.4.weight"] = n(1, m2, std=2.0 / math.sqrt(m2))
+        w["model.scorer.mlp.4.bias"] = n(1, std=0.05)
+    elif cfg.scorer_type == "weighted-dot":
+        for nm in ("proj_text", "proj_label"):
+            w[f"model.scorer.{nm}.weight"] = n(2 * Hh, Hh, std=1.0 / (fs * math.sqrt(Hh)))
+            w[f"model.scorer.{nm}.bias"] = n(2 * Hh, std=0.05)
+        w["model.scorer.out_mlp.0.weight"] = n(4 * Hh, 3 * Hh, std=1.0 / math.sqrt(3 * Hh))
+        w["model.scorer.out_mlp.0.bias"] = n(4 * Hh, std=0.05)
+        w["model.scorer.out_mlp.3.weight"] = n(1, 4 * Hh, std=2.0 / math.sqrt(4 * Hh))
+        w["model.scorer.out_mlp.3.bias"] = n(1, std=0.05)
     return w
 
 
@@ -191,12 +219,57 @@ def build_hf_module(cfg: ArchConfig, w: dict):
         def forward(self, t):
             return self.linear_2(F.gelu(self.linear_1(t)))
 
+    Hh = cfg.head_hidden_size
+
+    class Pooler(nn.Module):   # gliclass poolings.py (`M:`): first / last token, masked mean, masked max
+        def forward(self, hs, attention_mask):
+            if cfg.pooling_strategy == "first":
+                return hs[:, 0, :]
+            if cfg.pooling_strategy == "last":
+                return hs[:, -1, :]
+            m = attention_mask.unsqueeze(-1).to(hs.dtype)
+            if cfg.pooling_strategy == "avg":
+                return (hs * m).sum(dim=1) / m.sum(dim=1)
+            return hs.masked_fill(m == 0, torch.finfo(hs.dtype).min).max(dim=1)[0]
+
+    class ScorerDot(nn.Module):
+        def forward(self, t, l):
+            return torch.einsum("BD,BCD->BC", t, l)
+
+    class MLPScorer(nn.Module):   # cat[t, l] -> Linear-ReLU-Linear-ReLU-Linear(1)
+        def __init__(self):
+            super().__init__()
+            m1, m2 = cfg.mlp_hidden_size, cfg.mlp_hidden_size // 2
+            self.mlp = nn.Sequential(nn.Linear(2 * Hh, m1), nn.ReLU(), nn.Linear(m1, m2), nn.ReLU(), nn.Linear(m2, 1))
+
+        def forward(self, t, l):
+            te = t.unsqueeze(1).expand(-1, l.shape[1], -1)
+            return self.mlp(torch.cat([te, l], dim=-1)).squeeze(-1)
+
+    class ScorerWeightedDot(nn.Module):   # proj -> (.., Hh, 2) halves -> cat[t0, l0, t1*l1] -> Linear-ReLU-Linear(1)
+        def __init__(self):
+            super().__init__()
+            self.proj_text = nn.Linear(Hh, 2 * Hh)
+            self.proj_label = nn.Linear(Hh, 2 * Hh)
+            self.out_mlp = nn.Sequential(nn.Linear(3 * Hh, 4 * Hh), nn.Dropout(0.0), nn.ReLU(), nn.Linear(4 * Hh, 1))
+
+        def forward(self, t, l):
+            B, C = l.shape[0], l.shape[1]
+            lr = self.proj_label(l).view(B, C, -1, 2)
+            tr = self.proj_text(t).view(B, 1, -1, 2).expand(-1, C, -1, -1)
+            cat = torch.cat([tr[..., 0], lr[..., 0], tr[..., 1] * lr[..., 1]], dim=-1)
+            return self.out_mlp(cat).squeeze(-1)
+
     class UniEncoder(nn.Module):
         def __init__(self):
             super().__init__()
             self.encoder_model = DebertaV2Model(hf_cfg)
             self.text_projector = FeaturesProjector()
             self.classes_projector = FeaturesProjector()
+            self.pooler = Pooler()
+            self.scorer = {"simple": ScorerDot, "mlp": MLPScorer, "weighted-dot": ScorerWeightedDot}[cfg.scorer_type]()
+            if cfg.normalize_features:
+                self.logit_scale = nn.Parameter(torch.tensor(2.6592))
 
         def forward(self, input_ids, attention_mask):
             hs = self.encoder_model(input_ids, attention_mask=attention_mask)[0]
@@ -209,9 +282,15 @@ def build_hf_module(cfg: ArchConfig, w: dict):
             bi_cls, pos_cls = torch.where(class_token_mask)
             cls = torch.zeros(B, max_c, D, dtype=hs.dtype)
             cls[batch_idx, target_idx] = hs[bi_cls, pos_cls]
-            pooled = self.text_projector(hs[:, 0, :])
+            pooled = self.text_projector(self.pooler(hs, attention_mask))
             cls = self.classes_projector(cls)
-            return torch.einsum("BD,BCD->BC", pooled, cls)
+            if cfg.normalize_features:
+                pooled = pooled / (pooled.norm(p=2, dim=-1, keepdim=True) + 1e-8)
+                cls = cls / (cls.norm(p=2, dim=-1, keepdim=True) + 1e-8)
+            logits = self.scorer(pooled, cls)
+            if cfg.normalize_features:
+                logits = logits * self.logit_scale
+            return logits
 
     class GLiClassModel(nn.Module):
         def __init__(self):
