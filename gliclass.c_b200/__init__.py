@@ -88,6 +88,8 @@ _SIGS = {
     "glc_expanded_pos_rows": (_i, []),
     "glc_op_expand_pos": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
     "glc_op_attention_toeplitz": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "glc_op_expand_pos_rev": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
+    "glc_op_attention_shift": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_op_head_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp]),
     "glc_op_head_score": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
 }

@@ -1,0 +1,513 @@
+// K3 (third generation) — fused DeBERTa disentangled attention for sm_100a, head dim 64, with both
+// relative-position biases skewed in REGISTERS: no shared-memory staging, no gathers.
+//
+//   ctx[b,i,h,:] = softmax_j( (Q_i.K_j + Q_i.posK[idx(i-j)] + K_j.posQ[idx(i-j)]) / sqrt(3d) + mask_j ) . V_j
+//
+// (transformers DisentangledSelfAttention, T:229-345: scores T:237-251, c2p T:313-324, p2c T:327-343, masked
+// softmax T:256-259, context T:262-271; idx(delta) = clamp(bucket(delta)+span, 0, 2*span-1))
+//
+// The first-generation kernel (attention.cu) stages per-tile slices of Q.posK^T / posQ.K^T as fp16 in shared
+// memory and gathers two values per score; ncu shows it bound by the shared-memory data pipe (52 M wavefronts per
+// launch, 26 warp instructions per score).  Here the position tables are expanded at load to one row per DELTA
+//     EK [rho]   = posK[idx(2047 - rho)]      (expanded_pos_index)
+//     EQr[sigma] = posQ[idx(sigma - 2047)]    (expanded_pos_index_rev)
+// so that inside a (128-query, 64-key) tile (a = query row, b = key column) both biases are Toeplitz:
+//     c2p[a,b] = C[a, 127 - a + b]     C = Q_tile . EK[rho0 .. rho0+191]^T          rho0   = 1920 - q0 + k0
+//     p2c[a,b] = G[a + 63 - b, b]      G = EQr[sigma0 .. sigma0+191] . K_tile^T     sigma0 = 1984 + q0 - k0
+// and the skews are undone where the accumulators already are:
+//   * c2p — thread (row a) reads the 64-column window of C that holds its 32 keys' values (warp-uniform TMEM
+//     address), packs it to fp16 pairs and shifts it by (31 - lane) elements with a 5-stage barrel shifter
+//     (4 SEL stages on packed words + one PRMT stage): 4 ALU ops per score, static register indices only;
+//   * p2c — lane = table row, so the skew is a lane rotation that is UNIFORM per key column: the tensor core
+//     computes G three times with the A-operand window starting at rows 0 / 32 / 64 of the slice, which puts row
+//     a + s (s = 63 - b = 32 s0 + s1) in TMEM lane (a + s1) mod 32 of the same warp quarter in copy s0 or s0 + 1;
+//     one SEL (source lane picks the copy) + one SHFL.IDX per score.  Copy 0 is only needed for keys 32..63
+//     and copy 64 for keys 0..31, so the three copies take 128 TMEM columns.
+//
+// One CTA (320 threads) per (128-query tile, head, batch row), looping over 64-key tiles t:
+//   warp 0   TMA producer: ring A (x2) = K_t + the two 192-row slices, ring B (x2) = V_t
+//   warp 1   tcgen05 issuer (M = 128, fp32 accumulators in TMEM, all 512 columns):
+//              S = Q.K_t^T (64) | C (192) | G copies (64 + 32 + 32) | PV = P.V_t (64); Q and P are TMEM A operands (32 + 32)
+//   warps 2-9  softmax: thread = (query row / TMEM lane, 32-key half g); online softmax in registers,
+//              row max exchanged between the two halves through smem, P -> TMEM, O rescaled in registers.
+// Synchronisation is mbarrier based; every wait is bounded (ptx::mbar_wait traps on timeout).
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "kernels.h"
+#include "model_weights.h"
+#include "ptx.cuh"
+#include "tma_desc.h"
+
+namespace glc {
+namespace {
+
+constexpr int QT = 128;            // queries per CTA
+constexpr int KT = 64;             // keys per tile
+constexpr int D = 64;              // head dim
+constexpr int G = 2;               // key groups per tile: softmax thread = (query row, E-key group)
+constexpr int E = KT / G;          // scores per softmax thread per tile
+constexpr int NC = E + 32;         // C columns a thread loads: its E keys x the 32 lane shifts of its warp
+constexpr int NW = NC / 2;         // ... as fp16 pairs
+constexpr int SM_WARPS = 4 * G;    // 4 TMEM lane quarters x G groups
+constexpr int SM_THREADS = 32 * SM_WARPS;
+constexpr int ATT_THREADS = 64 + SM_THREADS;
+constexpr int SLICE = 192;         // table rows per tile (191 deltas + the never-consumed last row of copy 64)
+constexpr int EXP_CENTER = 2047;
+constexpr int EXP_ROWS = 4096;
+constexpr int TMAX = 2048 / KT;
+static_assert(E == 32 || E == 16, "key group width");
+static_assert(D / G == E, "output slice per thread = scores per thread");
+
+// shared memory map (bytes, from a 1024-aligned base)
+constexpr int OFF_Q = 0;                           // 128 x 128 B
+constexpr int OFF_K = OFF_Q + 16384;               // 2 x 8 KB
+constexpr int OFF_V = OFF_K + 16384;               // 2 x 8 KB
+constexpr int POS_BYTES = SLICE * 128;
+constexpr int OFF_EK = OFF_V + 16384;              // 2 x 192 x 128 B
+constexpr int OFF_EQ = OFF_EK + 2 * POS_BYTES;     // 2 x 192 x 128 B
+constexpr int OFF_XMAX = OFF_EQ + 2 * POS_BYTES;   // 2 x G x 128 floats (row-max exchange, double buffered by tile parity)
+constexpr int OFF_MASK = OFF_XMAX + 2 * G * QT * 4;   // uint32[68]: key-validity words of this batch row
+constexpr int OFF_BAR = OFF_MASK + 68 * 4;
+constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
+static_assert(OFF_BAR % 8 == 0, "barrier alignment");
+static_assert(ATT_SMEM <= 227 * 1024, "attention smem budget");
+
+// TMEM columns
+constexpr uint32_t TM_S = 0;       // 64
+constexpr uint32_t TM_Q = 64;      // 32: Q tile as fp16 pairs
+constexpr uint32_t TM_P = 96;      // 32: P tile as fp16 pairs
+constexpr uint32_t TM_C = 128;     // 192
+constexpr uint32_t TM_G32 = 320;   // 64: window rows 32..159, keys 0..63
+constexpr uint32_t TM_G64 = 384;   // 32: window rows 64..191, keys 0..31
+constexpr uint32_t TM_G0 = 416;    // 32: window rows 0..127,  keys 32..63
+constexpr uint32_t TM_PV = 448;    // 64
+
+struct ShiftParams {
+  const uint32_t* mask_bits; // [B][ceil(S/32)]
+  const int32_t* kv_len;     // [B]
+  __half* ctx;               // [B*S, H]
+  int B, S, heads, H;
+  float scale_log2;          // log2(e) / sqrt(3*d)
+};
+
+template <int N>
+__device__ __forceinline__ void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]);
+template <>
+__device__ __forceinline__ void tmem_ld_n<16>(uint32_t taddr, uint32_t (&r)[16]) { ptx::tmem_ld_x16(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&r)[32]) { ptx::tmem_ld_x32(taddr, r); }
+
+__device__ __forceinline__ uint32_t sel(bool p, uint32_t a, uint32_t b) { return p ? a : b; }
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ek,
+                       const __grid_constant__ CUtensorMap tm_eq, const ShiftParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  uint64_t* q_full = bars + 0;
+  uint64_t* a_full = bars + 1;       // [2]  K_t + slices landed
+  uint64_t* a_empty = bars + 3;      // [2]  ... consumed by the S / C / G MMAs
+  uint64_t* b_full = bars + 5;       // [2]  V_t landed
+  uint64_t* b_empty = bars + 7;      // [2]  ... consumed by the PV MMA
+  uint64_t* mma1_full = bars + 9;    // S, C, G accumulators of tile t ready
+  uint64_t* bias_free = bars + 10;   // softmax warps have drained them
+  uint64_t* p_full = bars + 11;      // P tile written
+  uint64_t* pv_full = bars + 12;     // PV accumulator ready
+  uint64_t* qt_full = bars + 13;     // Q tile copied into TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * QT;
+  const int head = blockIdx.y;
+  const int b = blockIdx.z;
+  const int kvlen = p.kv_len[b];
+  const int T = (kvlen + KT - 1) / KT;   // key tiles with at least one valid key
+
+  if (q0 >= kvlen) {
+    // padded queries only: their outputs are never read by valid rows
+    for (int e = threadIdx.x; e < QT * 8; e += ATT_THREADS) {
+      const int r = q0 + (e >> 3);
+      if (r < p.S)
+        *reinterpret_cast<uint4*>(p.ctx + ((int64_t)b * p.S + r) * p.H + head * D + (e & 7) * 8) = make_uint4(0, 0, 0, 0);
+    }
+    return;
+  }
+
+  if (threadIdx.x == 0) {
+    ptx::prefetch_tensormap(&tm_qkv);
+    ptx::prefetch_tensormap(&tm_ek);
+    ptx::prefetch_tensormap(&tm_eq);
+    ptx::mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
+    ptx::mbar_init(mma1_full, 1);
+    ptx::mbar_init(bias_free, SM_WARPS);
+    ptx::mbar_init(p_full, SM_WARPS);
+    ptx::mbar_init(pv_full, 1);
+    ptx::mbar_init(qt_full, SM_WARPS);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) ptx::tmem_alloc<512>(tmem_slot);
+  {
+    const int words = (p.S + 31) >> 5;
+    const int e = threadIdx.x - 64;
+    if (e >= 0 && e < 68) kmask[e] = (e < words) ? __ldg(p.mask_bits + (int64_t)b * words + e) : 0u;
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(q_full, QT * 128);
+      ptx::tma_load_3d(smem + OFF_Q, &tm_qkv, q_full, head * D, q0, b);
+      ptx::tma_load_3d(smem + OFF_Q + 8192, &tm_qkv, q_full, head * D, q0 + 64, b);
+      ptx::mbar_arrive_expect_tx(&b_full[0], KT * 128);
+      ptx::tma_load_3d(smem + OFF_V, &tm_qkv, &b_full[0], 2 * p.H + head * D, 0, b);
+      // ring A: K_x and the position slices of tile x; free once the bias MMAs of tile x-2 retired
+      auto load_a = [&](int x) {
+        const int k0 = x * KT;
+        const int rho0 = EXP_CENTER - (QT - 1) - q0 + k0;
+        const int sig0 = EXP_CENTER - (KT - 1) + q0 - k0;
+        const int st = x & 1;
+        ptx::mbar_wait(&a_empty[st], ((x >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&a_full[st], (uint32_t)(KT * 128 + 2 * POS_BYTES));
+        ptx::tma_load_3d(smem + OFF_K + st * 8192, &tm_qkv, &a_full[st], p.H + head * D, k0, b);
+#pragma unroll
+        for (int bx = 0; bx < SLICE / 64; ++bx) {
+          ptx::tma_load_3d(smem + OFF_EK + st * POS_BYTES + bx * 8192, &tm_ek, &a_full[st], 0, rho0 + bx * 64, head);
+          ptx::tma_load_3d(smem + OFF_EQ + st * POS_BYTES + bx * 8192, &tm_eq, &a_full[st], 0, sig0 + bx * 64, head);
+        }
+      };
+      // ring B: V_x; free once the PV MMA of tile x-2 retired
+      auto load_b = [&](int x) {
+        const int st = x & 1;
+        ptx::mbar_wait(&b_empty[st], ((x >> 1) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&b_full[st], KT * 128);
+        ptx::tma_load_3d(smem + OFF_V + st * 8192, &tm_qkv, &b_full[st], 2 * p.H + head * D, x * KT, b);
+      };
+      // issue order = order in which the buffers come free: bias(t) retires before PV(t-1)
+      load_a(0);
+      if (T > 1) load_a(1);
+      for (int t = 0; t < T; ++t) {
+        if (t + 2 < T) load_a(t + 2);
+        if (t + 1 < T) load_b(t + 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected issue)
+    constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
+    constexpr uint32_t idesc_n32 = ptx::idesc_f16(128, 32);
+    constexpr uint32_t idesc_c = ptx::idesc_f16(128, SLICE);
+    constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
+    ptx::mbar_wait(qt_full, 0);
+    ptx::tc_fence_after();
+    for (int t = 0; t <= T; ++t) {
+      if (t < T) {
+        const int st = t & 1;
+        const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
+        const uint64_t dEK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EK + st * POS_BYTES));
+        const uint64_t dEQ = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EQ + st * POS_BYTES));
+        ptx::mbar_wait(&a_full[st], (t >> 1) & 1);
+        if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);   // S, C and G accumulators drained
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          // A = Q from TMEM: 16 halves along K = 8 columns per step; descriptors advance 32 B (= 2) per step;
+          // 32 table/key rows = 4096 B = 256 in a descriptor
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ts(tmem + TM_S, tmem + TM_Q + 8 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::mma_f16_ts(tmem + TM_C, tmem + TM_Q + 8 * k, dEK + 2 * k, idesc_c, (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // rows 32..159 x keys 0..63
+            ptx::mma_f16_ss(tmem + TM_G32, dEQ + 256 + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // rows 64..191 x keys 0..31
+            ptx::mma_f16_ss(tmem + TM_G64, dEQ + 512 + 2 * k, dK + 2 * k, idesc_n32, (uint32_t)(k != 0));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // rows 0..127 x keys 32..63
+            ptx::mma_f16_ss(tmem + TM_G0, dEQ + 2 * k, dK + 256 + 2 * k, idesc_n32, (uint32_t)(k != 0));
+          ptx::mma_commit(&a_empty[st]);
+          ptx::mma_commit(mma1_full);
+        }
+        __syncwarp();
+      }
+      if (t > 0) {
+        const int tp = t - 1;
+        const int st = tp & 1;
+        const uint64_t dV = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_V + st * 8192));
+        ptx::mbar_wait(&b_full[st], (tp >> 1) & 1);
+        ptx::mbar_wait(p_full, tp & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)   // V is MN-major: 16 keys further = +2048 bytes = +128 in the descriptor
+            ptx::mma_f16_ts(tmem + TM_PV, tmem + TM_P + 8 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0));
+          ptx::mma_commit(&b_empty[st]);
+          ptx::mma_commit(pv_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax warps
+    const int sw = warp - 2;          // 0..SM_WARPS-1
+    const int g = sw >> 2;            // key group of the tile: keys [E*g, E*g+E)
+    const int qd = warp & 3;          // TMEM lane quarter
+    const int i = qd * 32 + lane;     // row in the query tile
+    const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
+    float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
+    const int b0 = g * E;             // first key column of this thread
+    const int bb = b0 & 31;
+
+    // ---- Q tile -> TMEM once (row i, halves [E*g, E*g+E) = 16-byte chunks of the swizzled row)
+    ptx::mbar_wait(q_full, 0);
+    {
+      const uint8_t* qrow = smem + OFF_Q + (i >> 3) * 1024 + (i & 7) * 128;
+#pragma unroll
+      for (int u = 0; u < E / 16; ++u) {
+        const int ch = (E / 8) * g + 2 * u;
+        const uint4 lo = *reinterpret_cast<const uint4*>(qrow + (((ch) ^ (i & 7)) << 4));
+        const uint4 hi = *reinterpret_cast<const uint4*>(qrow + (((ch + 1) ^ (i & 7)) << 4));
+        const uint32_t qr[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        ptx::tmem_st_x8(t_lane + TM_Q + (uint32_t)((E / 2) * g + 8 * u), qr);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(qt_full);
+    }
+
+    // tile-independent addresses and shift controls
+    const uint32_t a_s = t_lane + TM_S + (uint32_t)b0;
+    const uint32_t a_c = t_lane + TM_C + (uint32_t)(96 - 32 * qd + b0);      // window of this warp: its E keys x 32 lane shifts
+    const uint32_t a_lo = t_lane + (b0 < 32 ? TM_G32 + (uint32_t)b0 : TM_G0 + (uint32_t)bb);    // copy 32 s0
+    const uint32_t a_hi = t_lane + (b0 < 32 ? TM_G64 + (uint32_t)b0 : TM_G32 + (uint32_t)b0);   // copy 32 s0 + 32
+    const int sh = 31 - lane;                  // c2p: element shift inside the window
+    const bool sh16 = sh & 16, sh8 = sh & 8, sh4 = sh & 4, sh2 = sh & 2;
+    const uint32_t prmt_sel = (sh & 1) ? 0x5432u : 0x3210u;
+    const int rot0 = lane + 31 - bb;           // p2c: source lane of column jj is (rot0 - jj) & 31
+    const int thr0 = lane - 31 + bb;           // ... and this lane supplies the upper copy iff thr0 + jj < 0
+
+    float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
+    float o[E];
+#pragma unroll
+    for (int k = 0; k < E; ++k) o[k] = 0.f;
+    const float sc = p.scale_log2;
+
+    for (int t = 0; t < T; ++t) {
+      const int k0 = t * KT;
+      ptx::mbar_wait(mma1_full, t & 1);
+      ptx::tc_fence_after();
+
+      float s[E];
+      uint32_t w[NW];
+      {
+        uint32_t r[E];
+        tmem_ld_n<E>(a_s, r);
+        uint32_t c[NC];
+#pragma unroll
+        for (int u = 0; u < NC / 16; ++u) {
+          uint32_t cc[16];
+          ptx::tmem_ld_x16(a_c + 16 * u, cc);
+#pragma unroll
+          for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
+        }
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < E; ++jj) s[jj] = __uint_as_float(r[jj]);
+#pragma unroll
+        for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
+      }
+      // ---- p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
+#pragma unroll
+      for (int u = 0; u < E / 16; ++u) {
+        uint32_t lo[16], hi[16];
+        ptx::tmem_ld_x16(a_lo + 16 * u, lo);
+        ptx::tmem_ld_x16(a_hi + 16 * u, hi);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const int jj = 16 * u + k;
+          const uint32_t v = sel(thr0 + jj < 0, hi[k], lo[k]);
+          s[jj] += __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bias_free);
+
+      // ---- c2p: shift the packed window left by sh elements
+#pragma unroll
+      for (int k = 0; k < NW - 8; ++k) w[k] = sel(sh16, w[k + 8], w[k]);
+#pragma unroll
+      for (int k = 0; k < NW - 12; ++k) w[k] = sel(sh8, w[k + 4], w[k]);
+#pragma unroll
+      for (int k = 0; k < NW - 14; ++k) w[k] = sel(sh4, w[k + 2], w[k]);
+#pragma unroll
+      for (int k = 0; k < NW - 15; ++k) w[k] = sel(sh2, w[k + 1], w[k]);
+#pragma unroll
+      for (int m = 0; m < E / 2; ++m) {
+        const uint32_t x = __byte_perm(w[m], w[m + 1], prmt_sel);
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&x));
+        s[2 * m] += f.x;
+        s[2 * m + 1] += f.y;
+      }
+
+      const int kb = k0 + b0;
+      const uint32_t kbits = kmask[kb >> 5] >> (kb & 31);   // E <= 32 and kb is a multiple of E: no word straddling
+      if ((E == 32 && kbits != 0xffffffffu) || (E < 32 && (kbits & ((1u << (E & 31)) - 1u)) != ((1u << (E & 31)) - 1u))) {
+#pragma unroll
+        for (int jj = 0; jj < E; ++jj)
+          if (!((kbits >> jj) & 1u)) s[jj] = -CUDART_INF_F;
+      }
+      float mloc = s[0];
+#pragma unroll
+      for (int jj = 1; jj < E; ++jj) mloc = fmaxf(mloc, s[jj]);
+      // ---- row max shared between the key groups (double buffered by tile parity: the quarter barrier of
+      //      tile t+1 orders the reads of tile t before the writes of tile t+2)
+      float* xm = xmax + (t & 1) * (G * QT);
+      xm[g * QT + i] = mloc;
+      ptx::named_bar_sync(2 + qd, 32 * G);   // only the G warps of this lane quarter share rows
+      float m_new = m_run;
+#pragma unroll
+      for (int gg = 0; gg < G; ++gg) m_new = fmaxf(m_new, xm[gg * QT + i]);
+      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+      const float alpha = ptx::ex2((m_run - m_use) * sc);
+      const float neg_ms = -m_use * sc;
+      float psum = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < E; ++jj) {
+        const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
+        s[jj] = e;
+        psum += e;
+      }
+      l_run = l_run * alpha + psum;
+      m_run = m_new;
+
+      // ---- fold in PV of the previous tile (also guarantees the P buffer is free again)
+      if (t > 0) {
+        ptx::mbar_wait(pv_full, (t - 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t r[E];
+        tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
+      }
+      alpha_prev = alpha;
+
+      // ---- P tile -> TMEM: row i, fp16 pairs at columns (E/2) g ..
+#pragma unroll
+      for (int u = 0; u < E / 16; ++u) {
+        uint32_t pr[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) pr[v] = ptx::pack_f16(s[16 * u + 2 * v], s[16 * u + 2 * v + 1]);
+        ptx::tmem_st_x8(t_lane + TM_P + (uint32_t)((E / 2) * g + 8 * u), pr);
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(p_full);
+    }
+
+    // ---- last PV, normalise, write ctx
+    ptx::mbar_wait(pv_full, (T - 1) & 1);
+    ptx::tc_fence_after();
+    {
+      uint32_t r[E];
+      tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
+      ptx::tmem_ld_wait();
+#pragma unroll
+      for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
+    }
+    float* xs = xmax + (T & 1) * (G * QT);   // the buffer tile T-1 did not use
+    xs[g * QT + i] = l_run;
+    ptx::named_bar_sync(2 + qd, 32 * G);
+    float l_tot = 0.f;
+#pragma unroll
+    for (int gg = 0; gg < G; ++gg) l_tot += xs[gg * QT + i];
+    const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+    const int row = q0 + i;
+    if (row < p.S) {
+      __half* dst = p.ctx + ((int64_t)b * p.S + row) * p.H + head * D + b0;
+#pragma unroll
+      for (int v = 0; v < E / 8; ++v) {
+        uint4 o4;
+        o4.x = ptx::pack_f16(o[8 * v + 0] * inv, o[8 * v + 1] * inv);
+        o4.y = ptx::pack_f16(o[8 * v + 2] * inv, o[8 * v + 3] * inv);
+        o4.z = ptx::pack_f16(o[8 * v + 4] * inv, o[8 * v + 5] * inv);
+        o4.w = ptx::pack_f16(o[8 * v + 6] * inv, o[8 * v + 7] * inv);
+        reinterpret_cast<uint4*>(dst)[v] = o4;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc<512>(tmem);
+  }
+}
+
+}  // namespace
+
+void expanded_pos_index_rev(int buckets, int max_pos, int32_t* out /* [EXP_ROWS] */) {
+  // row sigma holds delta = sigma - EXP_CENTER; the last row (delta = +2048) is never consumed -> zero row
+  std::vector<int32_t> rel((size_t)2 * (EXP_CENTER + 1) - 1);
+  rel_index_table(EXP_CENTER + 1, buckets, max_pos, rel.data());   // rel[delta + EXP_CENTER]
+  for (int s = 0; s < EXP_ROWS - 1; ++s) out[s] = rel[(size_t)s];
+  out[EXP_ROWS - 1] = -1;
+}
+
+cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                            const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
+                            cudaStream_t stream) {
+  if (B <= 0 || S <= 0) return cudaSuccess;
+  if (S > 2048) return cudaErrorInvalidValue;   // reference MAX_LENGTH (include/configs.h:5)
+  const int H = heads * D;
+  // qkv viewed as [B][S][3H]; box 64 cols x 64 rows
+  uint64_t dq[3] = {(uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
+  uint64_t sq[2] = {(uint64_t)(3 * H) * 2, (uint64_t)S * 3 * H * 2};
+  uint32_t bq[3] = {64, 64, 1};
+  // expanded tables are [EXP_ROWS][ld_exp] row-major (head h = columns h*64..): dims (d, row, head)
+  uint64_t dp[3] = {64, (uint64_t)EXP_ROWS, (uint64_t)heads};
+  uint64_t sp[2] = {(uint64_t)ld_exp * 2, 128};
+  uint32_t bp[3] = {64, 64, 1};
+  CUtensorMap tm_qkv = make_tmap_16b(qkv, 3, dq, sq, bq);
+  CUtensorMap tm_ek = make_tmap_16b(exp_k, 3, dp, sp, bp);
+  CUtensorMap tm_eq = make_tmap_16b(exp_qr, 3, dp, sp, bp);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  ShiftParams p;
+  p.mask_bits = mask_bits;
+  p.kv_len = kv_len;
+  p.ctx = (__half*)ctx;
+  p.B = B; p.S = S; p.heads = heads; p.H = H;
+  p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
+  dim3 grid((S + QT - 1) / QT, heads, B);
+  attention_shift_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+  return cudaGetLastError();
+}
+
+}  // namespace glc

@@ -407,6 +407,29 @@ int glc_op_expand_pos(const void* pos_f16, int64_t ld_src, int buckets, int max_
     return fail(GLC_ERR_CUDA, std::string("glc_op_expand_pos: ") + e.what());
   }
 }
+int glc_op_expand_pos_rev(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst, int cols,
+                          void* stream) {
+  try {
+    const int ER = glc::expanded_pos_rows();
+    std::vector<int32_t> h(ER);
+    glc::expanded_pos_index_rev(buckets, max_pos, h.data());
+    int32_t* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, (size_t)ER * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(d, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = glc::expand_pos_table(pos_f16, ld_src, d, out_f16, ld_dst, cols, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (d) cudaFree(d);
+    if (e != cudaSuccess) return fail(GLC_ERR_CUDA, std::string("glc_op_expand_pos_rev: ") + cudaGetErrorString(e));
+    return GLC_OK;
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_op_expand_pos_rev: ") + e.what());
+  }
+}
+int glc_op_attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
+                           const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
+  GLC_TRY("glc_op_attention_shift",
+          glc::attention_shift(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
+}
 int glc_expanded_pos_rows(void) { return glc::expanded_pos_rows(); }
 int glc_op_attention_toeplitz(const void* qkv, const void* exp_k, const void* exp_q, int64_t ld_exp, const uint32_t* mask_bits,
                               const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {

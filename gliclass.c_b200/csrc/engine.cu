@@ -115,7 +115,14 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   // production attention = attention.cu (gather kernel, 360 us/launch at C2); GLC_ATTN_TOEPLITZ=1 selects the
   // tensor-core-bias experiment (attention_toeplitz.cu, 413 us/launch) for A/B comparisons
   const char* al = getenv("GLC_ATTN_TOEPLITZ");
-  attn_legacy_ = !(al && al[0] == '1');
+  attn_mode_ = (al && al[0] == '1') ? 1 : 0;
+  if (const char* am = getenv("GLC_ATTN")) {
+    const std::string m(am);
+    if (m == "gather") attn_mode_ = 0;
+    else if (m == "toeplitz") attn_mode_ = 1;
+    else if (m == "shift") attn_mode_ = 2;
+    else throw std::runtime_error("GLC_ATTN must be gather, toeplitz or shift (got '" + m + "')");
+  }
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
   const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
@@ -136,13 +143,19 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
 
   // index of the delta-expanded position tables (attention_toeplitz.cu): row rho <- pos_qk[idx(2047 - rho)]
   const int ER = expanded_pos_rows();
-  int32_t* d_exp_idx = nullptr;
-  if (!attn_legacy_) {
+  int32_t *d_exp_idx = nullptr, *d_exp_idx_rev = nullptr;
+  if (attn_mode_ != 0) {
     std::vector<int32_t> h(ER);
     expanded_pos_index(cfg_.buckets, cfg_.max_rel_pos, h.data());
     d_exp_idx = (int32_t*)dalloc((size_t)ER * 4);
     perm_allocs_.push_back(d_exp_idx);
     GLC_CUDA(cudaMemcpy(d_exp_idx, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice));
+    if (attn_mode_ == 2) {
+      expanded_pos_index_rev(cfg_.buckets, cfg_.max_rel_pos, h.data());
+      d_exp_idx_rev = (int32_t*)dalloc((size_t)ER * 4);
+      perm_allocs_.push_back(d_exp_idx_rev);
+      GLC_CUDA(cudaMemcpy(d_exp_idx_rev, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice));
+    }
   }
 
   layers_.resize(cfg_.layers);
@@ -176,10 +189,17 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
     perm_allocs_.push_back(d.pos_qk);
     GLC_CUDA(gemm_f16(rel_ln, H, d.wqkv, H, d.bqkv, d.pos_qk, 2 * H, R, 2 * H, H, 0, false, num_sms_, stream_));
     ++launches_;
-    if (!attn_legacy_) {
+    if (attn_mode_ != 0) {
       d.pos_exp = dalloc((size_t)ER * 2 * H * 2);
       perm_allocs_.push_back(d.pos_exp);
-      GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx, d.pos_exp, 2 * H, 2 * H, stream_));
+      if (attn_mode_ == 1) {
+        GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx, d.pos_exp, 2 * H, 2 * H, stream_));
+      } else {
+        // posQ half in sigma order, posK half in rho order (attention_shift.cu)
+        GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx_rev, d.pos_exp, 2 * H, H, stream_));
+        GLC_CUDA(expand_pos_table((const __half*)d.pos_qk + H, 2 * H, d_exp_idx, (__half*)d.pos_exp + H, 2 * H, H, stream_));
+        ++launches_;
+      }
       ++launches_;
     }
   }
@@ -435,12 +455,14 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st));
     if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
     const __half* pq = (const __half*)d.pos_qk;
-    if (attn_legacy_) {
+    const __half* pe = (const __half*)d.pos_exp;
+    if (attn_mode_ == 0) {
       GLC_LAUNCH(KC_ATTN, attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads,
                                           cfg_.buckets, num_sms_, st));
-    } else {
-      const __half* pe = (const __half*)d.pos_exp;
+    } else if (attn_mode_ == 1) {
       GLC_LAUNCH(KC_ATTN, attention_toeplitz(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
+    } else {
+      GLC_LAUNCH(KC_ATTN, attention_shift(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
     }
     if (cfg_.pooling == POOL_LAST) GLC_LAUNCH(KC_ATTN, pad_rows_mean_v(qkv_, d_mask, ctx_, B, S, H, st));
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);

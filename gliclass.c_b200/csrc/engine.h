@@ -33,7 +33,7 @@ struct DeviceLayer {
   float* b2 = nullptr;
   float *ln2g = nullptr, *ln2b = nullptr;
   void* pos_qk = nullptr; // fp16 [2*buckets, 2H]: cols [0,H) = query_proj(rel), [H,2H) = key_proj(rel)
-  void* pos_exp = nullptr; // fp16 [expanded_pos_rows(), 2H]: pos_qk expanded to one row per delta (row rho = pos_qk[idx(2047 - rho)])
+  void* pos_exp = nullptr; // fp16 [expanded_pos_rows(), 2H]: pos_qk expanded to one row per delta (row rho = pos_qk[idx(2047 - rho)]; in shift mode the posQ half [0,H) is stored in the opposite order, row sigma = idx(sigma - 2047))
 };
 
 struct DebugBuf { void* ptr = nullptr; size_t count = 0; };
@@ -108,7 +108,8 @@ class DeviceModel {
   ModelConfig cfg_;
   int max_tokens_ = 65536;
   bool debug_keep_ = false;
-  bool attn_legacy_ = true;    // false with GLC_ATTN_TOEPLITZ=1: tensor-core-bias experiment (A/B comparisons)
+  int attn_mode_ = 0;          // 0 gather kernel (attention.cu), 1 tensor-core-bias experiment (attention_toeplitz.cu),
+                               // 2 register-skew kernel (attention_shift.cu); env GLC_ATTN=gather|toeplitz|shift
   std::atomic<uint64_t> launches_{0};
 
   // weights

@@ -44,6 +44,13 @@ cudaError_t expand_pos_table(const void* pos_f16, int64_t ld_src, const int32_t*
 cudaError_t attention_toeplitz(const void* qkv, const void* exp_k, const void* exp_q, int64_t ld_exp,
                                const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                                cudaStream_t stream);
+// K3, third generation (attention_shift.cu): both biases skewed in registers (barrel shifter for c2p, lane rotation
+// for p2c).  exp_k as above; exp_qr is the posQ table expanded in the OPPOSITE order: row sigma = posQ[idx(sigma - 2047)]
+// (index from expanded_pos_index_rev).
+void expanded_pos_index_rev(int buckets, int max_pos, int32_t* out /* host, [expanded_pos_rows()] */);
+cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                            const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
+                            cudaStream_t stream);
 // slow CUDA-core restatement of the same op, used only by tests to localise bugs on the GPU
 cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
                             const uint32_t* mask_bits, void* ctx, int B, int S, int heads, int buckets,

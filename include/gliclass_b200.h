@@ -176,6 +176,16 @@ GLC_API int glc_op_expand_pos(const void* pos_f16, int64_t ld_src, int buckets, 
 GLC_API int glc_op_attention_toeplitz(const void* qkv_f16, const void* exp_k_f16, const void* exp_q_f16, int64_t ld_exp,
                                       const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S,
                                       int heads, void* stream);
+/* K3, production variant (csrc/attention_shift.cu): the same op with both relative-position biases skewed in registers
+ * (barrel shifter on the Q.EK^T accumulator window, lane rotation of the EQr.K^T accumulators).  exp_k as above;
+ * exp_qr is the posQ table expanded in the opposite order by glc_op_expand_pos_rev:
+ * out[sigma][0:cols) = pos[idx(sigma - 2047)][0:cols).  Replaces the attention sub-graph of the ORT session Run
+ * (reference src/model.c:173-182; arithmetic T:229-345). */
+GLC_API int glc_op_expand_pos_rev(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst,
+                                  int cols, void* stream);
+GLC_API int glc_op_attention_shift(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
+                                   const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
+                                   void* stream);
 /* K5a: pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] for the c-th <<LABEL>> token, else 0 */
 GLC_API int glc_op_head_gather(const void* h_f16, const int64_t* ids, int64_t class_token, void* pooled_f16,
                                void* cls_f16, int B, int S, int H, int C, void* stream);

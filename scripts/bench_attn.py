@@ -33,10 +33,20 @@ pos_q, pos_k = pos[:, :H], pos[:, H:]
 ER = L.glc_expanded_pos_rows()
 exp = torch.zeros(ER, 2 * H, dtype=torch.float16, device=dev)
 assert L.glc_op_expand_pos(pos.data_ptr(), 2 * H, 256, 512, exp.data_ptr(), 2 * H, 2 * H, None) == 0, pkg.last_error()
-LEGACY = os.environ.get("GLC_ATTN_TOEPLITZ") != "1"
+MODE = os.environ.get("GLC_ATTN", "toeplitz" if os.environ.get("GLC_ATTN_TOEPLITZ") == "1" else "gather")
+LEGACY = MODE == "gather"
+exps = torch.zeros(ER, 2 * H, dtype=torch.float16, device=dev)
+assert L.glc_op_expand_pos_rev(pos.data_ptr(), 2 * H, 256, 512, exps.data_ptr(), 2 * H, H, None) == 0, pkg.last_error()
+assert L.glc_op_expand_pos(pos[:, H:].data_ptr(), 2 * H, 256, 512, exps[:, H:].data_ptr(), 2 * H, H, None) == 0, pkg.last_error()
+print("attention mode:", MODE)
 
 
 def run(naive, out, nb=B):
+    if not naive and MODE == "shift":
+        rc = L.glc_op_attention_shift(qkv.data_ptr(), exps[:, H:].data_ptr(), exps.data_ptr(), 2 * H, bits.data_ptr(),
+                                      kv.data_ptr(), out.data_ptr(), nb, S, heads, None)
+        assert rc == 0, pkg.last_error()
+        return
     if not naive and not LEGACY:
         rc = L.glc_op_attention_toeplitz(qkv.data_ptr(), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, bits.data_ptr(),
                                          kv.data_ptr(), out.data_ptr(), nb, S, heads, None)

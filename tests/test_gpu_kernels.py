@@ -218,6 +218,19 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, naive, qk_std=1.8):
         rc = L.glc_op_attention_toeplitz(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv),
                                          _ptr(ctx), B, S, heads, None)
         _sync_check(pkg, rc, "glc_op_attention_toeplitz")
+    elif naive == "shift":
+        # register-skew kernel: posK half expanded in rho order, posQ half in the opposite (sigma) order
+        ER = L.glc_expanded_pos_rows()
+        exp = torch.full((ER, 2 * H), float("nan"), dtype=torch.float16, device=dev)
+        _sync_check(pkg, L.glc_op_expand_pos_rev(_ptr(pos), 2 * H, 256, 512, _ptr(exp), 2 * H, H, None), "expand_pos_rev")
+        _sync_check(pkg, L.glc_op_expand_pos(pos[:, H:].data_ptr(), 2 * H, 256, 512, exp[:, H:].data_ptr(), 2 * H, H, None),
+                    "expand_pos")
+        full = torch.from_numpy(pkg.rel_index_table(2048, 256, 512)).long().to(dev)    # idx[delta + 2047]
+        assert torch.equal(exp[:ER - 1, H:], pos[full.flip(0)][:, H:]) and (exp[ER - 1] == 0).all()
+        assert torch.equal(exp[:ER - 1, :H], pos[full][:, :H])                         # row sigma = posQ[idx(sigma - 2047)]
+        rc = L.glc_op_attention_shift(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv),
+                                      _ptr(ctx), B, S, heads, None)
+        _sync_check(pkg, rc, "glc_op_attention_shift")
     else:
         rc = L.glc_op_attention(_ptr(qkv), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, _ptr(rel), _ptr(bits), _ptr(kv),
                                 _ptr(ctx), B, S, heads, 256, int(naive), None)
@@ -267,6 +280,29 @@ def test_attention_toeplitz(pkg, dev, B, S, heads, lens):
         bad = torch.nonzero(full.max(-1).values > 1e-2)
         print("   first bad (b,row):", bad[:10].tolist())
     _report(f"attn-toeplitz B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
+
+
+@pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1])])
+def test_attention_shift(pkg, dev, B, S, heads, lens):
+    """register-skew attention kernel (csrc/attention_shift.cu) against the fp32 restatement"""
+    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive="shift")
+    v = mask.bool()
+    got, want = ctx[v], ref[v]
+    d = (got.float() - want.float()).abs()
+    if d.max().item() > 1e-2 or torch.isnan(got.float()).any():
+        full = (ctx.float() - ref.float()).abs().nan_to_num(99.0) * mask[..., None].float()
+        for b in range(B):
+            for h in range(heads):
+                row = [f"{full[b, q0:q0 + 128, h * 64:(h + 1) * 64].max().item():.3f}" for q0 in range(0, S, 128)]
+                print(f"   b{b} h{h} per-q-tile max err: {row}")
+        bad = torch.nonzero(full.max(-1).values > 1e-2)
+        print("   first bad (b,row):", bad[:10].tolist())
+    _report(f"attn-shift B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
+
+
+def test_attention_shift_softmax_peaked(pkg, dev):
+    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, naive="shift", qk_std=3.0)
+    _report("attn-shift peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
 
 
 def test_attention_toeplitz_softmax_peaked(pkg, dev):
