@@ -49,19 +49,11 @@ namespace {
 constexpr int QT = 128;            // queries per CTA
 constexpr int KT = 64;             // keys per tile
 constexpr int D = 64;              // head dim
-constexpr int G = 2;               // key groups per tile: softmax thread = (query row, E-key group)
-constexpr int E = KT / G;          // scores per softmax thread per tile
-constexpr int NC = E + 32;         // C columns a thread loads: its E keys x the 32 lane shifts of its warp
-constexpr int NW = NC / 2;         // ... as fp16 pairs
-constexpr int SM_WARPS = 4 * G;    // 4 TMEM lane quarters x G groups
-constexpr int SM_THREADS = 32 * SM_WARPS;
-constexpr int ATT_THREADS = 64 + SM_THREADS;
+constexpr int GMAX = 4;            // key groups per tile (template parameter G = 2 or 4): softmax thread = (query row, 64/G keys)
 constexpr int SLICE = 192;         // table rows per tile (191 deltas + the never-consumed last row of copy 64)
 constexpr int EXP_CENTER = 2047;
 constexpr int EXP_ROWS = 4096;
 constexpr int TMAX = 2048 / KT;
-static_assert(E == 32 || E == 16, "key group width");
-static_assert(D / G == E, "output slice per thread = scores per thread");
 
 // shared memory map (bytes, from a 1024-aligned base)
 constexpr int OFF_Q = 0;                           // 128 x 128 B
@@ -71,7 +63,7 @@ constexpr int POS_BYTES = SLICE * 128;
 constexpr int OFF_EK = OFF_V + 16384;              // 2 x 192 x 128 B
 constexpr int OFF_EQ = OFF_EK + 2 * POS_BYTES;     // 2 x 192 x 128 B
 constexpr int OFF_XMAX = OFF_EQ + 2 * POS_BYTES;   // 2 x G x 128 floats (row-max exchange, double buffered by tile parity)
-constexpr int OFF_MASK = OFF_XMAX + 2 * G * QT * 4;   // uint32[68]: key-validity words of this batch row
+constexpr int OFF_MASK = OFF_XMAX + 2 * GMAX * QT * 4;   // uint32[68]: key-validity words of this batch row
 constexpr int OFF_BAR = OFF_MASK + 68 * 4;
 constexpr int ATT_SMEM = OFF_BAR + 256 + 1024;
 static_assert(OFF_BAR % 8 == 0, "barrier alignment");
@@ -88,6 +80,7 @@ constexpr uint32_t TM_G0 = 416;    // 32: window rows 0..127,  keys 32..63
 constexpr uint32_t TM_PV = 448;    // 64
 
 struct ShiftParams {
+  long long* trace;          // TRACE instantiation only: [2 roles][TMAX][8] clock64 stamps of CTA (1,0,0)
   const uint32_t* mask_bits; // [B][ceil(S/32)]
   const int32_t* kv_len;     // [B]
   __half* ctx;               // [B*S, H]
@@ -104,9 +97,23 @@ __device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&r)[32])
 
 __device__ __forceinline__ uint32_t sel(bool p, uint32_t a, uint32_t b) { return p ? a : b; }
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+#define GLC_TRACE(role, tile, slot)                                                                              \
+  do {                                                                                                           \
+    if (TRACE && p.trace && (threadIdx.x & 31) == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)    \
+      p.trace[((role) * TMAX + (tile)) * 8 + (slot)] = clock64();                                                \
+  } while (0)
+
+template <int G, bool TRACE>
+__global__ void __launch_bounds__(64 + 128 * G, 1)
 attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ek,
                        const __grid_constant__ CUtensorMap tm_eq, const ShiftParams p) {
+  constexpr int E = KT / G;          // scores per softmax thread per tile
+  constexpr int NC = E + 32;         // C columns a thread loads: its E keys x the 32 lane shifts of its warp
+  constexpr int NW = NC / 2;         // ... as fp16 pairs
+  constexpr int SM_WARPS = 4 * G;    // 4 TMEM lane quarters x G groups
+  constexpr int ATT_THREADS = 64 + 32 * SM_WARPS;
+  static_assert(E == 32 || E == 16, "key group width");
+  static_assert(D / G == E, "output slice per thread = scores per thread");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -219,9 +226,12 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
         const uint64_t dEK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EK + st * POS_BYTES));
         const uint64_t dEQ = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EQ + st * POS_BYTES));
+        GLC_TRACE(1, t, 0);
         ptx::mbar_wait(&a_full[st], (t >> 1) & 1);
+        GLC_TRACE(1, t, 1);
         if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);   // S, C and G accumulators drained
         ptx::tc_fence_after();
+        GLC_TRACE(1, t, 2);
         if (ptx::elect_one()) {
           // A = Q from TMEM: 16 halves along K = 8 columns per step; descriptors advance 32 B (= 2) per step;
           // 32 table/key rows = 4096 B = 256 in a descriptor
@@ -244,6 +254,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
           ptx::mma_commit(mma1_full);
         }
         __syncwarp();
+        GLC_TRACE(1, t, 3);
       }
       if (t > 0) {
         const int tp = t - 1;
@@ -252,6 +263,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         ptx::mbar_wait(&b_full[st], (tp >> 1) & 1);
         ptx::mbar_wait(p_full, tp & 1);
         ptx::tc_fence_after();
+        GLC_TRACE(1, tp, 4);
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // V is MN-major: 16 keys further = +2048 bytes = +128 in the descriptor
@@ -310,8 +322,10 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
+      if (sw == 0) GLC_TRACE(0, t, 0);
       ptx::mbar_wait(mma1_full, t & 1);
       ptx::tc_fence_after();
+      if (sw == 0) GLC_TRACE(0, t, 1);
 
       float s[E];
       uint32_t w[NW];
@@ -349,6 +363,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bias_free);
+      if (sw == 0) GLC_TRACE(0, t, 2);
 
       // ---- c2p: shift the packed window left by sh elements
 #pragma unroll
@@ -381,7 +396,9 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       //      tile t+1 orders the reads of tile t before the writes of tile t+2)
       float* xm = xmax + (t & 1) * (G * QT);
       xm[g * QT + i] = mloc;
+      if (sw == 0) GLC_TRACE(0, t, 3);
       ptx::named_bar_sync(2 + qd, 32 * G);   // only the G warps of this lane quarter share rows
+      if (sw == 0) GLC_TRACE(0, t, 4);
       float m_new = m_run;
 #pragma unroll
       for (int gg = 0; gg < G; ++gg) m_new = fmaxf(m_new, xm[gg * QT + i]);
@@ -399,9 +416,11 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       m_run = m_new;
 
       // ---- fold in PV of the previous tile (also guarantees the P buffer is free again)
+      if (sw == 0) GLC_TRACE(0, t, 5);
       if (t > 0) {
         ptx::mbar_wait(pv_full, (t - 1) & 1);
         ptx::tc_fence_after();
+        if (sw == 0) GLC_TRACE(0, t, 6);
         uint32_t r[E];
         tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
         ptx::tmem_ld_wait();
@@ -422,6 +441,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(p_full);
+      if (sw == 0) GLC_TRACE(0, t, 7);
     }
 
     // ---- last PV, normalise, write ctx
@@ -491,22 +511,54 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   CUtensorMap tm_qkv = make_tmap_16b(qkv, 3, dq, sq, bq);
   CUtensorMap tm_ek = make_tmap_16b(exp_k, 3, dp, sp, bp);
   CUtensorMap tm_eq = make_tmap_16b(exp_qr, 3, dp, sp, bp);
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_shift_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (e != cudaSuccess) return e;
-    attr_set[dev & 63] = true;
-  }
   ShiftParams p;
+  p.trace = nullptr;
   p.mask_bits = mask_bits;
   p.kv_len = kv_len;
   p.ctx = (__half*)ctx;
   p.B = B; p.S = S; p.heads = heads; p.H = H;
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
   dim3 grid((S + QT - 1) / QT, heads, B);
-  attention_shift_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(attention_shift_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  // developer switches: GLC_ATTN_G=2|4 key groups per tile; GLC_ATTN_TRACE=<file> dumps per-tile clock64 stamps of
+  // CTA (1,0,0) (synchronous)
+  static const int groups = [] { const char* e = getenv("GLC_ATTN_G"); return (e && atoi(e) == 2) ? 2 : 4; }();
+  if (const char* tf = getenv("GLC_ATTN_TRACE")) {
+    const size_t n = 2 * TMAX * 8;
+    if (cudaMalloc(&p.trace, n * sizeof(long long)) != cudaSuccess) return cudaGetLastError();
+    cudaMemsetAsync(p.trace, 0, n * sizeof(long long), stream);
+    if (groups == 2) attention_shift_kernel<2, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+    else attention_shift_kernel<4, true><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    std::vector<long long> h(n);
+    cudaMemcpy(h.data(), p.trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
+    cudaFree(p.trace);
+    if (FILE* f = fopen(tf, "w")) {
+      long long t0 = 0;
+      for (size_t k = 0; k < n; ++k) if (h[k] && (!t0 || h[k] < t0)) t0 = h[k];
+      for (int role = 0; role < 2; ++role)
+        for (int t = 0; t < TMAX; ++t) {
+          if (!h[(role * TMAX + t) * 8 + 1]) continue;
+          fprintf(f, "%s t=%d", role ? "mma" : "smx", t);
+          for (int k = 0; k < 8; ++k) fprintf(f, " %lld", h[(role * TMAX + t) * 8 + k] ? h[(role * TMAX + t) * 8 + k] - t0 : -1);
+          fprintf(f, "\n");
+        }
+      fclose(f);
+    }
+    return e;
+  }
+  if (groups == 2) attention_shift_kernel<2, false><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+  else attention_shift_kernel<4, false><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
   return cudaGetLastError();
 }
 
