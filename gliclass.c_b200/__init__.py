@@ -90,6 +90,7 @@ _SIGS = {
     "glc_op_attention_toeplitz": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_op_expand_pos_rev": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
     "glc_op_attention_shift": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "glc_op_attention_stream": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_op_head_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp]),
     "glc_op_head_score": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
 }

@@ -103,7 +103,7 @@ __device__ __forceinline__ uint32_t sel(bool p, uint32_t a, uint32_t b) { return
       p.trace[((role) * TMAX + (tile)) * 8 + (slot)] = clock64();                                                \
   } while (0)
 
-template <int G, bool TRACE>
+template <int G, bool TRACE, bool HEXP>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ek,
                        const __grid_constant__ CUtensorMap tm_eq, const ShiftParams p) {
@@ -406,11 +406,31 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       const float alpha = ptx::ex2((m_run - m_use) * sc);
       const float neg_ms = -m_use * sc;
       float psum = 0.f;
+      uint32_t pk[E / 2];   // P as fp16 pairs
+      if (HEXP) {
+        // two exponentials per MUFU op on packed fp16 arguments (<= 0, so the dominant terms keep full fp16 precision);
+        // row sum from the same rounded values: 4 independent fp16x2 chains of 4, finished in fp32
+        __half2 acc[4];
 #pragma unroll
-      for (int jj = 0; jj < E; ++jj) {
-        const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
-        s[jj] = e;
-        psum += e;
+        for (int v = 0; v < E / 2; ++v) {
+          pk[v] = ptx::ex2_f16x2(ptx::pack_f16(fmaf(s[2 * v], sc, neg_ms), fmaf(s[2 * v + 1], sc, neg_ms)));
+          const __half2 h = *reinterpret_cast<const __half2*>(&pk[v]);
+          acc[v & 3] = (v < 4) ? h : __hadd2(acc[v & 3], h);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float2 f = __half22float2(acc[c]);
+          psum += f.x + f.y;
+        }
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < E; ++jj) {
+          const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
+          s[jj] = e;
+          psum += e;
+        }
+#pragma unroll
+        for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
       }
       l_run = l_run * alpha + psum;
       m_run = m_new;
@@ -434,7 +454,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       for (int u = 0; u < E / 16; ++u) {
         uint32_t pr[8];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) pr[v] = ptx::pack_f16(s[16 * u + 2 * v], s[16 * u + 2 * v + 1]);
+        for (int v = 0; v < 8; ++v) pr[v] = pk[8 * u + v];
         ptx::tmem_st_x8(t_lane + TM_P + (uint32_t)((E / 2) * g + 8 * u), pr);
       }
       ptx::tmem_st_wait();
@@ -523,22 +543,23 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_shift_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attention_shift_kernel<2, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<2, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<4, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<2, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_shift_kernel<4, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
   // developer switches: GLC_ATTN_G=2|4 key groups per tile; GLC_ATTN_TRACE=<file> dumps per-tile clock64 stamps of
   // CTA (1,0,0) (synchronous)
-  static const int groups = [] { const char* e = getenv("GLC_ATTN_G"); return (e && atoi(e) == 2) ? 2 : 4; }();
+  static const int groups = [] { const char* e = getenv("GLC_ATTN_G"); return (e && atoi(e) == 4) ? 4 : 2; }();
   if (const char* tf = getenv("GLC_ATTN_TRACE")) {
     const size_t n = 2 * TMAX * 8;
     if (cudaMalloc(&p.trace, n * sizeof(long long)) != cudaSuccess) return cudaGetLastError();
     cudaMemsetAsync(p.trace, 0, n * sizeof(long long), stream);
-    if (groups == 2) attention_shift_kernel<2, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
-    else attention_shift_kernel<4, true><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+    if (groups == 2) attention_shift_kernel<2, true, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+    else attention_shift_kernel<4, true, true><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
     cudaError_t e = cudaStreamSynchronize(stream);
     std::vector<long long> h(n);
     cudaMemcpy(h.data(), p.trace, n * sizeof(long long), cudaMemcpyDeviceToHost);
@@ -557,8 +578,10 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
     }
     return e;
   }
-  if (groups == 2) attention_shift_kernel<2, false><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
-  else attention_shift_kernel<4, false><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+  static const bool hexp = [] { const char* e = getenv("GLC_ATTN_HEXP"); return e && e[0] == '1'; }();   // no gain: ex2.f16x2 issues two MUFU ops on sm_100
+  if (groups == 2 && hexp) attention_shift_kernel<2, false, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+  else if (groups == 2) attention_shift_kernel<2, false, false><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+  else attention_shift_kernel<4, false, true><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
   return cudaGetLastError();
 }
 

@@ -430,6 +430,11 @@ int glc_op_attention_shift(const void* qkv, const void* exp_k, const void* exp_q
   GLC_TRY("glc_op_attention_shift",
           glc::attention_shift(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
 }
+int glc_op_attention_stream(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
+                            const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
+  GLC_TRY("glc_op_attention_stream",
+          glc::attention_stream(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
+}
 int glc_expanded_pos_rows(void) { return glc::expanded_pos_rows(); }
 int glc_op_attention_toeplitz(const void* qkv, const void* exp_k, const void* exp_q, int64_t ld_exp, const uint32_t* mask_bits,
                               const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {

@@ -112,16 +112,18 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
   graphs_on_ = getenv("GLC_NO_GRAPHS") == nullptr;
-  // production attention = attention.cu (gather kernel, 360 us/launch at C2); GLC_ATTN_TOEPLITZ=1 selects the
-  // tensor-core-bias experiment (attention_toeplitz.cu, 413 us/launch) for A/B comparisons
+  // production attention = attention_shift.cu (register-skew biases, 306 us/launch at C2); GLC_ATTN selects the other
+  // generations for A/B comparisons: gather (attention.cu, 360 us), toeplitz (attention_toeplitz.cu, 413 us),
+  // stream (attention_stream.cu, 321 us).  GLC_ATTN_TOEPLITZ=1 is the older spelling of GLC_ATTN=toeplitz.
   const char* al = getenv("GLC_ATTN_TOEPLITZ");
-  attn_mode_ = (al && al[0] == '1') ? 1 : 0;
+  attn_mode_ = (al && al[0] == '1') ? 1 : 2;
   if (const char* am = getenv("GLC_ATTN")) {
     const std::string m(am);
     if (m == "gather") attn_mode_ = 0;
     else if (m == "toeplitz") attn_mode_ = 1;
     else if (m == "shift") attn_mode_ = 2;
-    else throw std::runtime_error("GLC_ATTN must be gather, toeplitz or shift (got '" + m + "')");
+    else if (m == "stream") attn_mode_ = 3;
+    else throw std::runtime_error("GLC_ATTN must be gather, toeplitz, shift or stream (got '" + m + "')");
   }
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
@@ -150,7 +152,7 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
     d_exp_idx = (int32_t*)dalloc((size_t)ER * 4);
     perm_allocs_.push_back(d_exp_idx);
     GLC_CUDA(cudaMemcpy(d_exp_idx, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice));
-    if (attn_mode_ == 2) {
+    if (attn_mode_ >= 2) {
       expanded_pos_index_rev(cfg_.buckets, cfg_.max_rel_pos, h.data());
       d_exp_idx_rev = (int32_t*)dalloc((size_t)ER * 4);
       perm_allocs_.push_back(d_exp_idx_rev);
@@ -461,8 +463,10 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
                                           cfg_.buckets, num_sms_, st));
     } else if (attn_mode_ == 1) {
       GLC_LAUNCH(KC_ATTN, attention_toeplitz(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
-    } else {
+    } else if (attn_mode_ == 2) {
       GLC_LAUNCH(KC_ATTN, attention_shift(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
+    } else {
+      GLC_LAUNCH(KC_ATTN, attention_stream(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
     }
     if (cfg_.pooling == POOL_LAST) GLC_LAUNCH(KC_ATTN, pad_rows_mean_v(qkv_, d_mask, ctx_, B, S, H, st));
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);

@@ -108,8 +108,9 @@ class DeviceModel {
   ModelConfig cfg_;
   int max_tokens_ = 65536;
   bool debug_keep_ = false;
-  int attn_mode_ = 0;          // 0 gather kernel (attention.cu), 1 tensor-core-bias experiment (attention_toeplitz.cu),
-                               // 2 register-skew kernel (attention_shift.cu); env GLC_ATTN=gather|toeplitz|shift
+  int attn_mode_ = 2;          // 2 register-skew kernel (attention_shift.cu, production); experiments: 0 gather kernel (attention.cu),
+                               // 1 tensor-core bias adds (attention_toeplitz.cu), 3 two-stream variant (attention_stream.cu);
+                               // env GLC_ATTN=gather|toeplitz|shift|stream
   std::atomic<uint64_t> launches_{0};
 
   // weights

@@ -51,6 +51,11 @@ void expanded_pos_index_rev(int buckets, int max_pos, int32_t* out /* host, [exp
 cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
                             const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                             cudaStream_t stream);
+// K3, fourth generation (attention_stream.cu): the register-skew biases of attention_shift with two independent
+// key-half softmax streams per query row and the output accumulators resident in TMEM.  Same operands as attention_shift.
+cudaError_t attention_stream(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                             const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
+                             cudaStream_t stream);
 // slow CUDA-core restatement of the same op, used only by tests to localise bugs on the GPU
 cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
                             const uint32_t* mask_bits, void* ctx, int B, int S, int heads, int buckets,

@@ -186,6 +186,11 @@ GLC_API int glc_op_expand_pos_rev(const void* pos_f16, int64_t ld_src, int bucke
 GLC_API int glc_op_attention_shift(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
                                    const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
                                    void* stream);
+/* K3, two-stream variant of the same kernel (csrc/attention_stream.cu): same operands as glc_op_attention_shift; each
+ * query row is handled by two independent key-half softmax streams whose outputs accumulate in tensor memory. */
+GLC_API int glc_op_attention_stream(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
+                                    const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
+                                    void* stream);
 /* K5a: pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] for the c-th <<LABEL>> token, else 0 */
 GLC_API int glc_op_head_gather(const void* h_f16, const int64_t* ids, int64_t class_token, void* pooled_f16,
                                void* cls_f16, int B, int S, int H, int C, void* stream);

@@ -42,8 +42,9 @@ print("attention mode:", MODE)
 
 
 def run(naive, out, nb=B):
-    if not naive and MODE == "shift":
-        rc = L.glc_op_attention_shift(qkv.data_ptr(), exps[:, H:].data_ptr(), exps.data_ptr(), 2 * H, bits.data_ptr(),
+    if not naive and MODE in ("shift", "stream"):
+        op = L.glc_op_attention_shift if MODE == "shift" else L.glc_op_attention_stream
+        rc = op(qkv.data_ptr(), exps[:, H:].data_ptr(), exps.data_ptr(), 2 * H, bits.data_ptr(),
                                       kv.data_ptr(), out.data_ptr(), nb, S, heads, None)
         assert rc == 0, pkg.last_error()
         return

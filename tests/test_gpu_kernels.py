@@ -218,7 +218,7 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, naive, qk_std=1.8):
         rc = L.glc_op_attention_toeplitz(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv),
                                          _ptr(ctx), B, S, heads, None)
         _sync_check(pkg, rc, "glc_op_attention_toeplitz")
-    elif naive == "shift":
+    elif naive in ("shift", "stream"):
         # register-skew kernel: posK half expanded in rho order, posQ half in the opposite (sigma) order
         ER = L.glc_expanded_pos_rows()
         exp = torch.full((ER, 2 * H), float("nan"), dtype=torch.float16, device=dev)
@@ -228,9 +228,9 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, naive, qk_std=1.8):
         full = torch.from_numpy(pkg.rel_index_table(2048, 256, 512)).long().to(dev)    # idx[delta + 2047]
         assert torch.equal(exp[:ER - 1, H:], pos[full.flip(0)][:, H:]) and (exp[ER - 1] == 0).all()
         assert torch.equal(exp[:ER - 1, :H], pos[full][:, :H])                         # row sigma = posQ[idx(sigma - 2047)]
-        rc = L.glc_op_attention_shift(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv),
-                                      _ptr(ctx), B, S, heads, None)
-        _sync_check(pkg, rc, "glc_op_attention_shift")
+        op = L.glc_op_attention_shift if naive == "shift" else L.glc_op_attention_stream
+        rc = op(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
+        _sync_check(pkg, rc, "glc_op_attention_" + naive)
     else:
         rc = L.glc_op_attention(_ptr(qkv), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, _ptr(rel), _ptr(bits), _ptr(kv),
                                 _ptr(ctx), B, S, heads, 256, int(naive), None)
@@ -282,10 +282,11 @@ def test_attention_toeplitz(pkg, dev, B, S, heads, lens):
     _report(f"attn-toeplitz B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
 
 
+@pytest.mark.parametrize("kernel", ["shift", "stream"])
 @pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1])])
-def test_attention_shift(pkg, dev, B, S, heads, lens):
-    """register-skew attention kernel (csrc/attention_shift.cu) against the fp32 restatement"""
-    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive="shift")
+def test_attention_shift(pkg, dev, B, S, heads, lens, kernel):
+    """register-skew attention kernels (csrc/attention_shift.cu, csrc/attention_stream.cu) against the fp32 restatement"""
+    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive=kernel)
     v = mask.bool()
     got, want = ctx[v], ref[v]
     d = (got.float() - want.float()).abs()
@@ -297,12 +298,14 @@ def test_attention_shift(pkg, dev, B, S, heads, lens):
                 print(f"   b{b} h{h} per-q-tile max err: {row}")
         bad = torch.nonzero(full.max(-1).values > 1e-2)
         print("   first bad (b,row):", bad[:10].tolist())
-    _report(f"attn-shift B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
+    _report(f"attn-{kernel} B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
 
 
-def test_attention_shift_softmax_peaked(pkg, dev):
-    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, naive="shift", qk_std=3.0)
-    _report("attn-shift peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
+@pytest.mark.parametrize("kernel", ["shift", "stream"])
+def test_attention_shift_softmax_peaked(pkg, dev, kernel):
+    # large score magnitudes: the row maximum keeps growing across key tiles (exercises the O rescale of the stream kernel)
+    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, naive=kernel, qk_std=3.0)
+    _report(f"attn-{kernel} peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
 
 
 def test_attention_toeplitz_softmax_peaked(pkg, dev):
