@@ -184,6 +184,79 @@ residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
   }
 }
 
+// K4, bulk-copy variant: every warp owns a ring of LN_STAGES shared-memory stages, each holding one row of x and the
+// matching row of r, filled by cp.async.bulk (one elected lane, completion on the stage's mbarrier).  LN_STAGES rows
+// per warp are in flight (2 blocks x 8 warps x 4 stages x 3 KB = 192 KB per SM at H = 768) without holding them in
+// registers, so the loads of a warp never wait for its arithmetic.  No block-level synchronisation: each warp runs its
+// own pipeline over rows  warp_global, warp_global + total_warps, ...
+constexpr int LN_STAGES = 4;
+
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ptx::smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+
+template <int NC>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__ r, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t row_bytes = (uint32_t)H * 2u;
+  uint8_t* ring = ln_smem + (size_t)warp * LN_STAGES * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)ROWS_PER_BLOCK * LN_STAGES * 2 * row_bytes) + warp * LN_STAGES;
+  const int nwarps = gridDim.x * ROWS_PER_BLOCK;
+  const int row0 = blockIdx.x * ROWS_PER_BLOCK + warp;
+  if (row0 >= M) return;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
+    ptx::fence_barrier_init();
+  }
+  __syncwarp();
+  auto issue = [&](int rw, int s) {
+    if (lane == 0) {
+      uint8_t* dst = ring + (size_t)s * 2 * row_bytes;
+      ptx::mbar_arrive_expect_tx(&bars[s], 2 * row_bytes);
+      bulk_load(dst, x + (int64_t)rw * H, row_bytes, &bars[s]);
+      bulk_load(dst + row_bytes, r + (int64_t)rw * H, row_bytes, &bars[s]);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < LN_STAGES; ++s) {
+    const int rw = row0 + s * nwarps;
+    if (rw < M) issue(rw, s);
+  }
+  LnParams<NC> gb;
+  gb.load(lane, H, gamma, beta);
+  int it = 0;
+  for (int rw = row0; rw < M; rw += nwarps, ++it) {
+    const int s = it % LN_STAGES;
+    ptx::mbar_wait(&bars[s], (uint32_t)(it / LN_STAGES) & 1u);
+    const uint8_t* xs = ring + (size_t)s * 2 * row_bytes;
+    float v[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int e0 = (lane + 32 * c) * 8;
+      if (e0 < H) {
+        const uint4 xa = *reinterpret_cast<const uint4*>(xs + e0 * 2);
+        const uint4 ra = *reinterpret_cast<const uint4*>(xs + row_bytes + e0 * 2);
+        float t[8];
+        unpack8(xa, v[c]);
+        unpack8(ra, t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+      }
+    }
+    __syncwarp();   // every lane has read the stage: refill it
+    const int nxt = rw + LN_STAGES * nwarps;
+    if (nxt < M) issue(nxt, s);
+    ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)rw * H);
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 ln_f32_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -469,6 +542,26 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
   if (M <= 0) return cudaSuccess;
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
+    // bulk-copy ring variant (needs the residual operand and 16-byte rows); GLC_LN_BULK=0 keeps the register-prefetch kernel
+    static const bool bulk_on = [] { const char* e = getenv("GLC_LN_BULK"); return !(e && e[0] == '0'); }();
+    const size_t ring_bytes = (size_t)ROWS_PER_BLOCK * LN_STAGES * 2 * (size_t)H * 2 + ROWS_PER_BLOCK * LN_STAGES * 8;
+    if (bulk_on && r && (H * 2) % 16 == 0 && ring_bytes <= 112 * 1024) {
+      static bool attr_set[64][9] = {};
+      int dev = 0, sms = 148;
+      cudaGetDevice(&dev);
+      if (!attr_set[dev & 63][NC]) {
+        cudaError_t e = cudaFuncSetAttribute(residual_ln_bulk_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev & 63][NC] = true;
+      }
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+      const int per_sm = (int)((224 * 1024) / (ring_bytes + 1024));
+      if (blocks > sms * per_sm) blocks = sms * per_sm;
+      residual_ln_bulk_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, ring_bytes, stream>>>(
+          (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H);
+      return cudaGetLastError();
+    }
     int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
     const int cap = ln_grid_cap();   // a few resident blocks per SM, each warp walking several rows
     if (blocks > cap) blocks = cap;
