@@ -86,6 +86,7 @@ struct ShiftParams {
   __half* ctx;               // [B*S, H]
   int B, S, heads, H;
   float scale_log2;          // log2(e) / sqrt(3*d)
+  int swap_order;            // developer switch (GLC_ATTN_SWAP=0: both key groups walk the stages in the same order)
 };
 
 template <int N>
@@ -319,6 +320,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
     for (int k = 0; k < E; ++k) o[k] = 0.f;
     const float sc = p.scale_log2;
+    const bool swap_order = p.swap_order != 0;
 
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
@@ -327,60 +329,75 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       ptx::tc_fence_after();
       if (sw == 0) GLC_TRACE(0, t, 1);
 
+      // The two warps of a scheduler (key groups g, g+1 of the same lane quarter) walk the pre-maximum stages in opposite
+      // orders, so that one drains TMEM (64 B/clk port per quarter) while the other runs the ALU-pipe barrel shifter:
+      //   even g:  C|S drain -> barrel -> G drain + lane rotation        odd g:  G drain + lane rotation -> C|S drain -> barrel
       float s[E];
-      uint32_t w[NW];
-      {
-        uint32_t r[E];
-        tmem_ld_n<E>(a_s, r);
-        uint32_t c[NC];
 #pragma unroll
-        for (int u = 0; u < NC / 16; ++u) {
-          uint32_t cc[16];
-          ptx::tmem_ld_x16(a_c + 16 * u, cc);
+      for (int jj = 0; jj < E; ++jj) s[jj] = 0.f;
+      auto stage_c2p = [&]() {
+        uint32_t w[NW];
+        {
+          uint32_t r[E];
+          tmem_ld_n<E>(a_s, r);
+          uint32_t c[NC];
 #pragma unroll
-          for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
+          for (int u = 0; u < NC / 16; ++u) {
+            uint32_t cc[16];
+            ptx::tmem_ld_x16(a_c + 16 * u, cc);
+#pragma unroll
+            for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
+          }
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int jj = 0; jj < E; ++jj) s[jj] += __uint_as_float(r[jj]);
+#pragma unroll
+          for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
         }
-        ptx::tmem_ld_wait();
+        // shift the packed window left by sh elements
 #pragma unroll
-        for (int jj = 0; jj < E; ++jj) s[jj] = __uint_as_float(r[jj]);
+        for (int k = 0; k < NW - 8; ++k) w[k] = sel(sh16, w[k + 8], w[k]);
 #pragma unroll
-        for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
-      }
-      // ---- p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
+        for (int k = 0; k < NW - 12; ++k) w[k] = sel(sh8, w[k + 4], w[k]);
 #pragma unroll
-      for (int u = 0; u < E / 16; ++u) {
-        uint32_t lo[16], hi[16];
-        ptx::tmem_ld_x16(a_lo + 16 * u, lo);
-        ptx::tmem_ld_x16(a_hi + 16 * u, hi);
-        ptx::tmem_ld_wait();
+        for (int k = 0; k < NW - 14; ++k) w[k] = sel(sh4, w[k + 2], w[k]);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          const int jj = 16 * u + k;
-          const uint32_t v = sel(thr0 + jj < 0, hi[k], lo[k]);
-          s[jj] += __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+        for (int k = 0; k < NW - 15; ++k) w[k] = sel(sh2, w[k + 1], w[k]);
+#pragma unroll
+        for (int m = 0; m < E / 2; ++m) {
+          const uint32_t x = __byte_perm(w[m], w[m + 1], prmt_sel);
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&x));
+          s[2 * m] += f.x;
+          s[2 * m + 1] += f.y;
         }
+      };
+      // p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
+      auto stage_p2c = [&]() {
+#pragma unroll
+        for (int u = 0; u < E / 16; ++u) {
+          uint32_t lo[16], hi[16];
+          ptx::tmem_ld_x16(a_lo + 16 * u, lo);
+          ptx::tmem_ld_x16(a_hi + 16 * u, hi);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int jj = 16 * u + k;
+            const uint32_t v = sel(thr0 + jj < 0, hi[k], lo[k]);
+            s[jj] += __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+          }
+        }
+      };
+      if (!(g & 1) || !swap_order) {
+        stage_c2p();
+        stage_p2c();
+      } else {
+        stage_p2c();
+        stage_c2p();
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bias_free);
       if (sw == 0) GLC_TRACE(0, t, 2);
-
-      // ---- c2p: shift the packed window left by sh elements
-#pragma unroll
-      for (int k = 0; k < NW - 8; ++k) w[k] = sel(sh16, w[k + 8], w[k]);
-#pragma unroll
-      for (int k = 0; k < NW - 12; ++k) w[k] = sel(sh8, w[k + 4], w[k]);
-#pragma unroll
-      for (int k = 0; k < NW - 14; ++k) w[k] = sel(sh4, w[k + 2], w[k]);
-#pragma unroll
-      for (int k = 0; k < NW - 15; ++k) w[k] = sel(sh2, w[k + 1], w[k]);
-#pragma unroll
-      for (int m = 0; m < E / 2; ++m) {
-        const uint32_t x = __byte_perm(w[m], w[m + 1], prmt_sel);
-        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&x));
-        s[2 * m] += f.x;
-        s[2 * m + 1] += f.y;
-      }
 
       const int kb = k0 + b0;
       const uint32_t kbits = kmask[kb >> 5] >> (kb & 31);   // E <= 32 and kb is a multiple of E: no word straddling
@@ -405,49 +422,60 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
       const float alpha = ptx::ex2((m_run - m_use) * sc);
       const float neg_ms = -m_use * sc;
-      float psum = 0.f;
       uint32_t pk[E / 2];   // P as fp16 pairs
-      if (HEXP) {
-        // two exponentials per MUFU op on packed fp16 arguments (<= 0, so the dominant terms keep full fp16 precision);
-        // row sum from the same rounded values: 4 independent fp16x2 chains of 4, finished in fp32
-        __half2 acc[4];
+      // ... and the post-maximum stages too: even g  exponentials (MUFU) -> PV fold (TMEM read + FMA), odd g the reverse
+      auto stage_exp = [&]() {
+        float psum = 0.f;
+        if (HEXP) {
+          // two exponentials per MUFU op on packed fp16 arguments (<= 0, so the dominant terms keep full fp16 precision);
+          // row sum from the same rounded values: 4 independent fp16x2 chains of 4, finished in fp32
+          __half2 acc[4];
 #pragma unroll
-        for (int v = 0; v < E / 2; ++v) {
-          pk[v] = ptx::ex2_f16x2(ptx::pack_f16(fmaf(s[2 * v], sc, neg_ms), fmaf(s[2 * v + 1], sc, neg_ms)));
-          const __half2 h = *reinterpret_cast<const __half2*>(&pk[v]);
-          acc[v & 3] = (v < 4) ? h : __hadd2(acc[v & 3], h);
-        }
+          for (int v = 0; v < E / 2; ++v) {
+            pk[v] = ptx::ex2_f16x2(ptx::pack_f16(fmaf(s[2 * v], sc, neg_ms), fmaf(s[2 * v + 1], sc, neg_ms)));
+            const __half2 h = *reinterpret_cast<const __half2*>(&pk[v]);
+            acc[v & 3] = (v < 4) ? h : __hadd2(acc[v & 3], h);
+          }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float2 f = __half22float2(acc[c]);
-          psum += f.x + f.y;
+          for (int c = 0; c < 4; ++c) {
+            const float2 f = __half22float2(acc[c]);
+            psum += f.x + f.y;
+          }
+        } else {
+#pragma unroll
+          for (int jj = 0; jj < E; ++jj) {
+            const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
+            s[jj] = e;
+            psum += e;
+          }
+#pragma unroll
+          for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
         }
+        l_run = l_run * alpha + psum;
+        m_run = m_new;
+      };
+      // fold in PV of the previous tile (also guarantees the P buffer is free again)
+      auto stage_fold = [&]() {
+        if (sw == 0) GLC_TRACE(0, t, 5);
+        if (t > 0) {
+          ptx::mbar_wait(pv_full, (t - 1) & 1);
+          ptx::tc_fence_after();
+          if (sw == 0) GLC_TRACE(0, t, 6);
+          uint32_t r[E];
+          tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
+        }
+        alpha_prev = alpha;
+      };
+      if (!(g & 1) || !swap_order) {
+        stage_exp();
+        stage_fold();
       } else {
-#pragma unroll
-        for (int jj = 0; jj < E; ++jj) {
-          const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
-          s[jj] = e;
-          psum += e;
-        }
-#pragma unroll
-        for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
+        stage_fold();
+        stage_exp();
       }
-      l_run = l_run * alpha + psum;
-      m_run = m_new;
-
-      // ---- fold in PV of the previous tile (also guarantees the P buffer is free again)
-      if (sw == 0) GLC_TRACE(0, t, 5);
-      if (t > 0) {
-        ptx::mbar_wait(pv_full, (t - 1) & 1);
-        ptx::tc_fence_after();
-        if (sw == 0) GLC_TRACE(0, t, 6);
-        uint32_t r[E];
-        tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
-      }
-      alpha_prev = alpha;
 
       // ---- P tile -> TMEM: row i, fp16 pairs at columns (E/2) g ..
 #pragma unroll
@@ -538,6 +566,8 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   p.ctx = (__half*)ctx;
   p.B = B; p.S = S; p.heads = heads; p.H = H;
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
+  static const int swap_order = [] { const char* e = getenv("GLC_ATTN_SWAP"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.swap_order = swap_order;
   dim3 grid((S + QT - 1) / QT, heads, B);
   static bool attr_set[64] = {};
   int dev = 0;

@@ -189,7 +189,7 @@ residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
 // per warp are in flight (2 blocks x 8 warps x 4 stages x 3 KB = 192 KB per SM at H = 768) without holding them in
 // registers, so the loads of a warp never wait for its arithmetic.  No block-level synchronisation: each warp runs its
 // own pipeline over rows  warp_global, warp_global + total_warps, ...
-constexpr int LN_STAGES = 4;
+constexpr int LN_STAGES = 4;   // at most; rows wider than 1.7 KB get fewer stages (ring <= 110 KB per block, two blocks per SM)
 
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -201,18 +201,17 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__ r, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H) {
+                        const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H, int stages) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)H * 2u;
-  uint8_t* ring = ln_smem + (size_t)warp * LN_STAGES * 2 * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)ROWS_PER_BLOCK * LN_STAGES * 2 * row_bytes) + warp * LN_STAGES;
+  uint8_t* ring = ln_smem + (size_t)warp * stages * 2 * row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)ROWS_PER_BLOCK * stages * 2 * row_bytes) + warp * LN_STAGES;
   const int nwarps = gridDim.x * ROWS_PER_BLOCK;
   const int row0 = blockIdx.x * ROWS_PER_BLOCK + warp;
   if (row0 >= M) return;
   if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < LN_STAGES; ++s) ptx::mbar_init(&bars[s], 1);
+    for (int s = 0; s < stages; ++s) ptx::mbar_init(&bars[s], 1);
     ptx::fence_barrier_init();
   }
   __syncwarp();
@@ -224,17 +223,16 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
       bulk_load(dst + row_bytes, r + (int64_t)rw * H, row_bytes, &bars[s]);
     }
   };
-#pragma unroll
-  for (int s = 0; s < LN_STAGES; ++s) {
+  for (int s = 0; s < stages; ++s) {
     const int rw = row0 + s * nwarps;
     if (rw < M) issue(rw, s);
   }
   LnParams<NC> gb;
   gb.load(lane, H, gamma, beta);
-  int it = 0;
-  for (int rw = row0; rw < M; rw += nwarps, ++it) {
-    const int s = it % LN_STAGES;
-    ptx::mbar_wait(&bars[s], (uint32_t)(it / LN_STAGES) & 1u);
+  int s = 0;
+  uint32_t parity = 0;
+  for (int rw = row0; rw < M; rw += nwarps) {
+    ptx::mbar_wait(&bars[s], parity);
     const uint8_t* xs = ring + (size_t)s * 2 * row_bytes;
     float v[NC][8];
 #pragma unroll
@@ -251,9 +249,10 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
       }
     }
     __syncwarp();   // every lane has read the stage: refill it
-    const int nxt = rw + LN_STAGES * nwarps;
+    const int nxt = rw + stages * nwarps;
     if (nxt < M) issue(nxt, s);
     ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)rw * H);
+    if (++s == stages) { s = 0; parity ^= 1u; }
   }
 }
 
@@ -544,8 +543,11 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
     constexpr int NC = decltype(nc)::value;
     // bulk-copy ring variant (needs the residual operand and 16-byte rows); GLC_LN_BULK=0 keeps the register-prefetch kernel
     static const bool bulk_on = [] { const char* e = getenv("GLC_LN_BULK"); return !(e && e[0] == '0'); }();
-    const size_t ring_bytes = (size_t)ROWS_PER_BLOCK * LN_STAGES * 2 * (size_t)H * 2 + ROWS_PER_BLOCK * LN_STAGES * 8;
-    if (bulk_on && r && (H * 2) % 16 == 0 && ring_bytes <= 112 * 1024) {
+    const size_t stage_bytes = (size_t)ROWS_PER_BLOCK * 2 * (size_t)H * 2;   // one stage of all 8 warps
+    int stages = (int)((110 * 1024) / stage_bytes);
+    if (stages > LN_STAGES) stages = LN_STAGES;
+    const size_t ring_bytes = stage_bytes * stages + ROWS_PER_BLOCK * LN_STAGES * 8;
+    if (bulk_on && r && (H * 2) % 16 == 0 && stages >= 2) {
       static bool attr_set[64][9] = {};
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
@@ -559,7 +561,7 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
       const int per_sm = (int)((224 * 1024) / (ring_bytes + 1024));
       if (blocks > sms * per_sm) blocks = sms * per_sm;
       residual_ln_bulk_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, ring_bytes, stream>>>(
-          (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H);
+          (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages);
       return cudaGetLastError();
     }
     int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;

@@ -11,7 +11,7 @@ import __graft_entry__ as graft  # noqa: E402
 pkg = graft.load_package()
 L = pkg.lib()
 dev = torch.device("cuda", 0)
-M, H = 32768, 768
+M, H = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (32768, 768)
 g = torch.Generator().manual_seed(2)
 x = torch.randn(M, H, generator=g).to(torch.float16).to(dev)
 r = torch.randn(M, H, generator=g).to(torch.float16).to(dev)

@@ -129,7 +129,7 @@ def test_embed_ln(pkg, dev, H):
     _report(f"embed_ln H={H}", y, ref, 2e-3, 2e-3)
 
 
-@pytest.mark.parametrize("H,M", [(128, 300), (768, 4096), (1024, 1000)])
+@pytest.mark.parametrize("H,M", [(128, 300), (768, 4096), (1024, 1000), (768, 70001), (1024, 40003), (1536, 20000), (2048, 3000)])
 def test_residual_ln(pkg, dev, H, M):
     g = torch.Generator().manual_seed(H + M)
     x = torch.randn(M, H, generator=g).to(torch.float16).to(dev)
