@@ -391,3 +391,41 @@ def test_submit_collect_overlaps_and_matches(pkg, orc, golden_onnx):
         assert s.collect(t).shape[0] == 0
     finally:
         s.close()
+
+
+def test_rows_sharded_over_two_devices_match_one_device(pkg, orc, golden_onnx, golden):
+    """SURVEY.md §8e mode (1): one process, several GPUs — a big Run is split into contiguous row shards (one host
+    thread + stream per device, host gather), concurrent small Runs go round-robin.  Rows are independent, so the
+    logits must equal the single-device ones bit for bit, and C (the output width) must be the global maximum."""
+    if pkg.device_count() < 2:
+        pytest.skip("needs two B200s (run with gpurun --gpus 2)")
+    one = pkg.Session(golden_onnx, devices=[0])
+    two = pkg.Session(golden_onnx, devices=[0, 1])
+    assert two.info["num_devices"] == 2
+    try:
+        for case in ["full", "ragged", "short", "long"]:
+            ids, mask = golden[f"{case}.input_ids"], golden[f"{case}.attention_mask"]
+            assert np.array_equal(one.run_inference(ids, mask), two.run_inference(ids, mask)), case
+        # mixed label counts: the shard on device 1 has fewer labels than the one on device 0
+        cfg = orc.make_config("tiny")
+        ids, mask = orc.synth_inputs(cfg, 6, 96, [5, 4, 3, 1, 1, 0], seed=21, ragged=True)
+        ra, rb = one.run_inference(ids.numpy(), mask.numpy()), two.run_inference(ids.numpy(), mask.numpy())
+        assert ra.shape == rb.shape == (6, 5) and np.array_equal(ra, rb)
+        # concurrent small Runs (the reference's OpenMP loop) spread over both devices
+        want = one.run_inference(golden["short.input_ids"], golden["short.attention_mask"])
+        got, errs = {}, []
+
+        def work(k):
+            try:
+                got[k] = two.run_inference(golden["short.input_ids"], golden["short.attention_mask"])
+            except Exception as e:   # noqa: BLE001
+                errs.append(e)
+
+        th = [threading.Thread(target=work, args=(k,)) for k in range(8)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert not errs, errs
+        assert all(np.array_equal(got[k], want) for k in range(8))
+    finally:
+        one.close()
+        two.close()
