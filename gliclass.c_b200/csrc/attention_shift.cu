@@ -87,6 +87,7 @@ struct ShiftParams {
   int B, S, heads, H;
   float scale_log2;          // log2(e) / sqrt(3*d)
   int swap_order;            // developer switch (GLC_ATTN_SWAP=0: both key groups walk the stages in the same order)
+  int poly;                  // developer switch (GLC_ATTN_POLY=0: every exponential on the MUFU unit)
 };
 
 template <int N>
@@ -98,13 +99,31 @@ __device__ __forceinline__ void tmem_ld_n<32>(uint32_t taddr, uint32_t (&r)[32])
 
 __device__ __forceinline__ uint32_t sel(bool p, uint32_t a, uint32_t b) { return p ? a : b; }
 
+// 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5 — well
+// below the fp16 rounding of P): the exponential stage of a tile is bound by the MUFU unit (8 cycles per warp
+// instruction) while the FMA pipe idles, so every POLY_EVERY-th score of a thread takes this route instead.
+constexpr int POLY_EVERY = 4;
+__device__ __forceinline__ float exp2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float r = x - (t - 12582912.0f);    // [-0.5, 0.5]
+  float p = fmaf(0.05517090f, r, 0.24260953f);
+  p = fmaf(p, r, 0.69326097f);
+  p = fmaf(p, r, 0.99992818f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+template <bool POLY>
+__device__ __forceinline__ float exp2_sel(int jj, float x) {
+  return (POLY && (jj % POLY_EVERY) == POLY_EVERY - 1) ? exp2_poly(x) : ptx::ex2(x);
+}
+
 #define GLC_TRACE(role, tile, slot)                                                                              \
   do {                                                                                                           \
     if (TRACE && p.trace && (threadIdx.x & 31) == 0 && blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0)    \
       p.trace[((role) * TMAX + (tile)) * 8 + (slot)] = clock64();                                                \
   } while (0)
 
-template <int G, bool TRACE, bool HEXP>
+template <int G, bool TRACE, bool OTMEM>
 __global__ void __launch_bounds__(64 + 128 * G, 1)
 attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ek,
                        const __grid_constant__ CUtensorMap tm_eq, const ShiftParams p) {
@@ -123,12 +142,14 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   uint64_t* a_empty = bars + 3;      // [2]  ... consumed by the S / C / G MMAs
   uint64_t* b_full = bars + 5;       // [2]  V_t landed
   uint64_t* b_empty = bars + 7;      // [2]  ... consumed by the PV MMA
-  uint64_t* mma1_full = bars + 9;    // S, C, G accumulators of tile t ready
-  uint64_t* bias_free = bars + 10;   // softmax warps have drained them
+  uint64_t* sc_full = bars + 9;      // S and C accumulators of tile t ready
+  uint64_t* sc_free = bars + 10;     // ... drained by all softmax warps
+  uint64_t* g_full = bars + 15;      // G copies of tile t ready
+  uint64_t* g_free = bars + 16;      // ... drained
   uint64_t* p_full = bars + 11;      // P tile written
   uint64_t* pv_full = bars + 12;     // PV accumulator ready
   uint64_t* qt_full = bars + 13;     // Q tile copied into TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);   // bars 15, 16 follow
   uint32_t* kmask = reinterpret_cast<uint32_t*>(smem + OFF_MASK);
 
   const int warp = threadIdx.x >> 5;
@@ -156,8 +177,10 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     ptx::mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&a_full[s], 1); ptx::mbar_init(&a_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(&b_full[s], 1); ptx::mbar_init(&b_empty[s], 1); }
-    ptx::mbar_init(mma1_full, 1);
-    ptx::mbar_init(bias_free, SM_WARPS);
+    ptx::mbar_init(sc_full, 1);
+    ptx::mbar_init(sc_free, SM_WARPS);
+    ptx::mbar_init(g_full, 1);
+    ptx::mbar_init(g_free, SM_WARPS);
     ptx::mbar_init(p_full, SM_WARPS);
     ptx::mbar_init(pv_full, 1);
     ptx::mbar_init(qt_full, SM_WARPS);
@@ -230,7 +253,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         GLC_TRACE(1, t, 0);
         ptx::mbar_wait(&a_full[st], (t >> 1) & 1);
         GLC_TRACE(1, t, 1);
-        if (t > 0) ptx::mbar_wait(bias_free, (t - 1) & 1);   // S, C and G accumulators drained
+        if (t > 0) ptx::mbar_wait(sc_free, (t - 1) & 1);   // S and C accumulators drained
         ptx::tc_fence_after();
         GLC_TRACE(1, t, 2);
         if (ptx::elect_one()) {
@@ -242,6 +265,13 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::mma_f16_ts(tmem + TM_C, tmem + TM_Q + 8 * k, dEK + 2 * k, idesc_c, (uint32_t)(k != 0));
+          ptx::mma_commit(sc_full);
+        }
+        __syncwarp();
+        // the softmax warps drain S and C while the G copies are computed, and G while S, C of the next tile are
+        if (t > 0) ptx::mbar_wait(g_free, (t - 1) & 1);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // rows 32..159 x keys 0..63
             ptx::mma_f16_ss(tmem + TM_G32, dEQ + 256 + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
@@ -252,7 +282,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
           for (int k = 0; k < 4; ++k)   // rows 0..127 x keys 32..63
             ptx::mma_f16_ss(tmem + TM_G0, dEQ + 2 * k, dK + 256 + 2 * k, idesc_n32, (uint32_t)(k != 0));
           ptx::mma_commit(&a_empty[st]);
-          ptx::mma_commit(mma1_full);
+          ptx::mma_commit(g_full);
         }
         __syncwarp();
         GLC_TRACE(1, t, 3);
@@ -268,7 +298,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         if (ptx::elect_one()) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)   // V is MN-major: 16 keys further = +2048 bytes = +128 in the descriptor
-            ptx::mma_f16_ts(tmem + TM_PV, tmem + TM_P + 8 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0));
+            ptx::mma_f16_ts(tmem + TM_PV, tmem + TM_P + 8 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0 || (OTMEM && tp > 0)));
           ptx::mma_commit(&b_empty[st]);
           ptx::mma_commit(pv_full);
         }
@@ -321,12 +351,11 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     for (int k = 0; k < E; ++k) o[k] = 0.f;
     const float sc = p.scale_log2;
     const bool swap_order = p.swap_order != 0;
+    const bool poly = p.poly != 0;
 
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
       if (sw == 0) GLC_TRACE(0, t, 0);
-      ptx::mbar_wait(mma1_full, t & 1);
-      ptx::tc_fence_after();
       if (sw == 0) GLC_TRACE(0, t, 1);
 
       // The two warps of a scheduler (key groups g, g+1 of the same lane quarter) walk the pre-maximum stages in opposite
@@ -337,6 +366,8 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       for (int jj = 0; jj < E; ++jj) s[jj] = 0.f;
       auto stage_c2p = [&]() {
         uint32_t w[NW];
+        ptx::mbar_wait(sc_full, t & 1);
+        ptx::tc_fence_after();
         {
           uint32_t r[E];
           tmem_ld_n<E>(a_s, r);
@@ -349,6 +380,9 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
           }
           ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(sc_free);
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) s[jj] += __uint_as_float(r[jj]);
 #pragma unroll
@@ -373,12 +407,19 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       };
       // p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
       auto stage_p2c = [&]() {
+        ptx::mbar_wait(g_full, t & 1);
+        ptx::tc_fence_after();
 #pragma unroll
         for (int u = 0; u < E / 16; ++u) {
           uint32_t lo[16], hi[16];
           ptx::tmem_ld_x16(a_lo + 16 * u, lo);
           ptx::tmem_ld_x16(a_hi + 16 * u, hi);
           ptx::tmem_ld_wait();
+          if (u == E / 16 - 1) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(g_free);
+          }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int jj = 16 * u + k;
@@ -394,9 +435,6 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         stage_p2c();
         stage_c2p();
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bias_free);
       if (sw == 0) GLC_TRACE(0, t, 2);
 
       const int kb = k0 + b0;
@@ -419,27 +457,23 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       float m_new = m_run;
 #pragma unroll
       for (int gg = 0; gg < G; ++gg) m_new = fmaxf(m_new, xm[gg * QT + i]);
-      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      const float alpha = ptx::ex2((m_run - m_use) * sc);
-      const float neg_ms = -m_use * sc;
       uint32_t pk[E / 2];   // P as fp16 pairs
-      // ... and the post-maximum stages too: even g  exponentials (MUFU) -> PV fold (TMEM read + FMA), odd g the reverse
-      auto stage_exp = [&]() {
+      if (OTMEM) {
+        // O stays in TMEM, accumulated by the tensor core over all key tiles (FlashAttention-4 style): P is scaled with a
+        // STICKY maximum that is only raised when the row maximum grew by more than 2^8 (both warps of a row see the same
+        // xmax values, so they take the same decision); the rare rescale is a warp-local ld / multiply / st of this warp's
+        // 32 lanes x its 32 output columns.  No per-tile PV read-out, no fold.
+        const bool raise = (m_new - m_run) * sc > 8.0f;   // false when both are -inf (NaN), true for the first finite maximum
+        const float alpha = raise ? ptx::ex2((m_run - m_new) * sc) : 1.0f;   // m_run = -inf: 0 (l and O hold exact zeros)
+        if (raise) m_run = m_new;
+        const float neg_ms = (m_run == -CUDART_INF_F) ? 0.f : -m_run * sc;
         float psum = 0.f;
-        if (HEXP) {
-          // two exponentials per MUFU op on packed fp16 arguments (<= 0, so the dominant terms keep full fp16 precision);
-          // row sum from the same rounded values: 4 independent fp16x2 chains of 4, finished in fp32
-          __half2 acc[4];
+        if (poly) {
 #pragma unroll
-          for (int v = 0; v < E / 2; ++v) {
-            pk[v] = ptx::ex2_f16x2(ptx::pack_f16(fmaf(s[2 * v], sc, neg_ms), fmaf(s[2 * v + 1], sc, neg_ms)));
-            const __half2 h = *reinterpret_cast<const __half2*>(&pk[v]);
-            acc[v & 3] = (v < 4) ? h : __hadd2(acc[v & 3], h);
-          }
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const float2 f = __half22float2(acc[c]);
-            psum += f.x + f.y;
+          for (int jj = 0; jj < E; ++jj) {
+            const float e = exp2_sel<true>(jj, fmaf(s[jj], sc, neg_ms));
+            s[jj] = e;
+            psum += e;
           }
         } else {
 #pragma unroll
@@ -448,9 +482,43 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             s[jj] = e;
             psum += e;
           }
-#pragma unroll
-          for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
         }
+#pragma unroll
+        for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
+        l_run = l_run * alpha + psum;
+        if (sw == 0) GLC_TRACE(0, t, 5);
+        if (t > 0) {
+          ptx::mbar_wait(pv_full, (t - 1) & 1);   // P buffer free again, O stable
+          if (__any_sync(0xffffffffu, raise)) {
+            ptx::tc_fence_after();
+            uint32_t r[E];
+            tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < E / 8; ++u) {
+              uint32_t q8[8];
+#pragma unroll
+              for (int v = 0; v < 8; ++v) q8[v] = __float_as_uint(__uint_as_float(r[8 * u + v]) * alpha);
+              ptx::tmem_st_x8(t_lane + TM_PV + (uint32_t)(b0 + 8 * u), q8);
+            }
+          }
+        }
+        if (sw == 0) GLC_TRACE(0, t, 6);
+      } else {
+      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+      const float alpha = ptx::ex2((m_run - m_use) * sc);
+      const float neg_ms = -m_use * sc;
+      // ... and the post-maximum stages too: even g  exponentials (MUFU) -> PV fold (TMEM read + FMA), odd g the reverse
+      auto stage_exp = [&]() {
+        float psum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < E; ++jj) {
+          const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
+          s[jj] = e;
+          psum += e;
+        }
+#pragma unroll
+        for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
         l_run = l_run * alpha + psum;
         m_run = m_new;
       };
@@ -476,6 +544,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         stage_fold();
         stage_exp();
       }
+      }
 
       // ---- P tile -> TMEM: row i, fp16 pairs at columns (E/2) g ..
 #pragma unroll
@@ -500,7 +569,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
       ptx::tmem_ld_wait();
 #pragma unroll
-      for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
+      for (int k = 0; k < E; ++k) o[k] = OTMEM ? __uint_as_float(r[k]) : fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
     }
     float* xs = xmax + (T & 1) * (G * QT);   // the buffer tile T-1 did not use
     xs[g * QT + i] = l_run;
@@ -568,6 +637,8 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
   static const int swap_order = [] { const char* e = getenv("GLC_ATTN_SWAP"); return (e && e[0] == '0') ? 0 : 1; }();
   p.swap_order = swap_order;
+  static const int poly = [] { const char* e = getenv("GLC_ATTN_POLY"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.poly = poly;
   dim3 grid((S + QT - 1) / QT, heads, B);
   static bool attr_set[64] = {};
   int dev = 0;
@@ -608,8 +679,8 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
     }
     return e;
   }
-  static const bool hexp = [] { const char* e = getenv("GLC_ATTN_HEXP"); return e && e[0] == '1'; }();   // no gain: ex2.f16x2 issues two MUFU ops on sm_100
-  if (groups == 2 && hexp) attention_shift_kernel<2, false, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+  static const bool otmem = [] { const char* e = getenv("GLC_ATTN_OTMEM"); return !(e && e[0] == '0'); }();   // 0: per-tile PV read-out + fold in registers
+  if (groups == 2 && otmem) attention_shift_kernel<2, false, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
   else if (groups == 2) attention_shift_kernel<2, false, false><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
   else attention_shift_kernel<4, false, true><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
   return cudaGetLastError();

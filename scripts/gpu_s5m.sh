@@ -1,0 +1,11 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/s5m_*
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "shift and not stream" > gpurun_out/s5m_kernels.log 2>&1; echo "rc=$?" >> gpurun_out/s5m_kernels.log
+tail -n 5 gpurun_out/s5m_kernels.log
+for h in "1 1 1" "0 1 1" "1 0 1" "1 1 0" "1 1 1"; do
+  set -- $h
+  echo "== SWAP=$1 OTMEM=$2 POLY=$3" >> gpurun_out/s5m_attn.log
+  GLC_ATTN_SWAP=$1 GLC_ATTN_OTMEM=$2 GLC_ATTN_POLY=$3 GLC_ATTN=shift timeout 300 python scripts/bench_attn.py 64 512 12 20 >> gpurun_out/s5m_attn.log 2>&1
+done
+GLC_ATTN=shift GLC_ATTN_TRACE=gpurun_out/s5m_trace.txt timeout 300 python scripts/bench_attn.py 64 512 12 1 >> gpurun_out/s5m_attn.log 2>&1
+grep -v "mode\|parity" gpurun_out/s5m_attn.log; cat gpurun_out/s5m_trace.txt
