@@ -9,9 +9,17 @@ import gliclass_oracle as O
 def bf(x): return x.to(torch.bfloat16).float()
 def hf(x): return x.to(torch.float16).float()
 def ident(x): return x
+def mx8(x, blk=32):
+    # MXFP8-style: e4m3 elements, one power-of-two scale per `blk` consecutive elements of the last (contraction) dim
+    sh = x.shape; K = sh[-1]; pad = (-K) % blk
+    y = torch.nn.functional.pad(x, (0, pad)).reshape(-1, blk)
+    amax = y.abs().amax(-1, keepdim=True).clamp_min(1e-30)
+    sc = torch.exp2(torch.ceil(torch.log2(amax / 448.0)))
+    q = (y / sc).to(torch.float8_e4m3fn).float() * sc
+    return q.reshape(*sh[:-1], K + pad)[..., :K]
 
 @torch.no_grad()
-def forward_emul(w, cfg, ids, mask, act=bf, wt=bf, tmp_round=bf, resid_round=bf, bias_stage=hf, p_round=bf, head_round=bf):
+def forward_emul(w, cfg, ids, mask, act=bf, wt=bf, tmp_round=bf, resid_round=bf, bias_stage=hf, p_round=bf, head_round=bf, gin=ident):
     B, S = ids.shape; H, h, d = cfg.hidden_size, cfg.num_heads, cfg.head_dim
     eps = cfg.layer_norm_eps; span = cfg.position_buckets; E = O.ENC
     W = {k: (wt(v) if v.dim() == 2 else v) for k, v in w.items()}
@@ -28,7 +36,7 @@ def forward_emul(w, cfg, ids, mask, act=bf, wt=bf, tmp_round=bf, resid_round=bf,
         Wq, bq = W[p+"attention.self.query_proj.weight"], w[p+"attention.self.query_proj.bias"]
         Wk, bk = W[p+"attention.self.key_proj.weight"], w[p+"attention.self.key_proj.bias"]
         Wv, bv = W[p+"attention.self.value_proj.weight"], w[p+"attention.self.value_proj.bias"]
-        q = heads(act(x @ Wq.T + bq)); k = heads(act(x @ Wk.T + bk)); v = heads(act(x @ Wv.T + bv))
+        xg = gin(x); q = heads(act(xg @ Wq.T + bq)); k = heads(act(xg @ Wk.T + bk)); v = heads(act(xg @ Wv.T + bv))
         pq = heads(act(rel @ Wq.T + bq)[None])[0]; pk = heads(act(rel @ Wk.T + bk)[None])[0]
         s = q @ k.transpose(-1, -2)
         c2p = torch.gather(bias_stage(q @ pk.transpose(-1, -2)), -1, idx[None, None].expand(B, h, S, S))
@@ -38,11 +46,11 @@ def forward_emul(w, cfg, ids, mask, act=bf, wt=bf, tmp_round=bf, resid_round=bf,
         m = s.max(-1, keepdim=True).values
         pe = torch.exp(s - m); l_ = pe.sum(-1, keepdim=True)
         ctx = act(((p_round(pe) @ v) / l_).permute(0, 2, 1, 3).reshape(B, S, H))
-        t = tmp_round(ctx @ W[p+"attention.output.dense.weight"].T + w[p+"attention.output.dense.bias"])
+        t = tmp_round(gin(ctx) @ W[p+"attention.output.dense.weight"].T + w[p+"attention.output.dense.bias"])
         a_full = O._ln(t + xr, w[p+"attention.output.LayerNorm.weight"], w[p+"attention.output.LayerNorm.bias"], eps)
         ar = resid_round(a_full); a = act(a_full)
-        f = act(O._gelu(a @ W[p+"intermediate.dense.weight"].T + w[p+"intermediate.dense.bias"]))
-        t = tmp_round(f @ W[p+"output.dense.weight"].T + w[p+"output.dense.bias"])
+        f = act(O._gelu(gin(a) @ W[p+"intermediate.dense.weight"].T + w[p+"intermediate.dense.bias"]))
+        t = tmp_round(gin(f) @ W[p+"output.dense.weight"].T + w[p+"output.dense.bias"])
         x_full = O._ln(t + ar, w[p+"output.LayerNorm.weight"], w[p+"output.LayerNorm.bias"], eps)
         xr = resid_round(x_full); x = act(x_full)
     # head
@@ -67,6 +75,9 @@ if __name__ == "__main__":
         "weights fp32 only": dict(wt=ident),
         "act fp16": dict(act=hf, tmp_round=hf, resid_round=hf, p_round=hf, head_round=hf),
         "bias stage fp32": dict(bias_stage=ident),
+        "fp16 + W8 (mx e4m3 weights)": dict(act=hf, tmp_round=hf, resid_round=hf, p_round=hf, head_round=hf, wt=lambda x: mx8(hf(x))),
+        "fp16 + W8A8 (mx e4m3 both)": dict(act=hf, tmp_round=hf, resid_round=hf, p_round=hf, head_round=hf, wt=lambda x: mx8(hf(x)), gin=mx8),
+        "fp16 + W8 FFN only A8": dict(act=hf, tmp_round=hf, resid_round=hf, p_round=hf, head_round=hf, wt=lambda x: mx8(hf(x)), gin=ident),
         "all fp32 (sanity)": dict(act=ident, wt=ident, tmp_round=ident, resid_round=ident, bias_stage=ident, p_round=ident, head_round=ident),
     }
     for seed in (1, 2, 3):
