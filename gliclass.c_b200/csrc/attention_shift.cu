@@ -36,6 +36,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 #include <vector>
 
 #include "kernels.h"
@@ -244,67 +245,73 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
     ptx::mbar_wait(qt_full, 0);
     ptx::tc_fence_after();
-    for (int t = 0; t <= T; ++t) {
-      if (t < T) {
-        const int st = t & 1;
-        const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
-        const uint64_t dEK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EK + st * POS_BYTES));
-        const uint64_t dEQ = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EQ + st * POS_BYTES));
-        GLC_TRACE(1, t, 0);
-        ptx::mbar_wait(&a_full[st], (t >> 1) & 1);
-        GLC_TRACE(1, t, 1);
-        if (t > 0) ptx::mbar_wait(sc_free, (t - 1) & 1);   // S and C accumulators drained
-        ptx::tc_fence_after();
-        GLC_TRACE(1, t, 2);
-        if (ptx::elect_one()) {
-          // A = Q from TMEM: 16 halves along K = 8 columns per step; descriptors advance 32 B (= 2) per step;
-          // 32 table/key rows = 4096 B = 256 in a descriptor
+    auto issue_sc = [&](int t) {   // S = Q.K_t^T and C = Q.EK_slice^T (A = Q from TMEM)
+      const int st = t & 1;
+      const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
+      const uint64_t dEK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EK + st * POS_BYTES));
+      GLC_TRACE(1, t, 0);
+      ptx::mbar_wait(&a_full[st], (t >> 1) & 1);
+      GLC_TRACE(1, t, 1);
+      if (t > 0) ptx::mbar_wait(sc_free, (t - 1) & 1);   // S and C accumulators drained
+      ptx::tc_fence_after();
+      GLC_TRACE(1, t, 2);
+      if (ptx::elect_one()) {
+        // 16 halves along K = 8 TMEM columns per step; descriptors advance 32 B (= 2) per step
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ts(tmem + TM_S, tmem + TM_Q + 8 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+        for (int k = 0; k < 4; ++k)
+          ptx::mma_f16_ts(tmem + TM_S, tmem + TM_Q + 8 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            ptx::mma_f16_ts(tmem + TM_C, tmem + TM_Q + 8 * k, dEK + 2 * k, idesc_c, (uint32_t)(k != 0));
-          ptx::mma_commit(sc_full);
-        }
-        __syncwarp();
-        // the softmax warps drain S and C while the G copies are computed, and G while S, C of the next tile are
-        if (t > 0) ptx::mbar_wait(g_free, (t - 1) & 1);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // rows 32..159 x keys 0..63
-            ptx::mma_f16_ss(tmem + TM_G32, dEQ + 256 + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // rows 64..191 x keys 0..31
-            ptx::mma_f16_ss(tmem + TM_G64, dEQ + 512 + 2 * k, dK + 2 * k, idesc_n32, (uint32_t)(k != 0));
-#pragma unroll
-          for (int k = 0; k < 4; ++k)   // rows 0..127 x keys 32..63
-            ptx::mma_f16_ss(tmem + TM_G0, dEQ + 2 * k, dK + 256 + 2 * k, idesc_n32, (uint32_t)(k != 0));
-          ptx::mma_commit(&a_empty[st]);
-          ptx::mma_commit(g_full);
-        }
-        __syncwarp();
-        GLC_TRACE(1, t, 3);
+        for (int k = 0; k < 4; ++k)
+          ptx::mma_f16_ts(tmem + TM_C, tmem + TM_Q + 8 * k, dEK + 2 * k, idesc_c, (uint32_t)(k != 0));
+        ptx::mma_commit(sc_full);
       }
-      if (t > 0) {
-        const int tp = t - 1;
-        const int st = tp & 1;
-        const uint64_t dV = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_V + st * 8192));
-        ptx::mbar_wait(&b_full[st], (tp >> 1) & 1);
-        ptx::mbar_wait(p_full, tp & 1);
-        ptx::tc_fence_after();
-        GLC_TRACE(1, tp, 4);
-        if (ptx::elect_one()) {
+      __syncwarp();
+    };
+    auto issue_g = [&](int t) {    // the three row-shifted copies of G = EQr_slice . K_t^T; 32 table/key rows = 256 in a descriptor
+      const int st = t & 1;
+      const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
+      const uint64_t dEQ = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_EQ + st * POS_BYTES));
+      if (t > 0) ptx::mbar_wait(g_free, (t - 1) & 1);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)   // V is MN-major: 16 keys further = +2048 bytes = +128 in the descriptor
-            ptx::mma_f16_ts(tmem + TM_PV, tmem + TM_P + 8 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0 || (OTMEM && tp > 0)));
-          ptx::mma_commit(&b_empty[st]);
-          ptx::mma_commit(pv_full);
-        }
-        __syncwarp();
+        for (int k = 0; k < 4; ++k)   // rows 32..159 x keys 0..63
+          ptx::mma_f16_ss(tmem + TM_G32, dEQ + 256 + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // rows 64..191 x keys 0..31
+          ptx::mma_f16_ss(tmem + TM_G64, dEQ + 512 + 2 * k, dK + 2 * k, idesc_n32, (uint32_t)(k != 0));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // rows 0..127 x keys 32..63
+          ptx::mma_f16_ss(tmem + TM_G0, dEQ + 2 * k, dK + 256 + 2 * k, idesc_n32, (uint32_t)(k != 0));
+        ptx::mma_commit(&a_empty[st]);
+        ptx::mma_commit(g_full);
       }
-    }
+      __syncwarp();
+      GLC_TRACE(1, t, 3);
+    };
+    auto issue_pv = [&](int tp) {  // O (+)= P . V_tp
+      const int st = tp & 1;
+      const uint64_t dV = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_V + st * 8192));
+      ptx::mbar_wait(&b_full[st], (tp >> 1) & 1);
+      ptx::mbar_wait(p_full, tp & 1);
+      ptx::tc_fence_after();
+      GLC_TRACE(1, tp, 4);
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)   // V is MN-major: 16 keys further = +2048 bytes = +128 in the descriptor
+          ptx::mma_f16_ts(tmem + TM_PV, tmem + TM_P + 8 * k, dV + 128 * k, idesc_pv, (uint32_t)(k != 0 || (OTMEM && tp > 0)));
+        ptx::mma_commit(&b_empty[st]);
+        ptx::mma_commit(pv_full);
+      }
+      __syncwarp();
+    };
+      for (int t = 0; t <= T; ++t) {
+        if (t < T) {
+          issue_sc(t);
+          issue_g(t);   // the softmax warps drain S and C while the G copies are computed, and G while S, C of the next tile are
+        }
+        if (t > 0) issue_pv(t - 1);
+      }
   } else {
     // ------------------------------------------------------------------ softmax warps
     const int sw = warp - 2;          // 0..SM_WARPS-1
@@ -343,7 +350,8 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const bool sh16 = sh & 16, sh8 = sh & 8, sh4 = sh & 4, sh2 = sh & 2;
     const uint32_t prmt_sel = (sh & 1) ? 0x5432u : 0x3210u;
     const int rot0 = lane + 31 - bb;           // p2c: source lane of column jj is (rot0 - jj) & 31
-    const int thr0 = lane - 31 + bb;           // ... and this lane supplies the upper copy iff thr0 + jj < 0
+    const int thr0 = lane - 31 + bb;           // ... and this lane supplies the upper copy iff thr0 + jj < 0:
+    const uint32_t hi_mask = thr0 >= 0 ? 0u : (thr0 <= -32 ? 0xffffffffu : ((1u << (-thr0)) - 1u));   // bit jj, tile-invariant
 
     float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
     float o[E];
@@ -362,9 +370,8 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       // orders, so that one drains TMEM (64 B/clk port per quarter) while the other runs the ALU-pipe barrel shifter:
       //   even g:  C|S drain -> barrel -> G drain + lane rotation        odd g:  G drain + lane rotation -> C|S drain -> barrel
       float s[E];
-#pragma unroll
-      for (int jj = 0; jj < E; ++jj) s[jj] = 0.f;
-      auto stage_c2p = [&]() {
+      auto stage_c2p = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;   // the first stage of a tile assigns, the second accumulates
         uint32_t w[NW];
         ptx::mbar_wait(sc_full, t & 1);
         ptx::tc_fence_after();
@@ -384,7 +391,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(sc_free);
 #pragma unroll
-          for (int jj = 0; jj < E; ++jj) s[jj] += __uint_as_float(r[jj]);
+          for (int jj = 0; jj < E; ++jj) s[jj] = FIRST ? __uint_as_float(r[jj]) : s[jj] + __uint_as_float(r[jj]);
 #pragma unroll
           for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
         }
@@ -406,7 +413,8 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         }
       };
       // p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
-      auto stage_p2c = [&]() {
+      auto stage_p2c = [&](auto first_tag) {
+        constexpr bool FIRST = decltype(first_tag)::value;
         ptx::mbar_wait(g_full, t & 1);
         ptx::tc_fence_after();
 #pragma unroll
@@ -423,17 +431,18 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int jj = 16 * u + k;
-            const uint32_t v = sel(thr0 + jj < 0, hi[k], lo[k]);
-            s[jj] += __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+            const uint32_t v = sel((hi_mask >> jj) & 1u, hi[k], lo[k]);
+            const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+            s[jj] = FIRST ? pv : s[jj] + pv;
           }
         }
       };
       if (!(g & 1) || !swap_order) {
-        stage_c2p();
-        stage_p2c();
+        stage_c2p(std::true_type{});
+        stage_p2c(std::false_type{});
       } else {
-        stage_p2c();
-        stage_c2p();
+        stage_p2c(std::true_type{});
+        stage_c2p(std::false_type{});
       }
       if (sw == 0) GLC_TRACE(0, t, 2);
 

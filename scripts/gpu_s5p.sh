@@ -1,0 +1,10 @@
+mkdir -p gpurun_out
+rm -f gpurun_out/s5p_*
+timeout 600 python -m pytest tests/test_gpu_kernels.py -x -q -k "shift and not stream" > gpurun_out/s5p_kernels.log 2>&1; echo "rc=$?" >> gpurun_out/s5p_kernels.log
+tail -n 5 gpurun_out/s5p_kernels.log
+for h in 1 0 1 0; do
+  echo "== PIPE=$h" >> gpurun_out/s5p_attn.log
+  GLC_ATTN_PIPE=$h GLC_ATTN=shift timeout 300 python scripts/bench_attn.py 64 512 12 20 >> gpurun_out/s5p_attn.log 2>&1
+done
+GLC_ATTN=shift GLC_ATTN_TRACE=gpurun_out/s5p_trace.txt timeout 300 python scripts/bench_attn.py 64 512 12 1 >> gpurun_out/s5p_attn.log 2>&1
+grep -v "mode" gpurun_out/s5p_attn.log; cat gpurun_out/s5p_trace.txt
