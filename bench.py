@@ -33,9 +33,9 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 ARCH, BATCH, SEQ, LABELS = "base", 64, 512, 10
 WORKLOAD = "gliclass-base-v1.0 arch (DeBERTa-v3-base 12L/768), batch 64/GPU, seq 512, 10 labels, random-init ONNX"
 METRIC = "texts/sec gliclass-base seq512 10 labels"
-# ncu --set full capture of the four GEMM launches of one layer (profiles/r1c_kernels_ncu.md):
+# ncu --set full capture of the four GEMM launches of one layer (profiles/r1e_kernels_ncu.md):
 # QKV 154.0, out-proj 61.8, FFN1 204.3, FFN2 243.0 MB of DRAM traffic -> mean per launch
-NCU_GEMM_TRAFFIC_MB = 165.8
+NCU_GEMM_TRAFFIC_MB = 166.7
 
 
 def model_path(arch: str) -> str:
@@ -331,7 +331,7 @@ def main():
         "roofline": {"bound": "tensor", "kernel": "gemm_f16_2cta_kernel (QKV, out-proj, FFN1+GELU, FFN2)", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                      "traffic": NCU_GEMM_TRAFFIC_MB * 1e6 if (args.arch, B, S) == (ARCH, BATCH, SEQ) else None,
-                     "traffic_note": "dram__bytes_read+write per launch, mean over the four GEMM shapes, from profiles/r1c_kernels_ncu.md",
+                     "traffic_note": "dram__bytes_read+write per launch, mean over the four GEMM shapes, from profiles/r1e_kernels_ncu.md",
                      "peak_source": peak_src, "launches_timed": int(gemm_n),
                      "share_of_step": gemm_ms / ms_prof if ms_prof else None,
                      "timed_over": f"{args.steps} steps re-run with CUDA events around every launch ({ms_prof / args.steps:.3f} ms/step)"},
