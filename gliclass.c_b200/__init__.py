@@ -234,6 +234,17 @@ class Session:
         _check(lib().glc_collect(ticket[0]), "glc_collect")
         return ticket[3]
 
+    def submit_pinned(self, ids_ptr: int, mask_ptr: int, B: int, S: int, out_ptr: int, out_capacity: int):
+        """glc_submit on raw host pointers (bench.py's pipelined e2e leg); the buffers must stay valid until collect_raw."""
+        cc = C.c_int(0)
+        t = lib().glc_submit(self._h, ids_ptr, mask_ptr, B, S, out_ptr, out_capacity, C.byref(cc))
+        if not t:
+            raise GlcError(f"glc_submit failed: {last_error()}")
+        return t
+
+    def collect_raw(self, ticket) -> None:
+        _check(lib().glc_collect(ticket), "glc_collect")
+
     def coalesce_stats(self):
         """(merged launches, requests served by them) since load"""
         g, r = C.c_uint64(0), C.c_uint64(0)

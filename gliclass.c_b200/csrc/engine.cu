@@ -251,6 +251,7 @@ DeviceModel::~DeviceModel() {
   for (auto& kv : debug_) cudaFree(kv.second.ptr);
   for (auto& r : prof_recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : prof_pool_) cudaEventDestroy(e);
+  for (auto e : free_events_) cudaEventDestroy(e);
   if (stream_) cudaStreamDestroy(stream_);
 }
 
@@ -519,32 +520,52 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
   static const bool timing = getenv("GLC_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = timing ? now() : 0;
-  std::lock_guard<std::mutex> lk(mu);
-  GLC_CUDA(cudaSetDevice(device_));
-  int rows_mb = max_tokens_ / S;
-  if (rows_mb < 1) rows_mb = 1;
-  if (rows_mb > B) rows_mb = B;
-  ensure_workspace(rows_mb * S, rows_mb, C);
-  for (int r0 = 0; r0 < B; r0 += rows_mb) {
-    const int nb = (B - r0 < rows_mb) ? (B - r0) : rows_mb;
-    const size_t bytes = (size_t)nb * S * 8;
-    GLC_CUDA(cudaMemcpyAsync(ids_, ids + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
-    GLC_CUDA(cudaMemcpyAsync(mask_, mask + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
-    const bool want_p = dec && dec->probs, want_d = dec && dec->decisions;
-    forward(ids_, mask_, nb, S, C, logits_, want_p ? probs_ : nullptr, want_d ? decisions_ : nullptr,
-            dec ? dec->threshold : 0.5f, cacheable);
-    if (C > 0) {
-      if (logits)
-        GLC_CUDA(cudaMemcpyAsync(logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
-      if (want_p)
-        GLC_CUDA(cudaMemcpyAsync(dec->probs + (size_t)r0 * C, probs_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
-      if (want_d)
-        GLC_CUDA(cudaMemcpyAsync(dec->decisions + (size_t)r0 * C, decisions_, (size_t)nb * C, cudaMemcpyDeviceToHost, stream_));
+  // Enqueue under the device lock, wait OUTSIDE it on an event recorded behind this request's last copy: the next
+  // caller's H2D copies and graph launch are queued behind ours while we still wait, so back-to-back requests (two
+  // glc_submit tickets in flight, or two OpenMP workers) leave no bubble on the device.  One stream keeps the shared
+  // workspace and the id / mask / logits staging buffers safe: request N+1's copies execute after request N's forward
+  // and D2H in stream order.
+  cudaEvent_t done = nullptr;
+  double t1 = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    GLC_CUDA(cudaSetDevice(device_));
+    int rows_mb = max_tokens_ / S;
+    if (rows_mb < 1) rows_mb = 1;
+    if (rows_mb > B) rows_mb = B;
+    ensure_workspace(rows_mb * S, rows_mb, C);
+    for (int r0 = 0; r0 < B; r0 += rows_mb) {
+      const int nb = (B - r0 < rows_mb) ? (B - r0) : rows_mb;
+      const size_t bytes = (size_t)nb * S * 8;
+      GLC_CUDA(cudaMemcpyAsync(ids_, ids + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
+      GLC_CUDA(cudaMemcpyAsync(mask_, mask + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
+      const bool want_p = dec && dec->probs, want_d = dec && dec->decisions;
+      forward(ids_, mask_, nb, S, C, logits_, want_p ? probs_ : nullptr, want_d ? decisions_ : nullptr,
+              dec ? dec->threshold : 0.5f, cacheable);
+      if (C > 0) {
+        if (logits)
+          GLC_CUDA(cudaMemcpyAsync(logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+        if (want_p)
+          GLC_CUDA(cudaMemcpyAsync(dec->probs + (size_t)r0 * C, probs_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+        if (want_d)
+          GLC_CUDA(cudaMemcpyAsync(dec->decisions + (size_t)r0 * C, decisions_, (size_t)nb * C, cudaMemcpyDeviceToHost, stream_));
+      }
     }
-    if (r0 + rows_mb < B) GLC_CUDA(cudaStreamSynchronize(stream_));   // workspace reuse
+    if (free_events_.empty()) {
+      GLC_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    } else {
+      done = free_events_.back();
+      free_events_.pop_back();
+    }
+    GLC_CUDA(cudaEventRecord(done, stream_));
+    t1 = timing ? now() : 0;
   }
-  const double t1 = timing ? now() : 0;
-  GLC_CUDA(cudaStreamSynchronize(stream_));
+  const cudaError_t we = cudaEventSynchronize(done);
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    free_events_.push_back(done);
+  }
+  if (we != cudaSuccess) throw std::runtime_error(std::string("cudaEventSynchronize: ") + cudaGetErrorString(we));
   if (timing) fprintf(stderr, "glc run_host B=%d S=%d: enqueue %.1f us, wait %.1f us\n", B, S, t1 - t0, now() - t1);
 }
 

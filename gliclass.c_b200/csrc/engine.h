@@ -90,6 +90,7 @@ class DeviceModel {
   void profile_enable(bool on);
   void profile_collect(double* ms, uint64_t* n);
   std::mutex mu;
+  std::vector<cudaEvent_t> free_events_;   // completion events of run_host (guarded by mu)
 
  private:
   void ensure_workspace(int tokens, int B, int C);
