@@ -81,6 +81,7 @@ _SIGS = {
     "glc_onnx_role_name": (C.c_char_p, [_vp, _i]),
     "glc_rel_index_table": (_i, [_i, _i, _i, _vp]),
     "glc_op_gemm": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "glc_op_gemm_resid": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "glc_op_embed_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "glc_op_residual_ln": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
     "glc_op_mask_prep": (_i, [_vp, _vp, _vp, _i, _i, _vp]),

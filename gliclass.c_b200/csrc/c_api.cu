@@ -368,6 +368,11 @@ int glc_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const fl
   GLC_TRY("glc_op_gemm", glc::gemm_f16(A, lda, W, ldw, bias, C, ldc, M, N, K, act, out_f32 != 0, num_sms_current(),
                                        (cudaStream_t)stream));
 }
+int glc_op_gemm_resid(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* resid, int64_t ldr,
+                      void* C, int64_t ldc, int M, int N, int K, int act, int out_f32, void* stream) {
+  GLC_TRY("glc_op_gemm_resid", glc::gemm_f16_resid(A, lda, W, ldw, bias, resid, ldr, C, ldc, M, N, K, act, out_f32 != 0,
+                                                   num_sms_current(), (cudaStream_t)stream));
+}
 int glc_op_embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, const float* gamma, const float* beta, float eps,
                     void* y, int M, int H, int vocab, void* stream) {
   GLC_TRY("glc_op_embed_ln", glc::embed_ln(ids, mask, emb, gamma, beta, eps, y, M, H, vocab, (cudaStream_t)stream));

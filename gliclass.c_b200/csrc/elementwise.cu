@@ -205,8 +205,10 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)H * 2u;
-  uint8_t* ring = ln_smem + (size_t)warp * stages * 2 * row_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)ROWS_PER_BLOCK * stages * 2 * row_bytes) + warp * LN_STAGES;
+  const bool has_r = r != nullptr;   // without a residual operand (the GEMM epilogue already added it) a stage is one row
+  const uint32_t st_bytes = has_r ? 2 * row_bytes : row_bytes;
+  uint8_t* ring = ln_smem + (size_t)warp * stages * st_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + (size_t)ROWS_PER_BLOCK * stages * st_bytes) + warp * LN_STAGES;
   const int nwarps = gridDim.x * ROWS_PER_BLOCK;
   const int row0 = blockIdx.x * ROWS_PER_BLOCK + warp;
   if (row0 >= M) return;
@@ -217,10 +219,10 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
   __syncwarp();
   auto issue = [&](int rw, int s) {
     if (lane == 0) {
-      uint8_t* dst = ring + (size_t)s * 2 * row_bytes;
-      ptx::mbar_arrive_expect_tx(&bars[s], 2 * row_bytes);
+      uint8_t* dst = ring + (size_t)s * st_bytes;
+      ptx::mbar_arrive_expect_tx(&bars[s], st_bytes);
       bulk_load(dst, x + (int64_t)rw * H, row_bytes, &bars[s]);
-      bulk_load(dst + row_bytes, r + (int64_t)rw * H, row_bytes, &bars[s]);
+      if (has_r) bulk_load(dst + row_bytes, r + (int64_t)rw * H, row_bytes, &bars[s]);
     }
   };
   for (int s = 0; s < stages; ++s) {
@@ -233,19 +235,21 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
   uint32_t parity = 0;
   for (int rw = row0; rw < M; rw += nwarps) {
     ptx::mbar_wait(&bars[s], parity);
-    const uint8_t* xs = ring + (size_t)s * 2 * row_bytes;
+    const uint8_t* xs = ring + (size_t)s * st_bytes;
     float v[NC][8];
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int e0 = (lane + 32 * c) * 8;
       if (e0 < H) {
         const uint4 xa = *reinterpret_cast<const uint4*>(xs + e0 * 2);
-        const uint4 ra = *reinterpret_cast<const uint4*>(xs + row_bytes + e0 * 2);
-        float t[8];
         unpack8(xa, v[c]);
-        unpack8(ra, t);
+        if (has_r) {
+          const uint4 ra = *reinterpret_cast<const uint4*>(xs + row_bytes + e0 * 2);
+          float t[8];
+          unpack8(ra, t);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+          for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+        }
       }
     }
     __syncwarp();   // every lane has read the stage: refill it
@@ -543,11 +547,11 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
     constexpr int NC = decltype(nc)::value;
     // bulk-copy ring variant (needs the residual operand and 16-byte rows); GLC_LN_BULK=0 keeps the register-prefetch kernel
     static const bool bulk_on = [] { const char* e = getenv("GLC_LN_BULK"); return !(e && e[0] == '0'); }();
-    const size_t stage_bytes = (size_t)ROWS_PER_BLOCK * 2 * (size_t)H * 2;   // one stage of all 8 warps
+    const size_t stage_bytes = (size_t)ROWS_PER_BLOCK * (r ? 2 : 1) * (size_t)H * 2;   // one stage of all 8 warps
     int stages = (int)((110 * 1024) / stage_bytes);
     if (stages > LN_STAGES) stages = LN_STAGES;
     const size_t ring_bytes = stage_bytes * stages + ROWS_PER_BLOCK * LN_STAGES * 8;
-    if (bulk_on && r && (H * 2) % 16 == 0 && stages >= 2) {
+    if (bulk_on && (H * 2) % 16 == 0 && stages >= 2) {
       static bool attr_set[64][9] = {};
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);

@@ -125,6 +125,10 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
     else if (m == "stream") attn_mode_ = 3;
     else throw std::runtime_error("GLC_ATTN must be gather, toeplitz, shift or stream (got '" + m + "')");
   }
+  {
+    const char* fr = getenv("GLC_FUSE_RESID");
+    fuse_resid_ = fr && fr[0] == '1';   // measured: LN -0.1 ms, but the out-proj / FFN2 epilogues +0.28 ms per step -> off
+  }
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
 
   const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
@@ -471,11 +475,22 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     }
     if (cfg_.pooling == POOL_LAST) GLC_LAUNCH(KC_ATTN, pad_rows_mean_v(qkv_, d_mask, ctx_, B, S, H, st));
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
-    GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st));
-    GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));
+    // GLC_FUSE_RESID=1: the residual add rides in the GEMM epilogue and LN reads one tensor (slower in total, see engine ctor)
+    if (fuse_resid_) {
+      GLC_LAUNCH(KC_GEMM_OUT, gemm_f16_resid(ctx_, H, d.wo, H, d.bo, x_, H, tmp_, H, M, H, H, 0, false, num_sms_, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, nullptr, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));
+    } else {
+      GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));
+    }
     GLC_LAUNCH(KC_GEMM_FFN1, gemm_f16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st));
-    GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st));
-    GLC_LAUNCH(KC_LN, residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st));
+    if (fuse_resid_) {
+      GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16_resid(ffn_, I, d.w2, I, d.b2, x1_, H, tmp_, H, M, H, I, 0, false, num_sms_, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, nullptr, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st));
+    } else {
+      GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st));
+    }
     if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
   }
   if (C > 0) {

@@ -109,6 +109,7 @@ class DeviceModel {
   ModelConfig cfg_;
   int max_tokens_ = 65536;
   bool debug_keep_ = false;
+  bool fuse_resid_ = false;    // GLC_FUSE_RESID=1: residual add in the out-proj / FFN2 GEMM epilogues instead of the LN kernel
   int attn_mode_ = 2;          // 2 register-skew kernel (attention_shift.cu, production); experiments: 0 gather kernel (attention.cu),
                                // 1 tensor-core bias adds (attention_toeplitz.cu), 3 two-stream variant (attention_stream.cu);
                                // env GLC_ATTN=gather|toeplitz|shift|stream

@@ -63,17 +63,45 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Residual operand of the fused "+ r" epilogue: 32 fp16 of this lane's row (4 x 128-bit; the second half of every 32-byte
+// sector a load touches is the next load's data, so L1 serves it).  Issued BEFORE the TMEM load they are added to.
+struct ResidRow {
+  uint4 q[4];
+  __device__ __forceinline__ void load(const __half* __restrict__ resid, int64_t ldr, int row, int n, int M, int N) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      q[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (row < M && n + 8 * j + 8 <= N) q[j] = *reinterpret_cast<const uint4*>(resid + (int64_t)row * ldr + n + 8 * j);
+    }
+  }
+  __device__ __forceinline__ void add_to(float (&v)[32]) const {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2* h = reinterpret_cast<const __half2*>(&q[j]);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = __half22float2(h[k]);
+        v[8 * j + 2 * k] += f.x;
+        v[8 * j + 2 * k + 1] += f.y;
+      }
+    }
+  }
+};
+
 // Epilogue of one accumulator tile for one warp: TMEM lanes of this warp's quarter (t_row), the
 // 32-column chunks c = grp, grp+GROUPS, ...: tcgen05.ld -> +bias -> (erf-GELU) -> fp16/fp32 -> global.
 template <int BN, int ACT, bool OUT_F32>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, int row, const float* __restrict__ bias,
-                                              void* __restrict__ Cout, int64_t ldc, int M, int N) {
+                                              void* __restrict__ Cout, int64_t ldc, int M, int N,
+                                              const __half* __restrict__ resid, int64_t ldr) {
 #pragma unroll 1
   for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
+  const int n = n0 + c * 32;
+  ResidRow rr;
+  if (resid != nullptr && n < N) rr.load(resid, ldr, row, n, M, N);
   uint32_t r[32];
   ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
   ptx::tmem_ld_wait();
-  const int n = n0 + c * 32;
   if (n >= N) continue;   // warp-uniform
   float v[32];
 #pragma unroll
@@ -99,6 +127,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
+  if (resid != nullptr) rr.add_to(v);
   if (row < M) {
     if (OUT_F32) {
       float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + n;
@@ -129,13 +158,16 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, i
 //   stage: this warp's NBUF x 2 KB staging buffers (1024-byte aligned); row0: first tile row of the warp
 template <int BN, int ACT, int NBUF>
 __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
-                                                  const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int N) {
+                                                  const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int M, int N,
+                                                  const __half* __restrict__ resid, int64_t ldr) {
 #pragma unroll 1
   for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
+    const int n = n0 + c * 32;
+    ResidRow rr;
+    if (resid != nullptr && n < N) rr.load(resid, ldr, row0 + lane, n, M, N);
     uint32_t r[32];
     ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
     ptx::tmem_ld_wait();
-    const int n = n0 + c * 32;
     if (n >= N) continue;   // warp-uniform
     float v[32];
 #pragma unroll
@@ -161,6 +193,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
+    if (resid != nullptr) rr.add_to(v);
     // the bulk store that last read this staging buffer must have finished reading it
     if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
     __syncwarp();
@@ -190,7 +223,8 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n
 template <int BN, int ACT, bool OUT_F32>
 __global__ void __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
-                         const float* __restrict__ bias, void* __restrict__ Cout, int64_t ldc, int M, int N, int K) {
+                         const float* __restrict__ bias, void* __restrict__ Cout, int64_t ldc, int M, int N, int K,
+                         const __half* __restrict__ resid, int64_t ldr) {
   using Cfg = GemmCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment (128B-swizzle atoms) by pointer arithmetic on the __shared__ symbol: an
@@ -293,7 +327,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
+      epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -338,7 +372,7 @@ template <int BN_, int ACT, bool OUT_F32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
 gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                      const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias, void* __restrict__ Cout,
-                     int64_t ldc, int M, int N, int K) {
+                     int64_t ldc, int M, int N, int K, const __half* __restrict__ resid, int64_t ldr) {
   using Cfg = Gemm2Cfg<BN_>;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -448,9 +482,9 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
       if (OUT_F32)
-        epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
+        epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
       else
-        epilogue_tile_tma<BN, ACT, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, N);
+        epilogue_tile_tma<BN, ACT, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, resid, ldr);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tempty[acc]) & ptx::PEER_BIT_MASK);
@@ -470,7 +504,7 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
 template <int BN_, int ACT, bool OUT_F32>
 cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
-                             int M, int N, int K, int num_sms, cudaStream_t stream) {
+                             int M, int N, int K, int num_sms, cudaStream_t stream, const void* resid, int64_t ldr) {
   using Cfg = Gemm2Cfg<BN_>;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t sa[1] = {(uint64_t)lda * 2};
@@ -499,13 +533,13 @@ cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t 
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + Cfg::BN - 1) / Cfg::BN);
   const int max_cl = num_sms / 2;
   const int ncl = tiles < max_cl ? tiles : max_cl;
-  kern<<<2 * ncl, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, tm_c, bias, C, ldc, M, N, K);
+  kern<<<2 * ncl, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, tm_c, bias, C, ldc, M, N, K, (const __half*)resid, ldr);
   return cudaGetLastError();
 }
 
 template <int BN, int ACT, bool OUT_F32>
 cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
-                        int M, int N, int K, int num_sms, cudaStream_t stream) {
+                        int M, int N, int K, int num_sms, cudaStream_t stream, const void* resid, int64_t ldr) {
   using Cfg = GemmCfg<BN>;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t sa[1] = {(uint64_t)lda * 2};
@@ -526,7 +560,7 @@ cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, bias, C, ldc, M, N, K);
+  kern<<<grid, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, bias, C, ldc, M, N, K, (const __half*)resid, ldr);
   return cudaGetLastError();
 }
 
@@ -534,7 +568,14 @@ cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, 
 
 cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
                      int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream) {
+  return gemm_f16_resid(A, lda, W, ldw, bias, nullptr, 0, C, ldc, M, N, K, act, out_f32, num_sms, stream);
+}
+
+cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* resid,
+                           int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act, bool out_f32, int num_sms,
+                           cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return cudaErrorInvalidValue;
+  if (resid != nullptr && ((ldr % 8) || (reinterpret_cast<uintptr_t>(resid) & 15))) return cudaErrorInvalidValue;
   if ((lda % 8) || (ldw % 8) || (K % 8) || (N % 8) || (ldc % (out_f32 ? 4 : 8))) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15)
     return cudaErrorInvalidValue;
@@ -543,9 +584,9 @@ cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, con
   const bool wide = (N % 256 == 0) && tiles256 >= num_sms;
   if (act < 0 || act > 2) return cudaErrorInvalidValue;
   if (out_f32) {
-    if (act == 0) return launch_gemm<128, 0, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    if (act == 1) return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    return launch_gemm<128, 2, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    if (act == 0) return launch_gemm<128, 0, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+    if (act == 1) return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+    return launch_gemm<128, 2, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   }
   // CTA pairs (256 x 256 cluster tiles) whenever they fill the machine
   const int tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
@@ -558,19 +599,19 @@ cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, con
     const int64_t cost256 = (int64_t)((mt * ((N + 255) / 256) + ncl - 1) / ncl) * 256;
     const int64_t cost192 = (int64_t)((mt * ((N + 191) / 192) + ncl - 1) / ncl) * 192;
     if (!no_192 && act == 0 && N % 192 == 0 && cost192 * 100 < cost256 * 95)
-      return launch_gemm_2cta<192, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    if (act == 0) return launch_gemm_2cta<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    if (act == 1) return launch_gemm_2cta<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    return launch_gemm_2cta<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+      return launch_gemm_2cta<192, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+    if (act == 0) return launch_gemm_2cta<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+    if (act == 1) return launch_gemm_2cta<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+    return launch_gemm_2cta<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   }
   if (wide) {
-    if (act == 0) return launch_gemm<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    if (act == 1) return launch_gemm<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-    return launch_gemm<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+    if (act == 0) return launch_gemm<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+    if (act == 1) return launch_gemm<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+    return launch_gemm<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   }
-  if (act == 0) return launch_gemm<128, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-  if (act == 1) return launch_gemm<128, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
-  return launch_gemm<128, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream);
+  if (act == 0) return launch_gemm<128, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+  if (act == 1) return launch_gemm<128, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+  return launch_gemm<128, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
 }
 
 }  // namespace glc

@@ -14,6 +14,11 @@ namespace glc {
 cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
                      int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream);
 
+// K2 with the residual add fused into the epilogue: C = act(A W^T + bias) + resid (fp16 [M, ldr]); resid may be null.
+cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* resid,
+                           int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act, bool out_f32, int num_sms,
+                           cudaStream_t stream);
+
 // K1: y[m,:] = LN(word_emb[ids[m],:]) * gamma + beta, times mask[m]   (T:520-564)
 cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* word_emb_f16, const float* gamma,
                      const float* beta, float eps, void* y_f16, int M, int H, int vocab, cudaStream_t stream);

@@ -149,6 +149,10 @@ GLC_API int glc_rel_index_table(int S, int buckets, int max_pos, int32_t* out /*
  * TMA).  act: 0 none, 1 erf-GELU, 2 ReLU.  out_f32: C is fp32 instead of fp16.  ld* in elements. */
 GLC_API int glc_op_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
                         int M, int N, int K, int act, int out_f32, void* stream);
+/* K2 with the residual add of the layer fused into the epilogue (the "dense(ctx) + x" / "W2.gelu(..) + a" sums of
+ * T:49-53, T:408-412): C = act(A W^T + bias) + resid, resid fp16 [M, ldr] or NULL. */
+GLC_API int glc_op_gemm_resid(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* resid_f16,
+                              int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act, int out_f32, void* stream);
 /* K1: y[m,:] = (LN(word_emb[ids[m],:]) * gamma + beta) * (mask[m] != 0) */
 GLC_API int glc_op_embed_ln(const int64_t* ids, const int64_t* mask, const void* word_emb_f16, const float* gamma,
                             const float* beta, float eps, void* y_f16, int M, int H, int vocab, void* stream);

@@ -93,6 +93,45 @@ def test_gemm(pkg, dev, M, N, K, act, out_f32):
         _report(f"gemm {M}x{N}x{K} act{act}", C, ref, 2e-3, 2e-3)
 
 
+@pytest.mark.parametrize("M,N,K,act,out_f32", [
+    (32768, 768, 768, 0, False),    # out-proj + x on the CTA-pair path (256x192 tiles, TMA-store epilogue)
+    (4096, 768, 3072, 0, False),    # FFN2 + a at the batch-8 latency shape
+    (300, 128, 128, 1, False),      # single-CTA kernel, ragged M, activation before the add
+    (1000, 256, 128, 0, True),      # fp32 output
+    (20000, 1024, 1024, 0, False),  # large arch
+])
+def test_gemm_fused_residual(pkg, dev, M, N, K, act, out_f32):
+    """C = act(A W^T + b) + r: the residual add of the layer rides in the GEMM epilogue (T:49-53, T:408-412)"""
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(torch.float16).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.float16).to(dev)
+    bias = (torch.randn(N, generator=g) * 0.5).float().to(dev)
+    Rbig = torch.randn(M, N + 8, generator=g).to(torch.float16).to(dev)   # strided residual view
+    R = Rbig[:, :N]
+    C = torch.full((M, N), float("nan"), dtype=torch.float32 if out_f32 else torch.float16, device=dev)
+    rc = pkg.lib().glc_op_gemm_resid(_ptr(A), K, _ptr(W), K, _ptr(bias), R.data_ptr(), N + 8, _ptr(C), N, M, N, K, act,
+                                     int(out_f32), None)
+    _sync_check(pkg, rc, "glc_op_gemm_resid")
+    ref = A.float() @ W.float().t() + bias
+    if act == 1:
+        ref = torch.nn.functional.gelu(ref)
+    ref = ref + R.float()
+    _report(f"gemm+resid {M}x{N}x{K}", C, ref, 3e-3, 3e-3)
+
+
+@pytest.mark.parametrize("H,M", [(768, 70001), (1024, 40003), (128, 300)])
+def test_ln_without_residual_operand(pkg, dev, H, M):
+    g = torch.Generator().manual_seed(H + M)
+    x = (torch.randn(M, H, generator=g) * 1.7).to(torch.float16).to(dev)
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).float().to(dev)
+    beta = (0.02 * torch.randn(H, generator=g)).float().to(dev)
+    y = torch.empty(M, H, dtype=torch.float16, device=dev)
+    rc = pkg.lib().glc_op_residual_ln(_ptr(x), None, _ptr(gamma), _ptr(beta), 1e-7, _ptr(y), M, H, None)
+    _sync_check(pkg, rc, "glc_op_residual_ln(no residual)")
+    ref = torch.nn.functional.layer_norm(x.float(), (H,), gamma, beta, 1e-7)
+    _report(f"ln H={H}", y, ref, 2e-3, 2e-3)
+
+
 def test_gemm_strided_views(pkg, dev):
     # A and C as column slices of wider matrices (how qkv thirds / pos tables are addressed)
     M, N, K = 512, 256, 128
