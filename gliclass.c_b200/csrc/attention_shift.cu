@@ -89,6 +89,7 @@ struct ShiftParams {
   float scale_log2;          // log2(e) / sqrt(3*d)
   int swap_order;            // developer switch (GLC_ATTN_SWAP=0: both key groups walk the stages in the same order)
   int poly;                  // developer switch (GLC_ATTN_POLY=0: every exponential on the MUFU unit)
+  int c16;                   // developer switch (GLC_ATTN_C16=0: fp32 C accumulators, packed by the softmax threads)
 };
 
 template <int N>
@@ -241,7 +242,8 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected issue)
     constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
     constexpr uint32_t idesc_n32 = ptx::idesc_f16(128, 32);
-    constexpr uint32_t idesc_c = ptx::idesc_f16(128, SLICE);
+    // C accumulates in fp16 (C16): the softmax threads then read their window already packed (tcgen05.ld.pack::16b)
+    const uint32_t idesc_c = ptx::idesc_f16(128, SLICE, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.c16 ? 0u : 1u);
     constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
     ptx::mbar_wait(qt_full, 0);
     ptx::tc_fence_after();
@@ -360,6 +362,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const float sc = p.scale_log2;
     const bool swap_order = p.swap_order != 0;
     const bool poly = p.poly != 0;
+    const bool c16 = p.c16 != 0;
 
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
@@ -378,22 +381,30 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         {
           uint32_t r[E];
           tmem_ld_n<E>(a_s, r);
-          uint32_t c[NC];
+          if (E == 32 && c16) {
+            uint32_t cp[32];
+            ptx::tmem_ld_x32_pack16(a_c, cp);
+            ptx::tmem_ld_wait();
 #pragma unroll
-          for (int u = 0; u < NC / 16; ++u) {
-            uint32_t cc[16];
-            ptx::tmem_ld_x16(a_c + 16 * u, cc);
+            for (int k = 0; k < NW; ++k) w[k] = cp[k % 32];
+          } else {
+            uint32_t c[NC];
 #pragma unroll
-            for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
+            for (int u = 0; u < NC / 16; ++u) {
+              uint32_t cc[16];
+              ptx::tmem_ld_x16(a_c + 16 * u, cc);
+#pragma unroll
+              for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
+            }
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
           }
-          ptx::tmem_ld_wait();
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(sc_free);
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) s[jj] = FIRST ? __uint_as_float(r[jj]) : s[jj] + __uint_as_float(r[jj]);
-#pragma unroll
-          for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
         }
         // shift the packed window left by sh elements
 #pragma unroll
@@ -664,6 +675,8 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   // developer switches: GLC_ATTN_G=2|4 key groups per tile; GLC_ATTN_TRACE=<file> dumps per-tile clock64 stamps of
   // CTA (1,0,0) (synchronous)
   static const int groups = [] { const char* e = getenv("GLC_ATTN_G"); return (e && atoi(e) == 4) ? 4 : 2; }();
+  static const int c16 = [] { const char* e = getenv("GLC_ATTN_C16"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.c16 = (groups == 2) ? c16 : 0;
   if (const char* tf = getenv("GLC_ATTN_TRACE")) {
     const size_t n = 2 * TMAX * 8;
     if (cudaMalloc(&p.trace, n * sizeof(long long)) != cudaSuccess) return cudaGetLastError();
