@@ -367,7 +367,6 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
       if (sw == 0) GLC_TRACE(0, t, 0);
-      if (sw == 0) GLC_TRACE(0, t, 1);
 
       // The two warps of a scheduler (key groups g, g+1 of the same lane quarter) walk the pre-maximum stages in opposite
       // orders, so that one drains TMEM (64 B/clk port per quarter) while the other runs the ALU-pipe barrel shifter:
@@ -378,15 +377,25 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         uint32_t w[NW];
         ptx::mbar_wait(sc_full, t & 1);
         ptx::tc_fence_after();
+        if (sw == 0) GLC_TRACE(0, t, 1);
         {
           uint32_t r[E];
           tmem_ld_n<E>(a_s, r);
-          if (E == 32 && c16) {
-            uint32_t cp[32];
-            ptx::tmem_ld_x32_pack16(a_c, cp);
-            ptx::tmem_ld_wait();
+          if (c16) {
+            if constexpr (E == 32) {
+              uint32_t cp[32];
+              ptx::tmem_ld_x32_pack16(a_c, cp);
+              ptx::tmem_ld_wait();
 #pragma unroll
-            for (int k = 0; k < NW; ++k) w[k] = cp[k % 32];
+              for (int k = 0; k < NW; ++k) w[k] = cp[k % 32];
+            } else {
+              uint32_t cp[16], cq[8];
+              ptx::tmem_ld_x16_pack16(a_c, cp);
+              ptx::tmem_ld_x8_pack16(a_c + 32, cq);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int k = 0; k < NW; ++k) w[k] = k < 16 ? cp[k % 16] : cq[(k - 16) % 8];
+            }
           } else {
             uint32_t c[NC];
 #pragma unroll
@@ -403,6 +412,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(sc_free);
+          if (sw == 0) GLC_TRACE(0, t, 2);
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) s[jj] = FIRST ? __uint_as_float(r[jj]) : s[jj] + __uint_as_float(r[jj]);
         }
@@ -416,18 +426,15 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
         for (int k = 0; k < NW - 15; ++k) w[k] = sel(sh2, w[k + 1], w[k]);
 #pragma unroll
-        for (int m = 0; m < E / 2; ++m) {
-          const uint32_t x = __byte_perm(w[m], w[m + 1], prmt_sel);
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&x));
-          s[2 * m] += f.x;
-          s[2 * m + 1] += f.y;
-        }
+        for (int m = 0; m < E / 2; ++m) ptx::add_f16x2_to_f32(s[2 * m], s[2 * m + 1], __byte_perm(w[m], w[m + 1], prmt_sel));
+        if (sw == 0) GLC_TRACE(0, t, 3);
       };
       // p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
       auto stage_p2c = [&](auto first_tag) {
         constexpr bool FIRST = decltype(first_tag)::value;
         ptx::mbar_wait(g_full, t & 1);
         ptx::tc_fence_after();
+        if (sw == 0) GLC_TRACE(0, t, 4);
 #pragma unroll
         for (int u = 0; u < E / 16; ++u) {
           uint32_t lo[16], hi[16];
@@ -438,7 +445,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(g_free);
-          }
+              }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int jj = 16 * u + k;
@@ -455,7 +462,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         stage_p2c(std::true_type{});
         stage_c2p(std::false_type{});
       }
-      if (sw == 0) GLC_TRACE(0, t, 2);
+      if (sw == 0) GLC_TRACE(0, t, 6);
 
       const int kb = k0 + b0;
       const uint32_t kbits = kmask[kb >> 5] >> (kb & 31);   // E <= 32 and kb is a multiple of E: no word straddling
@@ -471,9 +478,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       //      tile t+1 orders the reads of tile t before the writes of tile t+2)
       float* xm = xmax + (t & 1) * (G * QT);
       xm[g * QT + i] = mloc;
-      if (sw == 0) GLC_TRACE(0, t, 3);
       ptx::named_bar_sync(2 + qd, 32 * G);   // only the G warps of this lane quarter share rows
-      if (sw == 0) GLC_TRACE(0, t, 4);
       float m_new = m_run;
 #pragma unroll
       for (int gg = 0; gg < G; ++gg) m_new = fmaxf(m_new, xm[gg * QT + i]);
@@ -506,7 +511,6 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
         for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
         l_run = l_run * alpha + psum;
-        if (sw == 0) GLC_TRACE(0, t, 5);
         if (t > 0) {
           ptx::mbar_wait(pv_full, (t - 1) & 1);   // P buffer free again, O stable
           if (__any_sync(0xffffffffu, raise)) {
@@ -523,7 +527,6 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             }
           }
         }
-        if (sw == 0) GLC_TRACE(0, t, 6);
       } else {
       const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
       const float alpha = ptx::ex2((m_run - m_use) * sc);
@@ -544,11 +547,9 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       };
       // fold in PV of the previous tile (also guarantees the P buffer is free again)
       auto stage_fold = [&]() {
-        if (sw == 0) GLC_TRACE(0, t, 5);
         if (t > 0) {
           ptx::mbar_wait(pv_full, (t - 1) & 1);
           ptx::tc_fence_after();
-          if (sw == 0) GLC_TRACE(0, t, 6);
           uint32_t r[E];
           tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
           ptx::tmem_ld_wait();
@@ -676,7 +677,7 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   // CTA (1,0,0) (synchronous)
   static const int groups = [] { const char* e = getenv("GLC_ATTN_G"); return (e && atoi(e) == 4) ? 4 : 2; }();
   static const int c16 = [] { const char* e = getenv("GLC_ATTN_C16"); return (e && e[0] == '0') ? 0 : 1; }();
-  p.c16 = (groups == 2) ? c16 : 0;
+  p.c16 = c16;
   if (const char* tf = getenv("GLC_ATTN_TRACE")) {
     const size_t n = 2 * TMAX * 8;
     if (cudaMalloc(&p.trace, n * sizeof(long long)) != cudaSuccess) return cudaGetLastError();

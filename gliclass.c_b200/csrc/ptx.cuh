@@ -224,6 +224,21 @@ __device__ __forceinline__ void tmem_ld_x32_pack16(uint32_t taddr, uint32_t (&r)
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_x16_pack16(uint32_t taddr, uint32_t (&r)[16]) {   // 32 columns -> 16 registers
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.pack::16b.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x8_pack16(uint32_t taddr, uint32_t (&r)[8]) {     // 16 columns -> 8 registers
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.pack::16b.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -321,6 +336,13 @@ __device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+// a += lo(packed), b += hi(packed) for a packed fp16 pair: sm_100's mixed-precision add (SASS FHADD) takes the fp16 operand
+// directly, so the pair costs two instructions instead of two conversions + two adds
+__device__ __forceinline__ void add_f16x2_to_f32(float& a, float& b, uint32_t packed) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tadd.rn.f32.f16 %0, lo, %0;\n\tadd.rn.f32.f16 %1, hi, %1;\n\t}"
+      : "+f"(a), "+f"(b)
+      : "r"(packed));
 }
 // two fp32 -> packed fp16x2, round to nearest, saturating to +-65504 instead of overflowing to inf
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
