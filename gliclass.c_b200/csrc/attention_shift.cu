@@ -88,7 +88,8 @@ struct ShiftParams {
   int B, S, heads, H;
   float scale_log2;          // log2(e) / sqrt(3*d)
   int swap_order;            // developer switch (GLC_ATTN_SWAP=0: both key groups walk the stages in the same order)
-  int poly;                  // developer switch (GLC_ATTN_POLY=0: every exponential on the MUFU unit)
+  int poly;                  // every poly-th exponential of a thread on the FMA pipe (GLC_ATTN_POLY=0: all on the MUFU unit; 2, 3, 4)
+  int g_once;                // developer switch (GLC_ATTN_GONCE=0: two load / wait rounds for the G chunks instead of one)
   int c16;                   // developer switch (GLC_ATTN_C16=0: fp32 C accumulators, packed by the softmax threads)
 };
 
@@ -104,7 +105,6 @@ __device__ __forceinline__ uint32_t sel(bool p, uint32_t a, uint32_t b) { return
 // 2^x on the FMA pipe (Cody-Waite split + degree-3 minimax polynomial on [-0.5, 0.5], max relative error 7.5e-5 — well
 // below the fp16 rounding of P): the exponential stage of a tile is bound by the MUFU unit (8 cycles per warp
 // instruction) while the FMA pipe idles, so every POLY_EVERY-th score of a thread takes this route instead.
-constexpr int POLY_EVERY = 4;
 __device__ __forceinline__ float exp2_poly(float x) {
   x = fmaxf(x, -125.0f);
   const float t = x + 12582912.0f;          // 1.5 * 2^23: round(x) lands in the low mantissa bits
@@ -114,9 +114,9 @@ __device__ __forceinline__ float exp2_poly(float x) {
   p = fmaf(p, r, 0.99992818f);
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-template <bool POLY>
+template <int EVERY>
 __device__ __forceinline__ float exp2_sel(int jj, float x) {
-  return (POLY && (jj % POLY_EVERY) == POLY_EVERY - 1) ? exp2_poly(x) : ptx::ex2(x);
+  return (EVERY > 0 && (jj % (EVERY > 0 ? EVERY : 1)) == EVERY - 1) ? exp2_poly(x) : ptx::ex2(x);
 }
 
 #define GLC_TRACE(role, tile, slot)                                                                              \
@@ -361,7 +361,8 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     for (int k = 0; k < E; ++k) o[k] = 0.f;
     const float sc = p.scale_log2;
     const bool swap_order = p.swap_order != 0;
-    const bool poly = p.poly != 0;
+    const int poly_every = p.poly;
+    const bool g_once = p.g_once != 0;
     const bool c16 = p.c16 != 0;
 
     for (int t = 0; t < T; ++t) {
@@ -435,6 +436,30 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         ptx::mbar_wait(g_full, t & 1);
         ptx::tc_fence_after();
         if (sw == 0) GLC_TRACE(0, t, 4);
+        if (E == 32 && g_once) {
+          // all four chunk loads in flight behind one wait (64 live registers) instead of two load / wait rounds
+          uint32_t lo[32], hi[32];
+          {
+            uint32_t a0[16], a1[16], b0_[16], b1[16];
+            ptx::tmem_ld_x16(a_lo, a0);
+            ptx::tmem_ld_x16(a_hi, b0_);
+            ptx::tmem_ld_x16(a_lo + 16, a1);
+            ptx::tmem_ld_x16(a_hi + 16, b1);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int k = 0; k < 16; ++k) { lo[k] = a0[k]; lo[(16 + k) % 32] = a1[k]; hi[k] = b0_[k]; hi[(16 + k) % 32] = b1[k]; }
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(g_free);
+#pragma unroll
+          for (int jj = 0; jj < E; ++jj) {
+            const uint32_t v = sel((hi_mask >> jj) & 1u, hi[jj % 32], lo[jj % 32]);
+            const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+            s[jj] = FIRST ? pv : s[jj] + pv;
+          }
+          return;
+        }
 #pragma unroll
         for (int u = 0; u < E / 16; ++u) {
           uint32_t lo[16], hi[16];
@@ -445,7 +470,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(g_free);
-              }
+          }
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int jj = 16 * u + k;
@@ -493,10 +518,24 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         if (raise) m_run = m_new;
         const float neg_ms = (m_run == -CUDART_INF_F) ? 0.f : -m_run * sc;
         float psum = 0.f;
-        if (poly) {
+        if (poly_every == 4) {
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) {
-            const float e = exp2_sel<true>(jj, fmaf(s[jj], sc, neg_ms));
+            const float e = exp2_sel<4>(jj, fmaf(s[jj], sc, neg_ms));
+            s[jj] = e;
+            psum += e;
+          }
+        } else if (poly_every == 3) {
+#pragma unroll
+          for (int jj = 0; jj < E; ++jj) {
+            const float e = exp2_sel<3>(jj, fmaf(s[jj], sc, neg_ms));
+            s[jj] = e;
+            psum += e;
+          }
+        } else if (poly_every == 2) {
+#pragma unroll
+          for (int jj = 0; jj < E; ++jj) {
+            const float e = exp2_sel<2>(jj, fmaf(s[jj], sc, neg_ms));
             s[jj] = e;
             psum += e;
           }
@@ -658,8 +697,10 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
   static const int swap_order = [] { const char* e = getenv("GLC_ATTN_SWAP"); return (e && e[0] == '0') ? 0 : 1; }();
   p.swap_order = swap_order;
-  static const int poly = [] { const char* e = getenv("GLC_ATTN_POLY"); return (e && e[0] == '0') ? 0 : 1; }();
+  static const int poly = [] { const char* e = getenv("GLC_ATTN_POLY"); const int v = e ? atoi(e) : 4; return (v == 1) ? 4 : ((v >= 2 && v <= 4) ? v : 0); }();
   p.poly = poly;
+  static const int g_once = [] { const char* e = getenv("GLC_ATTN_GONCE"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.g_once = g_once;
   dim3 grid((S + QT - 1) / QT, heads, B);
   static bool attr_set[64] = {};
   int dev = 0;
