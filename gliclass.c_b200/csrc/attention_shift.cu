@@ -354,6 +354,12 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const int rot0 = lane + 31 - bb;           // p2c: source lane of column jj is (rot0 - jj) & 31
     const int thr0 = lane - 31 + bb;           // ... and this lane supplies the upper copy iff thr0 + jj < 0:
     const uint32_t hi_mask = thr0 >= 0 ? 0u : (thr0 <= -32 ? 0xffffffffu : ((1u << (-thr0)) - 1u));   // bit jj, tile-invariant
+    uint32_t hm[E];   // ... expanded to full-word masks: the select is one LOP3, no predicate
+#pragma unroll
+    for (int jj = 0; jj < E; ++jj) {
+      hm[jj] = ((hi_mask >> jj) & 1u) ? 0xffffffffu : 0u;
+      asm volatile("" : "+r"(hm[jj]));   // opaque: otherwise the compiler turns the mask back into ISETP + SEL
+    }
 
     float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
     float o[E];
@@ -454,7 +460,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
           if (lane == 0) ptx::mbar_arrive(g_free);
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) {
-            const uint32_t v = sel((hi_mask >> jj) & 1u, hi[jj % 32], lo[jj % 32]);
+            const uint32_t v = (hi[jj % 32] & hm[jj]) | (lo[jj % 32] & ~hm[jj]);
             const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
             s[jj] = FIRST ? pv : s[jj] + pv;
           }
@@ -474,7 +480,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
           for (int k = 0; k < 16; ++k) {
             const int jj = 16 * u + k;
-            const uint32_t v = sel((hi_mask >> jj) & 1u, hi[k], lo[k]);
+            const uint32_t v = (hi[k] & hm[jj]) | (lo[k] & ~hm[jj]);
             const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
             s[jj] = FIRST ? pv : s[jj] + pv;
           }
@@ -496,9 +502,10 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         for (int jj = 0; jj < E; ++jj)
           if (!((kbits >> jj) & 1u)) s[jj] = -CUDART_INF_F;
       }
-      float mloc = s[0];
+      float mx[4] = {s[0], s[1], s[2], s[3]};
 #pragma unroll
-      for (int jj = 1; jj < E; ++jj) mloc = fmaxf(mloc, s[jj]);
+      for (int jj = 4; jj < E; ++jj) mx[jj & 3] = fmaxf(mx[jj & 3], s[jj]);
+      const float mloc = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
       // ---- row max shared between the key groups (double buffered by tile parity: the quarter barrier of
       //      tile t+1 orders the reads of tile t before the writes of tile t+2)
       float* xm = xmax + (t & 1) * (G * QT);
@@ -517,39 +524,39 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         const float alpha = raise ? ptx::ex2((m_run - m_new) * sc) : 1.0f;   // m_run = -inf: 0 (l and O hold exact zeros)
         if (raise) m_run = m_new;
         const float neg_ms = (m_run == -CUDART_INF_F) ? 0.f : -m_run * sc;
-        float psum = 0.f;
+        float ps[4] = {0.f, 0.f, 0.f, 0.f};
         if (poly_every == 4) {
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) {
             const float e = exp2_sel<4>(jj, fmaf(s[jj], sc, neg_ms));
             s[jj] = e;
-            psum += e;
+            ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
           }
         } else if (poly_every == 3) {
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) {
             const float e = exp2_sel<3>(jj, fmaf(s[jj], sc, neg_ms));
             s[jj] = e;
-            psum += e;
+            ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
           }
         } else if (poly_every == 2) {
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) {
             const float e = exp2_sel<2>(jj, fmaf(s[jj], sc, neg_ms));
             s[jj] = e;
-            psum += e;
+            ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
           }
         } else {
 #pragma unroll
           for (int jj = 0; jj < E; ++jj) {
             const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
             s[jj] = e;
-            psum += e;
+            ps[jj & 3] += e;
           }
         }
 #pragma unroll
         for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
-        l_run = l_run * alpha + psum;
+        l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
         if (t > 0) {
           ptx::mbar_wait(pv_full, (t - 1) & 1);   // P buffer free again, O stable
           if (__any_sync(0xffffffffu, raise)) {
