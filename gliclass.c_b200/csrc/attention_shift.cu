@@ -89,6 +89,7 @@ struct ShiftParams {
   float scale_log2;          // log2(e) / sqrt(3*d)
   int swap_order;            // developer switch (GLC_ATTN_SWAP=0: both key groups walk the stages in the same order)
   int poly;                  // every poly-th exponential of a thread on the FMA pipe (GLC_ATTN_POLY=0: all on the MUFU unit; 2, 3, 4)
+  int g16;                   // developer switch (GLC_ATTN_G16=0: fp32 G accumulators)
   int g_once;                // developer switch (GLC_ATTN_GONCE=0: two load / wait rounds for the G chunks instead of one)
   int c16;                   // developer switch (GLC_ATTN_C16=0: fp32 C accumulators, packed by the softmax threads)
 };
@@ -241,7 +242,6 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected issue)
     constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
-    constexpr uint32_t idesc_n32 = ptx::idesc_f16(128, 32);
     // C accumulates in fp16 (C16): the softmax threads then read their window already packed (tcgen05.ld.pack::16b)
     const uint32_t idesc_c = ptx::idesc_f16(128, SLICE, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.c16 ? 0u : 1u);
     constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
@@ -269,6 +269,9 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       }
       __syncwarp();
     };
+    // G accumulates in fp16 too (G16): lo / hi copies are read packed (two key columns per register)
+    const uint32_t idesc_g64 = ptx::idesc_f16(128, 64, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.g16 ? 0u : 1u);
+    const uint32_t idesc_g32 = ptx::idesc_f16(128, 32, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.g16 ? 0u : 1u);
     auto issue_g = [&](int t) {    // the three row-shifted copies of G = EQr_slice . K_t^T; 32 table/key rows = 256 in a descriptor
       const int st = t & 1;
       const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
@@ -278,13 +281,13 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // rows 32..159 x keys 0..63
-          ptx::mma_f16_ss(tmem + TM_G32, dEQ + 256 + 2 * k, dK + 2 * k, idesc_n64, (uint32_t)(k != 0));
+          ptx::mma_f16_ss(tmem + TM_G32, dEQ + 256 + 2 * k, dK + 2 * k, idesc_g64, (uint32_t)(k != 0));
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // rows 64..191 x keys 0..31
-          ptx::mma_f16_ss(tmem + TM_G64, dEQ + 512 + 2 * k, dK + 2 * k, idesc_n32, (uint32_t)(k != 0));
+          ptx::mma_f16_ss(tmem + TM_G64, dEQ + 512 + 2 * k, dK + 2 * k, idesc_g32, (uint32_t)(k != 0));
 #pragma unroll
         for (int k = 0; k < 4; ++k)   // rows 0..127 x keys 32..63
-          ptx::mma_f16_ss(tmem + TM_G0, dEQ + 2 * k, dK + 256 + 2 * k, idesc_n32, (uint32_t)(k != 0));
+          ptx::mma_f16_ss(tmem + TM_G0, dEQ + 2 * k, dK + 256 + 2 * k, idesc_g32, (uint32_t)(k != 0));
         ptx::mma_commit(&a_empty[st]);
         ptx::mma_commit(g_full);
       }
@@ -368,6 +371,13 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     const float sc = p.scale_log2;
     const bool swap_order = p.swap_order != 0;
     const int poly_every = p.poly;
+    const bool g16 = p.g16 != 0;
+    uint32_t hm2[E / 2];   // pair masks for the packed G path
+#pragma unroll
+    for (int m = 0; m < E / 2; ++m) {
+      hm2[m] = (hm[2 * m] & 0xffffu) | (hm[2 * m + 1] & 0xffff0000u);
+      asm volatile("" : "+r"(hm2[m]));
+    }
     const bool g_once = p.g_once != 0;
     const bool c16 = p.c16 != 0;
 
@@ -442,6 +452,26 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         ptx::mbar_wait(g_full, t & 1);
         ptx::tc_fence_after();
         if (sw == 0) GLC_TRACE(0, t, 4);
+        if (E == 32 && g16) {
+          // fp16 copies, two key columns per register: one LOP3 selects both halves, each half needs its own lane rotation
+          uint32_t lo[16], hi[16];
+          ptx::tmem_ld_x16_pack16(a_lo, lo);
+          ptx::tmem_ld_x16_pack16(a_hi, hi);
+          ptx::tmem_ld_wait();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(g_free);
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            const uint32_t v = (hi[m] & hm2[m]) | (lo[m] & ~hm2[m]);
+            const uint32_t x0 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m);        // low half = key 2m
+            const uint32_t x1 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m - 1);    // high half = key 2m + 1
+            if (FIRST) { s[2 * m] = 0.f; s[2 * m + 1] = 0.f; }
+            ptx::add_f16_lo_to_f32(s[2 * m], x0);
+            ptx::add_f16_hi_to_f32(s[2 * m + 1], x1);
+          }
+          return;
+        }
         if (E == 32 && g_once) {
           // all four chunk loads in flight behind one wait (64 live registers) instead of two load / wait rounds
           uint32_t lo[32], hi[32];
@@ -726,6 +756,8 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   static const int groups = [] { const char* e = getenv("GLC_ATTN_G"); return (e && atoi(e) == 4) ? 4 : 2; }();
   static const int c16 = [] { const char* e = getenv("GLC_ATTN_C16"); return (e && e[0] == '0') ? 0 : 1; }();
   p.c16 = c16;
+  static const int g16 = [] { const char* e = getenv("GLC_ATTN_G16"); return (e && e[0] == '0') ? 0 : 1; }();
+  p.g16 = (groups == 2) ? g16 : 0;
   if (const char* tf = getenv("GLC_ATTN_TRACE")) {
     const size_t n = 2 * TMAX * 8;
     if (cudaMalloc(&p.trace, n * sizeof(long long)) != cudaSuccess) return cudaGetLastError();

@@ -344,6 +344,12 @@ __device__ __forceinline__ void add_f16x2_to_f32(float& a, float& b, uint32_t pa
       : "+f"(a), "+f"(b)
       : "r"(packed));
 }
+__device__ __forceinline__ void add_f16_lo_to_f32(float& a, uint32_t packed) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, lo, %0;\n\t}" : "+f"(a) : "r"(packed));
+}
+__device__ __forceinline__ void add_f16_hi_to_f32(float& a, uint32_t packed) {
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, hi, %0;\n\t}" : "+f"(a) : "r"(packed));
+}
 // two fp32 -> packed fp16x2, round to nearest, saturating to +-65504 instead of overflowing to inf
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   uint32_t r;
