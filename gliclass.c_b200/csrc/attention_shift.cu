@@ -466,9 +466,13 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
             const uint32_t v = (hi[m] & hm2[m]) | (lo[m] & ~hm2[m]);
             const uint32_t x0 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m);        // low half = key 2m
             const uint32_t x1 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m - 1);    // high half = key 2m + 1
-            if (FIRST) { s[2 * m] = 0.f; s[2 * m + 1] = 0.f; }
-            ptx::add_f16_lo_to_f32(s[2 * m], x0);
-            ptx::add_f16_hi_to_f32(s[2 * m + 1], x1);
+            if (FIRST) {
+              s[2 * m] = ptx::f16_lo_to_f32(x0);
+              s[2 * m + 1] = ptx::f16_hi_to_f32(x1);
+            } else {
+              ptx::add_f16_lo_to_f32(s[2 * m], x0);
+              ptx::add_f16_hi_to_f32(s[2 * m + 1], x1);
+            }
           }
           return;
         }
@@ -532,10 +536,18 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
         for (int jj = 0; jj < E; ++jj)
           if (!((kbits >> jj) & 1u)) s[jj] = -CUDART_INF_F;
       }
-      float mx[4] = {s[0], s[1], s[2], s[3]};
+      // four independent chains of 3-input maxima (FMNMX3)
+      float mx[4];
 #pragma unroll
-      for (int jj = 4; jj < E; ++jj) mx[jj & 3] = fmaxf(mx[jj & 3], s[jj]);
-      const float mloc = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+      for (int c = 0; c < 4; ++c) {
+        constexpr int CH = E / 4;
+        float v = s[CH * c];
+#pragma unroll
+        for (int k = 1; k + 1 < CH; k += 2) v = fmaxf(fmaxf(v, s[CH * c + k]), s[CH * c + k + 1]);
+        if (CH % 2 == 0) v = fmaxf(v, s[CH * c + CH - 1]);
+        mx[c] = v;
+      }
+      const float mloc = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), mx[2]), mx[3]);
       // ---- row max shared between the key groups (double buffered by tile parity: the quarter barrier of
       //      tile t+1 orders the reads of tile t before the writes of tile t+2)
       float* xm = xmax + (t & 1) * (G * QT);

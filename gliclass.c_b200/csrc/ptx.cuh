@@ -350,6 +350,16 @@ __device__ __forceinline__ void add_f16_lo_to_f32(float& a, uint32_t packed) {
 __device__ __forceinline__ void add_f16_hi_to_f32(float& a, uint32_t packed) {
   asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tadd.rn.f32.f16 %0, hi, %0;\n\t}" : "+f"(a) : "r"(packed));
 }
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t packed) {
+  float f;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, lo;\n\t}" : "=f"(f) : "r"(packed));
+  return f;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t packed) {
+  float f;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, hi;\n\t}" : "=f"(f) : "r"(packed));
+  return f;
+}
 // two fp32 -> packed fp16x2, round to nearest, saturating to +-65504 instead of overflowing to inf
 __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   uint32_t r;
