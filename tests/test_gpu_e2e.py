@@ -429,3 +429,39 @@ def test_rows_sharded_over_two_devices_match_one_device(pkg, orc, golden_onnx, g
     finally:
         one.close()
         two.close()
+
+
+def test_full_size_properties_base_b64_s512(pkg, orc, model_cache):
+    """Size-independent properties at BASELINE.json configs[1]'s full size (64 texts x 512 tokens x 10 labels), where the
+    CPU oracle is too slow to check every row:
+      * rows are independent: permuting the batch rows permutes the logits, bit for bit (every row runs
+        through the same kernels with the same tile shapes whatever its position in the batch);
+      * padding invariance: right-padding every row with 64 pad tokens (id 0, mask 0) leaves the
+        logits unchanged up to fp16 rounding of re-tiled reductions;
+      * a row's logits do not depend on its neighbours: replacing the other 63 rows changes nothing, bit for bit;
+      * every logit is finite and the label columns of a row differ (the head really reads the <<LABEL>> positions)."""
+    path = os.path.join(model_cache, "base.onnx")
+    cfg, _ = orc.make_model_file("base", path, seed=0)
+    ids, mask = orc.synth_inputs(cfg, 64, 512, 10, seed=777)
+    ids, mask = ids.numpy(), mask.numpy()
+    sess = pkg.Session(path)
+    try:
+        out = sess.run_inference(ids, mask)
+        assert out.shape == (64, 10) and np.isfinite(out).all()
+        assert (np.ptp(out, axis=1) > 1e-4).all()
+        perm = np.random.RandomState(3).permutation(64)
+        out_p = sess.run_inference(ids[perm], mask[perm])
+        assert np.array_equal(out_p, out[perm]), "row permutation must permute the logits bit for bit"
+        other_ids, other_mask = orc.synth_inputs(cfg, 64, 512, 10, seed=778)
+        mixed_ids, mixed_mask = other_ids.numpy().copy(), other_mask.numpy().copy()
+        mixed_ids[5], mixed_mask[5] = ids[5], mask[5]
+        out_m = sess.run_inference(mixed_ids, mixed_mask)
+        assert np.array_equal(out_m[5], out[5]), "a row's logits must not depend on the other rows"
+        pad_ids = np.concatenate([ids, np.zeros((64, 64), dtype=ids.dtype)], axis=1)
+        pad_mask = np.concatenate([mask, np.zeros((64, 64), dtype=mask.dtype)], axis=1)
+        out_pad = sess.run_inference(pad_ids, pad_mask)
+        d = np.abs(out_pad - out).max()
+        print(f"padding invariance at B64 S512->576: max|d|={d:.3e}")
+        assert d <= 2e-3
+    finally:
+        sess.close()
