@@ -89,6 +89,7 @@ struct ShiftParams {
   float scale_log2;          // log2(e) / sqrt(3*d)
   int swap_order;            // developer switch (GLC_ATTN_SWAP=0: both key groups walk the stages in the same order)
   int poly;                  // every poly-th exponential of a thread on the FMA pipe (GLC_ATTN_POLY=0: all on the MUFU unit; 2, 3, 4)
+  int whatif;                // developer what-if switches (GLC_ATTN_WHATIF; results become wrong)
   int g16;                   // developer switch (GLC_ATTN_G16=0: fp32 G accumulators)
   int g_once;                // developer switch (GLC_ATTN_GONCE=0: two load / wait rounds for the G chunks instead of one)
   int c16;                   // developer switch (GLC_ATTN_C16=0: fp32 C accumulators, packed by the softmax threads)
@@ -243,7 +244,8 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     // ------------------------------------------------------------------ MMA issuer (warp-uniform loop, elected issue)
     constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
     // C accumulates in fp16 (C16): the softmax threads then read their window already packed (tcgen05.ld.pack::16b)
-    const uint32_t idesc_c = ptx::idesc_f16(128, SLICE, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.c16 ? 0u : 1u);
+    // what-if (p.whatif & 1, results wrong): only 64 of the 192 C columns, as a sliding C window would compute per tile
+    const uint32_t idesc_c = ptx::idesc_f16(128, (p.whatif & 1) ? 64 : SLICE, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.c16 ? 0u : 1u);
     constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
     ptx::mbar_wait(qt_full, 0);
     ptx::tc_fence_after();
@@ -768,6 +770,8 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
   static const int groups = [] { const char* e = getenv("GLC_ATTN_G"); return (e && atoi(e) == 4) ? 4 : 2; }();
   static const int c16 = [] { const char* e = getenv("GLC_ATTN_C16"); return (e && e[0] == '0') ? 0 : 1; }();
   p.c16 = c16;
+  static const int whatif = [] { const char* e = getenv("GLC_ATTN_WHATIF"); return e ? atoi(e) : 0; }();
+  p.whatif = whatif;
   static const int g16 = [] { const char* e = getenv("GLC_ATTN_G16"); return (e && e[0] == '0') ? 0 : 1; }();
   p.g16 = (groups == 2) ? g16 : 0;
   if (const char* tf = getenv("GLC_ATTN_TRACE")) {
