@@ -245,7 +245,7 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
     constexpr uint32_t idesc_n64 = ptx::idesc_f16(128, 64);
     // C accumulates in fp16 (C16): the softmax threads then read their window already packed (tcgen05.ld.pack::16b)
     // what-if (p.whatif & 1, results wrong): only 64 of the 192 C columns, as a sliding C window would compute per tile
-    const uint32_t idesc_c = ptx::idesc_f16(128, (p.whatif & 1) ? 64 : SLICE, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.c16 ? 0u : 1u);
+    const uint32_t idesc_c = ptx::idesc_f16(128, (TRACE && (p.whatif & 1)) ? 64 : SLICE, 0, 0, ptx::FMT_F16, ptx::FMT_F16, (TRACE ? p.c16 != 0 : true) ? 0u : 1u);
     constexpr uint32_t idesc_pv = ptx::idesc_f16(128, 64, 0, 1);   // B (=V) is MN-major
     ptx::mbar_wait(qt_full, 0);
     ptx::tc_fence_after();
@@ -272,8 +272,9 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       __syncwarp();
     };
     // G accumulates in fp16 too (G16): lo / hi copies are read packed (two key columns per register)
-    const uint32_t idesc_g64 = ptx::idesc_f16(128, 64, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.g16 ? 0u : 1u);
-    const uint32_t idesc_g32 = ptx::idesc_f16(128, 32, 0, 0, ptx::FMT_F16, ptx::FMT_F16, p.g16 ? 0u : 1u);
+    const bool g16_mma = TRACE ? p.g16 != 0 : (G == 2);
+    const uint32_t idesc_g64 = ptx::idesc_f16(128, 64, 0, 0, ptx::FMT_F16, ptx::FMT_F16, g16_mma ? 0u : 1u);
+    const uint32_t idesc_g32 = ptx::idesc_f16(128, 32, 0, 0, ptx::FMT_F16, ptx::FMT_F16, g16_mma ? 0u : 1u);
     auto issue_g = [&](int t) {    // the three row-shifted copies of G = EQr_slice . K_t^T; 32 table/key rows = 256 in a descriptor
       const int st = t & 1;
       const uint64_t dK = ptx::smem_desc_sw128(ptx::smem_u32(smem + OFF_K + st * 8192));
@@ -371,17 +372,19 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 #pragma unroll
     for (int k = 0; k < E; ++k) o[k] = 0.f;
     const float sc = p.scale_log2;
-    const bool swap_order = p.swap_order != 0;
-    const int poly_every = p.poly;
-    const bool g16 = p.g16 != 0;
+    // the developer switches are honoured by the TRACE instantiation only (the launcher picks it whenever one of them is
+    // off its default); in the production instantiation they are compile-time constants, so the other paths do not exist
+    const bool swap_order = TRACE ? p.swap_order != 0 : true;
+    const int poly_every = TRACE ? p.poly : 4;
+    const bool g16 = TRACE ? p.g16 != 0 : (G == 2);
     uint32_t hm2[E / 2];   // pair masks for the packed G path
 #pragma unroll
     for (int m = 0; m < E / 2; ++m) {
       hm2[m] = (hm[2 * m] & 0xffffu) | (hm[2 * m + 1] & 0xffff0000u);
       asm volatile("" : "+r"(hm2[m]));
     }
-    const bool g_once = p.g_once != 0;
-    const bool c16 = p.c16 != 0;
+    const bool g_once = TRACE ? p.g_once != 0 : true;
+    const bool c16 = TRACE ? p.c16 != 0 : true;
 
     for (int t = 0; t < T; ++t) {
       const int k0 = t * KT;
@@ -799,6 +802,13 @@ cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_
     return e;
   }
   static const bool otmem = [] { const char* e = getenv("GLC_ATTN_OTMEM"); return !(e && e[0] == '0'); }();   // 0: per-tile PV read-out + fold in registers
+  // a developer switch off its default: the TRACE instantiation (without a trace buffer) is the one that reads them
+  const bool dev_switches = swap_order != 1 || poly != 4 || g_once != 1 || c16 != 1 || whatif != 0 || (groups == 2 && g16 != 1);
+  if (dev_switches && otmem) {
+    if (groups == 2) attention_shift_kernel<2, true, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+    else attention_shift_kernel<4, true, true><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
+    return cudaGetLastError();
+  }
   if (groups == 2 && otmem) attention_shift_kernel<2, false, true><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
   else if (groups == 2) attention_shift_kernel<2, false, false><<<grid, 64 + 128 * 2, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
   else attention_shift_kernel<4, false, true><<<grid, 64 + 128 * 4, ATT_SMEM, stream>>>(tm_qkv, tm_ek, tm_eq, p);
