@@ -322,388 +322,399 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
       }
   } else {
     // ------------------------------------------------------------------ softmax warps
-    const int sw = warp - 2;          // 0..SM_WARPS-1
-    const int g = sw >> 2;            // key group of the tile: keys [E*g, E*g+E)
-    const int qd = warp & 3;          // TMEM lane quarter
-    const int i = qd * 32 + lane;     // row in the query tile
-    const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
-    float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
-    const int b0 = g * E;             // first key column of this thread
-    const int bb = b0 & 31;
+    // The loop below is instantiated once per key group (the group index is a compile-time constant inside: addresses,
+    // stage order and lane tables fold, and a warp walks a straight-line path) and dispatched on the warp's group here.
+    auto softmax_role = [&](auto gtag) {
+      const int sw = warp - 2;          // 0..SM_WARPS-1
+        constexpr int g = decltype(gtag)::value;   // key group of the tile: keys [E*g, E*g+E)
+      const int qd = warp & 3;          // TMEM lane quarter
+      const int i = qd * 32 + lane;     // row in the query tile
+      const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
+      float* xmax = reinterpret_cast<float*>(smem + OFF_XMAX);
+      const int b0 = g * E;             // first key column of this thread
+      const int bb = b0 & 31;
 
-    // ---- Q tile -> TMEM once (row i, halves [E*g, E*g+E) = 16-byte chunks of the swizzled row)
-    ptx::mbar_wait(q_full, 0);
-    {
-      const uint8_t* qrow = smem + OFF_Q + (i >> 3) * 1024 + (i & 7) * 128;
-#pragma unroll
-      for (int u = 0; u < E / 16; ++u) {
-        const int ch = (E / 8) * g + 2 * u;
-        const uint4 lo = *reinterpret_cast<const uint4*>(qrow + (((ch) ^ (i & 7)) << 4));
-        const uint4 hi = *reinterpret_cast<const uint4*>(qrow + (((ch + 1) ^ (i & 7)) << 4));
-        const uint32_t qr[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-        ptx::tmem_st_x8(t_lane + TM_Q + (uint32_t)((E / 2) * g + 8 * u), qr);
-      }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(qt_full);
-    }
-
-    // tile-independent addresses and shift controls
-    const uint32_t a_s = t_lane + TM_S + (uint32_t)b0;
-    const uint32_t a_c = t_lane + TM_C + (uint32_t)(96 - 32 * qd + b0);      // window of this warp: its E keys x 32 lane shifts
-    const uint32_t a_lo = t_lane + (b0 < 32 ? TM_G32 + (uint32_t)b0 : TM_G0 + (uint32_t)bb);    // copy 32 s0
-    const uint32_t a_hi = t_lane + (b0 < 32 ? TM_G64 + (uint32_t)b0 : TM_G32 + (uint32_t)b0);   // copy 32 s0 + 32
-    const int sh = 31 - lane;                  // c2p: element shift inside the window
-    const bool sh16 = sh & 16, sh8 = sh & 8, sh4 = sh & 4, sh2 = sh & 2;
-    const uint32_t prmt_sel = (sh & 1) ? 0x5432u : 0x3210u;
-    const int rot0 = lane + 31 - bb;           // p2c: source lane of column jj is (rot0 - jj) & 31
-    const int thr0 = lane - 31 + bb;           // ... and this lane supplies the upper copy iff thr0 + jj < 0:
-    const uint32_t hi_mask = thr0 >= 0 ? 0u : (thr0 <= -32 ? 0xffffffffu : ((1u << (-thr0)) - 1u));   // bit jj, tile-invariant
-    uint32_t hm[E];   // ... expanded to full-word masks: the select is one LOP3, no predicate
-#pragma unroll
-    for (int jj = 0; jj < E; ++jj) {
-      hm[jj] = ((hi_mask >> jj) & 1u) ? 0xffffffffu : 0u;
-      asm volatile("" : "+r"(hm[jj]));   // opaque: otherwise the compiler turns the mask back into ISETP + SEL
-    }
-
-    float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
-    float o[E];
-#pragma unroll
-    for (int k = 0; k < E; ++k) o[k] = 0.f;
-    const float sc = p.scale_log2;
-    // the developer switches are honoured by the TRACE instantiation only (the launcher picks it whenever one of them is
-    // off its default); in the production instantiation they are compile-time constants, so the other paths do not exist
-    const bool swap_order = TRACE ? p.swap_order != 0 : true;
-    const int poly_every = TRACE ? p.poly : 4;
-    const bool g16 = TRACE ? p.g16 != 0 : (G == 2);
-    uint32_t hm2[E / 2];   // pair masks for the packed G path
-#pragma unroll
-    for (int m = 0; m < E / 2; ++m) {
-      hm2[m] = (hm[2 * m] & 0xffffu) | (hm[2 * m + 1] & 0xffff0000u);
-      asm volatile("" : "+r"(hm2[m]));
-    }
-    const bool g_once = TRACE ? p.g_once != 0 : true;
-    const bool c16 = TRACE ? p.c16 != 0 : true;
-
-    for (int t = 0; t < T; ++t) {
-      const int k0 = t * KT;
-      if (sw == 0) GLC_TRACE(0, t, 0);
-
-      // The two warps of a scheduler (key groups g, g+1 of the same lane quarter) walk the pre-maximum stages in opposite
-      // orders, so that one drains TMEM (64 B/clk port per quarter) while the other runs the ALU-pipe barrel shifter:
-      //   even g:  C|S drain -> barrel -> G drain + lane rotation        odd g:  G drain + lane rotation -> C|S drain -> barrel
-      float s[E];
-      auto stage_c2p = [&](auto first_tag) {
-        constexpr bool FIRST = decltype(first_tag)::value;   // the first stage of a tile assigns, the second accumulates
-        uint32_t w[NW];
-        ptx::mbar_wait(sc_full, t & 1);
-        ptx::tc_fence_after();
-        if (sw == 0) GLC_TRACE(0, t, 1);
-        {
-          uint32_t r[E];
-          tmem_ld_n<E>(a_s, r);
-          if (c16) {
-            if constexpr (E == 32) {
-              uint32_t cp[32];
-              ptx::tmem_ld_x32_pack16(a_c, cp);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < NW; ++k) w[k] = cp[k % 32];
-            } else {
-              uint32_t cp[16], cq[8];
-              ptx::tmem_ld_x16_pack16(a_c, cp);
-              ptx::tmem_ld_x8_pack16(a_c + 32, cq);
-              ptx::tmem_ld_wait();
-#pragma unroll
-              for (int k = 0; k < NW; ++k) w[k] = k < 16 ? cp[k % 16] : cq[(k - 16) % 8];
-            }
-          } else {
-            uint32_t c[NC];
-#pragma unroll
-            for (int u = 0; u < NC / 16; ++u) {
-              uint32_t cc[16];
-              ptx::tmem_ld_x16(a_c + 16 * u, cc);
-#pragma unroll
-              for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
-            }
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
-          }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(sc_free);
-          if (sw == 0) GLC_TRACE(0, t, 2);
-#pragma unroll
-          for (int jj = 0; jj < E; ++jj) s[jj] = FIRST ? __uint_as_float(r[jj]) : s[jj] + __uint_as_float(r[jj]);
-        }
-        // shift the packed window left by sh elements
-#pragma unroll
-        for (int k = 0; k < NW - 8; ++k) w[k] = sel(sh16, w[k + 8], w[k]);
-#pragma unroll
-        for (int k = 0; k < NW - 12; ++k) w[k] = sel(sh8, w[k + 4], w[k]);
-#pragma unroll
-        for (int k = 0; k < NW - 14; ++k) w[k] = sel(sh4, w[k + 2], w[k]);
-#pragma unroll
-        for (int k = 0; k < NW - 15; ++k) w[k] = sel(sh2, w[k + 1], w[k]);
-#pragma unroll
-        for (int m = 0; m < E / 2; ++m) ptx::add_f16x2_to_f32(s[2 * m], s[2 * m + 1], __byte_perm(w[m], w[m + 1], prmt_sel));
-        if (sw == 0) GLC_TRACE(0, t, 3);
-      };
-      // p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
-      auto stage_p2c = [&](auto first_tag) {
-        constexpr bool FIRST = decltype(first_tag)::value;
-        ptx::mbar_wait(g_full, t & 1);
-        ptx::tc_fence_after();
-        if (sw == 0) GLC_TRACE(0, t, 4);
-        if (E == 32 && g16) {
-          // fp16 copies, two key columns per register: one LOP3 selects both halves, each half needs its own lane rotation
-          uint32_t lo[16], hi[16];
-          ptx::tmem_ld_x16_pack16(a_lo, lo);
-          ptx::tmem_ld_x16_pack16(a_hi, hi);
-          ptx::tmem_ld_wait();
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(g_free);
-#pragma unroll
-          for (int m = 0; m < 16; ++m) {
-            const uint32_t v = (hi[m] & hm2[m]) | (lo[m] & ~hm2[m]);
-            const uint32_t x0 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m);        // low half = key 2m
-            const uint32_t x1 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m - 1);    // high half = key 2m + 1
-            if (FIRST) {
-              s[2 * m] = ptx::f16_lo_to_f32(x0);
-              s[2 * m + 1] = ptx::f16_hi_to_f32(x1);
-            } else {
-              ptx::add_f16_lo_to_f32(s[2 * m], x0);
-              ptx::add_f16_hi_to_f32(s[2 * m + 1], x1);
-            }
-          }
-          return;
-        }
-        if (E == 32 && g_once) {
-          // all four chunk loads in flight behind one wait (64 live registers) instead of two load / wait rounds
-          uint32_t lo[32], hi[32];
-          {
-            uint32_t a0[16], a1[16], b0_[16], b1[16];
-            ptx::tmem_ld_x16(a_lo, a0);
-            ptx::tmem_ld_x16(a_hi, b0_);
-            ptx::tmem_ld_x16(a_lo + 16, a1);
-            ptx::tmem_ld_x16(a_hi + 16, b1);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int k = 0; k < 16; ++k) { lo[k] = a0[k]; lo[(16 + k) % 32] = a1[k]; hi[k] = b0_[k]; hi[(16 + k) % 32] = b1[k]; }
-          }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(g_free);
-#pragma unroll
-          for (int jj = 0; jj < E; ++jj) {
-            const uint32_t v = (hi[jj % 32] & hm[jj]) | (lo[jj % 32] & ~hm[jj]);
-            const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
-            s[jj] = FIRST ? pv : s[jj] + pv;
-          }
-          return;
-        }
-#pragma unroll
+      // ---- Q tile -> TMEM once (row i, halves [E*g, E*g+E) = 16-byte chunks of the swizzled row)
+      ptx::mbar_wait(q_full, 0);
+      {
+        const uint8_t* qrow = smem + OFF_Q + (i >> 3) * 1024 + (i & 7) * 128;
+  #pragma unroll
         for (int u = 0; u < E / 16; ++u) {
-          uint32_t lo[16], hi[16];
-          ptx::tmem_ld_x16(a_lo + 16 * u, lo);
-          ptx::tmem_ld_x16(a_hi + 16 * u, hi);
-          ptx::tmem_ld_wait();
-          if (u == E / 16 - 1) {
+          const int ch = (E / 8) * g + 2 * u;
+          const uint4 lo = *reinterpret_cast<const uint4*>(qrow + (((ch) ^ (i & 7)) << 4));
+          const uint4 hi = *reinterpret_cast<const uint4*>(qrow + (((ch + 1) ^ (i & 7)) << 4));
+          const uint32_t qr[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          ptx::tmem_st_x8(t_lane + TM_Q + (uint32_t)((E / 2) * g + 8 * u), qr);
+        }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(qt_full);
+      }
+
+      // tile-independent addresses and shift controls
+      const uint32_t a_s = t_lane + TM_S + (uint32_t)b0;
+      const uint32_t a_c = t_lane + TM_C + (uint32_t)(96 - 32 * qd + b0);      // window of this warp: its E keys x 32 lane shifts
+      const uint32_t a_lo = t_lane + (b0 < 32 ? TM_G32 + (uint32_t)b0 : TM_G0 + (uint32_t)bb);    // copy 32 s0
+      const uint32_t a_hi = t_lane + (b0 < 32 ? TM_G64 + (uint32_t)b0 : TM_G32 + (uint32_t)b0);   // copy 32 s0 + 32
+      const int sh = 31 - lane;                  // c2p: element shift inside the window
+      const bool sh16 = sh & 16, sh8 = sh & 8, sh4 = sh & 4, sh2 = sh & 2;
+      const uint32_t prmt_sel = (sh & 1) ? 0x5432u : 0x3210u;
+      const int rot0 = lane + 31 - bb;           // p2c: source lane of column jj is (rot0 - jj) & 31
+      const int thr0 = lane - 31 + bb;           // ... and this lane supplies the upper copy iff thr0 + jj < 0:
+      const uint32_t hi_mask = thr0 >= 0 ? 0u : (thr0 <= -32 ? 0xffffffffu : ((1u << (-thr0)) - 1u));   // bit jj, tile-invariant
+      uint32_t hm[E];   // ... expanded to full-word masks: the select is one LOP3, no predicate
+  #pragma unroll
+      for (int jj = 0; jj < E; ++jj) {
+        hm[jj] = ((hi_mask >> jj) & 1u) ? 0xffffffffu : 0u;
+        asm volatile("" : "+r"(hm[jj]));   // opaque: otherwise the compiler turns the mask back into ISETP + SEL
+      }
+
+      float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 1.f;
+      float o[E];
+  #pragma unroll
+      for (int k = 0; k < E; ++k) o[k] = 0.f;
+      const float sc = p.scale_log2;
+      // the developer switches are honoured by the TRACE instantiation only (the launcher picks it whenever one of them is
+      // off its default); in the production instantiation they are compile-time constants, so the other paths do not exist
+      const bool swap_order = TRACE ? p.swap_order != 0 : true;
+      const int poly_every = TRACE ? p.poly : 4;
+      const bool g16 = TRACE ? p.g16 != 0 : (G == 2);
+      uint32_t hm2[E / 2];   // pair masks for the packed G path
+  #pragma unroll
+      for (int m = 0; m < E / 2; ++m) {
+        hm2[m] = (hm[2 * m] & 0xffffu) | (hm[2 * m + 1] & 0xffff0000u);
+        asm volatile("" : "+r"(hm2[m]));
+      }
+      const bool g_once = TRACE ? p.g_once != 0 : true;
+      const bool c16 = TRACE ? p.c16 != 0 : true;
+
+      for (int t = 0; t < T; ++t) {
+        const int k0 = t * KT;
+        if (sw == 0) GLC_TRACE(0, t, 0);
+
+        // The two warps of a scheduler (key groups g, g+1 of the same lane quarter) walk the pre-maximum stages in opposite
+        // orders, so that one drains TMEM (64 B/clk port per quarter) while the other runs the ALU-pipe barrel shifter:
+        //   even g:  C|S drain -> barrel -> G drain + lane rotation        odd g:  G drain + lane rotation -> C|S drain -> barrel
+        float s[E];
+        auto stage_c2p = [&](auto first_tag) {
+          constexpr bool FIRST = decltype(first_tag)::value;   // the first stage of a tile assigns, the second accumulates
+          uint32_t w[NW];
+          ptx::mbar_wait(sc_full, t & 1);
+          ptx::tc_fence_after();
+          if (sw == 0) GLC_TRACE(0, t, 1);
+          {
+            uint32_t r[E];
+            tmem_ld_n<E>(a_s, r);
+            if (c16) {
+              if constexpr (E == 32) {
+                uint32_t cp[32];
+                ptx::tmem_ld_x32_pack16(a_c, cp);
+                ptx::tmem_ld_wait();
+  #pragma unroll
+                for (int k = 0; k < NW; ++k) w[k] = cp[k % 32];
+              } else {
+                uint32_t cp[16], cq[8];
+                ptx::tmem_ld_x16_pack16(a_c, cp);
+                ptx::tmem_ld_x8_pack16(a_c + 32, cq);
+                ptx::tmem_ld_wait();
+  #pragma unroll
+                for (int k = 0; k < NW; ++k) w[k] = k < 16 ? cp[k % 16] : cq[(k - 16) % 8];
+              }
+            } else {
+              uint32_t c[NC];
+  #pragma unroll
+              for (int u = 0; u < NC / 16; ++u) {
+                uint32_t cc[16];
+                ptx::tmem_ld_x16(a_c + 16 * u, cc);
+  #pragma unroll
+                for (int k = 0; k < 16; ++k) c[16 * u + k] = cc[k];
+              }
+              ptx::tmem_ld_wait();
+  #pragma unroll
+              for (int k = 0; k < NW; ++k) w[k] = ptx::pack_f16(__uint_as_float(c[2 * k]), __uint_as_float(c[2 * k + 1]));
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(sc_free);
+            if (sw == 0) GLC_TRACE(0, t, 2);
+  #pragma unroll
+            for (int jj = 0; jj < E; ++jj) s[jj] = FIRST ? __uint_as_float(r[jj]) : s[jj] + __uint_as_float(r[jj]);
+          }
+          // shift the packed window left by sh elements
+  #pragma unroll
+          for (int k = 0; k < NW - 8; ++k) w[k] = sel(sh16, w[k + 8], w[k]);
+  #pragma unroll
+          for (int k = 0; k < NW - 12; ++k) w[k] = sel(sh8, w[k + 4], w[k]);
+  #pragma unroll
+          for (int k = 0; k < NW - 14; ++k) w[k] = sel(sh4, w[k + 2], w[k]);
+  #pragma unroll
+          for (int k = 0; k < NW - 15; ++k) w[k] = sel(sh2, w[k + 1], w[k]);
+  #pragma unroll
+          for (int m = 0; m < E / 2; ++m) ptx::add_f16x2_to_f32(s[2 * m], s[2 * m + 1], __byte_perm(w[m], w[m + 1], prmt_sel));
+          if (sw == 0) GLC_TRACE(0, t, 3);
+        };
+        // p2c: lane rotation by s1 = 31 - (b mod 32), source lane picks the copy
+        auto stage_p2c = [&](auto first_tag) {
+          constexpr bool FIRST = decltype(first_tag)::value;
+          ptx::mbar_wait(g_full, t & 1);
+          ptx::tc_fence_after();
+          if (sw == 0) GLC_TRACE(0, t, 4);
+          if (E == 32 && g16) {
+            // fp16 copies, two key columns per register: one LOP3 selects both halves, each half needs its own lane rotation
+            uint32_t lo[16], hi[16];
+            ptx::tmem_ld_x16_pack16(a_lo, lo);
+            ptx::tmem_ld_x16_pack16(a_hi, hi);
+            ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(g_free);
+  #pragma unroll
+            for (int m = 0; m < 16; ++m) {
+              const uint32_t v = (hi[m] & hm2[m]) | (lo[m] & ~hm2[m]);
+              const uint32_t x0 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m);        // low half = key 2m
+              const uint32_t x1 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m - 1);    // high half = key 2m + 1
+              if (FIRST) {
+                s[2 * m] = ptx::f16_lo_to_f32(x0);
+                s[2 * m + 1] = ptx::f16_hi_to_f32(x1);
+              } else {
+                ptx::add_f16_lo_to_f32(s[2 * m], x0);
+                ptx::add_f16_hi_to_f32(s[2 * m + 1], x1);
+              }
+            }
+            return;
           }
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int jj = 16 * u + k;
-            const uint32_t v = (hi[k] & hm[jj]) | (lo[k] & ~hm[jj]);
-            const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
-            s[jj] = FIRST ? pv : s[jj] + pv;
+          if (E == 32 && g_once) {
+            // all four chunk loads in flight behind one wait (64 live registers) instead of two load / wait rounds
+            uint32_t lo[32], hi[32];
+            {
+              uint32_t a0[16], a1[16], b0_[16], b1[16];
+              ptx::tmem_ld_x16(a_lo, a0);
+              ptx::tmem_ld_x16(a_hi, b0_);
+              ptx::tmem_ld_x16(a_lo + 16, a1);
+              ptx::tmem_ld_x16(a_hi + 16, b1);
+              ptx::tmem_ld_wait();
+  #pragma unroll
+              for (int k = 0; k < 16; ++k) { lo[k] = a0[k]; lo[(16 + k) % 32] = a1[k]; hi[k] = b0_[k]; hi[(16 + k) % 32] = b1[k]; }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(g_free);
+  #pragma unroll
+            for (int jj = 0; jj < E; ++jj) {
+              const uint32_t v = (hi[jj % 32] & hm[jj]) | (lo[jj % 32] & ~hm[jj]);
+              const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+              s[jj] = FIRST ? pv : s[jj] + pv;
+            }
+            return;
           }
+  #pragma unroll
+          for (int u = 0; u < E / 16; ++u) {
+            uint32_t lo[16], hi[16];
+            ptx::tmem_ld_x16(a_lo + 16 * u, lo);
+            ptx::tmem_ld_x16(a_hi + 16 * u, hi);
+            ptx::tmem_ld_wait();
+            if (u == E / 16 - 1) {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) ptx::mbar_arrive(g_free);
+            }
+  #pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const int jj = 16 * u + k;
+              const uint32_t v = (hi[k] & hm[jj]) | (lo[k] & ~hm[jj]);
+              const float pv = __uint_as_float(__shfl_sync(0xffffffffu, v, rot0 - jj));
+              s[jj] = FIRST ? pv : s[jj] + pv;
+            }
+          }
+        };
+        if (!(g & 1) || !swap_order) {
+          stage_c2p(std::true_type{});
+          stage_p2c(std::false_type{});
+        } else {
+          stage_p2c(std::true_type{});
+          stage_c2p(std::false_type{});
         }
-      };
-      if (!(g & 1) || !swap_order) {
-        stage_c2p(std::true_type{});
-        stage_p2c(std::false_type{});
-      } else {
-        stage_p2c(std::true_type{});
-        stage_c2p(std::false_type{});
-      }
-      if (sw == 0) GLC_TRACE(0, t, 6);
+        if (sw == 0) GLC_TRACE(0, t, 6);
 
-      const int kb = k0 + b0;
-      const uint32_t kbits = kmask[kb >> 5] >> (kb & 31);   // E <= 32 and kb is a multiple of E: no word straddling
-      if ((E == 32 && kbits != 0xffffffffu) || (E < 32 && (kbits & ((1u << (E & 31)) - 1u)) != ((1u << (E & 31)) - 1u))) {
-#pragma unroll
-        for (int jj = 0; jj < E; ++jj)
-          if (!((kbits >> jj) & 1u)) s[jj] = -CUDART_INF_F;
-      }
-      // four independent chains of 3-input maxima (FMNMX3)
-      float mx[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        constexpr int CH = E / 4;
-        float v = s[CH * c];
-#pragma unroll
-        for (int k = 1; k + 1 < CH; k += 2) v = fmaxf(fmaxf(v, s[CH * c + k]), s[CH * c + k + 1]);
-        if (CH % 2 == 0) v = fmaxf(v, s[CH * c + CH - 1]);
-        mx[c] = v;
-      }
-      const float mloc = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), mx[2]), mx[3]);
-      // ---- row max shared between the key groups (double buffered by tile parity: the quarter barrier of
-      //      tile t+1 orders the reads of tile t before the writes of tile t+2)
-      float* xm = xmax + (t & 1) * (G * QT);
-      xm[g * QT + i] = mloc;
-      ptx::named_bar_sync(2 + qd, 32 * G);   // only the G warps of this lane quarter share rows
-      float m_new = m_run;
-#pragma unroll
-      for (int gg = 0; gg < G; ++gg) m_new = fmaxf(m_new, xm[gg * QT + i]);
-      uint32_t pk[E / 2];   // P as fp16 pairs
-      if (OTMEM) {
-        // O stays in TMEM, accumulated by the tensor core over all key tiles (FlashAttention-4 style): P is scaled with a
-        // STICKY maximum that is only raised when the row maximum grew by more than 2^8 (both warps of a row see the same
-        // xmax values, so they take the same decision); the rare rescale is a warp-local ld / multiply / st of this warp's
-        // 32 lanes x its 32 output columns.  No per-tile PV read-out, no fold.
-        const bool raise = (m_new - m_run) * sc > 8.0f;   // false when both are -inf (NaN), true for the first finite maximum
-        const float alpha = raise ? ptx::ex2((m_run - m_new) * sc) : 1.0f;   // m_run = -inf: 0 (l and O hold exact zeros)
-        if (raise) m_run = m_new;
-        const float neg_ms = (m_run == -CUDART_INF_F) ? 0.f : -m_run * sc;
-        float ps[4] = {0.f, 0.f, 0.f, 0.f};
-        if (poly_every == 4) {
-#pragma unroll
-          for (int jj = 0; jj < E; ++jj) {
-            const float e = exp2_sel<4>(jj, fmaf(s[jj], sc, neg_ms));
-            s[jj] = e;
-            ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
+        const int kb = k0 + b0;
+        const uint32_t kbits = kmask[kb >> 5] >> (kb & 31);   // E <= 32 and kb is a multiple of E: no word straddling
+        if ((E == 32 && kbits != 0xffffffffu) || (E < 32 && (kbits & ((1u << (E & 31)) - 1u)) != ((1u << (E & 31)) - 1u))) {
+  #pragma unroll
+          for (int jj = 0; jj < E; ++jj)
+            if (!((kbits >> jj) & 1u)) s[jj] = -CUDART_INF_F;
+        }
+        // four independent chains of 3-input maxima (FMNMX3)
+        float mx[4];
+  #pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          constexpr int CH = E / 4;
+          float v = s[CH * c];
+  #pragma unroll
+          for (int k = 1; k + 1 < CH; k += 2) v = fmaxf(fmaxf(v, s[CH * c + k]), s[CH * c + k + 1]);
+          if (CH % 2 == 0) v = fmaxf(v, s[CH * c + CH - 1]);
+          mx[c] = v;
+        }
+        const float mloc = fmaxf(fmaxf(fmaxf(mx[0], mx[1]), mx[2]), mx[3]);
+        // ---- row max shared between the key groups (double buffered by tile parity: the quarter barrier of
+        //      tile t+1 orders the reads of tile t before the writes of tile t+2)
+        float* xm = xmax + (t & 1) * (G * QT);
+        xm[g * QT + i] = mloc;
+        ptx::named_bar_sync(2 + qd, 32 * G);   // only the G warps of this lane quarter share rows
+        float m_new = m_run;
+  #pragma unroll
+        for (int gg = 0; gg < G; ++gg) m_new = fmaxf(m_new, xm[gg * QT + i]);
+        uint32_t pk[E / 2];   // P as fp16 pairs
+        if (OTMEM) {
+          // O stays in TMEM, accumulated by the tensor core over all key tiles (FlashAttention-4 style): P is scaled with a
+          // STICKY maximum that is only raised when the row maximum grew by more than 2^8 (both warps of a row see the same
+          // xmax values, so they take the same decision); the rare rescale is a warp-local ld / multiply / st of this warp's
+          // 32 lanes x its 32 output columns.  No per-tile PV read-out, no fold.
+          const bool raise = (m_new - m_run) * sc > 8.0f;   // false when both are -inf (NaN), true for the first finite maximum
+          const float alpha = raise ? ptx::ex2((m_run - m_new) * sc) : 1.0f;   // m_run = -inf: 0 (l and O hold exact zeros)
+          if (raise) m_run = m_new;
+          const float neg_ms = (m_run == -CUDART_INF_F) ? 0.f : -m_run * sc;
+          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+          if (poly_every == 4) {
+  #pragma unroll
+            for (int jj = 0; jj < E; ++jj) {
+              const float e = exp2_sel<4>(jj, fmaf(s[jj], sc, neg_ms));
+              s[jj] = e;
+              ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
+            }
+          } else if (poly_every == 3) {
+  #pragma unroll
+            for (int jj = 0; jj < E; ++jj) {
+              const float e = exp2_sel<3>(jj, fmaf(s[jj], sc, neg_ms));
+              s[jj] = e;
+              ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
+            }
+          } else if (poly_every == 2) {
+  #pragma unroll
+            for (int jj = 0; jj < E; ++jj) {
+              const float e = exp2_sel<2>(jj, fmaf(s[jj], sc, neg_ms));
+              s[jj] = e;
+              ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
+            }
+          } else {
+  #pragma unroll
+            for (int jj = 0; jj < E; ++jj) {
+              const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
+              s[jj] = e;
+              ps[jj & 3] += e;
+            }
           }
-        } else if (poly_every == 3) {
-#pragma unroll
-          for (int jj = 0; jj < E; ++jj) {
-            const float e = exp2_sel<3>(jj, fmaf(s[jj], sc, neg_ms));
-            s[jj] = e;
-            ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
-          }
-        } else if (poly_every == 2) {
-#pragma unroll
-          for (int jj = 0; jj < E; ++jj) {
-            const float e = exp2_sel<2>(jj, fmaf(s[jj], sc, neg_ms));
-            s[jj] = e;
-            ps[jj & 3] += e;   // four independent chains instead of one 32-deep dependent one
+  #pragma unroll
+          for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
+          l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
+          if (t > 0) {
+            ptx::mbar_wait(pv_full, (t - 1) & 1);   // P buffer free again, O stable
+            if (__any_sync(0xffffffffu, raise)) {
+              ptx::tc_fence_after();
+              uint32_t r[E];
+              tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
+              ptx::tmem_ld_wait();
+  #pragma unroll
+              for (int u = 0; u < E / 8; ++u) {
+                uint32_t q8[8];
+  #pragma unroll
+                for (int v = 0; v < 8; ++v) q8[v] = __float_as_uint(__uint_as_float(r[8 * u + v]) * alpha);
+                ptx::tmem_st_x8(t_lane + TM_PV + (uint32_t)(b0 + 8 * u), q8);
+              }
+            }
           }
         } else {
-#pragma unroll
+        const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
+        const float alpha = ptx::ex2((m_run - m_use) * sc);
+        const float neg_ms = -m_use * sc;
+        // ... and the post-maximum stages too: even g  exponentials (MUFU) -> PV fold (TMEM read + FMA), odd g the reverse
+        auto stage_exp = [&]() {
+          float psum = 0.f;
+  #pragma unroll
           for (int jj = 0; jj < E; ++jj) {
             const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
             s[jj] = e;
-            ps[jj & 3] += e;
+            psum += e;
           }
-        }
-#pragma unroll
-        for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
-        l_run = l_run * alpha + ((ps[0] + ps[1]) + (ps[2] + ps[3]));
-        if (t > 0) {
-          ptx::mbar_wait(pv_full, (t - 1) & 1);   // P buffer free again, O stable
-          if (__any_sync(0xffffffffu, raise)) {
+  #pragma unroll
+          for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
+          l_run = l_run * alpha + psum;
+          m_run = m_new;
+        };
+        // fold in PV of the previous tile (also guarantees the P buffer is free again)
+        auto stage_fold = [&]() {
+          if (t > 0) {
+            ptx::mbar_wait(pv_full, (t - 1) & 1);
             ptx::tc_fence_after();
             uint32_t r[E];
             tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
             ptx::tmem_ld_wait();
-#pragma unroll
-            for (int u = 0; u < E / 8; ++u) {
-              uint32_t q8[8];
-#pragma unroll
-              for (int v = 0; v < 8; ++v) q8[v] = __float_as_uint(__uint_as_float(r[8 * u + v]) * alpha);
-              ptx::tmem_st_x8(t_lane + TM_PV + (uint32_t)(b0 + 8 * u), q8);
-            }
+  #pragma unroll
+            for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
           }
+          alpha_prev = alpha;
+        };
+        if (!(g & 1) || !swap_order) {
+          stage_exp();
+          stage_fold();
+        } else {
+          stage_fold();
+          stage_exp();
         }
-      } else {
-      const float m_use = (m_new == -CUDART_INF_F) ? 0.f : m_new;
-      const float alpha = ptx::ex2((m_run - m_use) * sc);
-      const float neg_ms = -m_use * sc;
-      // ... and the post-maximum stages too: even g  exponentials (MUFU) -> PV fold (TMEM read + FMA), odd g the reverse
-      auto stage_exp = [&]() {
-        float psum = 0.f;
-#pragma unroll
-        for (int jj = 0; jj < E; ++jj) {
-          const float e = ptx::ex2(fmaf(s[jj], sc, neg_ms));
-          s[jj] = e;
-          psum += e;
         }
-#pragma unroll
-        for (int v = 0; v < E / 2; ++v) pk[v] = ptx::pack_f16(s[2 * v], s[2 * v + 1]);
-        l_run = l_run * alpha + psum;
-        m_run = m_new;
-      };
-      // fold in PV of the previous tile (also guarantees the P buffer is free again)
-      auto stage_fold = [&]() {
-        if (t > 0) {
-          ptx::mbar_wait(pv_full, (t - 1) & 1);
-          ptx::tc_fence_after();
-          uint32_t r[E];
-          tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int k = 0; k < E; ++k) o[k] = fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
+
+        // ---- P tile -> TMEM: row i, fp16 pairs at columns (E/2) g ..
+  #pragma unroll
+        for (int u = 0; u < E / 16; ++u) {
+          uint32_t pr[8];
+  #pragma unroll
+          for (int v = 0; v < 8; ++v) pr[v] = pk[8 * u + v];
+          ptx::tmem_st_x8(t_lane + TM_P + (uint32_t)((E / 2) * g + 8 * u), pr);
         }
-        alpha_prev = alpha;
-      };
-      if (!(g & 1) || !swap_order) {
-        stage_exp();
-        stage_fold();
-      } else {
-        stage_fold();
-        stage_exp();
-      }
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(p_full);
+        if (sw == 0) GLC_TRACE(0, t, 7);
       }
 
-      // ---- P tile -> TMEM: row i, fp16 pairs at columns (E/2) g ..
-#pragma unroll
-      for (int u = 0; u < E / 16; ++u) {
-        uint32_t pr[8];
-#pragma unroll
-        for (int v = 0; v < 8; ++v) pr[v] = pk[8 * u + v];
-        ptx::tmem_st_x8(t_lane + TM_P + (uint32_t)((E / 2) * g + 8 * u), pr);
+      // ---- last PV, normalise, write ctx
+      ptx::mbar_wait(pv_full, (T - 1) & 1);
+      ptx::tc_fence_after();
+      {
+        uint32_t r[E];
+        tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
+        ptx::tmem_ld_wait();
+  #pragma unroll
+        for (int k = 0; k < E; ++k) o[k] = OTMEM ? __uint_as_float(r[k]) : fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
       }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(p_full);
-      if (sw == 0) GLC_TRACE(0, t, 7);
-    }
-
-    // ---- last PV, normalise, write ctx
-    ptx::mbar_wait(pv_full, (T - 1) & 1);
-    ptx::tc_fence_after();
+      float* xs = xmax + (T & 1) * (G * QT);   // the buffer tile T-1 did not use
+      xs[g * QT + i] = l_run;
+      ptx::named_bar_sync(2 + qd, 32 * G);
+      float l_tot = 0.f;
+  #pragma unroll
+      for (int gg = 0; gg < G; ++gg) l_tot += xs[gg * QT + i];
+      const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
+      const int row = q0 + i;
+      if (row < p.S) {
+        __half* dst = p.ctx + ((int64_t)b * p.S + row) * p.H + head * D + b0;
+  #pragma unroll
+        for (int v = 0; v < E / 8; ++v) {
+          uint4 o4;
+          o4.x = ptx::pack_f16(o[8 * v + 0] * inv, o[8 * v + 1] * inv);
+          o4.y = ptx::pack_f16(o[8 * v + 2] * inv, o[8 * v + 3] * inv);
+          o4.z = ptx::pack_f16(o[8 * v + 4] * inv, o[8 * v + 5] * inv);
+          o4.w = ptx::pack_f16(o[8 * v + 6] * inv, o[8 * v + 7] * inv);
+          reinterpret_cast<uint4*>(dst)[v] = o4;
+        }
+      }
+    };
     {
-      uint32_t r[E];
-      tmem_ld_n<E>(t_lane + TM_PV + (uint32_t)b0, r);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int k = 0; k < E; ++k) o[k] = OTMEM ? __uint_as_float(r[k]) : fmaf(o[k], alpha_prev, __uint_as_float(r[k]));
-    }
-    float* xs = xmax + (T & 1) * (G * QT);   // the buffer tile T-1 did not use
-    xs[g * QT + i] = l_run;
-    ptx::named_bar_sync(2 + qd, 32 * G);
-    float l_tot = 0.f;
-#pragma unroll
-    for (int gg = 0; gg < G; ++gg) l_tot += xs[gg * QT + i];
-    const float inv = l_tot > 0.f ? 1.0f / l_tot : 0.f;
-    const int row = q0 + i;
-    if (row < p.S) {
-      __half* dst = p.ctx + ((int64_t)b * p.S + row) * p.H + head * D + b0;
-#pragma unroll
-      for (int v = 0; v < E / 8; ++v) {
-        uint4 o4;
-        o4.x = ptx::pack_f16(o[8 * v + 0] * inv, o[8 * v + 1] * inv);
-        o4.y = ptx::pack_f16(o[8 * v + 2] * inv, o[8 * v + 3] * inv);
-        o4.z = ptx::pack_f16(o[8 * v + 4] * inv, o[8 * v + 5] * inv);
-        o4.w = ptx::pack_f16(o[8 * v + 6] * inv, o[8 * v + 7] * inv);
-        reinterpret_cast<uint4*>(dst)[v] = o4;
-      }
+      const int gsel = (warp - 2) >> 2;
+      if (gsel == 0) softmax_role(std::integral_constant<int, 0>{});
+      else if (gsel == 1) softmax_role(std::integral_constant<int, 1>{});
+      else if (G > 2 && gsel == 2) softmax_role(std::integral_constant<int, (G > 2 ? 2 : 0)>{});
+      else if (G > 2) softmax_role(std::integral_constant<int, (G > 2 ? 3 : 0)>{});
     }
   }
 
