@@ -90,7 +90,7 @@ struct ResidRow {
 
 // Epilogue of one accumulator tile for one warp: TMEM lanes of this warp's quarter (t_row), the
 // 32-column chunks c = grp, grp+GROUPS, ...: tcgen05.ld -> +bias -> (erf-GELU) -> fp16/fp32 -> global.
-template <int BN, int ACT, bool OUT_F32>
+template <int BN, int ACT, bool OUT_F32, bool RESID>
 __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, int row, const float* __restrict__ bias,
                                               void* __restrict__ Cout, int64_t ldc, int M, int N,
                                               const __half* __restrict__ resid, int64_t ldr) {
@@ -98,7 +98,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, i
   for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
   const int n = n0 + c * 32;
   ResidRow rr;
-  if (resid != nullptr && n < N) rr.load(resid, ldr, row, n, M, N);
+  if (RESID && n < N) rr.load(resid, ldr, row, n, M, N);
   uint32_t r[32];
   ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
   ptx::tmem_ld_wait();
@@ -127,7 +127,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, i
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
   }
-  if (resid != nullptr) rr.add_to(v);
+  if (RESID) rr.add_to(v);
   if (row < M) {
     if (OUT_F32) {
       float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + n;
@@ -156,7 +156,7 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, i
 // every STG (32 L1 line visits per instruction: the epilogue then outlasts a K=768 tile's MMAs); here
 // the 32 x 32 chunk is written once to a 64B-swizzled staging buffer and stored by one bulk tensor copy.
 //   stage: this warp's NBUF x 2 KB staging buffers (1024-byte aligned); row0: first tile row of the warp
-template <int BN, int ACT, int NBUF>
+template <int BN, int ACT, int NBUF, bool RESID>
 __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
                                                   const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int M, int N,
                                                   const __half* __restrict__ resid, int64_t ldr) {
@@ -164,7 +164,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n
   for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
     const int n = n0 + c * 32;
     ResidRow rr;
-    if (resid != nullptr && n < N) rr.load(resid, ldr, row0 + lane, n, M, N);
+    if (RESID && n < N) rr.load(resid, ldr, row0 + lane, n, M, N);
     uint32_t r[32];
     ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
     ptx::tmem_ld_wait();
@@ -193,7 +193,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n
 #pragma unroll
       for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
     }
-    if (resid != nullptr) rr.add_to(v);
+    if (RESID) rr.add_to(v);
     // the bulk store that last read this staging buffer must have finished reading it
     if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
     __syncwarp();
@@ -220,7 +220,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n
   }
 }
 
-template <int BN, int ACT, bool OUT_F32>
+template <int BN, int ACT, bool OUT_F32, bool RESID>
 __global__ void __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                          const float* __restrict__ bias, void* __restrict__ Cout, int64_t ldc, int M, int N, int K,
@@ -327,7 +327,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
+      epilogue_tile<BN, ACT, OUT_F32, RESID>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -368,7 +368,7 @@ struct Gemm2Cfg {
   static constexpr uint32_t TMEM_COLS = 512;   // two BN-column accumulators
 };
 
-template <int BN_, int ACT, bool OUT_F32>
+template <int BN_, int ACT, bool OUT_F32, bool RESID>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
 gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                      const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias, void* __restrict__ Cout,
@@ -482,9 +482,9 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
       if (OUT_F32)
-        epilogue_tile<BN, ACT, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
+        epilogue_tile<BN, ACT, OUT_F32, RESID>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
       else
-        epilogue_tile_tma<BN, ACT, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, resid, ldr);
+        epilogue_tile_tma<BN, ACT, NBUF, RESID>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, resid, ldr);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tempty[acc]) & ptx::PEER_BIT_MASK);
@@ -521,14 +521,14 @@ cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t 
     uint32_t bc[2] = {32, 32};
     tm_c = make_tmap_16b(C, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
   }
-  auto kern = gemm_f16_2cta_kernel<BN_, ACT, OUT_F32>;
-  static bool attr_set[64] = {};
+  auto kern = resid ? gemm_f16_2cta_kernel<BN_, ACT, OUT_F32, true> : gemm_f16_2cta_kernel<BN_, ACT, OUT_F32, false>;
+  static bool attr_set[64][2] = {};
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
+  if (!attr_set[dev & 63][resid ? 1 : 0]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set[dev & 63] = true;
+    attr_set[dev & 63][resid ? 1 : 0] = true;
   }
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + Cfg::BN - 1) / Cfg::BN);
   const int max_cl = num_sms / 2;
@@ -549,14 +549,14 @@ cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, 
   uint32_t bw[2] = {BK, BN};
   CUtensorMap tm_a = make_tmap_16b(A, 2, da, sa, ba);
   CUtensorMap tm_w = make_tmap_16b(W, 2, dw, sw, bw);
-  auto kern = gemm_f16_tcgen05_kernel<BN, ACT, OUT_F32>;
-  static bool attr_set[64] = {};   // per template instantiation, per device
+  auto kern = resid ? gemm_f16_tcgen05_kernel<BN, ACT, OUT_F32, true> : gemm_f16_tcgen05_kernel<BN, ACT, OUT_F32, false>;
+  static bool attr_set[64][2] = {};   // per template instantiation, per device
   int dev = 0;
   cudaGetDevice(&dev);
-  if (!attr_set[dev & 63]) {
+  if (!attr_set[dev & 63][resid ? 1 : 0]) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) return e;
-    attr_set[dev & 63] = true;
+    attr_set[dev & 63][resid ? 1 : 0] = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
