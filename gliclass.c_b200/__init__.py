@@ -34,7 +34,7 @@ class GlcError(RuntimeError):
 class glc_opts(C.Structure):
     _fields_ = [("struct_size", C.c_uint32), ("num_devices", C.c_int32), ("device_ids", C.c_int32 * 8),
                 ("weight_dtype", C.c_int32), ("max_tokens", C.c_int32), ("num_heads", C.c_int32),
-                ("reserved", C.c_int32 * 8)]
+                ("preln_f32", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class glc_info(C.Structure):
@@ -42,7 +42,8 @@ class glc_info(C.Structure):
                 ("inter", C.c_int32), ("head_hidden", C.c_int32), ("buckets", C.c_int32), ("max_rel_pos", C.c_int32),
                 ("ln_eps", C.c_float), ("class_token", C.c_int64), ("num_devices", C.c_int32),
                 ("weight_dtype", C.c_int32), ("pooling", C.c_int32), ("scorer", C.c_int32),
-                ("normalize_features", C.c_int32), ("logit_scale", C.c_float)]
+                ("normalize_features", C.c_int32), ("logit_scale", C.c_float), ("projector_act", C.c_int32),
+                ("class_pos_offset", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -85,13 +86,12 @@ _SIGS = {
     "glc_op_embed_ln": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _vp]),
     "glc_op_residual_ln": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
     "glc_op_mask_prep": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
-    "glc_op_attention": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "glc_op_attention_naive": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "glc_op_attention_rows": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_expanded_pos_rows": (_i, []),
     "glc_op_expand_pos": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
-    "glc_op_attention_toeplitz": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_op_expand_pos_rev": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
     "glc_op_attention_shift": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "glc_op_attention_stream": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_op_head_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp]),
     "glc_op_head_score": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
 }
@@ -152,7 +152,7 @@ class Session:
     """reference create_ort_session (src/model.c:217-281) + run_inference (src/model.c:122-207)."""
 
     def __init__(self, model_path: str, devices: Optional[Sequence[int]] = None, max_tokens: int = 0,
-                 weight_dtype: str = "default"):
+                 weight_dtype: str = "default", preln_f32: bool = False, num_heads: int = 0):
         L = lib()
         o = glc_opts()
         o.struct_size = C.sizeof(glc_opts)
@@ -161,6 +161,8 @@ class Session:
             for k, d in enumerate(devices):
                 o.device_ids[k] = int(d)
         o.max_tokens = int(max_tokens)
+        o.preln_f32 = 1 if preln_f32 else 0
+        o.num_heads = int(num_heads)
         o.weight_dtype = {"default": 0, "fp16": 1, "bf16": 2, "fp8": 3}[weight_dtype]
         self._h = L.glc_load(os.fsencode(model_path), C.byref(o))
         if not self._h:
@@ -298,6 +300,71 @@ class Session:
         if n < 0:
             raise GlcError(f"debug_fetch({name}) -> {n}: {last_error()}")
         return out[:n]
+
+
+SHIM_E2E_PATH = os.path.join(_HERE, "lib", "libglc_shim_e2e.so")
+
+
+class ShimSession:
+    """The reference's own calling sequence (src/model.c: flatten_int_array -> create_tensor -> run_inference, outputs
+    read as src/postprocessor.c does) over the ORT-named entry points of the library, through tools/shim_e2e.c.  Every
+    call mallocs pageable int64 copies of the inputs exactly like flatten_int_array (model.c:17-29)."""
+
+    def __init__(self, model_path: str, num_threads: int = 8):
+        lib()   # the engine library must be loaded first (the helper links against it)
+        if not os.path.exists(SHIM_E2E_PATH):
+            raise GlcError(f"{SHIM_E2E_PATH} not found: run the build")
+        L = C.CDLL(SHIM_E2E_PATH)
+        L.shim_e2e_open.restype = _vp
+        L.shim_e2e_open.argtypes = [C.c_char_p, _i]
+        L.shim_e2e_ok.restype = _i
+        L.shim_e2e_ok.argtypes = [_vp]
+        L.shim_e2e_error.restype = C.c_char_p
+        L.shim_e2e_error.argtypes = [_vp]
+        L.shim_e2e_close.restype = None
+        L.shim_e2e_close.argtypes = [_vp]
+        L.shim_e2e_run.restype = _i
+        L.shim_e2e_run.argtypes = [_vp, _vp, _vp, _i, _i, _vp, C.c_size_t, C.POINTER(_i)]
+        L.shim_e2e_time.restype = _i
+        L.shim_e2e_time.argtypes = [_vp, _vp, _vp, _i, _i, _vp, C.c_size_t, _i, C.POINTER(C.c_double)]
+        self._L = L
+        self._h = L.shim_e2e_open(os.fsencode(model_path), int(num_threads))
+        if not self._h or not L.shim_e2e_ok(self._h):
+            msg = (L.shim_e2e_error(self._h) or b"").decode("utf-8", "replace")
+            if self._h:
+                L.shim_e2e_close(self._h)
+                self._h = None
+            raise GlcError(f"ORT shim CreateSession failed: {msg}")
+
+    def run(self, input_ids: np.ndarray, attention_mask: np.ndarray, max_classes: int = 512) -> np.ndarray:
+        ids = np.ascontiguousarray(input_ids, dtype=np.int64)
+        mask = np.ascontiguousarray(attention_mask, dtype=np.int64)
+        B, S = ids.shape
+        out = np.empty(B * max_classes, dtype=np.float32)
+        cc = C.c_int(0)
+        if self._L.shim_e2e_run(self._h, ids.ctypes.data, mask.ctypes.data, B, S, out.ctypes.data, out.size, C.byref(cc)) != 0:
+            raise GlcError("shim Run failed: " + (self._L.shim_e2e_error(self._h) or b"").decode("utf-8", "replace"))
+        return out[: B * cc.value].reshape(B, cc.value).copy()
+
+    def time_runs(self, ids: np.ndarray, mask: np.ndarray, out: np.ndarray, steps: int) -> float:
+        """wall seconds of `steps` back-to-back reference-style run_inference calls on pageable buffers"""
+        B, S = ids.shape
+        sec = C.c_double(0.0)
+        if self._L.shim_e2e_time(self._h, ids.ctypes.data, mask.ctypes.data, B, S, out.ctypes.data, out.size, int(steps),
+                                 C.byref(sec)) != 0:
+            raise GlcError("shim Run failed: " + (self._L.shim_e2e_error(self._h) or b"").decode("utf-8", "replace"))
+        return float(sec.value)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.shim_e2e_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def decide(logits: np.ndarray, threshold: float = 0.5):

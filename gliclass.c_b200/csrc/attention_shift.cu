@@ -728,14 +728,6 @@ attention_shift_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_
 
 }  // namespace
 
-void expanded_pos_index_rev(int buckets, int max_pos, int32_t* out /* [EXP_ROWS] */) {
-  // row sigma holds delta = sigma - EXP_CENTER; the last row (delta = +2048) is never consumed -> zero row
-  std::vector<int32_t> rel((size_t)2 * (EXP_CENTER + 1) - 1);
-  rel_index_table(EXP_CENTER + 1, buckets, max_pos, rel.data());   // rel[delta + EXP_CENTER]
-  for (int s = 0; s < EXP_ROWS - 1; ++s) out[s] = rel[(size_t)s];
-  out[EXP_ROWS - 1] = -1;
-}
-
 cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
                             const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                             cudaStream_t stream) {

@@ -21,6 +21,7 @@ struct glc_model {
   int weight_dtype;
 };
 struct glc_ticket {
+  std::promise<int> done;
   std::future<int> fut;
   std::string err;
   int C = 0;
@@ -42,6 +43,7 @@ void fill_info(const glc::ModelConfig& c, glc_info* o) {
   o->head_hidden = c.head_hidden; o->buckets = c.buckets; o->max_rel_pos = c.max_rel_pos; o->ln_eps = c.ln_eps;
   o->class_token = c.class_token;
   o->pooling = c.pooling; o->scorer = c.scorer; o->normalize_features = c.normalize ? 1 : 0; o->logit_scale = c.logit_scale;
+  o->projector_act = c.proj_act; o->class_pos_offset = c.class_pos_offset;
 }
 }  // namespace
 
@@ -57,10 +59,22 @@ glc_model* glc_load(const char* onnx_path, const glc_opts* opts) {
     std::vector<int> devices;
     int max_tokens = 0;
     int dtype = GLC_DTYPE_FP16;
+    int want_heads = 0;
+    bool preln_f32 = false;
 
-    if (opts && opts->struct_size >= sizeof(glc_opts)) {
-      for (int i = 0; i < opts->num_devices && i < 8; ++i) devices.push_back(opts->device_ids[i]);
+    if (opts) {
+      if (opts->struct_size != sizeof(glc_opts)) {
+        fail(GLC_ERR_ARG, "glc_load: glc_opts.struct_size does not match this library's sizeof(glc_opts) (header / library mismatch)");
+        return nullptr;
+      }
+      if (opts->num_devices < 0 || opts->num_devices > 8 || opts->max_tokens < 0 || opts->num_heads < 0) {
+        fail(GLC_ERR_ARG, "glc_load: negative or out-of-range field in glc_opts");
+        return nullptr;
+      }
+      for (int i = 0; i < opts->num_devices; ++i) devices.push_back(opts->device_ids[i]);
       max_tokens = opts->max_tokens;
+      want_heads = opts->num_heads;
+      preln_f32 = opts->preln_f32 != 0;
       if (opts->weight_dtype != GLC_DTYPE_DEFAULT) dtype = opts->weight_dtype;
     }
     if (dtype != GLC_DTYPE_FP16) {
@@ -80,7 +94,16 @@ glc_model* glc_load(const char* onnx_path, const glc_opts* opts) {
         } else {
           std::stringstream ss(env);
           std::string tok;
-          while (std::getline(ss, tok, ',')) if (!tok.empty()) devices.push_back(atoi(tok.c_str()));
+          while (std::getline(ss, tok, ',')) {
+            if (tok.empty()) continue;
+            char* endp = nullptr;
+            const long v = strtol(tok.c_str(), &endp, 10);
+            if (*endp != '\0' || v < 0 || v > 1023) {
+              fail(GLC_ERR_ARG, "glc_load: GLC_DEVICES must be 'all' or a comma-separated list of device ordinals (got '" + std::string(env) + "')");
+              return nullptr;
+            }
+            devices.push_back((int)v);
+          }
         }
       }
       if (devices.empty()) devices.push_back(0);
@@ -89,9 +112,31 @@ glc_model* glc_load(const char* onnx_path, const glc_opts* opts) {
       fail(GLC_ERR_CUDA, "glc_load: no usable sm_100 CUDA device (this engine has no CPU fallback)");
       return nullptr;
     }
+    {
+      int ndev = 0;
+      cudaGetDeviceCount(&ndev);
+      for (size_t i = 0; i < devices.size(); ++i) {
+        if (devices[i] < 0 || devices[i] >= ndev) {
+          fail(GLC_ERR_ARG, "glc_load: device ordinal " + std::to_string(devices[i]) + " out of range (" + std::to_string(ndev) + " visible)");
+          return nullptr;
+        }
+        for (size_t j = 0; j < i; ++j)
+          if (devices[j] == devices[i]) { fail(GLC_ERR_ARG, "glc_load: device listed twice"); return nullptr; }
+      }
+    }
     if (const char* mt = getenv("GLC_MAX_TOKENS")) if (max_tokens <= 0) max_tokens = atoi(mt);
     glc_model* h = new glc_model;
-    h->m = new glc::Model(onnx_path, devices, max_tokens);
+    h->m = nullptr;
+    try {
+      h->m = new glc::Model(onnx_path, devices, max_tokens, preln_f32);
+      if (want_heads > 0 && want_heads != h->m->cfg().heads)
+        throw std::runtime_error("glc_opts.num_heads = " + std::to_string(want_heads) + " but the graph has " +
+                                 std::to_string(h->m->cfg().heads) + " attention heads");
+    } catch (...) {
+      delete h->m;
+      delete h;
+      throw;
+    }
     h->weight_dtype = dtype;
     return h;
   } catch (const std::exception& e) {
@@ -178,9 +223,11 @@ int glc_run_device(glc_model* m, int slot, const int64_t* d_ids, const int64_t* 
 
 int glc_sync(glc_model* m, int slot) {
   if (!m || slot < 0 || slot >= m->m->num_devices()) return fail(GLC_ERR_ARG, "glc_sync: bad argument");
-  cudaSetDevice(m->m->dev(slot).device());
-  cudaError_t e = cudaStreamSynchronize(m->m->dev(slot).stream());
-  if (e != cudaSuccess) return fail(GLC_ERR_CUDA, std::string("glc_sync: ") + cudaGetErrorString(e));
+  try {
+    m->m->dev(slot).check_overflow_sync();   // takes the device lock (a stream capture may be in progress on another thread)
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_sync: ") + e.what());
+  }
   return GLC_OK;
 }
 
@@ -208,21 +255,23 @@ glc_ticket* glc_submit(glc_model* m, const int64_t* input_ids, const int64_t* at
     t->C = C;
     glc::Model* mm = m->m;
     if (B == 0 || S == 0 || C == 0) {
-      std::promise<int> p;
-      p.set_value(GLC_OK);
-      t->fut = p.get_future();
+      t->fut = t->done.get_future();
+      t->done.set_value(GLC_OK);
       return t;
     }
-    // one host thread per in-flight request: it blocks in the coalescing queue / on the device like a
-    // reference OpenMP worker would block in g_ort->Run, while the submitting thread goes on tokenising
-    t->fut = std::async(std::launch::async, [mm, t, input_ids, attention_mask, B, S, C, logits_out]() -> int {
+    // a fixed pool of host threads (GLC_SUBMIT_THREADS, default 8) serves the in-flight requests: each blocks in the
+    // coalescing queue / on the device like a reference OpenMP worker would block in g_ort->Run, while the
+    // submitting thread goes on tokenising
+    t->fut = t->done.get_future();
+    mm->submit_queue().post([mm, t, input_ids, attention_mask, B, S, C, logits_out]() {
+      int rc = GLC_OK;
       try {
         mm->run(input_ids, attention_mask, B, S, C, logits_out);
-        return (int)GLC_OK;
       } catch (const std::exception& e) {
         t->err = std::string("glc_submit: ") + e.what();
-        return (int)GLC_ERR_CUDA;
+        rc = GLC_ERR_CUDA;
       }
+      t->done.set_value(rc);
     });
     return t;
   } catch (const std::exception& e) {
@@ -384,15 +433,10 @@ int glc_op_residual_ln(const void* x, const void* r, const float* gamma, const f
 int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, void* stream) {
   GLC_TRY("glc_op_mask_prep", glc::mask_prep(mask, bits, kv_len, B, S, (cudaStream_t)stream));
 }
-int glc_op_attention(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
-                     const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads, int buckets,
-                     int naive, void* stream) {
-  if (naive) {
-    GLC_TRY("glc_op_attention(naive)", glc::attention_naive(qkv, pos_k, pos_q, ld_pos, rel_idx, mask_bits, ctx, B, S, heads,
-                                                             buckets, (cudaStream_t)stream));
-  }
-  GLC_TRY("glc_op_attention", glc::attention_fused(qkv, pos_k, pos_q, ld_pos, rel_idx, mask_bits, kv_len, ctx, B, S, heads,
-                                                   buckets, num_sms_current(), (cudaStream_t)stream));
+int glc_op_attention_naive(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
+                           const uint32_t* mask_bits, void* ctx, int B, int S, int heads, int buckets, void* stream) {
+  GLC_TRY("glc_op_attention_naive", glc::attention_naive(qkv, pos_k, pos_q, ld_pos, rel_idx, mask_bits, ctx, B, S, heads,
+                                                          buckets, (cudaStream_t)stream));
 }
 int glc_op_expand_pos(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst, int cols,
                       void* stream) {
@@ -435,17 +479,12 @@ int glc_op_attention_shift(const void* qkv, const void* exp_k, const void* exp_q
   GLC_TRY("glc_op_attention_shift",
           glc::attention_shift(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
 }
-int glc_op_attention_stream(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
-                            const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
-  GLC_TRY("glc_op_attention_stream",
-          glc::attention_stream(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
+int glc_op_attention_rows(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
+                          const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
+  GLC_TRY("glc_op_attention_rows",
+          glc::attention_rows(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
 }
 int glc_expanded_pos_rows(void) { return glc::expanded_pos_rows(); }
-int glc_op_attention_toeplitz(const void* qkv, const void* exp_k, const void* exp_q, int64_t ld_exp, const uint32_t* mask_bits,
-                              const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
-  GLC_TRY("glc_op_attention_toeplitz",
-          glc::attention_toeplitz(qkv, exp_k, exp_q, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
-}
 int glc_op_head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S, int H,
                        int C, void* stream) {
   GLC_TRY("glc_op_head_gather", glc::head_gather(h, ids, class_token, pooled, cls, B, S, H, C, (cudaStream_t)stream));

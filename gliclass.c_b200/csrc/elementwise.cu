@@ -45,6 +45,23 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
+// Saturation probe for fp16-stored pre-LN sums: the GEMM epilogue packs with cvt.rn.satfinite, so a value beyond the
+// fp16 range arrives here as +-65504 instead of inf.  Any |x + r| >= 6e4 raises the engine's overflow flag (checked by
+// the host after the forward: the Run fails loudly instead of returning logits computed from clamped activations).
+constexpr float SAT_LIMIT = 6.0e4f;
+template <int NC>
+__device__ __forceinline__ void sat_probe(const float (&v)[NC][8], int lane, int H, int* __restrict__ flag) {
+  if (flag == nullptr) return;
+  float amax = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+    if ((lane + 32 * c) * 8 < H) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[c][i]));
+    }
+  if (!(amax < SAT_LIMIT)) *flag = 1;   // also catches NaN
+}
+
 // gamma / beta of this lane's chunks, fetched up front so that their (L2) latency overlaps the row loads
 template <int NC>
 struct LnParams {
@@ -140,7 +157,7 @@ template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   __half* __restrict__ y, int M, int H) {
+                   __half* __restrict__ y, int M, int H, int* __restrict__ flag) {
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * ROWS_PER_BLOCK;
   int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
@@ -179,8 +196,43 @@ residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
     row += stride;
     const bool more = row < M;   // warp-uniform
     if (more) fetch(row);
+    sat_probe<NC>(v, lane, H, flag);
     ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)cur * H);
     if (!more) break;
+  }
+}
+
+// K4 with the pre-LN sum kept in fp32 (GLC_PRELN_F32=1, the robust mode for checkpoints whose dense outputs leave the
+// fp16 range): x fp32 [M,H] straight from the GEMM's fp32 epilogue, r fp16.  One row per warp, no prefetch ring — this
+// mode trades speed for range.
+template <int NC>
+__global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
+residual_ln_xf32_kernel(const float* __restrict__ x, const __half* __restrict__ r, const float* __restrict__ gamma,
+                        const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H) {
+  const int lane = threadIdx.x & 31;
+  const int stride = gridDim.x * ROWS_PER_BLOCK;
+  LnParams<NC> gb;
+  gb.load(lane, H, gamma, beta);
+  for (int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5); row < M; row += stride) {
+    const float* xs = x + (int64_t)row * H;
+    float v[NC][8];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int e0 = (lane + 32 * c) * 8;
+      if (e0 < H) {
+        const float4 a = *reinterpret_cast<const float4*>(xs + e0);
+        const float4 b = *reinterpret_cast<const float4*>(xs + e0 + 4);
+        v[c][0] = a.x; v[c][1] = a.y; v[c][2] = a.z; v[c][3] = a.w;
+        v[c][4] = b.x; v[c][5] = b.y; v[c][6] = b.z; v[c][7] = b.w;
+        if (r) {
+          float t[8];
+          unpack8(ld_stream(r + (int64_t)row * H + e0), t);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+        }
+      }
+    }
+    ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)row * H);
   }
 }
 
@@ -201,7 +253,8 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__ r, const float* __restrict__ gamma,
-                        const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H, int stages) {
+                        const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H, int stages,
+                        int* __restrict__ flag) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)H * 2u;
@@ -255,6 +308,7 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
     __syncwarp();   // every lane has read the stage: refill it
     const int nxt = rw + stages * nwarps;
     if (nxt < M) issue(nxt, s);
+    sat_probe<NC>(v, lane, H, flag);
     ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)rw * H);
     if (++s == stages) { s = 0; parity ^= 1u; }
   }
@@ -306,7 +360,7 @@ __global__ void mask_prep_kernel(const int64_t* __restrict__ mask, uint32_t* __r
 __global__ void __launch_bounds__(128)
 head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
                    int64_t class_token, int pool_mode, __half* __restrict__ pooled, __half* __restrict__ cls, int B, int S,
-                   int H, int C) {
+                   int H, int C, int pos_offset) {
   extern __shared__ int pos_s[];   // [C] per block (one batch row per block)
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -318,7 +372,7 @@ head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids
       const uint32_t m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int c = count + __popc(m & ((1u << lane) - 1u));
-        if (c < C) pos_s[c] = j;
+        if (c < C) pos_s[c] = (j + pos_offset < S) ? j + pos_offset : S - 1;   // embed_class_token=false reads the next token
       }
       count += __popc(m);
     }
@@ -541,10 +595,18 @@ cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, c
 }
 
 cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y, int M,
-                        int H, cudaStream_t stream) {
+                        int H, cudaStream_t stream, int* overflow_flag, bool x_is_f32) {
   if (M <= 0) return cudaSuccess;
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
+    if (x_is_f32) {
+      int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
+      const int cap = ln_grid_cap();
+      if (blocks > cap) blocks = cap;
+      residual_ln_xf32_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, 0, stream>>>((const float*)x, (const __half*)r, gamma, beta, eps,
+                                                                              (__half*)y, M, H);
+      return cudaGetLastError();
+    }
     // bulk-copy ring variant (needs the residual operand and 16-byte rows); GLC_LN_BULK=0 keeps the register-prefetch kernel
     static const bool bulk_on = [] { const char* e = getenv("GLC_LN_BULK"); return !(e && e[0] == '0'); }();
     const size_t stage_bytes = (size_t)ROWS_PER_BLOCK * (r ? 2 : 1) * (size_t)H * 2;   // one stage of all 8 warps
@@ -565,14 +627,14 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
       const int per_sm = (int)((224 * 1024) / (ring_bytes + 1024));
       if (blocks > sms * per_sm) blocks = sms * per_sm;
       residual_ln_bulk_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, ring_bytes, stream>>>(
-          (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages);
+          (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages, overflow_flag);
       return cudaGetLastError();
     }
     int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
     const int cap = ln_grid_cap();   // a few resident blocks per SM, each warp walking several rows
     if (blocks > cap) blocks = cap;
     residual_ln_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, 0, stream>>>(
-        (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H);
+        (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H, overflow_flag);
     return cudaGetLastError();
   });
 }
@@ -596,15 +658,15 @@ cudaError_t mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int 
 
 cudaError_t head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S,
                         int H, int C, cudaStream_t stream) {
-  return head_gather_pool(h, ids, nullptr, class_token, 0, pooled, cls, B, S, H, C, stream);
+  return head_gather_pool(h, ids, nullptr, class_token, 0, pooled, cls, B, S, H, C, stream, 0);
 }
 
 cudaError_t head_gather_pool(const void* h, const int64_t* ids, const int64_t* mask, int64_t class_token, int pool_mode,
-                             void* pooled, void* cls, int B, int S, int H, int C, cudaStream_t stream) {
+                             void* pooled, void* cls, int B, int S, int H, int C, cudaStream_t stream, int class_pos_offset) {
   if (B <= 0) return cudaSuccess;
-  if (H % 8 != 0 || pool_mode < 0 || pool_mode > 3 || (pool_mode >= 2 && !mask)) return cudaErrorInvalidValue;
+  if (H % 8 != 0 || pool_mode < 0 || pool_mode > 3 || (pool_mode >= 2 && !mask) || class_pos_offset < 0) return cudaErrorInvalidValue;
   head_gather_kernel<<<B, 128, (size_t)(C > 0 ? C : 1) * sizeof(int), stream>>>(
-      (const __half*)h, ids, mask, class_token, pool_mode, (__half*)pooled, (__half*)cls, B, S, H, C);
+      (const __half*)h, ids, mask, class_token, pool_mode, (__half*)pooled, (__half*)cls, B, S, H, C, class_pos_offset);
   return cudaGetLastError();
 }
 

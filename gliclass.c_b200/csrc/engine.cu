@@ -27,6 +27,10 @@ namespace glc {
 
 namespace {
 
+const char* const kOverflowMsg =
+    "fp16 activation overflow: a dense output before a LayerNorm reached +-65504 and was clamped, so the logits would be "
+    "wrong; reload the model with GLC_PRELN_F32=1 (glc_opts.preln_f32 = 1) to keep the pre-LayerNorm sums in fp32";
+
 // fp32 -> fp16, round to nearest even, saturating to +-65504 (weights of this family are O(1))
 inline uint16_t f32_to_f16(float f) {
   uint32_t x;
@@ -98,7 +102,7 @@ void DeviceModel::upload_w16(void** dst, const float* src, size_t n) {
   GLC_CUDA(cudaMemcpy(*dst, h.data(), n * 2, cudaMemcpyHostToDevice));
 }
 
-DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : device_(device), cfg_(w.cfg) {
+DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool preln_f32) : device_(device), cfg_(w.cfg) {
   GLC_CUDA(cudaSetDevice(device_));
   cudaDeviceProp prop;
   GLC_CUDA(cudaGetDeviceProperties(&prop, device_));
@@ -112,24 +116,31 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
   graphs_on_ = getenv("GLC_NO_GRAPHS") == nullptr;
-  // production attention = attention_shift.cu (register-skew biases, 306 us/launch at C2); GLC_ATTN selects the other
-  // generations for A/B comparisons: gather (attention.cu, 360 us), toeplitz (attention_toeplitz.cu, 413 us),
-  // stream (attention_stream.cu, 321 us).  GLC_ATTN_TOEPLITZ=1 is the older spelling of GLC_ATTN=toeplitz.
-  const char* al = getenv("GLC_ATTN_TOEPLITZ");
-  attn_mode_ = (al && al[0] == '1') ? 1 : 2;
+  // production attention = attention_rows.cu (row-owner warpgroups rotating over key tiles); GLC_ATTN=shift selects the
+  // previous production kernel (attention_shift.cu) for A/B comparisons.  The three earlier generations live under
+  // experiments/attention_generations/ and are not part of this library.
+  attn_mode_ = 0;
   if (const char* am = getenv("GLC_ATTN")) {
     const std::string m(am);
-    if (m == "gather") attn_mode_ = 0;
-    else if (m == "toeplitz") attn_mode_ = 1;
-    else if (m == "shift") attn_mode_ = 2;
-    else if (m == "stream") attn_mode_ = 3;
-    else throw std::runtime_error("GLC_ATTN must be gather, toeplitz, shift or stream (got '" + m + "')");
+    if (m == "rows") attn_mode_ = 0;
+    else if (m == "shift") attn_mode_ = 1;
+    else throw std::runtime_error("GLC_ATTN must be rows or shift (got '" + m + "')");
   }
   {
     const char* fr = getenv("GLC_FUSE_RESID");
     fuse_resid_ = fr && fr[0] == '1';   // measured: LN -0.1 ms, but the out-proj / FFN2 epilogues +0.28 ms per step -> off
   }
+  {
+    const char* pf = getenv("GLC_PRELN_F32");
+    preln_f32_ = preln_f32 || (pf && pf[0] == '1');
+    if (preln_f32_) fuse_resid_ = false;
+  }
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  d_overflow_ = (int*)dalloc(sizeof(int));
+  perm_allocs_.push_back(d_overflow_);
+  GLC_CUDA(cudaMemset(d_overflow_, 0, sizeof(int)));
+  GLC_CUDA(cudaMallocHost((void**)&h_overflow_, 64 * sizeof(int)));
+  memset(h_overflow_, 0, 64 * sizeof(int));
 
   const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
   const HostTensor& we = w.at("emb.word");
@@ -147,21 +158,19 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
   GLC_CUDA(ln_f32_to_f16(rel_f32, rel_g, rel_b, cfg_.ln_eps, rel_ln, R, H, stream_));
   ++launches_;
 
-  // index of the delta-expanded position tables (attention_toeplitz.cu): row rho <- pos_qk[idx(2047 - rho)]
+  // index of the delta-expanded position tables: posK half row rho <- pos_qk[idx(2047 - rho)], posQ half row sigma <- idx(sigma - 2047)
   const int ER = expanded_pos_rows();
   int32_t *d_exp_idx = nullptr, *d_exp_idx_rev = nullptr;
-  if (attn_mode_ != 0) {
+  {
     std::vector<int32_t> h(ER);
     expanded_pos_index(cfg_.buckets, cfg_.max_rel_pos, h.data());
     d_exp_idx = (int32_t*)dalloc((size_t)ER * 4);
     perm_allocs_.push_back(d_exp_idx);
     GLC_CUDA(cudaMemcpy(d_exp_idx, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice));
-    if (attn_mode_ >= 2) {
-      expanded_pos_index_rev(cfg_.buckets, cfg_.max_rel_pos, h.data());
-      d_exp_idx_rev = (int32_t*)dalloc((size_t)ER * 4);
-      perm_allocs_.push_back(d_exp_idx_rev);
-      GLC_CUDA(cudaMemcpy(d_exp_idx_rev, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice));
-    }
+    expanded_pos_index_rev(cfg_.buckets, cfg_.max_rel_pos, h.data());
+    d_exp_idx_rev = (int32_t*)dalloc((size_t)ER * 4);
+    perm_allocs_.push_back(d_exp_idx_rev);
+    GLC_CUDA(cudaMemcpy(d_exp_idx_rev, h.data(), (size_t)ER * 4, cudaMemcpyHostToDevice));
   }
 
   layers_.resize(cfg_.layers);
@@ -195,19 +204,12 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens) : de
     perm_allocs_.push_back(d.pos_qk);
     GLC_CUDA(gemm_f16(rel_ln, H, d.wqkv, H, d.bqkv, d.pos_qk, 2 * H, R, 2 * H, H, 0, false, num_sms_, stream_));
     ++launches_;
-    if (attn_mode_ != 0) {
-      d.pos_exp = dalloc((size_t)ER * 2 * H * 2);
-      perm_allocs_.push_back(d.pos_exp);
-      if (attn_mode_ == 1) {
-        GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx, d.pos_exp, 2 * H, 2 * H, stream_));
-      } else {
-        // posQ half in sigma order, posK half in rho order (attention_shift.cu)
-        GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx_rev, d.pos_exp, 2 * H, H, stream_));
-        GLC_CUDA(expand_pos_table((const __half*)d.pos_qk + H, 2 * H, d_exp_idx, (__half*)d.pos_exp + H, 2 * H, H, stream_));
-        ++launches_;
-      }
-      ++launches_;
-    }
+    // posQ half in sigma order, posK half in rho order (one row per relative distance)
+    d.pos_exp = dalloc((size_t)ER * 2 * H * 2);
+    perm_allocs_.push_back(d.pos_exp);
+    GLC_CUDA(expand_pos_table(d.pos_qk, 2 * H, d_exp_idx_rev, d.pos_exp, 2 * H, H, stream_));
+    GLC_CUDA(expand_pos_table((const __half*)d.pos_qk + H, 2 * H, d_exp_idx, (__half*)d.pos_exp + H, 2 * H, H, stream_));
+    launches_ += 2;
   }
   upload_w16(&t1w_, w.at("text.1.w").data.data(), (size_t)Hh * H);
   upload_f32(&t1b_, w.at("text.1.b"));
@@ -241,6 +243,7 @@ void DeviceModel::drop_graphs() {
   for (auto& kv : graphs_)
     if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
   graphs_.clear();
+  graphs_live_ = 0;
 }
 
 DeviceModel::~DeviceModel() {
@@ -251,6 +254,10 @@ DeviceModel::~DeviceModel() {
   for (void* p : perm_allocs_) cudaFree(p);
   if (h_ids_) { cudaFreeHost(h_ids_); cudaFreeHost(h_mask_); }
   if (h_logits_) { cudaFreeHost(h_logits_); cudaFreeHost(h_probs_); cudaFreeHost(h_dec_); }
+  if (h_overflow_) cudaFreeHost(h_overflow_);
+  for (auto& b : h_in_) if (b.p) cudaFreeHost(b.p);
+  for (auto e : h_in_ev_) if (e) cudaEventDestroy(e);
+  for (auto& b : out_pool_) if (b.p) cudaFreeHost(b.p);
   for (auto& kv : rel_tables_) cudaFree(kv.second);
   for (auto& kv : debug_) cudaFree(kv.second.ptr);
   for (auto& r : prof_recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -289,7 +296,7 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   x1_ = A(M * H * 2);
   qkv_ = A(M * 3 * H * 2);
   ctx_ = A(M * H * 2);
-  tmp_ = A(M * H * 2);
+  tmp_ = A(M * H * (preln_f32_ ? 4 : 2));
   ffn_ = A(M * I * 2);
   mask_bits_ = (uint32_t*)A(((M + 31) / 32 + (size_t)ws_B_) * 4);
   kv_len_ = (int32_t*)A((size_t)ws_B_ * 4);
@@ -411,7 +418,13 @@ void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, in
   uint32_t thr;
   memcpy(&thr, &threshold, 4);
   const GraphKey key{B, S, C, d_ids, d_mask, d_logits, d_probs, d_decisions, thr};
+  if (graphs_.size() >= (size_t)kMaxGraphKeys && !graphs_.count(key)) {
+    // unbounded variety of shapes (pad-to-longest batches): forget the placeholders of shapes seen only once
+    for (auto it = graphs_.begin(); it != graphs_.end();)
+      it = it->second.exec ? std::next(it) : graphs_.erase(it);
+  }
   GraphEntry& e = graphs_[key];
+  e.last_use = ++graph_clock_;
   if (e.exec) {
     GLC_CUDA(cudaGraphLaunch(e.exec, stream_));
     launches_ += e.launches;
@@ -421,10 +434,16 @@ void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, in
     forward_eager(d_ids, d_mask, B, S, C, d_logits, d_probs, d_decisions, threshold);
     return;
   }
-  if (graphs_.size() > 64) {   // unbounded variety of shapes (pad-to-longest batches): stop caching new ones
-    graphs_.erase(key);
-    forward_eager(d_ids, d_mask, B, S, C, d_logits, d_probs, d_decisions, threshold);
-    return;
+  if (graphs_live_ >= kMaxGraphs) {   // evict the least recently replayed graph
+    auto victim = graphs_.end();
+    for (auto it = graphs_.begin(); it != graphs_.end(); ++it)
+      if (it->second.exec && (victim == graphs_.end() || it->second.last_use < victim->second.last_use)) victim = it;
+    if (victim != graphs_.end()) {
+      GLC_CUDA(cudaStreamSynchronize(stream_));   // the victim may still be executing
+      cudaGraphExecDestroy(victim->second.exec);
+      graphs_.erase(victim);
+      --graphs_live_;
+    }
   }
   const uint64_t before = launches_.load();
   GLC_CUDA(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
@@ -437,20 +456,22 @@ void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, in
     throw;
   }
   GLC_CUDA(cudaStreamEndCapture(stream_, &g));
-  e.launches = launches_.load() - before;
   cudaGraphExec_t exec = nullptr;
   cudaError_t ie = cudaGraphInstantiate(&exec, g, 0);
   cudaGraphDestroy(g);
   if (ie != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie));
-  e.exec = exec;
-  GLC_CUDA(cudaGraphLaunch(e.exec, stream_));
+  GraphEntry& e2 = graphs_[key];   // (the eviction above may have rebalanced the map: look the entry up again)
+  e2.launches = launches_.load() - before;
+  e2.exec = exec;
+  e2.last_use = graph_clock_;
+  ++graphs_live_;
+  GLC_CUDA(cudaGraphLaunch(e2.exec, stream_));
 }
 
 void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits,
                                 float* d_probs, uint8_t* d_decisions, float threshold) {
   const int H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
   const int M = B * S;
-  const int32_t* rel = rel_table(S);
   cudaStream_t st = stream_;
   uint64_t n = 0;
 
@@ -461,43 +482,39 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     const DeviceLayer& d = layers_[l];
     GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st));
     if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
-    const __half* pq = (const __half*)d.pos_qk;
     const __half* pe = (const __half*)d.pos_exp;
     if (attn_mode_ == 0) {
-      GLC_LAUNCH(KC_ATTN, attention_fused(qkv_, pq + H, pq, 2 * H, rel, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads,
-                                          cfg_.buckets, num_sms_, st));
-    } else if (attn_mode_ == 1) {
-      GLC_LAUNCH(KC_ATTN, attention_toeplitz(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
-    } else if (attn_mode_ == 2) {
-      GLC_LAUNCH(KC_ATTN, attention_shift(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
+      GLC_LAUNCH(KC_ATTN, attention_rows(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
     } else {
-      GLC_LAUNCH(KC_ATTN, attention_stream(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
+      GLC_LAUNCH(KC_ATTN, attention_shift(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
     }
     if (cfg_.pooling == POOL_LAST) GLC_LAUNCH(KC_ATTN, pad_rows_mean_v(qkv_, d_mask, ctx_, B, S, H, st));
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
     // GLC_FUSE_RESID=1: the residual add rides in the GEMM epilogue and LN reads one tensor (slower in total, see engine ctor)
     if (fuse_resid_) {
       GLC_LAUNCH(KC_GEMM_OUT, gemm_f16_resid(ctx_, H, d.wo, H, d.bo, x_, H, tmp_, H, M, H, H, 0, false, num_sms_, st));
-      GLC_LAUNCH(KC_LN, residual_ln(tmp_, nullptr, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, nullptr, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st, d_overflow_));
     } else {
-      GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, false, num_sms_, st));
-      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st));
+      GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, preln_f32_, num_sms_, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st, d_overflow_, preln_f32_));
     }
     GLC_LAUNCH(KC_GEMM_FFN1, gemm_f16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st));
     if (fuse_resid_) {
       GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16_resid(ffn_, I, d.w2, I, d.b2, x1_, H, tmp_, H, M, H, I, 0, false, num_sms_, st));
-      GLC_LAUNCH(KC_LN, residual_ln(tmp_, nullptr, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, nullptr, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st, d_overflow_));
     } else {
-      GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, false, num_sms_, st));
-      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st));
+      GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16(ffn_, I, d.w2, I, d.b2, tmp_, H, M, H, I, 0, preln_f32_, num_sms_, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st, d_overflow_, preln_f32_));
     }
     if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
   }
   if (C > 0) {
-    GLC_LAUNCH(KC_HEAD_MISC, head_gather_pool(x_, d_ids, d_mask, cfg_.class_token, cfg_.pooling, pooled_, cls_, B, S, H, C, st));
-    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, 1, false, num_sms_, st));
+    const int pa = cfg_.proj_act;
+    GLC_LAUNCH(KC_HEAD_MISC, head_gather_pool(x_, d_ids, d_mask, cfg_.class_token, cfg_.pooling, pooled_, cls_, B, S, H, C, st,
+                                              cfg_.class_pos_offset));
+    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, pa, false, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st));
-    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, 1, false, num_sms_, st));
+    GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, pa, false, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cmid_, Hh, c2w_, Hh, c2b_, kvec_, Hh, B * C, Hh, Hh, 0, true, num_sms_, st));
     const bool nrm = cfg_.normalize;
     const float eps = cfg_.norm_eps, ls = nrm ? cfg_.logit_scale : 1.0f;
@@ -529,6 +546,39 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
   launches_ += n;
 }
 
+namespace {
+bool is_pinned(const void* p) {
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+}  // namespace
+
+DeviceModel::PinnedBlock DeviceModel::take_out_block(size_t bytes) {   // caller holds mu
+  for (size_t i = 0; i < out_pool_.size(); ++i)
+    if (out_pool_[i].bytes >= bytes) {
+      PinnedBlock b = out_pool_[i];
+      out_pool_.erase(out_pool_.begin() + (long)i);
+      return b;
+    }
+  PinnedBlock b;
+  b.bytes = bytes < 4096 ? 4096 : bytes;
+  GLC_CUDA(cudaMallocHost(&b.p, b.bytes));
+  return b;
+}
+
+void DeviceModel::check_overflow_sync() {
+  std::lock_guard<std::mutex> lk(mu);
+  GLC_CUDA(cudaSetDevice(device_));
+  int v = 0;
+  GLC_CUDA(cudaMemcpyAsync(&h_overflow_[63], d_overflow_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+  GLC_CUDA(cudaMemsetAsync(d_overflow_, 0, sizeof(int), stream_));
+  GLC_CUDA(cudaStreamSynchronize(stream_));
+  v = h_overflow_[63];
+  if (v) throw std::runtime_error(kOverflowMsg);
+}
+
 void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,
                            const DecisionOut* dec, bool cacheable) {
   if (B <= 0 || S <= 0) return;
@@ -540,8 +590,21 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
   // glc_submit tickets in flight, or two OpenMP workers) leave no bubble on the device.  One stream keeps the shared
   // workspace and the id / mask / logits staging buffers safe: request N+1's copies execute after request N's forward
   // and D2H in stream order.
+  // Pageable caller buffers (what the reference passes: malloc'd int64 arrays, src/model.c:17-29, and ORT-owned output)
+  // never meet cudaMemcpyAsync directly — that call degrades to a synchronous staged copy which would hold `mu` for the
+  // whole forward.  Inputs are copied into one of two pinned slots, outputs land in a pinned block that is copied to the
+  // caller after the completion event.
+  const bool want_p = dec && dec->probs, want_d = dec && dec->decisions;
+  const bool in_pinned = is_pinned(ids) && is_pinned(mask);
+  const bool out_pinned = is_pinned(logits) && (!want_p || is_pinned(dec->probs)) && (!want_d || is_pinned(dec->decisions));
+  const size_t nout = (size_t)B * (size_t)(C > 0 ? C : 0);
+  PinnedBlock ob;
+  float* o_logits = logits;
+  float* o_probs = want_p ? dec->probs : nullptr;
+  uint8_t* o_dec = want_d ? dec->decisions : nullptr;
   cudaEvent_t done = nullptr;
   double t1 = 0;
+  uint32_t oslot = 0;
   {
     std::lock_guard<std::mutex> lk(mu);
     GLC_CUDA(cudaSetDevice(device_));
@@ -549,23 +612,54 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
     if (rows_mb < 1) rows_mb = 1;
     if (rows_mb > B) rows_mb = B;
     ensure_workspace(rows_mb * S, rows_mb, C);
+    if (!out_pinned && nout > 0) {
+      ob = take_out_block(nout * 9);
+      o_logits = logits ? (float*)ob.p : nullptr;
+      o_probs = want_p ? (float*)ob.p + nout : nullptr;
+      o_dec = want_d ? (uint8_t*)((float*)ob.p + 2 * nout) : nullptr;
+    }
     for (int r0 = 0; r0 < B; r0 += rows_mb) {
       const int nb = (B - r0 < rows_mb) ? (B - r0) : rows_mb;
       const size_t bytes = (size_t)nb * S * 8;
-      GLC_CUDA(cudaMemcpyAsync(ids_, ids + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
-      GLC_CUDA(cudaMemcpyAsync(mask_, mask + (size_t)r0 * S, bytes, cudaMemcpyHostToDevice, stream_));
-      const bool want_p = dec && dec->probs, want_d = dec && dec->decisions;
+      const int64_t* src_i = ids + (size_t)r0 * S;
+      const int64_t* src_m = mask + (size_t)r0 * S;
+      if (!in_pinned) {
+        const int k = h_in_next_;
+        h_in_next_ ^= 1;
+        PinnedBlock& hb = h_in_[k];
+        if (hb.bytes < 2 * bytes) {
+          if (hb.p) { GLC_CUDA(cudaStreamSynchronize(stream_)); cudaFreeHost(hb.p); hb.p = nullptr; }
+          hb.bytes = 2 * (size_t)rows_mb * S * 8;
+          GLC_CUDA(cudaMallocHost(&hb.p, hb.bytes));
+        }
+        if (!h_in_ev_[k]) GLC_CUDA(cudaEventCreateWithFlags(&h_in_ev_[k], cudaEventDisableTiming));
+        else GLC_CUDA(cudaEventSynchronize(h_in_ev_[k]));   // the H2D that last read this slot has finished
+        memcpy(hb.p, src_i, bytes);
+        memcpy((uint8_t*)hb.p + bytes, src_m, bytes);
+        src_i = (const int64_t*)hb.p;
+        src_m = (const int64_t*)((uint8_t*)hb.p + bytes);
+        GLC_CUDA(cudaMemcpyAsync(ids_, src_i, bytes, cudaMemcpyHostToDevice, stream_));
+        GLC_CUDA(cudaMemcpyAsync(mask_, src_m, bytes, cudaMemcpyHostToDevice, stream_));
+        GLC_CUDA(cudaEventRecord(h_in_ev_[k], stream_));
+      } else {
+        GLC_CUDA(cudaMemcpyAsync(ids_, src_i, bytes, cudaMemcpyHostToDevice, stream_));
+        GLC_CUDA(cudaMemcpyAsync(mask_, src_m, bytes, cudaMemcpyHostToDevice, stream_));
+      }
       forward(ids_, mask_, nb, S, C, logits_, want_p ? probs_ : nullptr, want_d ? decisions_ : nullptr,
               dec ? dec->threshold : 0.5f, cacheable);
       if (C > 0) {
-        if (logits)
-          GLC_CUDA(cudaMemcpyAsync(logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
-        if (want_p)
-          GLC_CUDA(cudaMemcpyAsync(dec->probs + (size_t)r0 * C, probs_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
-        if (want_d)
-          GLC_CUDA(cudaMemcpyAsync(dec->decisions + (size_t)r0 * C, decisions_, (size_t)nb * C, cudaMemcpyDeviceToHost, stream_));
+        if (o_logits)
+          GLC_CUDA(cudaMemcpyAsync(o_logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+        if (o_probs)
+          GLC_CUDA(cudaMemcpyAsync(o_probs + (size_t)r0 * C, probs_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+        if (o_dec)
+          GLC_CUDA(cudaMemcpyAsync(o_dec + (size_t)r0 * C, decisions_, (size_t)nb * C, cudaMemcpyDeviceToHost, stream_));
       }
     }
+    // this request's copy of the fp16-saturation flag; the device flag is cleared behind it for the next request
+    oslot = overflow_seq_++ % 63u;
+    GLC_CUDA(cudaMemcpyAsync(&h_overflow_[oslot], d_overflow_, sizeof(int), cudaMemcpyDeviceToHost, stream_));
+    GLC_CUDA(cudaMemsetAsync(d_overflow_, 0, sizeof(int), stream_));
     if (free_events_.empty()) {
       GLC_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
     } else {
@@ -576,11 +670,19 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
     t1 = timing ? now() : 0;
   }
   const cudaError_t we = cudaEventSynchronize(done);
+  const int overflowed = (we == cudaSuccess) ? h_overflow_[oslot] : 0;
+  if (we == cudaSuccess && !overflowed && ob.p) {
+    if (logits) memcpy(logits, o_logits, nout * 4);
+    if (want_p) memcpy(dec->probs, o_probs, nout * 4);
+    if (want_d) memcpy(dec->decisions, o_dec, nout);
+  }
   {
     std::lock_guard<std::mutex> lk(mu);
     free_events_.push_back(done);
+    if (ob.p) out_pool_.push_back(ob);
   }
   if (we != cudaSuccess) throw std::runtime_error(std::string("cudaEventSynchronize: ") + cudaGetErrorString(we));
+  if (overflowed) throw std::runtime_error(kOverflowMsg);
   if (timing) fprintf(stderr, "glc run_host B=%d S=%d: enqueue %.1f us, wait %.1f us\n", B, S, t1 - t0, now() - t1);
 }
 
@@ -700,16 +802,68 @@ void DeviceModel::run_group(std::vector<HostReq*>& group) {
 
 // ---------------------------------------------------------------------------------------------
 
-Model::Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens) {
+TaskQueue::TaskQueue(int threads) {
+  for (int i = 0; i < threads; ++i) th_.emplace_back([this] { loop(); });
+}
+
+TaskQueue::~TaskQueue() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    stop_ = true;
+  }
+  cv_.notify_all();
+  for (auto& t : th_) t.join();
+}
+
+void TaskQueue::post(std::function<void()> fn) {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    q_.push_back(std::move(fn));
+  }
+  cv_.notify_one();
+}
+
+void TaskQueue::loop() {
+  for (;;) {
+    std::function<void()> fn;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [this] { return stop_ || !q_.empty(); });
+      if (q_.empty()) return;   // stop requested and drained
+      fn = std::move(q_.front());
+      q_.pop_front();
+    }
+    fn();
+  }
+}
+
+Model::Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens, bool preln_f32) {
   ModelWeights w;
   load_model_weights(onnx_path, &w);
   cfg_ = w.cfg;
   if (devices.empty()) throw std::runtime_error("no CUDA device selected");
-  for (int d : devices) devs_.emplace_back(new DeviceModel(d, w, max_tokens));
+  for (int d : devices) devs_.emplace_back(new DeviceModel(d, w, max_tokens, preln_f32));
+  if (devs_.size() > 1)
+    for (size_t i = 0; i < devs_.size(); ++i) workers_.emplace_back(new TaskQueue(1));
   const char* co = getenv("GLC_COALESCE");
   coalesce_ = !(co && co[0] == '0');
   coalesce_tokens_ = (max_tokens > 0 ? max_tokens : 65536) / 2;
   if (const char* ct = getenv("GLC_COALESCE_TOKENS")) coalesce_tokens_ = atoi(ct);
+}
+
+Model::~Model() {
+  submit_q_.reset();   // drains in-flight submits before the devices go away
+  workers_.clear();
+}
+
+TaskQueue& Model::submit_queue() {
+  std::lock_guard<std::mutex> lk(submit_mu_);
+  if (!submit_q_) {
+    int n = 8;   // in-flight glc_submit requests served concurrently (each blocks in the coalescing queue like an OpenMP worker)
+    if (const char* e = getenv("GLC_SUBMIT_THREADS")) n = atoi(e) > 0 ? atoi(e) : n;
+    submit_q_.reset(new TaskQueue(n));
+  }
+  return *submit_q_;
 }
 
 void Model::coalesce_stats(uint64_t* groups, uint64_t* requests) const {
@@ -751,15 +905,21 @@ void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, fl
     }
     return;
   }
-  // large call: contiguous row shards, one host thread per device, host gather into `logits`
+  // large call: contiguous row shards, one PERSISTENT host thread per device (workers_), host gather into `logits`
   const int per = (B + G - 1) / G;
-  std::vector<std::thread> th;
   std::vector<std::exception_ptr> err(G);
+  std::mutex lmu;
+  std::condition_variable lcv;
+  int pending = 0;
   for (int g = 0; g < G; ++g) {
     const int r0 = g * per;
     const int nb = (r0 >= B) ? 0 : ((B - r0 < per) ? B - r0 : per);
     if (nb == 0) continue;
-    auto work = [&, g, r0, nb]() {
+    {
+      std::lock_guard<std::mutex> lk(lmu);
+      ++pending;
+    }
+    workers_[g]->post([&, g, r0, nb]() {
       try {
         DecisionOut sub;
         if (dec) {
@@ -772,11 +932,14 @@ void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, fl
       } catch (...) {
         err[g] = std::current_exception();
       }
-    };
-    if (g == G - 1 || r0 + per >= B) { work(); break; }
-    th.emplace_back(work);
+      std::lock_guard<std::mutex> lk(lmu);
+      if (--pending == 0) lcv.notify_all();
+    });
   }
-  for (auto& t : th) t.join();
+  {
+    std::unique_lock<std::mutex> lk(lmu);
+    lcv.wait(lk, [&] { return pending == 0; });
+  }
   for (auto& e : err)
     if (e) std::rethrow_exception(e);
 }

@@ -10,10 +10,12 @@
 #include <condition_variable>
 #include <deque>
 #include <exception>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <tuple>
 #include <vector>
 
@@ -50,7 +52,7 @@ enum KernelCat { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTN, KC_GEMM_OUT, KC_LN, KC_GEMM
 
 class DeviceModel {
  public:
-  DeviceModel(int device, const ModelWeights& w, int max_tokens);
+  DeviceModel(int device, const ModelWeights& w, int max_tokens, bool preln_f32 = false);
   ~DeviceModel();
   DeviceModel(const DeviceModel&) = delete;
 
@@ -83,6 +85,8 @@ class DeviceModel {
 
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
+  // throws when the last forwards on this device saturated an fp16 pre-LN sum (see kernels.h residual_ln); clears the flag
+  void check_overflow_sync();
   uint64_t launches() const { return launches_.load(); }
   int64_t debug_fetch(const std::string& name, float* out, size_t capacity);
   // profiler: when enabled every launch is bracketed by CUDA events on stream(); collect() syncs
@@ -110,9 +114,20 @@ class DeviceModel {
   int max_tokens_ = 65536;
   bool debug_keep_ = false;
   bool fuse_resid_ = false;    // GLC_FUSE_RESID=1: residual add in the out-proj / FFN2 GEMM epilogues instead of the LN kernel
-  int attn_mode_ = 2;          // 2 register-skew kernel (attention_shift.cu, production); experiments: 0 gather kernel (attention.cu),
-                               // 1 tensor-core bias adds (attention_toeplitz.cu), 3 two-stream variant (attention_stream.cu);
-                               // env GLC_ATTN=gather|toeplitz|shift|stream
+  bool preln_f32_ = false;     // GLC_PRELN_F32=1 / glc_opts.preln_f32: out-proj and FFN2 outputs (the pre-LN sums) stay fp32
+  int* d_overflow_ = nullptr;  // set by the LN kernels when a pre-LN sum hit the fp16 saturation value
+  int* h_overflow_ = nullptr;  // pinned ring of per-request copies of the flag
+  uint32_t overflow_seq_ = 0;
+  // pinned staging for pageable caller buffers (the reference's malloc'd tensors, src/model.c:17-29): two input slots
+  // (ids | mask of one micro-batch) used alternately, each guarded by the event of its last H2D copy; output blocks are
+  // taken from a free list per request and copied to the caller after the request's completion event
+  struct PinnedBlock { void* p = nullptr; size_t bytes = 0; };
+  PinnedBlock h_in_[2];
+  cudaEvent_t h_in_ev_[2] = {nullptr, nullptr};
+  int h_in_next_ = 0;
+  std::vector<PinnedBlock> out_pool_;
+  PinnedBlock take_out_block(size_t bytes);
+  int attn_mode_ = 0;          // 0 attention_rows.cu (production), 1 attention_shift.cu (env GLC_ATTN=rows|shift)
   std::atomic<uint64_t> launches_{0};
 
   // weights
@@ -152,8 +167,11 @@ class DeviceModel {
              std::tie(o.B, o.S, o.C, o.ids, o.mask, o.logits, o.probs, o.dec, o.thr);
     }
   };
-  struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; uint64_t launches = 0; };
+  struct GraphEntry { int seen = 0; cudaGraphExec_t exec = nullptr; uint64_t launches = 0; uint64_t last_use = 0; };
   std::map<GraphKey, GraphEntry> graphs_;
+  uint64_t graph_clock_ = 0;
+  int graphs_live_ = 0;        // instantiated graphs (placeholders of shapes seen once do not count)
+  static constexpr int kMaxGraphs = 48, kMaxGraphKeys = 512;
   bool graphs_on_ = true;
   void drop_graphs();
   // coalescing queue + pinned staging of merged groups (touched only by the current leader)
@@ -175,9 +193,28 @@ class DeviceModel {
   friend struct ProfScope;
 };
 
+// one persistent host thread per device of a multi-GPU model: runs that device's row shard of a large Run
+// (replaces a std::thread spawned per call) and the asynchronous glc_submit requests
+class TaskQueue {
+ public:
+  explicit TaskQueue(int threads);
+  ~TaskQueue();
+  void post(std::function<void()> fn);
+
+ private:
+  void loop();
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<std::function<void()>> q_;
+  std::vector<std::thread> th_;
+  bool stop_ = false;
+};
+
 class Model {
  public:
-  Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens);
+  Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens, bool preln_f32 = false);
+  ~Model();
+  TaskQueue& submit_queue();
   int num_classes(const int64_t* ids, int B, int S) const;
   void run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits, const DecisionOut* dec = nullptr);
   const ModelConfig& cfg() const { return cfg_; }
@@ -190,6 +227,9 @@ class Model {
   ModelConfig cfg_;
   std::vector<std::unique_ptr<DeviceModel>> devs_;
   std::atomic<uint32_t> rr_{0};
+  std::vector<std::unique_ptr<TaskQueue>> workers_;   // one single-thread queue per device (multi-GPU models only)
+  std::unique_ptr<TaskQueue> submit_q_;               // glc_submit requests (created on first use)
+  std::mutex submit_mu_;
   bool coalesce_ = true;        // GLC_COALESCE=0 disables
   int coalesce_tokens_ = 0;     // requests up to this many tokens go through the coalescing queue
 };

@@ -24,8 +24,11 @@ cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* word_e
                      const float* beta, float eps, void* y_f16, int M, int H, int vocab, cudaStream_t stream);
 
 // K4: y = LN(x + r) * gamma + beta   (T:49-53, T:408-412); r may be null (plain LN).
-cudaError_t residual_ln(const void* x_f16, const void* r_f16, const float* gamma, const float* beta, float eps,
-                        void* y_f16, int M, int H, cudaStream_t stream);
+// overflow_flag (device int, may be null) is set to 1 when a pre-LN sum reaches the fp16 saturation value (the GEMM
+// epilogue clamps at +-65504): the engine turns that into a loud Run failure.  x_is_f32: x is the fp32 output of the
+// GEMM's fp32 epilogue (robust mode, GLC_PRELN_F32=1) instead of fp16.
+cudaError_t residual_ln(const void* x, const void* r_f16, const float* gamma, const float* beta, float eps,
+                        void* y_f16, int M, int H, cudaStream_t stream, int* overflow_flag = nullptr, bool x_is_f32 = false);
 // plain LN on fp32 rows -> fp16 (load-time LN of rel_embeddings, T:597-601)
 cudaError_t ln_f32_to_f16(const float* x, const float* gamma, const float* beta, float eps, void* y_f16, int M, int H,
                            cudaStream_t stream);
@@ -33,35 +36,28 @@ cudaError_t ln_f32_to_f16(const float* x, const float* gamma, const float* beta,
 // key-validity words for attention: bits[b][w] bit j = mask[b][32w+j] != 0 ; kv_len[b] = 1 + last valid key
 cudaError_t mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, cudaStream_t stream);
 
-// K3: fused disentangled attention (T:229-345).  qkv fp16 [B*S,3H] (Q | K | V, head-major
-// inside each third); pos_k/pos_q fp16 [2*buckets][ld_pos] row-major (head h = columns h*64..);
-// rel_idx int32 [2*Spad-1] with Spad = S rounded up to 128; ctx fp16 [B*S,H].
-cudaError_t attention_fused(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
-                            const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
-                            int buckets, int num_sms, cudaStream_t stream);
-// K3, second generation (attention_toeplitz.cu): same op with the two relative-position biases added by the
-// tensor core.  exp_k / exp_q are the position tables expanded to one row per delta by expand_pos_table:
-// fp16 [expanded_pos_rows()][ld_exp], row rho = pos[idx(2047 - rho)].
+// K3: fused disentangled attention (T:229-345).  qkv fp16 [B*S,3H] (Q | K | V, head-major inside each third);
+// ctx fp16 [B*S,H].  The kernels read the per-layer position projections expanded at load to one row per relative
+// distance (expand_pos_table): exp_k [expanded_pos_rows()][ld_exp], row rho = posK[idx(2047 - rho)] (index from
+// expanded_pos_index), exp_qr in the OPPOSITE order, row sigma = posQ[idx(sigma - 2047)] (expanded_pos_index_rev).
 int expanded_pos_rows();
 void expanded_pos_index(int buckets, int max_pos, int32_t* out /* host, [expanded_pos_rows()] */);
+void expanded_pos_index_rev(int buckets, int max_pos, int32_t* out /* host, [expanded_pos_rows()] */);
 cudaError_t expand_pos_table(const void* pos_f16, int64_t ld_src, const int32_t* d_exp_index, void* out_f16, int64_t ld_dst,
                              int cols, cudaStream_t stream);
-cudaError_t attention_toeplitz(const void* qkv, const void* exp_k, const void* exp_q, int64_t ld_exp,
-                               const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
-                               cudaStream_t stream);
-// K3, third generation (attention_shift.cu): both biases skewed in registers (barrel shifter for c2p, lane rotation
-// for p2c).  exp_k as above; exp_qr is the posQ table expanded in the OPPOSITE order: row sigma = posQ[idx(sigma - 2047)]
-// (index from expanded_pos_index_rev).
-void expanded_pos_index_rev(int buckets, int max_pos, int32_t* out /* host, [expanded_pos_rows()] */);
+// production kernel (attention_rows.cu): same register skews, but a softmax thread owns a whole query row of a 64-key
+// tile and three warpgroups rotate over the key tiles (tile t -> group t mod 3), chaining the sticky row maximum from
+// tile to tile: no lock-step exchange, three warps per scheduler in different phases of their tiles.
+cudaError_t attention_rows(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                           const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
+                           cudaStream_t stream);
+// previous production kernel (attention_shift.cu): both biases skewed in registers (barrel shifter for c2p, lane rotation for
+// p2c); the two warps that share a query row split the 64 keys of a tile and exchange the row maximum.
 cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
                             const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                             cudaStream_t stream);
-// K3, fourth generation (attention_stream.cu): the register-skew biases of attention_shift with two independent
-// key-half softmax streams per query row and the output accumulators resident in TMEM.  Same operands as attention_shift.
-cudaError_t attention_stream(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
-                             const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
-                             cudaStream_t stream);
-// slow CUDA-core restatement of the same op, used only by tests to localise bugs on the GPU
+// slow CUDA-core restatement of the same op on the UNEXPANDED tables (pos_k / pos_q fp16 [2*buckets][ld_pos], rel_idx
+// int32 [2*Spad-1] with Spad = S rounded up to 128), used only by tests to localise bugs on the GPU
 cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,
                             const uint32_t* mask_bits, void* ctx, int B, int S, int heads, int buckets,
                             cudaStream_t stream);
@@ -75,8 +71,10 @@ cudaError_t head_gather(const void* h_f16, const int64_t* ids, int64_t class_tok
                         int B, int S, int H, int C, cudaStream_t stream);
 // K5a with the pooling strategies of the gliclass package: pool_mode 0 first token, 1 last token (h[b,S-1,:]),
 // 2 masked mean, 3 masked max over the sequence (mask required for 2/3)
+// class_pos_offset = 1 reads each class row one position after its <<LABEL>> token (gliclass embed_class_token=false)
 cudaError_t head_gather_pool(const void* h_f16, const int64_t* ids, const int64_t* mask, int64_t class_token, int pool_mode,
-                             void* pooled_f16, void* cls_f16, int B, int S, int H, int C, cudaStream_t stream);
+                             void* pooled_f16, void* cls_f16, int B, int S, int H, int C, cudaStream_t stream,
+                             int class_pos_offset = 0);
 // K5b generalised: logits[b,c] = scale * <t[b*t_stride..], k[b,c,:]> / ((|t|+eps)(|k|+eps) if normalize) + bias, then the
 // sigmoid / strict-threshold epilogue.  t_stride = 0: shared weight row (last Linear(K->1) of the MLP scorers).
 cudaError_t head_score_ex(const float* t, int64_t t_stride, const float* k, float* logits, float* probs, uint8_t* decisions,

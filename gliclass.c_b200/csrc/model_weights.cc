@@ -34,6 +34,7 @@ const OnnxNode* find_node(const OnnxGraph& g, const std::string& suffix, const c
 HostTensor to_host(const OnnxTensor& t) {
   HostTensor h;
   h.dims = t.dims;
+  if (t.numel() < 0) throw std::runtime_error("onnx: bad dimensions in " + t.name);
   h.data.resize((size_t)t.numel());
   tensor_to_float(t, h.data.data());
   return h;
@@ -166,6 +167,10 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
     const OnnxNode* pq = find_node(g, s + "/attention/self/query_proj_1/MatMul", "MatMul");
     const OnnxNode* cq = find_node(g, s + "/attention/self/query_proj/MatMul", "MatMul");
     if (!pq) throw std::runtime_error("onnx: layer " + std::to_string(l) + " has no query_proj_1 (share_att_key p2c|c2p model expected)");
+    // pos_att_type must be exactly {c2p, p2c}: the kernel's 1/sqrt(3d) scale and both bias terms are hard-wired (T:237-242)
+    if (!find_node(g, s + "/attention/self/key_proj_1/MatMul", "MatMul"))
+      throw std::runtime_error("onnx: layer " + std::to_string(l) + " has no key_proj_1: pos_att_type without c2p is not supported");
+    if (pq->inputs.size() != 2 || cq->inputs.size() != 2) throw std::runtime_error("onnx: MatMul arity at " + pq->name);
     if (g.resolve(pq->inputs[1]) != g.resolve(cq->inputs[1])) {
       // not an alias: accept only if values are identical
       const OnnxTensor* a = g.resolve(pq->inputs[1]);
@@ -199,10 +204,10 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
 
   // ---- log-bucket constants: Div(abs_pos, mid) -> Log -> Div(., log((max_pos-1)/mid))
   for (auto& n : g.nodes) {
-    if (n.op_type != "Log") continue;
+    if (n.op_type != "Log" || n.inputs.empty() || n.outputs.empty()) continue;
     float mid = 0.f, lg = 0.f;
     auto pit = g.producer_of.find(n.inputs[0]);
-    if (pit != g.producer_of.end() && g.nodes[pit->second].op_type == "Div" &&
+    if (pit != g.producer_of.end() && g.nodes[pit->second].op_type == "Div" && g.nodes[pit->second].inputs.size() == 2 &&
         g.scalar_float(g.nodes[pit->second].inputs[1], &mid) && mid > 0.f) {
       for (auto& m : g.nodes)
         if (m.op_type == "Div" && m.inputs.size() == 2 && m.inputs[0] == n.outputs[0] &&
@@ -223,6 +228,20 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
   }
   if (c.class_token < 0) throw std::runtime_error("onnx: Equal(input_ids, class_token_index) not found");
 
+  // ---- encoder / head variants this engine does NOT implement: refuse them instead of returning wrong logits
+  // (gliclass config: use_lstm, position_biased_input / token types / embed_proj of DeBERTa-v2, conv layer)
+  for (auto& n : g.nodes) {
+    if (n.op_type == "LSTM" || n.op_type == "GRU" || n.op_type == "RNN")
+      throw std::runtime_error("onnx: recurrent layer (" + n.op_type + " at " + n.name + "): use_lstm models are not supported");
+    if (n.op_type == "Conv" || n.op_type == "ConvTranspose")
+      throw std::runtime_error("onnx: convolution (" + n.name + "): DeBERTa conv_kernel_size > 0 is not supported");
+  }
+  for (const char* bad : {"embeddings.position_embeddings.weight", "embeddings.token_type_embeddings.weight",
+                          "embeddings.embed_proj.weight"})
+    if (find_named(g, bad))
+      throw std::runtime_error(std::string("onnx: initializer ") + bad + " present: position_biased_input / token types / "
+                               "embedding_size != hidden_size are not supported");
+
   // ---- head
   load_linear(g, "/text_projector/linear_1", "text.1", out);
   load_linear(g, "/text_projector/linear_2", "text.2", out);
@@ -230,6 +249,52 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
   load_linear(g, "/classes_projector/linear_2", "cls.2", out);
   c.head_hidden = (int)out->at("text.2.w").dims[0];
   int64_t Hh_ = c.head_hidden;
+  // projector activation (gliclass config.projector_hidden_act): the nodes between linear_1 and linear_2 of a projector
+  {
+    auto act_of = [&](const std::string& scope) -> int {
+      bool erf = false, relu = false, other = false;
+      std::string what;
+      for (auto& n : g.nodes) {
+        if (n.name.find(scope) == std::string::npos) continue;
+        if (n.name.find("/linear_1/") != std::string::npos || n.name.find("/linear_2/") != std::string::npos) continue;
+        if (n.op_type == "Erf") erf = true;
+        else if (n.op_type == "Relu") relu = true;
+        else if (n.op_type == "Tanh" || n.op_type == "Sigmoid" || n.op_type == "Softplus" || n.op_type == "LeakyRelu" ||
+                 n.op_type == "Elu" || n.op_type == "Selu" || n.op_type == "HardSigmoid" || n.op_type == "PRelu") {
+          other = true;
+          what = n.op_type;
+        }
+      }
+      if (other || (erf && relu)) throw std::runtime_error("onnx: unsupported projector activation (" + what + ") under " + scope);
+      if (erf) return 1;    // erf-GELU
+      if (relu) return 2;   // ReLU
+      throw std::runtime_error("onnx: no activation found between linear_1 and linear_2 of " + scope);
+    };
+    c.proj_act = act_of("/text_projector/");
+    if (act_of("/classes_projector/") != c.proj_act)
+      throw std::runtime_error("onnx: text and class projectors use different activations");
+  }
+  // embed_class_token = false: class rows are gathered one position AFTER each <<LABEL>> token.  In the traced graph that
+  // is an Add(+1) on the NonZero-derived positions, outside the encoder scope.
+  c.class_pos_offset = 0;
+  for (auto& n : g.nodes) {
+    if (n.op_type != "Add" || n.inputs.size() != 2 || n.name.find("/encoder_model/") != std::string::npos) continue;
+    int64_t one = 0;
+    int other = -1;
+    if (g.scalar_int(n.inputs[1], &one) && one == 1) other = 0;
+    else if (g.scalar_int(n.inputs[0], &one) && one == 1) other = 1;
+    if (other < 0) continue;
+    std::string v = n.inputs[other];
+    for (int hop = 0; hop < 8; ++hop) {
+      auto pit = g.producer_of.find(v);
+      if (pit == g.producer_of.end()) break;
+      const OnnxNode& pn = g.nodes[pit->second];
+      if (pn.op_type == "NonZero") { c.class_pos_offset = 1; break; }
+      if (pn.inputs.empty()) break;
+      v = pn.inputs[0];
+    }
+    if (c.class_pos_offset) break;
+  }
   // pooling strategy: whatever produces the input of text_projector.linear_1
   {
     const OnnxNode* l1 = find_node(g, "/text_projector/linear_1/Gemm", "Gemm");
@@ -319,6 +384,13 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
   }
   expect("text.1.w", {Hh, H}); expect("text.2.w", {Hh, Hh});
   expect("cls.1.w", {Hh, H}); expect("cls.2.w", {Hh, Hh});
+  for (const char* r : {"text.1.b", "text.2.b", "cls.1.b", "cls.2.b"}) expect(r, {Hh});
+  if (c.scorer == SCORER_MLP) {
+    expect("scorer.mlp.0.b", {(int64_t)c.mlp1}); expect("scorer.mlp.2.b", {(int64_t)c.mlp2}); expect("scorer.mlp.4.b", {1});
+  } else if (c.scorer == SCORER_WEIGHTED_DOT) {
+    expect("scorer.pt.b", {2 * Hh}); expect("scorer.pl.b", {2 * Hh}); expect("scorer.o1.b", {4 * Hh}); expect("scorer.o2.b", {1});
+  }
+  for (const char* r : {"emb.ln.g", "emb.ln.b", "rel.ln.g", "rel.ln.b"}) expect(r, {H});
 }
 
 void rel_index_table(int S, int buckets, int max_pos, int32_t* out) {

@@ -29,6 +29,8 @@ struct ModelConfig {
   float norm_eps = 1e-8f;       // x / (|x| + eps)
   float logit_scale = 1.0f;
   int mlp1 = 0, mlp2 = 0;       // MLP scorer widths (cat[t,l] -> mlp1 -> mlp2 -> 1)
+  int proj_act = 1;             // projector_hidden_act between linear_1 and linear_2: 1 erf-GELU, 2 ReLU (others are refused)
+  int class_pos_offset = 0;     // embed_class_token=false: class rows are read one position after each <<LABEL>> token
 };
 enum { POOL_FIRST = 0, POOL_LAST = 1, POOL_AVG = 2, POOL_MAX = 3 };
 enum { SCORER_DOT = 0, SCORER_MLP = 1, SCORER_WEIGHTED_DOT = 2 };

@@ -9,6 +9,7 @@
 #include "onnx_reader.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <stdexcept>
 
@@ -77,6 +78,7 @@ void parse_tensor(Cursor c, OnnxTensor* t) {
         t->float_data.resize(old + n);
         memcpy(t->float_data.data() + old, s.p, n * 4);
       } else if (wt == 5) {
+        if (c.end - c.p < 4) throw std::runtime_error("onnx: truncated fixed32 in float_data");
         float v; memcpy(&v, c.p, 4); c.p += 4; t->float_data.push_back(v);
       } else c.skip(wt);
     } else if (f == 7) {  // int64_data
@@ -88,9 +90,22 @@ void parse_tensor(Cursor c, OnnxTensor* t) {
       Cursor s = c.sub();
       t->raw = s.p;
       t->raw_bytes = (size_t)(s.end - s.p);
-    } else if (f == 13 || (f == 14 && wt == 0)) {
-      if (f == 14) { if (c.varint() == 1) t->external = true; }
-      else { t->external = true; c.skip(wt); }
+    } else if (f == 13 && wt == 2) {   // external_data: repeated StringStringEntryProto{key=1, value=2}
+      t->external = true;
+      Cursor s = c.sub();
+      std::string key, val;
+      while (!s.done()) {
+        int w2;
+        uint32_t f2 = s.tag(&w2);
+        if (f2 == 1 && w2 == 2) key = s.str();
+        else if (f2 == 2 && w2 == 2) val = s.str();
+        else s.skip(w2);
+      }
+      if (key == "location") t->ext_location = val;
+      else if (key == "offset") t->ext_offset = strtoull(val.c_str(), nullptr, 10);
+      else if (key == "length") t->ext_length = strtoull(val.c_str(), nullptr, 10);
+    } else if (f == 14 && wt == 0) {
+      if (c.varint() == 1) t->external = true;
     } else {
       c.skip(wt);
     }
@@ -102,7 +117,11 @@ void parse_attr(Cursor c, OnnxAttr* a) {
     int wt;
     uint32_t f = c.tag(&wt);
     if (f == 1 && wt == 2) a->name = c.str();
-    else if (f == 2 && wt == 5) { memcpy(&a->f, c.p, 4); c.p += 4; }
+    else if (f == 2 && wt == 5) {
+      if (c.end - c.p < 4) throw std::runtime_error("onnx: truncated fixed32 attribute");
+      memcpy(&a->f, c.p, 4);
+      c.p += 4;
+    }
     else if (f == 3 && wt == 0) a->i = (int64_t)c.varint();
     else if (f == 5 && wt == 2) { a->has_t = true; parse_tensor(c.sub(), &a->t); }
     else if (f == 8) {
@@ -183,10 +202,38 @@ void OnnxGraph::load(const std::string& path) {
     } else c.skip(wt);
   }
   if (!saw_graph) throw std::runtime_error("onnx: no graph in " + path);
+  // external-data tensors (models > 2 GB): raw bytes live in a sidecar file next to model.onnx
+  const std::string dir = path.find_last_of('/') == std::string::npos ? std::string(".") : path.substr(0, path.find_last_of('/'));
   for (size_t i = 0; i < initializers.size(); ++i) {
-    if (initializers[i].external)
-      throw std::runtime_error("onnx: external-data tensors are not supported (" + initializers[i].name + ")");
-    init_by_name[initializers[i].name] = (int)i;
+    OnnxTensor& t = initializers[i];
+    for (int64_t d : t.dims)
+      if (d < 0) throw std::runtime_error("onnx: negative dimension in " + t.name);
+    if (t.numel() < 0) throw std::runtime_error("onnx: element count overflow in " + t.name);
+    if (t.external) {
+      if (t.ext_location.empty() || t.ext_location.find("..") != std::string::npos || t.ext_location[0] == '/')
+        throw std::runtime_error("onnx: external tensor " + t.name + " has no usable relative location");
+      auto it = ext_files.find(t.ext_location);
+      if (it == ext_files.end()) {
+        const std::string ep = dir + "/" + t.ext_location;
+        FILE* ef = fopen(ep.c_str(), "rb");
+        if (!ef) throw std::runtime_error("onnx: cannot open external data file " + ep);
+        fseek(ef, 0, SEEK_END);
+        const long esz = ftell(ef);
+        fseek(ef, 0, SEEK_SET);
+        std::vector<uint8_t> buf((size_t)(esz > 0 ? esz : 0));
+        const size_t egot = buf.empty() ? 0 : fread(buf.data(), 1, buf.size(), ef);
+        fclose(ef);
+        if (egot != buf.size()) throw std::runtime_error("onnx: short read " + ep);
+        it = ext_files.emplace(t.ext_location, std::move(buf)).first;
+      }
+      const std::vector<uint8_t>& buf = it->second;
+      const uint64_t len = t.ext_length ? t.ext_length : (buf.size() > t.ext_offset ? buf.size() - t.ext_offset : 0);
+      if (t.ext_offset > buf.size() || len > buf.size() - t.ext_offset)
+        throw std::runtime_error("onnx: external tensor " + t.name + " lies outside " + t.ext_location);
+      t.raw = buf.data() + t.ext_offset;
+      t.raw_bytes = (size_t)len;
+    }
+    init_by_name[t.name] = (int)i;
   }
   for (size_t i = 0; i < nodes.size(); ++i)
     for (auto& o : nodes[i].outputs) producer_of[o] = (int)i;
@@ -237,6 +284,17 @@ bool OnnxGraph::scalar_float(const std::string& value, float* out) const {
 
 void tensor_to_float(const OnnxTensor& t, float* out) {
   int64_t n = t.numel();
+  if (n < 0) throw std::runtime_error("onnx: element count overflow in " + t.name);
+  if (t.data_type == 16 && t.raw) {   // bfloat16 raw
+    if ((int64_t)t.raw_bytes != n * 2) throw std::runtime_error("onnx: raw size mismatch for " + t.name);
+    for (int64_t i = 0; i < n; ++i) {
+      uint16_t h;
+      memcpy(&h, t.raw + 2 * i, 2);
+      const uint32_t u = (uint32_t)h << 16;
+      memcpy(out + i, &u, 4);
+    }
+    return;
+  }
   if (t.data_type != 1) throw std::runtime_error("onnx: tensor " + t.name + " is not float32");
   if (t.raw) {
     if ((int64_t)t.raw_bytes != n * 4) throw std::runtime_error("onnx: raw size mismatch for " + t.name);

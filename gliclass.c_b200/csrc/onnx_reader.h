@@ -19,8 +19,18 @@ struct OnnxTensor {
   size_t raw_bytes = 0;
   std::vector<float> float_data;   // when stored as repeated float
   std::vector<int64_t> int64_data; // when stored as repeated int64
-  int64_t numel() const { int64_t n = 1; for (auto d : dims) n *= d; return n; }
-  bool external = false;
+  // element count; -1 on a negative dimension or int64 overflow (crafted files)
+  int64_t numel() const {
+    int64_t n = 1;
+    for (auto d : dims) {
+      if (d < 0 || (d > 0 && n > INT64_MAX / d)) return -1;
+      n *= d;
+    }
+    return n;
+  }
+  bool external = false;        // data_location = EXTERNAL: raw points into OnnxGraph::ext_files after load()
+  std::string ext_location;
+  uint64_t ext_offset = 0, ext_length = 0;
 };
 
 struct OnnxAttr {
@@ -44,6 +54,7 @@ struct OnnxNode {
 
 struct OnnxGraph {
   std::vector<uint8_t> file;   // owns the bytes; tensors point into it
+  std::unordered_map<std::string, std::vector<uint8_t>> ext_files;   // external-data sidecars, keyed by relative location
   int64_t ir_version = 0;
   int64_t opset = 0;
   std::string producer;

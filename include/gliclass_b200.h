@@ -37,8 +37,12 @@ typedef struct glc_opts {
   int32_t device_ids[8];
   int32_t weight_dtype;      /* GLC_DTYPE_DEFAULT or GLC_DTYPE_FP16 */
   int32_t max_tokens;        /* micro-batch cap in tokens per device launch (0 = default 65536) */
-  int32_t num_heads;         /* 0 = infer from graph */
-  int32_t reserved[8];
+  int32_t num_heads;         /* 0 = infer from graph; otherwise it must equal the graph's head count (glc_load fails if not) */
+  int32_t preln_f32;         /* 1 = keep the pre-LayerNorm sums (out-proj / FFN2 outputs) in fp32 instead of fp16: for
+                              * checkpoints whose dense outputs leave the fp16 range.  Default 0: such a checkpoint makes
+                              * glc_run FAIL with an overflow error instead of returning logits from clamped values.
+                              * Env GLC_PRELN_F32=1 does the same. */
+  int32_t reserved[7];
 } glc_opts;
 
 typedef struct glc_info {
@@ -52,6 +56,8 @@ typedef struct glc_info {
   int32_t scorer;              /* 0 simple (dot), 1 mlp, 2 weighted-dot */
   int32_t normalize_features;  /* features x / (|x| + eps), logits * logit_scale */
   float logit_scale;
+  int32_t projector_act;       /* projector_hidden_act: 1 erf-GELU, 2 ReLU */
+  int32_t class_pos_offset;    /* 0: class rows at the <<LABEL>> positions (embed_class_token=true); 1: one position later */
 } glc_info;
 
 GLC_API const char* glc_last_error(void);
@@ -161,40 +167,33 @@ GLC_API int glc_op_residual_ln(const void* x_f16, const void* r_f16, const float
                                float eps, void* y_f16, int M, int H, void* stream);
 /* attention-mask packing: bits[b][w] bit j = mask[b][32w+j] != 0; kv_len[b] = 1 + last valid key */
 GLC_API int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, void* stream);
-/* K3: fused disentangled attention for one layer.  qkv fp16 [B*S,3H] (Q|K|V); pos_k / pos_q fp16
- * [2*buckets][ld_pos] row-major (head h at columns h*64..); rel_idx int32 [2*Spad-1] built with
- * glc_rel_index_table(Spad) where Spad = S rounded up to 128; mask_bits/kv_len from
- * glc_op_mask_prep; ctx fp16 [B*S,H].  naive != 0 runs the slow CUDA-core restatement instead
- * (tests only). */
-GLC_API int glc_op_attention(const void* qkv_f16, const void* pos_k_f16, const void* pos_q_f16, int64_t ld_pos,
-                             const int32_t* rel_idx, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16,
-                             int B, int S, int heads, int buckets, int naive, void* stream);
-/* K3, experimental variant (csrc/attention_toeplitz.cu; engine uses it only with GLC_ATTN_TOEPLITZ=1): the same op with both relative-position biases added by
- * the tensor core.  It reads the position tables expanded to one row per relative distance:
- * glc_op_expand_pos writes out[rho][0:cols) = pos[idx(2047 - rho)][0:cols) for rho in [0, glc_expanded_pos_rows())
- * (idx = glc_rel_index_table; the last row is zero) and synchronises `stream`.  exp_k / exp_q: fp16
- * [glc_expanded_pos_rows()][ld_exp], head h at columns h*64... */
+/* K3: fused disentangled attention for one layer (replaces the attention sub-graph of the ORT session Run, reference
+ * src/model.c:173-182; arithmetic T:229-345).  qkv fp16 [B*S,3H] (Q|K|V); mask_bits / kv_len from glc_op_mask_prep; ctx
+ * fp16 [B*S,H].  The kernels read the position projections expanded to one row per relative distance:
+ *   glc_op_expand_pos      out[rho][0:cols)   = pos[idx(2047 - rho)][0:cols)    (posK half)
+ *   glc_op_expand_pos_rev  out[sigma][0:cols) = pos[idx(sigma - 2047)][0:cols)  (posQ half)
+ * for rho, sigma in [0, glc_expanded_pos_rows()); idx = glc_rel_index_table, the last row is zero; both synchronise
+ * `stream`.  exp_k / exp_qr: fp16 [glc_expanded_pos_rows()][ld_exp], head h at columns h*64...
+ *   glc_op_attention_rows   production kernel (csrc/attention_rows.cu): register skews of both biases, one softmax
+ *                           thread per query row of a 64-key tile, three warpgroups rotating over the key tiles.
+ *   glc_op_attention_shift  previous production kernel (csrc/attention_shift.cu), kept for A/B runs (GLC_ATTN=shift).
+ *   glc_op_attention_naive  slow CUDA-core restatement on the UNEXPANDED tables (pos_k / pos_q fp16 [2*buckets][ld_pos],
+ *                           rel_idx int32 [2*Spad-1] from glc_rel_index_table(Spad), Spad = S rounded up to 128): the
+ *                           on-GPU debugging oracle of the tests. */
 GLC_API int glc_expanded_pos_rows(void);
 GLC_API int glc_op_expand_pos(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst,
                               int cols, void* stream);
-GLC_API int glc_op_attention_toeplitz(const void* qkv_f16, const void* exp_k_f16, const void* exp_q_f16, int64_t ld_exp,
-                                      const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S,
-                                      int heads, void* stream);
-/* K3, production variant (csrc/attention_shift.cu): the same op with both relative-position biases skewed in registers
- * (barrel shifter on the Q.EK^T accumulator window, lane rotation of the EQr.K^T accumulators).  exp_k as above;
- * exp_qr is the posQ table expanded in the opposite order by glc_op_expand_pos_rev:
- * out[sigma][0:cols) = pos[idx(sigma - 2047)][0:cols).  Replaces the attention sub-graph of the ORT session Run
- * (reference src/model.c:173-182; arithmetic T:229-345). */
 GLC_API int glc_op_expand_pos_rev(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst,
                                   int cols, void* stream);
+GLC_API int glc_op_attention_rows(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
+                                  const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
+                                  void* stream);
 GLC_API int glc_op_attention_shift(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
                                    const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
                                    void* stream);
-/* K3, two-stream variant of the same kernel (csrc/attention_stream.cu): same operands as glc_op_attention_shift; each
- * query row is handled by two independent key-half softmax streams whose outputs accumulate in tensor memory. */
-GLC_API int glc_op_attention_stream(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
-                                    const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
-                                    void* stream);
+GLC_API int glc_op_attention_naive(const void* qkv_f16, const void* pos_k_f16, const void* pos_q_f16, int64_t ld_pos,
+                                   const int32_t* rel_idx, const uint32_t* mask_bits, void* ctx_f16, int B, int S, int heads,
+                                   int buckets, void* stream);
 /* K5a: pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] for the c-th <<LABEL>> token, else 0 */
 GLC_API int glc_op_head_gather(const void* h_f16, const int64_t* ids, int64_t class_token, void* pooled_f16,
                                void* cls_f16, int B, int S, int H, int C, void* stream);

@@ -146,8 +146,10 @@ def forward_restated(w: dict, cfg: ArchConfig, input_ids: torch.Tensor, attentio
         a = _ln(ctx @ w[p + "attention.output.dense.weight"].T + w[p + "attention.output.dense.bias"] + x,
                 w[p + "attention.output.LayerNorm.weight"], w[p + "attention.output.LayerNorm.bias"], eps)
         f = _gelu(a @ w[p + "intermediate.dense.weight"].T + w[p + "intermediate.dense.bias"])
-        x = _ln(f @ w[p + "output.dense.weight"].T + w[p + "output.dense.bias"] + a,
-                w[p + "output.LayerNorm.weight"], w[p + "output.LayerNorm.bias"], eps)
+        pre2 = f @ w[p + "output.dense.weight"].T + w[p + "output.dense.bias"] + a
+        if return_intermediates and l == 0:
+            inter["preln2_0"] = pre2                  # the pre-LayerNorm sum of layer 0's FFN (fp16-range stress tests)
+        x = _ln(pre2, w[p + "output.LayerNorm.weight"], w[p + "output.LayerNorm.bias"], eps)
         inter[f"h{l}"] = x
 
     logits = head_restated(w, cfg, x, input_ids, attention_mask)
@@ -174,6 +176,8 @@ def head_restated(w: dict, cfg: ArchConfig, hseq: torch.Tensor, input_ids: torch
     cls = torch.zeros(B, C, H, dtype=hseq.dtype)
     for b in range(B):
         pos = torch.nonzero(m[b]).flatten()
+        if not cfg.embed_class_token:        # gliclass: class_indices += 1 (the token after <<LABEL>>)
+            pos = pos + 1
         cls[b, : len(pos)] = hseq[b, pos]
     if cfg.pooling_strategy == "first":
         pooled = hseq[:, 0, :]
@@ -189,8 +193,10 @@ def head_restated(w: dict, cfg: ArchConfig, hseq: torch.Tensor, input_ids: torch
     def lin(t, name):
         return t @ w[name + ".weight"].T + w[name + ".bias"]
 
+    act = {"gelu": _gelu, "relu": torch.relu, "tanh": torch.tanh}[cfg.projector_hidden_act]
+
     def proj(t, name):
-        return lin(_gelu(lin(t, f"model.{name}.linear_1")), f"model.{name}.linear_2")
+        return lin(act(lin(t, f"model.{name}.linear_1")), f"model.{name}.linear_2")
 
     t = proj(pooled, "text_projector")          # [B,Hh]
     kcls = proj(cls, "classes_projector")       # [B,C,Hh]   (zero rows still get the biases)

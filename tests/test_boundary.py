@@ -185,3 +185,86 @@ def test_onnx_reader_detects_head_variant(pkg, orc, model_cache, variant):
         assert np.array_equal(f.tensor(role + ".w"), w[name + ".weight"].numpy()), role
         assert np.array_equal(f.tensor(role + ".b"), w[name + ".bias"].numpy()), role
     f.close()
+
+
+def test_onnx_reader_detects_projector_act_and_class_offset(pkg, orc, model_cache):
+    """projector_hidden_act and embed_class_token are config-dependent in the gliclass package; the loader
+    reads them off the graph (Erf vs Relu under /text_projector, Add(+1) on the NonZero-derived class positions)."""
+    f = pkg.OnnxFile(os.path.join(GOLDEN, "model.onnx"))
+    assert f.info["projector_act"] == 1 and f.info["class_pos_offset"] == 0
+    f.close()
+    path = os.path.join(model_cache, "tiny_relu_noembed.onnx")
+    orc.make_model_file("tiny", path, projector_hidden_act="relu", embed_class_token=False)
+    f = pkg.OnnxFile(path)
+    assert f.info["projector_act"] == 2 and f.info["class_pos_offset"] == 1
+    f.close()
+
+
+def test_onnx_reader_refuses_unsupported_variants(pkg, orc, model_cache, tmp_path):
+    """variants the engine does not implement must fail at load, not return wrong logits"""
+    path = os.path.join(model_cache, "tiny_tanh.onnx")
+    orc.make_model_file("tiny", path, projector_hidden_act="tanh")
+    with pytest.raises(pkg.GlcError, match="unsupported projector activation"):
+        pkg.OnnxFile(path)
+    # an LSTM anywhere in the graph (gliclass use_lstm): append a minimal NodeProto{op_type="LSTM"} to the GraphProto
+    raw = open(os.path.join(GOLDEN, "model.onnx"), "rb").read()
+
+    def varint(n):
+        out = b""
+        while True:
+            b7 = n & 0x7f
+            n >>= 7
+            out += bytes([b7 | (0x80 if n else 0)])
+            if not n:
+                return out
+
+    # ModelProto: find the graph field (tag 0x3a) — rebuild the file with one more node appended inside it
+    pos, fields = 0, []
+    while pos < len(raw):
+        tag = raw[pos]
+        assert tag & 0x80 == 0
+        wt, p2 = tag & 7, pos + 1
+        if wt == 0:
+            while raw[p2] & 0x80:
+                p2 += 1
+            p2 += 1
+            fields.append((tag, raw[pos:p2], None))
+        elif wt == 2:
+            n, sh = 0, 0
+            while True:
+                b7 = raw[p2]
+                n |= (b7 & 0x7f) << sh
+                sh += 7
+                p2 += 1
+                if not b7 & 0x80:
+                    break
+            fields.append((tag, None, raw[p2:p2 + n]))
+            p2 += n
+        else:
+            raise AssertionError(wt)
+        pos = p2
+    node = b"\x1a\x05/lstm" + b"\x22\x04LSTM"          # NodeProto{name=3, op_type=4}
+    out = b""
+    for tag, whole, payload in fields:
+        if whole is not None:
+            out += whole
+        else:
+            if tag == 0x3a:
+                payload = payload + b"\x0a" + varint(len(node)) + node
+            out += bytes([tag]) + varint(len(payload)) + payload
+    bad = tmp_path / "lstm.onnx"
+    bad.write_bytes(out)
+    with pytest.raises(pkg.GlcError, match="use_lstm"):
+        pkg.OnnxFile(str(bad))
+
+
+def test_glc_load_validates_options(pkg, golden_onnx, monkeypatch):
+    """a wrong struct_size, a garbage GLC_DEVICES or an out-of-range ordinal fail loudly"""
+    L = pkg.lib()
+    o = pkg.glc_opts()
+    o.struct_size = 12
+    assert not L.glc_load(os.fsencode(golden_onnx), ctypes.byref(o))
+    assert "struct_size" in pkg.last_error()
+    monkeypatch.setenv("GLC_DEVICES", "zero")
+    assert not L.glc_load(os.fsencode(golden_onnx), None)
+    assert "GLC_DEVICES" in pkg.last_error()

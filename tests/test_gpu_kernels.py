@@ -226,7 +226,8 @@ def _attention_ref(qkv, pos_k, pos_q, idx, mask, heads):
     return (p @ v).permute(0, 2, 1, 3).reshape(B, S, H)
 
 
-def _run_attention(pkg, dev, B, S, heads, lens, seed, naive, qk_std=1.8):
+def _run_attention(pkg, dev, B, S, heads, lens, seed, kernel, qk_std=1.8):
+    """kernel: 'naive' (CUDA-core restatement on the unexpanded tables), 'rows' (production) or 'shift'"""
     H = heads * 64
     R = 512
     g = torch.Generator().manual_seed(seed)
@@ -247,33 +248,23 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, naive, qk_std=1.8):
     _sync_check(pkg, L.glc_op_mask_prep(_ptr(mask), _ptr(bits), _ptr(kv), B, S, None), "mask_prep")
     ctx = torch.full((B, S, H), float("nan"), dtype=torch.float16, device=dev)
     pos_q, pos_k = pos[:, :H], pos[:, H:]
-    if naive == "toeplitz":
-        # production kernel: position tables expanded to one row per relative distance, biases added by the tensor core
-        ER = L.glc_expanded_pos_rows()
-        exp = torch.full((ER, 2 * H), float("nan"), dtype=torch.float16, device=dev)
-        _sync_check(pkg, L.glc_op_expand_pos(_ptr(pos), 2 * H, 256, 512, _ptr(exp), 2 * H, 2 * H, None), "expand_pos")
-        full = torch.from_numpy(pkg.rel_index_table(2048, 256, 512)).long().to(dev)    # idx[delta + 2047]
-        assert torch.equal(exp[:ER - 1], pos[full.flip(0)]) and (exp[ER - 1] == 0).all()   # row rho = pos[idx(2047 - rho)]
-        rc = L.glc_op_attention_toeplitz(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv),
-                                         _ptr(ctx), B, S, heads, None)
-        _sync_check(pkg, rc, "glc_op_attention_toeplitz")
-    elif naive in ("shift", "stream"):
-        # register-skew kernel: posK half expanded in rho order, posQ half in the opposite (sigma) order
+    if kernel in ("rows", "shift"):
+        # posK half expanded in rho order, posQ half in the opposite (sigma) order, one row per relative distance
         ER = L.glc_expanded_pos_rows()
         exp = torch.full((ER, 2 * H), float("nan"), dtype=torch.float16, device=dev)
         _sync_check(pkg, L.glc_op_expand_pos_rev(_ptr(pos), 2 * H, 256, 512, _ptr(exp), 2 * H, H, None), "expand_pos_rev")
         _sync_check(pkg, L.glc_op_expand_pos(pos[:, H:].data_ptr(), 2 * H, 256, 512, exp[:, H:].data_ptr(), 2 * H, H, None),
                     "expand_pos")
         full = torch.from_numpy(pkg.rel_index_table(2048, 256, 512)).long().to(dev)    # idx[delta + 2047]
-        assert torch.equal(exp[:ER - 1, H:], pos[full.flip(0)][:, H:]) and (exp[ER - 1] == 0).all()
-        assert torch.equal(exp[:ER - 1, :H], pos[full][:, :H])                         # row sigma = posQ[idx(sigma - 2047)]
-        op = L.glc_op_attention_shift if naive == "shift" else L.glc_op_attention_stream
+        assert torch.equal(exp[:ER - 1, H:], pos[full.flip(0)][:, H:]) and (exp[ER - 1] == 0).all()   # row rho = posK[idx(2047 - rho)]
+        assert torch.equal(exp[:ER - 1, :H], pos[full][:, :H])                                        # row sigma = posQ[idx(sigma - 2047)]
+        op = L.glc_op_attention_rows if kernel == "rows" else L.glc_op_attention_shift
         rc = op(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
-        _sync_check(pkg, rc, "glc_op_attention_" + naive)
+        _sync_check(pkg, rc, "glc_op_attention_" + kernel)
     else:
-        rc = L.glc_op_attention(_ptr(qkv), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, _ptr(rel), _ptr(bits), _ptr(kv),
-                                _ptr(ctx), B, S, heads, 256, int(naive), None)
-        _sync_check(pkg, rc, "glc_op_attention")
+        rc = L.glc_op_attention_naive(_ptr(qkv), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, _ptr(rel), _ptr(bits),
+                                      _ptr(ctx), B, S, heads, 256, None)
+        _sync_check(pkg, rc, "glc_op_attention_naive")
     ii = torch.arange(S, device=dev)
     idx = rel.long()[(ii[:, None] - ii[None, :]) + (Spad - 1)]
     ref = _attention_ref(qkv, pos_k.contiguous(), pos_q.contiguous(), idx, mask, heads)
@@ -284,6 +275,7 @@ ATT_CASES = [
     # B, S, heads, lens
     (1, 64, 1, [64]),              # one key tile, one (partial) query tile
     (1, 128, 2, [128]),            # two key tiles
+    (1, 192, 1, [192]),            # three key tiles: every softmax group of attention_rows gets exactly one
     (2, 256, 2, [256, 256]),       # 2 q tiles x 4 k tiles: off-diagonal slices
     (2, 512, 2, [512, 300]),       # log-bucket region + ragged
     (3, 200, 2, [200, 37, 129]),   # S not a multiple of 64/128
@@ -298,34 +290,16 @@ def test_attention_naive_kernel(pkg, dev, B, S, heads, lens):
     """the slow CUDA-core restatement must agree with torch: it is the on-GPU debugging oracle"""
     if B * S * heads > 2 * 1024 * 4:
         pytest.skip("naive kernel only checked on small cases")
-    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive=True)
+    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, kernel="naive")
     v = mask.bool()
     _report(f"attn-naive B{B} S{S} h{heads}", ctx[v], ref[v], 3e-3, 3e-3)
 
 
+@pytest.mark.parametrize("kernel", ["rows", "shift"])
 @pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1])])
-def test_attention_toeplitz(pkg, dev, B, S, heads, lens):
-    """production attention kernel (csrc/attention_toeplitz.cu) against the fp32 restatement"""
-    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive="toeplitz")
-    v = mask.bool()
-    got, want = ctx[v], ref[v]
-    d = (got.float() - want.float()).abs()
-    if d.max().item() > 1e-2 or torch.isnan(got.float()).any():
-        full = (ctx.float() - ref.float()).abs().nan_to_num(99.0) * mask[..., None].float()
-        for b in range(B):
-            for h in range(heads):
-                row = [f"{full[b, q0:q0 + 128, h * 64:(h + 1) * 64].max().item():.3f}" for q0 in range(0, S, 128)]
-                print(f"   b{b} h{h} per-q-tile max err: {row}")
-        bad = torch.nonzero(full.max(-1).values > 1e-2)
-        print("   first bad (b,row):", bad[:10].tolist())
-    _report(f"attn-toeplitz B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
-
-
-@pytest.mark.parametrize("kernel", ["shift", "stream"])
-@pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1])])
-def test_attention_shift(pkg, dev, B, S, heads, lens, kernel):
-    """register-skew attention kernels (csrc/attention_shift.cu, csrc/attention_stream.cu) against the fp32 restatement"""
-    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive=kernel)
+def test_attention(pkg, dev, B, S, heads, lens, kernel):
+    """attention kernels (csrc/attention_rows.cu = production, csrc/attention_shift.cu) against the fp32 restatement"""
+    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, kernel=kernel)
     v = mask.bool()
     got, want = ctx[v], ref[v]
     d = (got.float() - want.float()).abs()
@@ -340,44 +314,46 @@ def test_attention_shift(pkg, dev, B, S, heads, lens, kernel):
     _report(f"attn-{kernel} B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
 
 
-@pytest.mark.parametrize("kernel", ["shift", "stream"])
-def test_attention_shift_softmax_peaked(pkg, dev, kernel):
-    # large score magnitudes: the row maximum keeps growing across key tiles (exercises the O rescale of the stream kernel)
-    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, naive=kernel, qk_std=3.0)
+@pytest.mark.parametrize("kernel", ["rows", "shift"])
+def test_attention_softmax_peaked(pkg, dev, kernel):
+    # large score magnitudes: the row maximum keeps growing across key tiles (exercises the sticky-maximum chain and the
+    # rescale of the TMEM-resident output accumulator)
+    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, kernel=kernel, qk_std=3.0)
     _report(f"attn-{kernel} peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
 
 
-def test_attention_toeplitz_softmax_peaked(pkg, dev):
-    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, naive="toeplitz", qk_std=3.0)
-    _report("attn-toeplitz peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
-
-
-@pytest.mark.parametrize("B,S,heads,lens", ATT_CASES)
-def test_attention_fused(pkg, dev, B, S, heads, lens):
-    ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, naive=False)
-    v = mask.bool()
-    got, want = ctx[v], ref[v]
-    d = (got.float() - want.float()).abs()
-    if d.max().item() > 1e-2 or torch.isnan(got.float()).any():
-        # localise: per (batch, head, 128-row query tile) error map
-        H = heads * 64
-        full = (ctx.float() - ref.float()).abs().nan_to_num(99.0) * mask[..., None].float()
-        for b in range(B):
-            for h in range(heads):
-                row = []
-                for q0 in range(0, S, 128):
-                    row.append(f"{full[b, q0:q0 + 128, h * 64:(h + 1) * 64].max().item():.3f}")
-                print(f"   b{b} h{h} per-q-tile max err: {row}")
-        # first bad row: show which columns
-        bad = torch.nonzero(full.max(-1).values > 1e-2)
-        print("   first bad (b,row):", bad[:10].tolist())
-    _report(f"attn-fused B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
-
-
-def test_attention_fused_softmax_peaked(pkg, dev):
-    # large score magnitudes: exercises the online-softmax rescale path across key tiles
-    ctx, ref, mask = _run_attention(pkg, dev, 1, 512, 2, [512], seed=99, naive=False, qk_std=3.0)
-    _report("attn-fused peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
+def test_attention_rows_growing_maximum(pkg, dev):
+    """keys sorted so that every tile raises the row maximum by far more than 2^8: every group of attention_rows rescales
+    O in turn and the partial row sums of the other groups must follow the chained maximum"""
+    B, S, heads = 1, 512, 1
+    H = 64
+    L = pkg.lib()
+    g = torch.Generator().manual_seed(4)
+    q = torch.randn(S, H, generator=g)
+    kdir = torch.randn(H, generator=g)
+    kdir = kdir / kdir.norm()
+    # K_j = a_j * dir with a_j growing along the sequence; Q rows have a positive component along dir
+    q = q * 0.3 + 2.0 * kdir
+    k = torch.linspace(0.0, 60.0, S)[:, None] * kdir[None, :] + 0.1 * torch.randn(S, H, generator=g)
+    v = torch.randn(S, H, generator=g)
+    qkv = torch.cat([q, k, v], -1)[None].to(torch.float16).to(dev)
+    pos = (torch.randn(512, 2 * H, generator=g) * 0.5).to(torch.float16).to(dev)
+    mask = torch.ones(B, S, dtype=torch.long, device=dev)
+    bits = torch.zeros(B, S // 32, dtype=torch.int32, device=dev)
+    kv = torch.zeros(B, dtype=torch.int32, device=dev)
+    _sync_check(pkg, L.glc_op_mask_prep(_ptr(mask), _ptr(bits), _ptr(kv), B, S, None), "mask_prep")
+    ER = L.glc_expanded_pos_rows()
+    exp = torch.zeros(ER, 2 * H, dtype=torch.float16, device=dev)
+    _sync_check(pkg, L.glc_op_expand_pos_rev(_ptr(pos), 2 * H, 256, 512, _ptr(exp), 2 * H, H, None), "expand_pos_rev")
+    _sync_check(pkg, L.glc_op_expand_pos(pos[:, H:].data_ptr(), 2 * H, 256, 512, exp[:, H:].data_ptr(), 2 * H, H, None), "expand_pos")
+    ctx = torch.full((B, S, H), float("nan"), dtype=torch.float16, device=dev)
+    rc = L.glc_op_attention_rows(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
+    _sync_check(pkg, rc, "glc_op_attention_rows")
+    rel = torch.from_numpy(pkg.rel_index_table(S, 256, 512)).to(dev)
+    ii = torch.arange(S, device=dev)
+    idx = rel.long()[(ii[:, None] - ii[None, :]) + (S - 1)]
+    ref = _attention_ref(qkv, pos[:, H:].contiguous(), pos[:, :H].contiguous(), idx, mask, heads)
+    _report("attn-rows growing maximum", ctx[0], ref[0], 2e-2, 2e-2)
 
 
 # ---------------------------------------------------------------------------------------------

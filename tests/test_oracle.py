@@ -51,6 +51,19 @@ def test_golden_fixture_reproducible(orc, golden):
     assert (allv > 0).any() and (allv < 0).any() and allv.std() > 0.3
 
 
+@pytest.mark.parametrize("arch,S,labels,rows", [("base", 512, 10, 2), ("large", 1024, 50, 1)])
+def test_deep_arch_fixtures_are_discriminating(orc, arch, S, labels, rows):
+    """VERDICT r1 / SURVEY H2: the 12- and 24-layer random-init fixtures must not collapse — each row's logits spread over
+    its labels (std > 0.3, range >= 1) and straddle the threshold, so that decision parity on the GPU means something."""
+    cfg = orc.make_config(arch)
+    w = orc.init_weights(cfg, 0)
+    ids, mask = orc.synth_inputs(cfg, rows, S, labels, seed=1236, ragged=True, min_frac=0.6)
+    lg = orc.forward_restated(w, cfg, ids, mask).numpy()
+    for r in range(rows):
+        assert lg[r].std() > 0.3 and np.ptp(lg[r]) >= 1.0, (arch, r, lg[r].std(), np.ptp(lg[r]))
+    assert (lg > 0).any() and (lg < 0).any()
+
+
 def test_config_json_schema():
     # same keys as reference ONNX_CONVERTING/convert_to_onnx.py:19-28
     cfg = json.load(open(os.path.join(GOLDEN, "config.json")))

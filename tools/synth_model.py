@@ -40,12 +40,15 @@ class ArchConfig:
     scorer_type: str = "simple"            # simple (dot) | weighted-dot | mlp
     normalize_features: bool = False       # L2-normalise text / class features, logits *= logit_scale
     mlp_hidden_size: int = 256             # MLPScorer: cat[t,l] -> 256 -> 128 -> 1
+    embed_class_token: bool = True         # False: class rows are read one position AFTER each <<LABEL>> token
+    projector_hidden_act: str = "gelu"     # gelu (erf) | relu
 
     def __post_init__(self):
         if self.head_hidden_size == 0:
             self.head_hidden_size = self.hidden_size
         assert self.pooling_strategy in ("first", "last", "avg", "max"), self.pooling_strategy
         assert self.scorer_type in ("simple", "weighted-dot", "mlp"), self.scorer_type
+        assert self.projector_hidden_act in ("gelu", "relu", "tanh"), self.projector_hidden_act
 
     @property
     def head_dim(self) -> int:
@@ -145,7 +148,63 @@ def init_weights(cfg: ArchConfig, seed: int = 0) -> dict[str, torch.Tensor]:
         w["model.scorer.out_mlp.0.bias"] = n(4 * Hh, std=0.05)
         w["model.scorer.out_mlp.3.weight"] = n(1, 4 * Hh, std=2.0 / math.sqrt(4 * Hh))
         w["model.scorer.out_mlp.3.bias"] = n(1, std=0.05)
+    if cfg.num_layers >= DEEP_INIT_MIN_LAYERS:
+        _trained_like_structure(w, cfg)
     return w
+
+
+# Deep random post-LN stacks collapse: every layer adds a token-independent component (the mean of
+# GELU through W2, near-uniform attention averages), so after 12-24 layers all positions hold almost
+# the same vector, the <<LABEL>> rows (one token id!) become identical and a row's logits span 1e-2
+# on one side of the threshold — decision parity is then vacuous and a label-position bug passes
+# (SURVEY.md H2).  A trained GLiClass tells its labels apart because attention at a
+# <<LABEL>> position reads the label-name tokens that follow it.  The three deterministic edits below
+# give a random net that property without leaving the well-conditioned regime (no gain above 1.4):
+#   1. residual branches at half gain (out-proj and FFN2 weights x 0.5): a layer perturbs a token, it
+#      does not replace it, so token identity survives the depth;
+#   2. FFN2 rows centred (zero sum over the intermediate units): the mean of GELU no longer adds the
+#      same vector to every position;
+#   3. "local" attention: rows delta = -1, -2, -3 of rel_embeddings get a common direction v and every
+#      head's query bias gets the matching direction, so Q_i . posK[idx(i - j)] carries a constant
+#      +LOCAL_LOGIT softmax logit for the three tokens after position i (c2p term, T:313-324) — peaked,
+#      position-specific attention, which is also what makes a rel-pos indexing bug visible.
+# Applied to the >= 6-layer architectures (small / base / large); tiny / mini keep the plain init their
+# committed fixtures were generated with.
+DEEP_INIT_MIN_LAYERS = 6
+LOCAL_LOGIT = 8.0
+LOCAL_OFFSETS = (-1, -2, -3)
+BRANCH_GAIN = 0.5
+
+
+def _trained_like_structure(w: dict, cfg: ArchConfig) -> None:
+    g = torch.Generator().manual_seed(977)
+    H, d, span = cfg.hidden_size, cfg.head_dim, cfg.position_buckets
+    v = torch.randn(H, generator=g)
+    v = v - v.mean()
+    v = v / v.norm()
+    rel = w[ENC + "encoder.rel_embeddings.weight"]
+    rows = [o + span for o in LOCAL_OFFSETS]
+    amp = rel[0].norm()
+    for r in rows:
+        rel[r] += amp * v
+    gam, bet = w[ENC + "encoder.LayerNorm.weight"], w[ENC + "encoder.LayerNorm.bias"]
+    mu = rel.mean(-1, keepdim=True)
+    var = ((rel - mu) ** 2).mean(-1, keepdim=True)
+    relln = (rel - mu) / torch.sqrt(var + cfg.layer_norm_eps) * gam + bet
+    scale = math.sqrt(3 * d)
+    for l in range(cfg.num_layers):
+        p = f"{ENC}encoder.layer.{l}."
+        w[p + "attention.output.dense.weight"] *= BRANCH_GAIN
+        w2 = w[p + "output.dense.weight"]
+        w2 -= w2.mean(dim=1, keepdim=True)
+        w2 *= BRANCH_GAIN
+        Wk, bk = w[p + "attention.self.key_proj.weight"], w[p + "attention.self.key_proj.bias"]
+        bq = w[p + "attention.self.query_proj.bias"]
+        posk = relln[: 2 * span] @ Wk.T + bk
+        for hh in range(cfg.num_heads):
+            sl = slice(hh * d, (hh + 1) * d)
+            u = posk[rows][:, sl].mean(0) - posk[:, sl].mean(0)
+            bq[sl] += u / (u.norm() ** 2) * LOCAL_LOGIT * scale
 
 
 # --------------------------------------------------------------------------------------------
@@ -217,7 +276,8 @@ def build_hf_module(cfg: ArchConfig, w: dict):
             self.linear_2 = nn.Linear(cfg.head_hidden_size, cfg.head_hidden_size)
 
         def forward(self, t):
-            return self.linear_2(F.gelu(self.linear_1(t)))
+            act = {"gelu": F.gelu, "relu": F.relu, "tanh": torch.tanh}[cfg.projector_hidden_act]
+            return self.linear_2(act(self.linear_1(t)))
 
     Hh = cfg.head_hidden_size
 
@@ -280,6 +340,8 @@ def build_hf_module(cfg: ArchConfig, w: dict):
             ar = torch.arange(max_c, dtype=attention_mask.dtype).unsqueeze(0).expand(B, -1)
             batch_idx, target_idx = torch.where(ar < num_class_tokens)
             bi_cls, pos_cls = torch.where(class_token_mask)
+            if not cfg.embed_class_token:
+                pos_cls = pos_cls + 1
             cls = torch.zeros(B, max_c, D, dtype=hs.dtype)
             cls[batch_idx, target_idx] = hs[bi_cls, pos_cls]
             pooled = self.text_projector(self.pooler(hs, attention_mask))
