@@ -1,6 +1,6 @@
 // Helpers around the K3 attention kernels:
 //   * the position tables expanded to one row per relative distance (load time, input independent),
-//   * a slow CUDA-core restatement of the attention op (tests only: the on-GPU debugging oracle that localises a
+//   * a slow CUDA-core restatement of the attention op (tests only: the on-GPU reference that localises a
 //     bug to a (batch, head, row) without a host round trip).
 // Arithmetic: transformers DisentangledSelfAttention, T:229-345; idx(delta) = clamp(bucket(delta) + span, 0, 2 span - 1)
 // (SURVEY.md App. A.6).
