@@ -93,6 +93,8 @@ def forward_restated(w: dict, cfg: ArchConfig, input_ids: torch.Tensor, attentio
     Follows T:520-564 (embeddings), T:597-628 (rel-emb LN, mask, rel-pos), T:229-345 (attention),
     T:42-53 / T:384-446 (out/FFN/LN) and SURVEY.md App. B (head).
     """
+    if cfg.backbone == "qwen2":
+        return forward_restated_qwen2(w, cfg, input_ids, attention_mask, return_intermediates)
     B, S = input_ids.shape
     H, h, d = cfg.hidden_size, cfg.num_heads, cfg.head_dim
     eps = cfg.layer_norm_eps
@@ -153,6 +155,68 @@ def forward_restated(w: dict, cfg: ArchConfig, input_ids: torch.Tensor, attentio
         inter[f"h{l}"] = x
 
     logits = head_restated(w, cfg, x, input_ids, attention_mask)
+    if return_intermediates:
+        return logits, inter
+    return logits
+
+
+# --------------------------------------------------------------------------------------------
+# decoder backbone: Qwen2 with bidirectional attention
+# (Q: = transformers/models/qwen2/modeling_qwen2.py, 5.5.0: MLP Q:46-48, rotary Q:102-114, rotate_half /
+#  apply_rotary_pos_emb Q:117-147, eager attention Q:160-185, attention Q:206-246, RMSNorm Q:258-264, decoder layer
+#  Q:280-310, model Q:353-410.  The causal mask of Q:378-393 is replaced by a key-padding mask: GLiClass's decoder
+#  backbones are used as bidirectional encoders, `M:` SURVEY.md §8 f4.)
+# --------------------------------------------------------------------------------------------
+
+
+def _rms(x, g, eps):
+    return x * torch.rsqrt((x * x).mean(-1, keepdim=True) + eps) * g
+
+
+@torch.no_grad()
+def forward_restated_qwen2(w: dict, cfg: ArchConfig, input_ids: torch.Tensor, attention_mask: torch.Tensor,
+                           return_intermediates: bool = False):
+    B, S = input_ids.shape
+    d, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
+    eps = cfg.rms_norm_eps
+    inter = {}
+    h = w[ENC + "embed_tokens.weight"][input_ids]                                     # [B,S,H]
+    inter["emb"] = h
+    inv_freq = 1.0 / (cfg.rope_theta ** (torch.arange(0, d, 2, dtype=torch.int64).float() / d))
+    freqs = torch.arange(S).float()[:, None] * inv_freq[None, :]                      # [S,d/2]
+    emb = torch.cat([freqs, freqs], -1)
+    cos, sin = emb.cos()[None, None], emb.sin()[None, None]                           # [1,1,S,d]
+
+    def rot(x):
+        x1, x2 = x[..., : d // 2], x[..., d // 2:]
+        return torch.cat([-x2, x1], -1)
+
+    fmin = torch.finfo(torch.float32).min
+    add = (1.0 - attention_mask.float())[:, None, None, :] * fmin                     # key padding only (bidirectional)
+    for l in range(cfg.num_layers):
+        p = f"{ENC}layers.{l}."
+        x = _rms(h, w[p + "input_layernorm.weight"], eps)
+        q = (x @ w[p + "self_attn.q_proj.weight"].T + w[p + "self_attn.q_proj.bias"]).view(B, S, nh, d).transpose(1, 2)
+        k = (x @ w[p + "self_attn.k_proj.weight"].T + w[p + "self_attn.k_proj.bias"]).view(B, S, nkv, d).transpose(1, 2)
+        v = (x @ w[p + "self_attn.v_proj.weight"].T + w[p + "self_attn.v_proj.bias"]).view(B, S, nkv, d).transpose(1, 2)
+        q = q * cos + rot(q) * sin
+        k = k * cos + rot(k) * sin
+        rep = nh // nkv
+        kk = k[:, :, None].expand(B, nkv, rep, S, d).reshape(B, nh, S, d)
+        vv = v[:, :, None].expand(B, nkv, rep, S, d).reshape(B, nh, S, d)
+        a = torch.softmax(q @ kk.transpose(-1, -2) * (d ** -0.5) + add, dim=-1)
+        ctx = (a @ vv).transpose(1, 2).reshape(B, S, nh * d)
+        if return_intermediates and l == 0:
+            inter["ctx0"] = ctx
+        h = h + ctx @ w[p + "self_attn.o_proj.weight"].T
+        x = _rms(h, w[p + "post_attention_layernorm.weight"], eps)
+        g = x @ w[p + "mlp.gate_proj.weight"].T
+        u = x @ w[p + "mlp.up_proj.weight"].T
+        h = h + (F.silu(g) * u) @ w[p + "mlp.down_proj.weight"].T
+        inter[f"h{l}"] = h
+    hs = _rms(h, w[ENC + "norm.weight"], eps)
+    inter["final"] = hs
+    logits = head_restated(w, cfg, hs, input_ids, attention_mask)
     if return_intermediates:
         return logits, inter
     return logits

@@ -42,6 +42,12 @@ class ArchConfig:
     mlp_hidden_size: int = 256             # MLPScorer: cat[t,l] -> 256 -> 128 -> 1
     embed_class_token: bool = True         # False: class rows are read one position AFTER each <<LABEL>> token
     projector_hidden_act: str = "gelu"     # gelu (erf) | relu
+    # decoder backbones (reference Readme.md:91-94: gliclass-qwen-1.5B / gliclass-llama-1.3B; BASELINE.json configs[4])
+    backbone: str = "deberta"              # deberta | qwen2
+    num_kv_heads: int = 0                  # qwen2: grouped-query attention (0 -> num_heads)
+    kv_head_dim: int = 0                   # qwen2: head dim when it is not hidden_size / num_heads
+    rope_theta: float = 1.0e6
+    rms_norm_eps: float = 1.0e-6
 
     def __post_init__(self):
         if self.head_hidden_size == 0:
@@ -49,10 +55,13 @@ class ArchConfig:
         assert self.pooling_strategy in ("first", "last", "avg", "max"), self.pooling_strategy
         assert self.scorer_type in ("simple", "weighted-dot", "mlp"), self.scorer_type
         assert self.projector_hidden_act in ("gelu", "relu", "tanh"), self.projector_hidden_act
+        assert self.backbone in ("deberta", "qwen2"), self.backbone
+        if self.num_kv_heads == 0:
+            self.num_kv_heads = self.num_heads
 
     @property
     def head_dim(self) -> int:
-        return self.hidden_size // self.num_heads
+        return self.kv_head_dim or self.hidden_size // self.num_heads
 
 
 ARCHS = {
@@ -64,6 +73,11 @@ ARCHS = {
     "small": dict(vocab_size=128003, hidden_size=768, num_layers=6, num_heads=12, intermediate_size=3072),
     "base": dict(vocab_size=128003, hidden_size=768, num_layers=12, num_heads=12, intermediate_size=3072),
     "large": dict(vocab_size=128003, hidden_size=1024, num_layers=24, num_heads=16, intermediate_size=4096),
+    # decoder backbones: Qwen2 (RMSNorm, RoPE theta 1e6, GQA, SwiGLU, QKV bias), bidirectional attention (LLM2Vec style)
+    "qwen-mini": dict(backbone="qwen2", vocab_size=2051, hidden_size=512, num_layers=3, num_heads=4, num_kv_heads=2,
+                      kv_head_dim=128, intermediate_size=1536, class_token_index=2049, sep_token_index=2050),
+    "qwen1.5b": dict(backbone="qwen2", vocab_size=151938, hidden_size=1536, num_layers=28, num_heads=12, num_kv_heads=2,
+                     kv_head_dim=128, intermediate_size=8960, class_token_index=151936, sep_token_index=151937),
 }
 
 
@@ -92,6 +106,8 @@ def init_weights(cfg: ArchConfig, seed: int = 0) -> dict[str, torch.Tensor]:
     WEIGHTS to 16 bits moves logits by several 1e-2 (scripts/emulate_precision.py, DESIGN.md
     "Numerics"); that says nothing about a kernel, so the fixtures stay out of it.
     """
+    if cfg.backbone == "qwen2":
+        return init_weights_qwen2(cfg, seed)
     g = torch.Generator().manual_seed(seed)
     H, I, Hh = cfg.hidden_size, cfg.intermediate_size, cfg.head_hidden_size
 
@@ -207,6 +223,65 @@ def _trained_like_structure(w: dict, cfg: ArchConfig) -> None:
             bq[sl] += u / (u.norm() ** 2) * LOCAL_LOGIT * scale
 
 
+def _init_head(w: dict, cfg: ArchConfig, n) -> None:
+    """the GLiClass head tensors (same draws as in init_weights, shared with the decoder backbones)"""
+    H, Hh = cfg.hidden_size, cfg.head_hidden_size
+    s2 = 1.2 / math.sqrt(Hh) / (Hh ** 0.25)
+    for pj in ("text_projector", "classes_projector"):
+        w[f"model.{pj}.linear_1.weight"] = n(Hh, H, std=1.4 / math.sqrt(H))
+        w[f"model.{pj}.linear_1.bias"] = n(Hh, std=0.02)
+        w[f"model.{pj}.linear_2.weight"] = n(Hh, Hh, std=s2)
+        w[f"model.{pj}.linear_2.bias"] = n(Hh, std=0.02)
+    if cfg.normalize_features:
+        w["model.logit_scale"] = torch.tensor(2.6592) + n(1, std=0.05)[0]
+    assert cfg.scorer_type == "simple", "decoder-backbone fixtures use the dot scorer"
+
+
+QWEN_LOCAL_PAIRS = 16      # rotary pairs (the highest frequencies) that carry the local-attention bias
+QWEN_LOCAL_LOGIT = 8.0
+
+
+def init_weights_qwen2(cfg: ArchConfig, seed: int = 0) -> dict[str, torch.Tensor]:
+    """Random-init Qwen2 backbone (HF Qwen2Model parameter names under model.encoder_model.) + GLiClass head.
+
+    Pre-norm residual stream: the branch outputs (o_proj, down_proj) are scaled by 1/sqrt(2L) so the stream stays O(1)
+    over the depth.  As for the DeBERTa fixtures, a random decoder averages over all keys and cannot tell two <<LABEL>>
+    tokens apart; here the q / k biases of every head get a common component on the QWEN_LOCAL_PAIRS highest-frequency
+    rotary pairs, so that (R_i b_q).(R_j b_k) = beta^2 sum_p cos((i - j) theta_p) peaks at |i - j| <= 3 with a softmax
+    logit of QWEN_LOCAL_LOGIT: position-specific, peaked attention through the RoPE path itself."""
+    g = torch.Generator().manual_seed(seed)
+    H, I, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_layers
+    d, nh, nkv = cfg.head_dim, cfg.num_heads, cfg.num_kv_heads
+
+    def n(*shape, std=0.05, mean=0.0):
+        return (torch.randn(*shape, generator=g) * std + mean).float()
+
+    w: dict[str, torch.Tensor] = {}
+    w[ENC + "embed_tokens.weight"] = n(cfg.vocab_size, H, std=1.0)
+    branch = 1.0 / math.sqrt(2.0 * L)
+    beta = math.sqrt(QWEN_LOCAL_LOGIT * math.sqrt(d) / QWEN_LOCAL_PAIRS)
+    for l in range(L):
+        p = f"{ENC}layers.{l}."
+        w[p + "input_layernorm.weight"] = n(H, std=0.1, mean=1.0)
+        w[p + "post_attention_layernorm.weight"] = n(H, std=0.1, mean=1.0)
+        w[p + "self_attn.q_proj.weight"] = n(nh * d, H, std=1.2 / math.sqrt(H))
+        w[p + "self_attn.k_proj.weight"] = n(nkv * d, H, std=1.2 / math.sqrt(H))
+        w[p + "self_attn.v_proj.weight"] = n(nkv * d, H, std=1.0 / math.sqrt(H))
+        bq, bk = n(nh * d, std=0.02), n(nkv * d, std=0.02)
+        bq.view(nh, d)[:, :QWEN_LOCAL_PAIRS] += beta
+        bk.view(nkv, d)[:, :QWEN_LOCAL_PAIRS] += beta
+        w[p + "self_attn.q_proj.bias"] = bq
+        w[p + "self_attn.k_proj.bias"] = bk
+        w[p + "self_attn.v_proj.bias"] = n(nkv * d, std=0.02)
+        w[p + "self_attn.o_proj.weight"] = n(H, nh * d, std=branch * 2.0 / math.sqrt(nh * d))
+        w[p + "mlp.gate_proj.weight"] = n(I, H, std=1.0 / math.sqrt(H))
+        w[p + "mlp.up_proj.weight"] = n(I, H, std=1.0 / math.sqrt(H))
+        w[p + "mlp.down_proj.weight"] = n(H, I, std=branch * 2.0 / math.sqrt(I))
+    w[ENC + "norm.weight"] = n(H, std=0.1, mean=1.0)
+    _init_head(w, cfg, n)
+    return w
+
+
 # --------------------------------------------------------------------------------------------
 # synthetic inputs (SURVEY.md §8d; layout of reference src/preprocessor.c:96-108 with
 # prompt_first=false and src/tokenizer.c:44-84 pad-to-longest, pad id 0 / mask 0)
@@ -257,8 +332,11 @@ def build_hf_module(cfg: ArchConfig, w: dict):
     Attribute names mirror the gliclass package (model.encoder_model / text_projector /
     classes_projector) so exported node / initializer names carry the same scopes.
     """
-    from transformers import DebertaV2Config, DebertaV2Model
     import torch.nn as nn
+
+    if cfg.backbone == "qwen2":
+        return _build_hf_module_qwen2(cfg, w)
+    from transformers import DebertaV2Config, DebertaV2Model
 
     hf_cfg = DebertaV2Config(
         vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_layers,
@@ -370,6 +448,92 @@ def build_hf_module(cfg: ArchConfig, w: dict):
     return m
 
 
+def _build_hf_module_qwen2(cfg: ArchConfig, w: dict):
+    """GLiClassModel-shaped module around transformers.Qwen2Model with BIDIRECTIONAL attention (the causal mask is replaced
+    by a key-padding mask, as LLM2Vec-style encoders built on decoder checkpoints do; `M:` for the gliclass package)."""
+    from transformers import Qwen2Config, Qwen2Model
+    import torch.nn as nn
+
+    hf_cfg = Qwen2Config(
+        vocab_size=cfg.vocab_size, hidden_size=cfg.hidden_size, num_hidden_layers=cfg.num_layers,
+        num_attention_heads=cfg.num_heads, num_key_value_heads=cfg.num_kv_heads, head_dim=cfg.head_dim,
+        intermediate_size=cfg.intermediate_size, hidden_act="silu", rms_norm_eps=cfg.rms_norm_eps,
+        rope_parameters={"rope_type": "default", "rope_theta": cfg.rope_theta}, max_position_embeddings=4096,
+        attention_dropout=0.0, use_sliding_window=False, tie_word_embeddings=False, pad_token_id=0)
+    hf_cfg._attn_implementation = "eager"
+    Hh = cfg.head_hidden_size
+
+    class FeaturesProjector(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.linear_1 = nn.Linear(cfg.hidden_size, Hh)
+            self.linear_2 = nn.Linear(Hh, Hh)
+
+        def forward(self, t):
+            act = {"gelu": F.gelu, "relu": F.relu, "tanh": torch.tanh}[cfg.projector_hidden_act]
+            return self.linear_2(act(self.linear_1(t)))
+
+    class UniEncoder(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.encoder_model = Qwen2Model(hf_cfg)
+            self.text_projector = FeaturesProjector()
+            self.classes_projector = FeaturesProjector()
+            if cfg.normalize_features:
+                self.logit_scale = nn.Parameter(torch.tensor(2.6592))
+
+        def forward(self, input_ids, attention_mask):
+            B, S = input_ids.shape
+            # bidirectional: additive [B,1,S,S] mask, 0 where the KEY is valid, finfo.min where it is padding
+            neg = torch.finfo(torch.float32).min
+            add = (1.0 - attention_mask.to(torch.float32))[:, None, None, :] * neg
+            add = add.expand(B, 1, S, S)
+            hs = self.encoder_model(input_ids, attention_mask={"full_attention": add})[0]
+            D = hs.shape[-1]
+            class_token_mask = input_ids == cfg.class_token_index
+            num_class_tokens = torch.sum(class_token_mask, dim=-1, keepdim=True)
+            max_c = num_class_tokens.max()
+            ar = torch.arange(max_c, dtype=attention_mask.dtype).unsqueeze(0).expand(B, -1)
+            batch_idx, target_idx = torch.where(ar < num_class_tokens)
+            bi_cls, pos_cls = torch.where(class_token_mask)
+            if not cfg.embed_class_token:
+                pos_cls = pos_cls + 1
+            cls = torch.zeros(B, max_c, D, dtype=hs.dtype)
+            cls[batch_idx, target_idx] = hs[bi_cls, pos_cls]
+            if cfg.pooling_strategy == "first":
+                pooled = hs[:, 0, :]
+            elif cfg.pooling_strategy == "last":
+                pooled = hs[:, -1, :]
+            else:
+                m = attention_mask.unsqueeze(-1).to(hs.dtype)
+                pooled = (hs * m).sum(dim=1) / m.sum(dim=1) if cfg.pooling_strategy == "avg" else \
+                    hs.masked_fill(m == 0, torch.finfo(hs.dtype).min).max(dim=1)[0]
+            pooled = self.text_projector(pooled)
+            cls = self.classes_projector(cls)
+            if cfg.normalize_features:
+                pooled = pooled / (pooled.norm(p=2, dim=-1, keepdim=True) + 1e-8)
+                cls = cls / (cls.norm(p=2, dim=-1, keepdim=True) + 1e-8)
+            logits = torch.einsum("BD,BCD->BC", pooled, cls)
+            if cfg.normalize_features:
+                logits = logits * self.logit_scale
+            return logits
+
+    class GLiClassModel(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.model = UniEncoder()
+
+        def forward(self, input_ids, attention_mask):
+            return self.model(input_ids, attention_mask)
+
+    m = GLiClassModel().eval()
+    sd = m.state_dict()
+    missing = [k for k in sd if k not in w and "inv_freq" not in k]
+    assert not missing, missing
+    m.load_state_dict({k: v for k, v in w.items()}, strict=False)
+    return m
+
+
 def export_onnx(module, cfg: ArchConfig, path: str, S: int = 24, n_labels: int = 3) -> None:
     """The reference's export call (convert_to_onnx.py:62-79), opset 14, legacy TorchScript path.
 
@@ -407,8 +571,14 @@ def make_model_file(arch: str, path: str, seed: int = 0, **over):
 
 def flops_per_text(cfg: ArchConfig, S: int, C: int) -> float:
     """Algorithmic FLOPs per text: pos projections hoisted and excluded."""
-    L, H, R = cfg.num_layers, cfg.hidden_size, 2 * cfg.position_buckets
     Hh = cfg.head_hidden_size
+    if cfg.backbone == "qwen2":
+        # SURVEY.md §8d: L (2 S H (2 H + 2 H_kv) + 6 S H I + 4 S^2 H) with H = heads * head_dim for the attention terms
+        L, H, I = cfg.num_layers, cfg.hidden_size, cfg.intermediate_size
+        Hq, Hkv = cfg.num_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim
+        return (L * (2.0 * S * H * (2 * Hq + 2 * Hkv) + 6.0 * S * H * I + 4.0 * S * S * Hq) +
+                (1 + C) * (2.0 * H * Hh + 2.0 * Hh * Hh) + 2.0 * C * Hh)
+    L, H, R = cfg.num_layers, cfg.hidden_size, 2 * cfg.position_buckets
     return L * (24.0 * S * H * H + 4.0 * S * S * H + 4.0 * S * R * H) + (1 + C) * (2.0 * H * Hh + 2.0 * Hh * Hh) + 2.0 * C * Hh
 
 
