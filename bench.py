@@ -442,7 +442,7 @@ def main():
                      "peak_source": peak_src, "launches_timed": int(gemm_n),
                      "share_of_step": gemm_ms / ms_prof if ms_prof else None,
                      "timed_over": f"{args.steps} steps re-run with CUDA events around every launch ({ms_prof / args.steps:.3f} ms/step)"},
-        "roofline_attention": {"bound": "tensor", "kernel": "attention_rows_kernel (QK^T, c2p, p2c, PV: 4 S^2 H + 4 S R H per text per layer)",
+        "roofline_attention": {"bound": "tensor", "kernel": "attention_persist_kernel (QK^T, c2p, p2c, PV: 4 S^2 H + 4 S R H per text per layer)",
                                "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf if peak_tf else None,
                                "us_per_launch": 1e3 * att_ms / att_n if att_n else None, "launches_timed": int(att_n),
                                "traffic": tr.get("attention"), "share_of_step": att_ms / ms_prof if ms_prof else None},

@@ -484,6 +484,11 @@ int glc_op_attention_rows(const void* qkv, const void* exp_k, const void* exp_qr
   GLC_TRY("glc_op_attention_rows",
           glc::attention_rows(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
 }
+int glc_op_attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
+                             const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
+  GLC_TRY("glc_op_attention_persist", glc::attention_persist(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads,
+                                                             num_sms_current(), (cudaStream_t)stream));
+}
 int glc_expanded_pos_rows(void) { return glc::expanded_pos_rows(); }
 int glc_op_head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S, int H,
                        int C, void* stream) {

@@ -116,15 +116,16 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
   graphs_on_ = getenv("GLC_NO_GRAPHS") == nullptr;
-  // production attention = attention_rows.cu (row-owner warpgroups rotating over key tiles); GLC_ATTN=shift selects the
-  // previous production kernel (attention_shift.cu) for A/B comparisons.  The three earlier generations live under
-  // experiments/attention_generations/ and are not part of this library.
-  attn_mode_ = 0;
+  // production attention = attention_persist.cu (persistent CTAs, row-owner warpgroups rotating over key tiles, position
+  // tables resident in shared memory for S <= 512); GLC_ATTN=rows | shift select the two previous production kernels for
+  // A/B comparisons.  The three earlier generations live under experiments/attention_generations/.
+  attn_mode_ = 2;
   if (const char* am = getenv("GLC_ATTN")) {
     const std::string m(am);
     if (m == "rows") attn_mode_ = 0;
     else if (m == "shift") attn_mode_ = 1;
-    else throw std::runtime_error("GLC_ATTN must be rows or shift (got '" + m + "')");
+    else if (m == "persist") attn_mode_ = 2;
+    else throw std::runtime_error("GLC_ATTN must be persist, rows or shift (got '" + m + "')");
   }
   {
     const char* fr = getenv("GLC_FUSE_RESID");
@@ -483,7 +484,9 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st));
     if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
     const __half* pe = (const __half*)d.pos_exp;
-    if (attn_mode_ == 0) {
+    if (attn_mode_ == 2) {
+      GLC_LAUNCH(KC_ATTN, attention_persist(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, num_sms_, st));
+    } else if (attn_mode_ == 0) {
       GLC_LAUNCH(KC_ATTN, attention_rows(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
     } else {
       GLC_LAUNCH(KC_ATTN, attention_shift(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));

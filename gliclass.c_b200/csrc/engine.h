@@ -127,7 +127,7 @@ class DeviceModel {
   int h_in_next_ = 0;
   std::vector<PinnedBlock> out_pool_;
   PinnedBlock take_out_block(size_t bytes);
-  int attn_mode_ = 0;          // 0 attention_rows.cu (production), 1 attention_shift.cu (env GLC_ATTN=rows|shift)
+  int attn_mode_ = 2;          // 2 attention_persist.cu (production), 0 attention_rows.cu, 1 attention_shift.cu (env GLC_ATTN=persist|rows|shift)
   std::atomic<uint64_t> launches_{0};
 
   // weights

@@ -51,6 +51,12 @@ cudaError_t expand_pos_table(const void* pos_f16, int64_t ld_src, const int32_t*
 cudaError_t attention_rows(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
                            const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                            cudaStream_t stream);
+// persistent form of attention_rows (attention_persist.cu): one CTA per SM for the whole launch, work items dealt out in
+// contiguous chunks ordered (head, query tile, batch row); for S <= 512 the expanded table windows of the CTA's
+// (head, query tile) stay resident in shared memory, so a tile costs 16 KB of L2 traffic instead of 48 KB.
+cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                              const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
+                              int num_sms, cudaStream_t stream);
 // previous production kernel (attention_shift.cu): both biases skewed in registers (barrel shifter for c2p, lane rotation for
 // p2c); the two warps that share a query row split the 64 keys of a tile and exchange the row maximum.
 cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,

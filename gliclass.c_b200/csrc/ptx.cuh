@@ -38,12 +38,17 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                "r"(bytes)
                : "memory");
 }
+// try_wait suspends the thread in hardware until the phase completes or the time hint (ns) expires: it is woken by the
+// arrival, so a long hint costs no latency, while the default (short) hint makes a waiting warp spin through TRYWAIT +
+// BRA pairs that compete with the working warps of its scheduler for issue slots (ncu: 570 of 1370 issue slots per
+// tile period in the attention kernel were such spins).
+constexpr uint32_t MBAR_SUSPEND_NS = 0x100000u;   // ~1 ms
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
-      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(MBAR_SUSPEND_NS)
       : "memory");
   return ok != 0;
 }
@@ -58,12 +63,12 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a trap (sticky CUDA error), never as a hang
-// that would hold the GPU until an external timeout.  try_wait suspends the thread for a
-// hardware-defined interval, so the spin count (no clock reads in the loop) bounds seconds.
+// that would hold the GPU until an external timeout.  try_wait suspends the thread for up to
+// MBAR_SUSPEND_NS per call, so the spin count (no clock reads in the loop) bounds the wait to a few seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (++spins > (1u << 12)) {
 #ifdef GLC_DEBUG_BARRIERS
       printf("glc: mbarrier timeout block=(%d,%d,%d) thread=%d bar=%u parity=%u\n", blockIdx.x, blockIdx.y, blockIdx.z,
              threadIdx.x, smem_u32(bar), parity);

@@ -174,6 +174,8 @@ GLC_API int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_le
  *   glc_op_expand_pos_rev  out[sigma][0:cols) = pos[idx(sigma - 2047)][0:cols)  (posQ half)
  * for rho, sigma in [0, glc_expanded_pos_rows()); idx = glc_rel_index_table, the last row is zero; both synchronise
  * `stream`.  exp_k / exp_qr: fp16 [glc_expanded_pos_rows()][ld_exp], head h at columns h*64...
+ *   glc_op_attention_persist  persistent form of the rows kernel (csrc/attention_persist.cu): one CTA per SM, position
+ *                           tables resident in shared memory for S <= 512.
  *   glc_op_attention_rows   production kernel (csrc/attention_rows.cu): register skews of both biases, one softmax
  *                           thread per query row of a 64-key tile, three warpgroups rotating over the key tiles.
  *   glc_op_attention_shift  previous production kernel (csrc/attention_shift.cu), kept for A/B runs (GLC_ATTN=shift).
@@ -188,6 +190,9 @@ GLC_API int glc_op_expand_pos_rev(const void* pos_f16, int64_t ld_src, int bucke
 GLC_API int glc_op_attention_rows(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
                                   const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
                                   void* stream);
+GLC_API int glc_op_attention_persist(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
+                                     const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
+                                     void* stream);
 GLC_API int glc_op_attention_shift(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
                                    const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
                                    void* stream);

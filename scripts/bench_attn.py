@@ -39,8 +39,8 @@ assert rc == 0, pkg.last_error()
 torch.cuda.synchronize()
 fl = 4.0 * B * S * S * H + 4.0 * B * S * 512 * H
 mode = os.environ.get("GLC_ATTN", "both")
-for name in (("rows", "shift") if mode == "both" else (mode,)):
-    op = {"rows": L.glc_op_attention_rows, "shift": L.glc_op_attention_shift}[name]
+for name in (("persist", "rows", "shift") if mode == "both" else (mode,)):
+    op = {"rows": L.glc_op_attention_rows, "shift": L.glc_op_attention_shift, "persist": L.glc_op_attention_persist}[name]
     ctx = torch.zeros(B, S, H, dtype=torch.float16, device=dev)
 
     def run():

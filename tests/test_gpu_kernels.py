@@ -248,7 +248,7 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, kernel, qk_std=1.8):
     _sync_check(pkg, L.glc_op_mask_prep(_ptr(mask), _ptr(bits), _ptr(kv), B, S, None), "mask_prep")
     ctx = torch.full((B, S, H), float("nan"), dtype=torch.float16, device=dev)
     pos_q, pos_k = pos[:, :H], pos[:, H:]
-    if kernel in ("rows", "shift"):
+    if kernel in ("rows", "shift", "persist"):
         # posK half expanded in rho order, posQ half in the opposite (sigma) order, one row per relative distance
         ER = L.glc_expanded_pos_rows()
         exp = torch.full((ER, 2 * H), float("nan"), dtype=torch.float16, device=dev)
@@ -258,7 +258,7 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, kernel, qk_std=1.8):
         full = torch.from_numpy(pkg.rel_index_table(2048, 256, 512)).long().to(dev)    # idx[delta + 2047]
         assert torch.equal(exp[:ER - 1, H:], pos[full.flip(0)][:, H:]) and (exp[ER - 1] == 0).all()   # row rho = posK[idx(2047 - rho)]
         assert torch.equal(exp[:ER - 1, :H], pos[full][:, :H])                                        # row sigma = posQ[idx(sigma - 2047)]
-        op = L.glc_op_attention_rows if kernel == "rows" else L.glc_op_attention_shift
+        op = {"rows": L.glc_op_attention_rows, "shift": L.glc_op_attention_shift, "persist": L.glc_op_attention_persist}[kernel]
         rc = op(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
         _sync_check(pkg, rc, "glc_op_attention_" + kernel)
     else:
@@ -295,8 +295,8 @@ def test_attention_naive_kernel(pkg, dev, B, S, heads, lens):
     _report(f"attn-naive B{B} S{S} h{heads}", ctx[v], ref[v], 3e-3, 3e-3)
 
 
-@pytest.mark.parametrize("kernel", ["rows", "shift"])
-@pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1])])
+@pytest.mark.parametrize("kernel", ["persist", "rows", "shift"])
+@pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1]), (70, 384, 3, [384] * 35 + list(range(1, 36)))])
 def test_attention(pkg, dev, B, S, heads, lens, kernel):
     """attention kernels (csrc/attention_rows.cu = production, csrc/attention_shift.cu) against the fp32 restatement"""
     ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, kernel=kernel)
@@ -314,7 +314,7 @@ def test_attention(pkg, dev, B, S, heads, lens, kernel):
     _report(f"attn-{kernel} B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
 
 
-@pytest.mark.parametrize("kernel", ["rows", "shift"])
+@pytest.mark.parametrize("kernel", ["persist", "rows", "shift"])
 def test_attention_softmax_peaked(pkg, dev, kernel):
     # large score magnitudes: the row maximum keeps growing across key tiles (exercises the sticky-maximum chain and the
     # rescale of the TMEM-resident output accumulator)
