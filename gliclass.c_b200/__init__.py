@@ -43,7 +43,7 @@ class glc_info(C.Structure):
                 ("ln_eps", C.c_float), ("class_token", C.c_int64), ("num_devices", C.c_int32),
                 ("weight_dtype", C.c_int32), ("pooling", C.c_int32), ("scorer", C.c_int32),
                 ("normalize_features", C.c_int32), ("logit_scale", C.c_float), ("projector_act", C.c_int32),
-                ("class_pos_offset", C.c_int32)]
+                ("class_pos_offset", C.c_int32), ("backbone", C.c_int32), ("kv_heads", C.c_int32), ("head_dim", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -93,6 +93,9 @@ _SIGS = {
     "glc_op_expand_pos": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
     "glc_op_expand_pos_rev": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
     "glc_op_attention_shift": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "glc_op_add_rmsnorm": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
+    "glc_op_rope": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _vp]),
+    "glc_op_attention_flash128": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "glc_op_head_gather": (_i, [_vp, _vp, _i64, _vp, _vp, _i, _i, _i, _i, _vp]),
     "glc_op_head_score": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _i, _vp]),
 }

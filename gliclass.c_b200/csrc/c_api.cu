@@ -44,6 +44,7 @@ void fill_info(const glc::ModelConfig& c, glc_info* o) {
   o->class_token = c.class_token;
   o->pooling = c.pooling; o->scorer = c.scorer; o->normalize_features = c.normalize ? 1 : 0; o->logit_scale = c.logit_scale;
   o->projector_act = c.proj_act; o->class_pos_offset = c.class_pos_offset;
+  o->backbone = c.backbone; o->kv_heads = c.kv_heads; o->head_dim = c.backbone == glc::BACKBONE_QWEN2 ? c.head_dim : (c.heads ? c.hidden / c.heads : 0);
 }
 }  // namespace
 
@@ -490,6 +491,27 @@ int glc_op_attention_persist(const void* qkv, const void* exp_k, const void* exp
                                                              num_sms_current(), (cudaStream_t)stream));
 }
 int glc_expanded_pos_rows(void) { return glc::expanded_pos_rows(); }
+int glc_op_add_rmsnorm(float* h, const void* delta_f16, const float* g, float eps, void* y_f16, int M, int H, void* stream) {
+  GLC_TRY("glc_op_add_rmsnorm", glc::add_rmsnorm(h, delta_f16, g, eps, y_f16, M, H, (cudaStream_t)stream));
+}
+int glc_op_rope(void* qkv_f16, int64_t ld, const float* inv_freq, int M, int S, int n_rot_heads, int head_dim, void* stream) {
+  try {
+    void* cs = nullptr;
+    cudaError_t e = cudaMalloc(&cs, (size_t)S * (head_dim / 2) * 8);
+    if (e == cudaSuccess) e = glc::rope_table(inv_freq, cs, S, head_dim, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = glc::rope_inplace(qkv_f16, ld, cs, M, S, n_rot_heads, head_dim, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (cs) cudaFree(cs);
+    return wrap("glc_op_rope", e);
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_op_rope: ") + e.what());
+  }
+}
+int glc_op_attention_flash128(const void* qkv_f16, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S,
+                              int heads, int kv_heads, void* stream) {
+  GLC_TRY("glc_op_attention_flash128",
+          glc::attention_flash128(qkv_f16, mask_bits, kv_len, ctx_f16, B, S, heads, kv_heads, (cudaStream_t)stream));
+}
 int glc_op_head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S, int H,
                        int C, void* stream) {
   GLC_TRY("glc_op_head_gather", glc::head_gather(h, ids, class_token, pooled, cls, B, S, H, C, (cudaStream_t)stream));

@@ -110,8 +110,12 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
     throw std::runtime_error("device " + std::to_string(device_) + " (" + prop.name + ", sm_" + std::to_string(prop.major) +
                              std::to_string(prop.minor) + ") is not sm_100: this engine has no fallback path");
   num_sms_ = prop.multiProcessorCount;
-  if (cfg_.hidden / cfg_.heads != 64)
+  if (cfg_.backbone == BACKBONE_DEBERTA && cfg_.hidden / cfg_.heads != 64)
     throw std::runtime_error("attention kernel requires head dim 64 (got " + std::to_string(cfg_.hidden / cfg_.heads) + ")");
+  if (cfg_.backbone == BACKBONE_QWEN2 && cfg_.head_dim != 128)
+    throw std::runtime_error("decoder-backbone attention kernel requires head dim 128 (got " + std::to_string(cfg_.head_dim) + ")");
+  if (cfg_.backbone == BACKBONE_QWEN2 && cfg_.pooling == POOL_LAST)
+    throw std::runtime_error("pooling_strategy 'last' is not supported with a decoder backbone (padded rows are not computed)");
   if (max_tokens > 0) max_tokens_ = max_tokens;
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
@@ -143,7 +147,54 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
   GLC_CUDA(cudaMallocHost((void**)&h_overflow_, 64 * sizeof(int)));
   memset(h_overflow_, 0, 64 * sizeof(int));
 
-  const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets, Hh = cfg_.head_hidden;
+  if (cfg_.backbone == BACKBONE_QWEN2) init_qwen2(w);
+  else init_deberta(w);
+  init_head(w);
+  GLC_CUDA(cudaStreamSynchronize(stream_));
+}
+
+// decoder backbone (Qwen2): fused QKV (q heads | kv heads K | kv heads V), gate / up rows interleaved in blocks of 32 for
+// the SwiGLU GEMM epilogue, RMSNorm weights, rotary inverse frequencies
+void DeviceModel::init_qwen2(const ModelWeights& w) {
+  const int H = cfg_.hidden, I = cfg_.inter, d = cfg_.head_dim;
+  const int Wq = cfg_.heads * d, Wkv = cfg_.kv_heads * d, Wqkv = Wq + 2 * Wkv;
+  if (I % 32) throw std::runtime_error("decoder backbone: intermediate size must be a multiple of 32");
+  const HostTensor& we = w.at("emb.word");
+  upload_w16(&word_emb_, we.data.data(), we.data.size());
+  upload_f32(&norm_g_, w.at("norm.g"));
+  upload_f32(&rope_inv_freq_, w.at("rope.inv_freq"));
+  layers_.resize(cfg_.layers);
+  std::vector<float> cat((size_t)Wqkv * H), bcat((size_t)Wqkv), gu((size_t)2 * I * H);
+  for (int l = 0; l < cfg_.layers; ++l) {
+    DeviceLayer& dl = layers_[l];
+    const std::string r = "layer." + std::to_string(l);
+    memcpy(cat.data(), w.at(r + ".q.w").data.data(), (size_t)Wq * H * 4);
+    memcpy(cat.data() + (size_t)Wq * H, w.at(r + ".k.w").data.data(), (size_t)Wkv * H * 4);
+    memcpy(cat.data() + (size_t)(Wq + Wkv) * H, w.at(r + ".v.w").data.data(), (size_t)Wkv * H * 4);
+    memcpy(bcat.data(), w.at(r + ".q.b").data.data(), (size_t)Wq * 4);
+    memcpy(bcat.data() + Wq, w.at(r + ".k.b").data.data(), (size_t)Wkv * 4);
+    memcpy(bcat.data() + Wq + Wkv, w.at(r + ".v.b").data.data(), (size_t)Wkv * 4);
+    upload_w16(&dl.wqkv, cat.data(), cat.size());
+    HostTensor hb;
+    hb.data = bcat;
+    upload_f32(&dl.bqkv, hb);
+    GLC_CUDA(cudaStreamSynchronize(stream_));   // hb is a temporary
+    upload_w16(&dl.wo, w.at(r + ".o.w").data.data(), (size_t)H * Wq);
+    const float* gw = w.at(r + ".gate.w").data.data();
+    const float* uw = w.at(r + ".up.w").data.data();
+    for (int j = 0; j < I / 32; ++j) {
+      memcpy(gu.data() + (size_t)(64 * j) * H, gw + (size_t)(32 * j) * H, (size_t)32 * H * 4);
+      memcpy(gu.data() + (size_t)(64 * j + 32) * H, uw + (size_t)(32 * j) * H, (size_t)32 * H * 4);
+    }
+    upload_w16(&dl.w1, gu.data(), gu.size());
+    upload_w16(&dl.w2, w.at(r + ".down.w").data.data(), (size_t)H * I);
+    upload_f32(&dl.ln1g, w.at(r + ".ln1.g"));
+    upload_f32(&dl.ln2g, w.at(r + ".ln2.g"));
+  }
+}
+
+void DeviceModel::init_deberta(const ModelWeights& w) {
+  const int H = cfg_.hidden, I = cfg_.inter, R = 2 * cfg_.buckets;
   const HostTensor& we = w.at("emb.word");
   upload_w16(&word_emb_, we.data.data(), we.data.size());
   upload_f32(&emb_g_, w.at("emb.ln.g"));
@@ -212,6 +263,10 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
     GLC_CUDA(expand_pos_table((const __half*)d.pos_qk + H, 2 * H, d_exp_idx, (__half*)d.pos_exp + H, 2 * H, H, stream_));
     launches_ += 2;
   }
+}
+
+void DeviceModel::init_head(const ModelWeights& w) {
+  const int H = cfg_.hidden, Hh = cfg_.head_hidden;
   upload_w16(&t1w_, w.at("text.1.w").data.data(), (size_t)Hh * H);
   upload_f32(&t1b_, w.at("text.1.b"));
   upload_w16(&t2w_, w.at("text.2.w").data.data(), (size_t)Hh * Hh);
@@ -237,7 +292,6 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
     upload_f32(&last_w_, w.at("scorer.o2.w"));
     last_b_ = w.at("scorer.o2.b").data.at(0);
   }
-  GLC_CUDA(cudaStreamSynchronize(stream_));
 }
 
 void DeviceModel::drop_graphs() {
@@ -260,6 +314,7 @@ DeviceModel::~DeviceModel() {
   for (auto e : h_in_ev_) if (e) cudaEventDestroy(e);
   for (auto& b : out_pool_) if (b.p) cudaFreeHost(b.p);
   for (auto& kv : rel_tables_) cudaFree(kv.second);
+  for (auto& kv : rope_tables_) cudaFree(kv.second);
   for (auto& kv : debug_) cudaFree(kv.second.ptr);
   for (auto& r : prof_recs_) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   for (auto e : prof_pool_) cudaEventDestroy(e);
@@ -279,6 +334,16 @@ const int32_t* DeviceModel::rel_table(int S) {
   return d;
 }
 
+const void* DeviceModel::rope_table_for(int S) {
+  auto it = rope_tables_.find(S);
+  if (it != rope_tables_.end()) return it->second;
+  void* d = dalloc((size_t)S * (cfg_.head_dim / 2) * 8);
+  GLC_CUDA(rope_table(rope_inv_freq_, d, S, cfg_.head_dim, stream_));
+  GLC_CUDA(cudaStreamSynchronize(stream_));   // (first sight of a shape runs eagerly, never inside a graph capture)
+  rope_tables_[S] = d;
+  return d;
+}
+
 void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   const int rows = B * (C > 0 ? C : 1);
   if (tokens <= ws_tokens_ && B <= ws_B_ && rows <= ws_rows_) return;
@@ -290,13 +355,16 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   ws_B_ = B > ws_B_ ? B : ws_B_;
   ws_rows_ = rows > ws_rows_ ? rows : ws_rows_;
   const size_t M = (size_t)ws_tokens_, H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
+  const bool dec = cfg_.backbone == BACKBONE_QWEN2;
+  const size_t Wq = dec ? (size_t)cfg_.heads * cfg_.head_dim : H, Wqkv = dec ? Wq + 2 * (size_t)cfg_.kv_heads * cfg_.head_dim : 3 * H;
   auto A = [&](size_t bytes) { void* p = dalloc(bytes); ws_allocs_.push_back(p); return p; };
   ids_ = (int64_t*)A(M * 8);
   mask_ = (int64_t*)A(M * 8);
   x_ = A(M * H * 2);
-  x1_ = A(M * H * 2);
-  qkv_ = A(M * 3 * H * 2);
-  ctx_ = A(M * H * 2);
+  x1_ = dec ? nullptr : A(M * H * 2);
+  h32_ = dec ? (float*)A(M * H * 4) : nullptr;   // decoder backbone: fp32 residual stream
+  qkv_ = A(M * Wqkv * 2);
+  ctx_ = A(M * Wq * 2);
   tmp_ = A(M * H * (preln_f32_ ? 4 : 2));
   ffn_ = A(M * I * 2);
   mask_bits_ = (uint32_t*)A(((M + 31) / 32 + (size_t)ws_B_) * 4);
@@ -477,6 +545,27 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
   uint64_t n = 0;
 
   GLC_LAUNCH(KC_EMBED, mask_prep(d_mask, mask_bits_, kv_len_, B, S, st));
+  if (cfg_.backbone == BACKBONE_QWEN2) {
+    // decoder backbone (transformers modeling_qwen2.py Q:353-410, bidirectional): pre-norm residual stream in fp32
+    const int d = cfg_.head_dim, nh = cfg_.heads, nkv = cfg_.kv_heads;
+    const int Wq = nh * d, Wqkv = Wq + 2 * nkv * d;
+    const void* cs = rope_table_for(S);
+    GLC_LAUNCH(KC_EMBED, embed_rows_f32(d_ids, word_emb_, h32_, M, H, cfg_.vocab, st));
+    for (int l = 0; l < cfg_.layers; ++l) {
+      const DeviceLayer& dl = layers_[l];
+      GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, l == 0 ? nullptr : tmp_, dl.ln1g, cfg_.rms_eps, x_, M, H, st));
+      GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, dl.wqkv, H, dl.bqkv, qkv_, Wqkv, M, Wqkv, H, 0, false, num_sms_, st));
+      GLC_LAUNCH(KC_EMBED, rope_inplace(qkv_, Wqkv, cs, M, S, nh + nkv, d, st));
+      GLC_LAUNCH(KC_ATTN, attention_flash128(qkv_, mask_bits_, kv_len_, ctx_, B, S, nh, nkv, st));
+      if (l == 0) keep("ctx0", ctx_, (size_t)M * Wq);
+      GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, Wq, dl.wo, Wq, nullptr, tmp_, H, M, H, Wq, 0, false, num_sms_, st));
+      GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, tmp_, dl.ln2g, cfg_.rms_eps, x_, M, H, st));
+      GLC_LAUNCH(KC_GEMM_FFN1, gemm_f16(x_, H, dl.w1, H, nullptr, ffn_, I, M, 2 * I, H, 3, false, num_sms_, st));
+      GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16(ffn_, I, dl.w2, I, nullptr, tmp_, H, M, H, I, 0, false, num_sms_, st));
+    }
+    GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, tmp_, norm_g_, cfg_.rms_eps, x_, M, H, st));
+    keep("final", x_, (size_t)M * H);
+  } else {
   GLC_LAUNCH(KC_EMBED, embed_ln(d_ids, d_mask, word_emb_, emb_g_, emb_b_, cfg_.ln_eps, x_, M, H, cfg_.vocab, st));
   keep("emb", x_, (size_t)M * H);
   for (int l = 0; l < cfg_.layers; ++l) {
@@ -510,6 +599,7 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
       GLC_LAUNCH(KC_LN, residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st, d_overflow_, preln_f32_));
     }
     if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
+  }
   }
   if (C > 0) {
     const int pa = cfg_.proj_act;

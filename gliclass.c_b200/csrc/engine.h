@@ -97,6 +97,10 @@ class DeviceModel {
   std::vector<cudaEvent_t> free_events_;   // completion events of run_host (guarded by mu)
 
  private:
+  void init_deberta(const ModelWeights& w);
+  void init_qwen2(const ModelWeights& w);
+  void init_head(const ModelWeights& w);
+  const void* rope_table_for(int S);
   void ensure_workspace(int tokens, int B, int C);
   void run_group(std::vector<HostReq*>& group);
   void forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
@@ -142,6 +146,10 @@ class DeviceModel {
   float* last_w_ = nullptr;     // fp32 weight row of the final Linear(K -> 1)
   float last_b_ = 0.f;
   std::map<int, int32_t*> rel_tables_;   // keyed by Spad
+  // decoder backbone (Qwen2): final RMSNorm weight, rotary inverse frequencies, (cos, sin) tables per sequence length
+  float *norm_g_ = nullptr, *rope_inv_freq_ = nullptr;
+  std::map<int, void*> rope_tables_;
+  float* h32_ = nullptr;                 // fp32 residual stream [M,H]
 
   // workspace
   int ws_tokens_ = 0, ws_B_ = 0, ws_rows_ = 0;

@@ -32,7 +32,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 template <int ACT>
 struct EpiCfg {
-  static constexpr int GROUPS = (ACT == 1) ? 4 : 2;        // epilogue warp groups (4 warps each)
+  static constexpr int GROUPS = (ACT == 1 || ACT == 3) ? 4 : 2;   // epilogue warp groups (4 warps each)
   static constexpr int THREADS = 64 + 128 * GROUPS;
 };
 
@@ -61,6 +61,17 @@ __device__ __forceinline__ float gelu_erf(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(q * x));
   const float hx = 0.5f * x;
   return fmaf(hx, t, hx);
+}
+
+// SwiGLU (ACT = 3; Qwen2 / Llama MLP, transformers modeling_qwen2.py:46-48): the weight rows are interleaved in blocks
+// of 32 — rows [64 j, 64 j + 32) = gate_proj rows [32 j, 32 j + 32), rows [64 j + 32, 64 j + 64) = the matching up_proj
+// rows — so an epilogue warp holds a gate chunk and its up chunk and writes silu(gate) * up: the output has N / 2 columns.
+// silu(x) = x sigmoid(x) = 0.5 x (1 + tanh(0.5 x)): one MUFU op.
+__device__ __forceinline__ float silu_mul(float g, float u) {
+  float t;
+  const float hg = 0.5f * g;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(hg));
+  return fmaf(hg, t, hg) * u;
 }
 
 // Residual operand of the fused "+ r" epilogue: 32 fp16 of this lane's row (4 x 128-bit; the second half of every 32-byte
@@ -150,6 +161,90 @@ __device__ __forceinline__ void epilogue_tile(uint32_t t_row, int grp, int n0, i
     }
   }
 }
+}
+
+// SwiGLU epilogue, direct stores (small problems / fp32 output): chunk pairs (gate, up) -> 32 output columns
+template <int BN, bool OUT_F32>
+__device__ __forceinline__ void epilogue_tile_swiglu(uint32_t t_row, int grp, int n0, int row, const float* __restrict__ bias,
+                                                     void* __restrict__ Cout, int64_t ldc, int M, int N) {
+#pragma unroll 1
+  for (int pc = grp; pc < BN / 64; pc += EpiCfg<3>::GROUPS) {
+    const int n = n0 + pc * 64;          // gate columns [n, n+32), up columns [n+32, n+64) of the interleaved GEMM
+    uint32_t rg[32], ru[32];
+    ptx::tmem_ld_x32(t_row + (uint32_t)(pc * 64), rg);
+    ptx::tmem_ld_x32(t_row + (uint32_t)(pc * 64 + 32), ru);
+    ptx::tmem_ld_wait();
+    if (n + 64 > N) continue;            // warp-uniform (N is a multiple of 64 for this activation)
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
+      if (bias != nullptr) { g += __ldg(bias + n + j); u += __ldg(bias + n + 32 + j); }
+      v[j] = silu_mul(g, u);
+    }
+    if (row < M) {
+      const int no = n / 2;
+      if (OUT_F32) {
+        float* dst = reinterpret_cast<float*>(Cout) + (int64_t)row * ldc + no;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) reinterpret_cast<float4*>(dst)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+      } else {
+        __half* dst = reinterpret_cast<__half*>(Cout) + (int64_t)row * ldc + no;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = ptx::pack_f16(v[8 * j + 0], v[8 * j + 1]);
+          o.y = ptx::pack_f16(v[8 * j + 2], v[8 * j + 3]);
+          o.z = ptx::pack_f16(v[8 * j + 4], v[8 * j + 5]);
+          o.w = ptx::pack_f16(v[8 * j + 6], v[8 * j + 7]);
+          reinterpret_cast<uint4*>(dst)[j] = o;
+        }
+      }
+    }
+  }
+}
+
+// SwiGLU epilogue through shared memory + TMA store (tm_c describes the [M, N/2] output)
+template <int BN, int NBUF>
+__device__ __forceinline__ void epilogue_tile_tma_swiglu(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
+                                                         const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int N) {
+#pragma unroll 1
+  for (int pc = grp; pc < BN / 64; pc += EpiCfg<3>::GROUPS) {
+    const int n = n0 + pc * 64;
+    uint32_t rg[32], ru[32];
+    ptx::tmem_ld_x32(t_row + (uint32_t)(pc * 64), rg);
+    ptx::tmem_ld_x32(t_row + (uint32_t)(pc * 64 + 32), ru);
+    ptx::tmem_ld_wait();
+    if (n + 64 > N) continue;   // warp-uniform
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
+      if (bias != nullptr) { g += __ldg(bias + n + j); u += __ldg(bias + n + 32 + j); }
+      v[j] = silu_mul(g, u);
+    }
+    if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
+    __syncwarp();
+    uint8_t* sb = stage + buf * 2048;
+    uint8_t* srow = sb + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 o;
+      o.x = ptx::pack_f16(v[8 * j + 0], v[8 * j + 1]);
+      o.y = ptx::pack_f16(v[8 * j + 2], v[8 * j + 3]);
+      o.z = ptx::pack_f16(v[8 * j + 4], v[8 * j + 5]);
+      o.w = ptx::pack_f16(v[8 * j + 6], v[8 * j + 7]);
+      *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = o;
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tm_c, sb, n / 2, row0);
+      ptx::bulk_commit_group();
+    }
+    buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+  }
 }
 
 // fp16 epilogue through shared memory + TMA store.  A warp's direct stores put 32 different rows in
@@ -327,7 +422,10 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      epilogue_tile<BN, ACT, OUT_F32, RESID>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
+      if (ACT == 3)
+        epilogue_tile_swiglu<BN, OUT_F32>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
+      else
+        epilogue_tile<BN, ACT, OUT_F32, RESID>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty[acc]);
@@ -481,7 +579,11 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      if (OUT_F32)
+      if (ACT == 3 && OUT_F32)
+        epilogue_tile_swiglu<BN, true>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
+      else if (ACT == 3)
+        epilogue_tile_tma_swiglu<BN, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, N);
+      else if (OUT_F32)
         epilogue_tile<BN, ACT, OUT_F32, RESID>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
       else
         epilogue_tile_tma<BN, ACT, NBUF, RESID>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, resid, ldr);
@@ -516,7 +618,7 @@ cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t 
   CUtensorMap tm_w = make_tmap_16b(W, 2, dw, sw, bw);
   CUtensorMap tm_c = tm_a;   // unused by the fp32-output instantiation
   if (!OUT_F32) {
-    uint64_t dc[2] = {(uint64_t)N, (uint64_t)M};
+    uint64_t dc[2] = {(uint64_t)(ACT == 3 ? N / 2 : N), (uint64_t)M};
     uint64_t sc[1] = {(uint64_t)ldc * 2};
     uint32_t bc[2] = {32, 32};
     tm_c = make_tmap_16b(C, 2, dc, sc, bc, CU_TENSOR_MAP_SWIZZLE_64B);
@@ -582,7 +684,14 @@ cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ld
   // 128x256 tiles when that still fills the machine; otherwise 128x128 (more tiles, less tail)
   const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
   const bool wide = (N % 256 == 0) && tiles256 >= num_sms;
-  if (act < 0 || act > 2) return cudaErrorInvalidValue;
+  if (act < 0 || act > 3) return cudaErrorInvalidValue;
+  if (act == 3) {
+    // SwiGLU: gate / up rows interleaved in blocks of 32 (see silu_mul); output [M, N/2]
+    if (N % 64 != 0 || resid != nullptr || out_f32) return cudaErrorInvalidValue;
+    const int t2 = ((M + 255) / 256) * ((N + 255) / 256);
+    if (t2 >= num_sms / 2 && N >= 256) return launch_gemm_2cta<256, 3, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, nullptr, 0);
+    return launch_gemm<128, 3, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, nullptr, 0);
+  }
   if (out_f32) {
     if (act == 0) return launch_gemm<128, 0, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
     if (act == 1) return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);

@@ -10,7 +10,8 @@ namespace glc {
 // fp16 rather than bf16 because bf16's 8-bit mantissa cannot meet the 2e-2 logit parity bar on
 // this model family (DESIGN.md "Numerics").
 //
-// K2: C[M,N] = act(A[M,K] W[N,K]^T + bias); A, W fp16, fp32 accumulate; C fp16 or fp32.  act: 0 none, 1 erf-GELU, 2 ReLU.
+// K2: C[M,N] = act(A[M,K] W[N,K]^T + bias); A, W fp16, fp32 accumulate; C fp16 or fp32.  act: 0 none, 1 erf-GELU, 2 ReLU,
+// 3 SwiGLU (W rows interleaved in blocks of 32: gate rows, then the matching up rows; C is [M, N/2] = silu(gate) * up).
 cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M,
                      int N, int K, int act, bool out_f32, int num_sms, cudaStream_t stream);
 
@@ -18,6 +19,20 @@ cudaError_t gemm_f16(const void* A, int64_t lda, const void* W, int64_t ldw, con
 cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, const void* resid,
                            int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act, bool out_f32, int num_sms,
                            cudaStream_t stream);
+
+// decoder backbone (decoder.cu): fp32 residual stream h, fp16 normalised activations
+cudaError_t embed_rows_f32(const int64_t* ids, const void* emb_f16, float* h, int M, int H, int vocab, cudaStream_t stream);
+// h += delta (fp16 [M,H], may be null); y = rmsnorm(h) * g
+cudaError_t add_rmsnorm(float* h, const void* delta_f16, const float* g, float eps, void* y_f16, int M, int H, cudaStream_t stream);
+// (cos, sin) float2 table [S, head_dim / 2] from the rotary inverse frequencies
+cudaError_t rope_table(const float* inv_freq, void* cs_f32x2, int S, int head_dim, cudaStream_t stream);
+// rotary embedding in place on the first n_rot_heads heads (q heads, then kv heads) of qkv fp16 [M, ld]
+cudaError_t rope_inplace(void* qkv_f16, int64_t ld, const void* cs_f32x2, int M, int S, int n_rot_heads, int head_dim,
+                         cudaStream_t stream);
+// plain (bias-free) flash attention for head dim 128 with grouped-query heads, bidirectional, key padding mask:
+// qkv fp16 [B*S, (heads + 2 kv_heads) * 128] (Q heads | K heads | V heads), ctx fp16 [B*S, heads * 128]
+cudaError_t attention_flash128(const void* qkv_f16, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S,
+                               int heads, int kv_heads, cudaStream_t stream);
 
 // K1: y[m,:] = LN(word_emb[ids[m],:]) * gamma + beta, times mask[m]   (T:520-564)
 cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* word_emb_f16, const float* gamma,

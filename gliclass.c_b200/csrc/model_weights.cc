@@ -127,11 +127,111 @@ const HostTensor& ModelWeights::at(const std::string& role) const {
   return it->second;
 }
 
+namespace {
+
+// MatMul-only Linear (no bias Add after it): o_proj / gate_proj / up_proj / down_proj of the decoder backbones
+void load_linear_nobias(const OnnxGraph& g, const std::string& scope, const std::string& role, ModelWeights* out) {
+  const OnnxNode* mm = find_node(g, scope + "/MatMul", "MatMul");
+  if (!mm || mm->inputs.size() != 2) throw std::runtime_error("onnx: no MatMul node for scope " + scope);
+  const OnnxTensor* w = g.resolve(mm->inputs[1]);
+  if (!w || w->dims.size() != 2) throw std::runtime_error("onnx: no constant 2-D weight at " + mm->name);
+  out->t[role + ".w"] = transpose2d(to_host(*w));   // [in,out] -> [out,in]
+}
+
+// Qwen2-style decoder stack traced from transformers' Qwen2Model (modeling_qwen2.py): scopes /layers.<l>/self_attn/
+// {q,k,v,o}_proj, /layers.<l>/mlp/{gate,up,down}_proj, RMSNorm weights as named initializers.
+void load_qwen2_encoder(const OnnxGraph& g, ModelWeights* out) {
+  ModelConfig& c = out->cfg;
+  c.backbone = BACKBONE_QWEN2;
+  const OnnxTensor* we = find_named(g, "embed_tokens.weight");
+  if (!we || we->dims.size() != 2) throw std::runtime_error("onnx: embed_tokens.weight not found");
+  c.vocab = (int)we->dims[0];
+  c.hidden = (int)we->dims[1];
+  out->t["emb.word"] = to_host(*we);
+  for (auto& n : g.nodes)
+    if (n.op_type == "Trilu")
+      throw std::runtime_error("onnx: causal attention mask (Trilu at " + n.name + "): decoder backbones are supported as "
+                               "bidirectional encoders only");
+  // rotary inverse frequencies: the float constant expanded in /rotary_emb/Expand
+  {
+    const OnnxNode* ex = find_node(g, "/rotary_emb/Expand", "Expand");
+    const OnnxTensor* f = ex && !ex->inputs.empty() ? g.resolve(ex->inputs[0]) : nullptr;
+    if (!f || f->data_type != 1 || f->numel() < 8) throw std::runtime_error("onnx: rotary inv_freq constant not found");
+    HostTensor h = to_host(*f);
+    h.dims = {(int64_t)h.data.size()};
+    c.head_dim = 2 * (int)h.data.size();
+    out->t["rope.inv_freq"] = h;
+  }
+  int L = 0;
+  while (find_node(g, "/layers." + std::to_string(L) + "/self_attn/q_proj/MatMul")) ++L;
+  if (L == 0) throw std::runtime_error("onnx: no decoder layers found");
+  c.layers = L;
+  auto named_vec = [&](const std::string& name, const std::string& role) {
+    const OnnxTensor* t = find_named(g, name);
+    if (!t || t->numel() != c.hidden) throw std::runtime_error("onnx: " + name + " not found");
+    out->t[role] = to_host(*t);
+  };
+  for (int l = 0; l < L; ++l) {
+    const std::string s = "/layers." + std::to_string(l), r = "layer." + std::to_string(l), nm = "layers." + std::to_string(l) + ".";
+    load_linear(g, s + "/self_attn/q_proj", r + ".q", out);
+    load_linear(g, s + "/self_attn/k_proj", r + ".k", out);
+    load_linear(g, s + "/self_attn/v_proj", r + ".v", out);
+    load_linear_nobias(g, s + "/self_attn/o_proj", r + ".o", out);
+    load_linear_nobias(g, s + "/mlp/gate_proj", r + ".gate", out);
+    load_linear_nobias(g, s + "/mlp/up_proj", r + ".up", out);
+    load_linear_nobias(g, s + "/mlp/down_proj", r + ".down", out);
+    named_vec(nm + "input_layernorm.weight", r + ".ln1.g");
+    named_vec(nm + "post_attention_layernorm.weight", r + ".ln2.g");
+    // hidden_act must be SiLU (Sigmoid + Mul under /mlp)
+    bool sig = false;
+    for (auto& n : g.nodes)
+      if (n.name.find(s + "/mlp/") != std::string::npos && n.op_type == "Sigmoid") sig = true;
+    if (!sig) throw std::runtime_error("onnx: layer " + std::to_string(l) + " MLP activation is not SiLU");
+  }
+  named_vec("encoder_model.norm.weight", "norm.g");
+  if (const OnnxNode* n = find_node(g, "/layers.0/input_layernorm/Add", "Add")) {
+    float e;
+    for (auto& in : n->inputs)
+      if (g.scalar_float(in, &e) && e > 0.f && e < 1e-2f) c.rms_eps = e;
+  }
+  c.inter = (int)out->at("layer.0.gate.w").dims[0];
+  const int64_t qo = out->at("layer.0.q.w").dims[0], ko = out->at("layer.0.k.w").dims[0];
+  if (c.head_dim <= 0 || qo % c.head_dim || ko % c.head_dim) throw std::runtime_error("onnx: q/k projection widths do not match the rotary head dim");
+  c.heads = (int)(qo / c.head_dim);
+  c.kv_heads = (int)(ko / c.head_dim);
+  if (c.kv_heads <= 0 || c.heads % c.kv_heads) throw std::runtime_error("onnx: heads not divisible by kv heads");
+  auto expect = [&](const std::string& role, std::vector<int64_t> d) {
+    if (out->at(role).dims != d) throw std::runtime_error("weights: unexpected shape for " + role);
+  };
+  const int64_t H = c.hidden, I = c.inter, Q = qo, K = ko;
+  for (int l = 0; l < L; ++l) {
+    const std::string r = "layer." + std::to_string(l);
+    expect(r + ".q.w", {Q, H}); expect(r + ".q.b", {Q});
+    expect(r + ".k.w", {K, H}); expect(r + ".k.b", {K});
+    expect(r + ".v.w", {K, H}); expect(r + ".v.b", {K});
+    expect(r + ".o.w", {H, Q});
+    expect(r + ".gate.w", {I, H}); expect(r + ".up.w", {I, H}); expect(r + ".down.w", {H, I});
+  }
+}
+
+void load_head(const OnnxGraph& g, ModelWeights* out);
+void load_deberta_encoder(const OnnxGraph& g, ModelWeights* out);
+
+}  // namespace
+
 void load_model_weights(const std::string& path, ModelWeights* out) {
   OnnxGraph g;
   g.load(path);
   if (g.input_names.size() < 2 || g.input_names[0] != "input_ids" || g.input_names[1] != "attention_mask")
     throw std::runtime_error("onnx: expected graph inputs (input_ids, attention_mask)");
+  if (find_named(g, "embed_tokens.weight")) load_qwen2_encoder(g, out);
+  else load_deberta_encoder(g, out);
+  load_head(g, out);
+}
+
+namespace {
+
+void load_deberta_encoder(const OnnxGraph& g, ModelWeights* out) {
   ModelConfig& c = out->cfg;
 
   // ---- embeddings
@@ -219,6 +319,10 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
     break;
   }
 
+}
+
+void load_head(const OnnxGraph& g, ModelWeights* out) {
+  ModelConfig& c = out->cfg;
   // ---- class token id: Equal(input_ids, Constant)
   for (auto& n : g.nodes) {
     if (n.op_type != "Equal" || n.inputs.size() != 2) continue;
@@ -376,7 +480,7 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
     if (out->at(role).dims != d) throw std::runtime_error("weights: unexpected shape for " + role);
   };
   int64_t H = c.hidden, I = c.inter, Hh = c.head_hidden;
-  for (int l = 0; l < L; ++l) {
+  for (int l = 0; l < c.layers && c.backbone == BACKBONE_DEBERTA; ++l) {
     std::string r = "layer." + std::to_string(l);
     for (const char* p : {".q", ".k", ".v", ".o"}) { expect(r + p + ".w", {H, H}); expect(r + p + ".b", {H}); }
     expect(r + ".ffn1.w", {I, H}); expect(r + ".ffn1.b", {I});
@@ -390,8 +494,11 @@ void load_model_weights(const std::string& path, ModelWeights* out) {
   } else if (c.scorer == SCORER_WEIGHTED_DOT) {
     expect("scorer.pt.b", {2 * Hh}); expect("scorer.pl.b", {2 * Hh}); expect("scorer.o1.b", {4 * Hh}); expect("scorer.o2.b", {1});
   }
-  for (const char* r : {"emb.ln.g", "emb.ln.b", "rel.ln.g", "rel.ln.b"}) expect(r, {H});
+  if (c.backbone == BACKBONE_DEBERTA)
+    for (const char* r : {"emb.ln.g", "emb.ln.b", "rel.ln.g", "rel.ln.b"}) expect(r, {H});
 }
+
+}  // namespace
 
 void rel_index_table(int S, int buckets, int max_pos, int32_t* out) {
   // make_log_bucket_position in fp32, as traced (T:57-69): mid = buckets/2

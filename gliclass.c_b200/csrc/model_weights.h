@@ -15,8 +15,14 @@ struct HostTensor {
   std::vector<float> data;
 };
 
+enum { BACKBONE_DEBERTA = 0, BACKBONE_QWEN2 = 1 };
+
 struct ModelConfig {
+  int backbone = BACKBONE_DEBERTA;   // which layer stack feeds the head (reference Readme.md:91-94 lists both families)
   int vocab = 0, hidden = 0, layers = 0, heads = 0, inter = 0;
+  // decoder backbones (Qwen2 / Llama style): grouped-query attention, rotary embedding, RMSNorm, SwiGLU
+  int kv_heads = 0, head_dim = 0;
+  float rms_eps = 1e-6f;
   int head_hidden = 0;          // projector width
   int buckets = 256;            // position_buckets (= att_span); rel table has 2*buckets rows
   int max_rel_pos = 512;        // max_position in make_log_bucket_position
@@ -35,6 +41,9 @@ struct ModelConfig {
 enum { POOL_FIRST = 0, POOL_LAST = 1, POOL_AVG = 2, POOL_MAX = 3 };
 enum { SCORER_DOT = 0, SCORER_MLP = 1, SCORER_WEIGHTED_DOT = 2 };
 
+// Decoder-backbone roles (BACKBONE_QWEN2): emb.word [V,H]; layer.<l>.{q,k,v}.w [heads*d | kv*d, H] .b; layer.<l>.o.w
+// [H, heads*d]; layer.<l>.{gate,up}.w [I,H]; layer.<l>.down.w [H,I]; layer.<l>.ln1.g / ln2.g [H] (RMSNorm); norm.g [H];
+// rope.inv_freq [d/2].
 // Linear weights are stored [out, in] row-major (torch Linear layout == the K-major "B"
 // operand of the tcgen05 GEMM); ONNX MatMul initializers ([in, out]) are transposed on load.
 struct ModelWeights {

@@ -58,6 +58,8 @@ typedef struct glc_info {
   float logit_scale;
   int32_t projector_act;       /* projector_hidden_act: 1 erf-GELU, 2 ReLU */
   int32_t class_pos_offset;    /* 0: class rows at the <<LABEL>> positions (embed_class_token=true); 1: one position later */
+  int32_t backbone;            /* 0 DeBERTa-v2/v3 encoder, 1 Qwen2-style decoder stack used bidirectionally (Readme.md:91-94) */
+  int32_t kv_heads, head_dim;  /* decoder backbones: grouped-query kv heads, head dim (128) */
 } glc_info;
 
 GLC_API const char* glc_last_error(void);
@@ -199,6 +201,20 @@ GLC_API int glc_op_attention_shift(const void* qkv_f16, const void* exp_k_f16, c
 GLC_API int glc_op_attention_naive(const void* qkv_f16, const void* pos_k_f16, const void* pos_q_f16, int64_t ld_pos,
                                    const int32_t* rel_idx, const uint32_t* mask_bits, void* ctx_f16, int B, int S, int heads,
                                    int buckets, void* stream);
+/* ---- decoder-backbone kernels (Qwen2-style stack: reference Readme.md:91-94, BASELINE.json configs[4]) ----
+ * glc_op_add_rmsnorm: h fp32 [M,H] += delta (fp16 [M,H], NULL = none); y fp16 = h * rsqrt(mean(h^2) + eps) * g
+ * glc_op_rope: rotary embedding in place on the first n_rot_heads heads of qkv fp16 [M, ld] (head j = columns j*head_dim..),
+ *              position = row % S, pairs (p, p + head_dim/2), angle = position * inv_freq[p]; synchronises `stream`
+ * glc_op_attention_flash128: bidirectional grouped-query flash attention, head dim 128, key padding mask:
+ *              qkv fp16 [B*S, (heads + 2 kv_heads) * 128] = Q heads | K heads | V heads; ctx fp16 [B*S, heads * 128]
+ * The SwiGLU MLP is glc_op_gemm with act = 3 (W rows interleaved in blocks of 32: gate rows then the matching up rows;
+ * C is [M, N/2] = silu(gate) * up). */
+GLC_API int glc_op_add_rmsnorm(float* h_f32, const void* delta_f16, const float* g, float eps, void* y_f16, int M, int H,
+                               void* stream);
+GLC_API int glc_op_rope(void* qkv_f16, int64_t ld, const float* inv_freq, int M, int S, int n_rot_heads, int head_dim,
+                        void* stream);
+GLC_API int glc_op_attention_flash128(const void* qkv_f16, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16,
+                                      int B, int S, int heads, int kv_heads, void* stream);
 /* K5a: pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] for the c-th <<LABEL>> token, else 0 */
 GLC_API int glc_op_head_gather(const void* h_f16, const int64_t* ids, int64_t class_token, void* pooled_f16,
                                void* cls_f16, int B, int S, int H, int C, void* stream);

@@ -268,3 +268,23 @@ def test_glc_load_validates_options(pkg, golden_onnx, monkeypatch):
     monkeypatch.setenv("GLC_DEVICES", "zero")
     assert not L.glc_load(os.fsencode(golden_onnx), None)
     assert "GLC_DEVICES" in pkg.last_error()
+
+
+def test_onnx_reader_qwen2_backbone(pkg, orc, model_cache):
+    """decoder backbone: roles, grouped-query geometry and rotary frequencies read off a Qwen2Model trace, bit exact"""
+    path = os.path.join(model_cache, "qwen-mini.onnx")
+    cfg, w = orc.make_model_file("qwen-mini", path, seed=0)
+    f = pkg.OnnxFile(path)
+    i = f.info
+    assert (i["backbone"], i["layers"], i["hidden"], i["heads"], i["kv_heads"], i["head_dim"], i["inter"]) == (1, 3, 512, 4, 2, 128, 1536)
+    assert i["class_token"] == cfg.class_token_index
+    E = orc.ENC
+    for role, name in (("emb.word", "embed_tokens.weight"), ("layer.1.q.w", "layers.1.self_attn.q_proj.weight"),
+                       ("layer.1.k.b", "layers.1.self_attn.k_proj.bias"), ("layer.2.o.w", "layers.2.self_attn.o_proj.weight"),
+                       ("layer.0.gate.w", "layers.0.mlp.gate_proj.weight"), ("layer.0.up.w", "layers.0.mlp.up_proj.weight"),
+                       ("layer.2.down.w", "layers.2.mlp.down_proj.weight"), ("layer.1.ln1.g", "layers.1.input_layernorm.weight"),
+                       ("layer.1.ln2.g", "layers.1.post_attention_layernorm.weight"), ("norm.g", "norm.weight")):
+        assert np.array_equal(f.tensor(role), w[E + name].numpy()), role
+    inv = 1.0 / (cfg.rope_theta ** (np.arange(0, 128, 2, dtype=np.float32) / 128))
+    assert np.allclose(f.tensor("rope.inv_freq"), inv, rtol=1e-6)
+    f.close()

@@ -569,3 +569,42 @@ def test_full_size_properties_base_b64_s512(pkg, orc, model_cache):
         assert d <= 2e-3
     finally:
         sess.close()
+
+
+def test_qwen2_backbone_mini_parity(pkg, orc, model_cache):
+    """Decoder backbone (reference Readme.md:91-94; BASELINE.json configs[4] architecture family): a 3-layer Qwen2-style stack
+    (GQA 4q/2kv x d=128, RoPE theta 1e6, RMSNorm, SwiGLU, QKV bias; bidirectional) behind the same head, against the oracle —
+    which is pinned to transformers' Qwen2Model (tests/test_oracle.py)."""
+    path = os.path.join(model_cache, "qwen-mini.onnx")
+    cfg, w = orc.make_model_file("qwen-mini", path, seed=0)
+    sess = pkg.Session(path)
+    try:
+        assert sess.info["backbone"] == 1 and sess.info["layers"] == 3 and sess.info["heads"] == 4
+        assert sess.info["kv_heads"] == 2 and sess.info["head_dim"] == 128
+        for B, S, labels, ragged, seed in ((6, 300, [4, 2, 3, 1, 4, 5], True, 31), (4, 512, 6, False, 32), (2, 1100, 8, True, 33)):
+            ids, mask = orc.synth_inputs(cfg, B, S, labels, seed=seed, ragged=ragged)
+            ref = orc.forward_restated(w, cfg, ids, mask).numpy()
+            out = sess.run_inference(ids.numpy(), mask.numpy())
+            _check_logits(f"qwen-mini/B{B}S{S}{'/ragged' if ragged else ''}", out, ref, orc)
+    finally:
+        sess.close()
+
+
+def test_qwen2_1p5b_arch_sample_row(pkg, orc, model_cache):
+    """BASELINE.json configs[4]: gliclass-qwen-1.5B architecture (Qwen2 28L/1536, 12q/2kv x 128, SwiGLU 8960), batch 32 x
+    seq 1024 x 20 labels on the GPU (weights > 2 GB: the ONNX file uses external-data tensors); the CPU oracle checks one
+    sampled row (2.9 TFLOP per text in fp32 on the host)."""
+    path = os.path.join(model_cache, "qwen1.5b", "model.onnx")
+    cfg, w = orc.make_model_file("qwen1.5b", path, seed=0)
+    sess = pkg.Session(path)
+    try:
+        assert (sess.info["layers"], sess.info["hidden"], sess.info["heads"], sess.info["kv_heads"], sess.info["inter"]) == (28, 1536, 12, 2, 8960)
+        ids, mask = orc.synth_inputs(cfg, 32, 1024, 20, seed=1239, ragged=True, min_frac=0.6)
+        out = sess.run_inference(ids.numpy(), mask.numpy())
+        assert out.shape == (32, 20) and np.isfinite(out).all()
+        rows = [21]
+        ref = orc.forward_restated(w, cfg, ids[rows], mask[rows]).numpy()
+        print(f"qwen1.5b ref logits std {ref.std():.3f} range [{ref.min():.2f},{ref.max():.2f}]")
+        _check_logits("qwen1.5b/B32S1024/20 labels row 21", out[rows], ref, orc, tol=4e-2)
+    finally:
+        sess.close()

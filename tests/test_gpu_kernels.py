@@ -393,3 +393,95 @@ def test_head_gather_and_score(pkg, dev):
     ref = torch.einsum("bd,bcd->bc", t, k)
     _report("head_score", logits, ref, 1e-4, 1e-5)
     assert torch.equal(dec.bool(), torch.sigmoid(logits) > 0.5)
+
+
+# ---------------------------------------------------------------------------------------------
+# decoder-backbone kernels (Qwen2-style stack)
+# ---------------------------------------------------------------------------------------------
+
+
+@pytest.mark.parametrize("H,M", [(512, 300), (1536, 1000), (2048, 77)])
+def test_add_rmsnorm(pkg, dev, H, M):
+    g = torch.Generator().manual_seed(H + M)
+    h = (torch.randn(M, H, generator=g) * 3).to(dev)
+    delta = torch.randn(M, H, generator=g).to(torch.float16).to(dev)
+    w = (torch.randn(H, generator=g) * 0.1 + 1).to(dev)
+    for d in (delta, None):
+        hh = h.clone()
+        y = torch.empty(M, H, dtype=torch.float16, device=dev)
+        _sync_check(pkg, pkg.lib().glc_op_add_rmsnorm(_ptr(hh), _ptr(d), _ptr(w), 1e-6, _ptr(y), M, H, None), "add_rmsnorm")
+        ref_h = h + (d.float() if d is not None else 0)
+        ref_y = ref_h * torch.rsqrt((ref_h * ref_h).mean(-1, keepdim=True) + 1e-6) * w
+        assert torch.equal(hh, ref_h) or (hh - ref_h).abs().max().item() < 1e-6
+        _report(f"add_rmsnorm H{H} M{M} delta={d is not None}", y, ref_y, 2e-3, 2e-3)
+
+
+def test_rope(pkg, dev):
+    B, S, nh, nkv, d = 2, 333, 4, 2, 128
+    W = (nh + 2 * nkv) * d
+    g = torch.Generator().manual_seed(1)
+    qkv = torch.randn(B * S, W, generator=g).to(torch.float16).to(dev)
+    inv = (1.0 / (1.0e6 ** (torch.arange(0, d, 2).float() / d))).to(dev)
+    out = qkv.clone()
+    _sync_check(pkg, pkg.lib().glc_op_rope(_ptr(out), W, _ptr(inv), B * S, S, nh + nkv, d, None), "rope")
+    pos = torch.arange(S, device=dev).float().repeat(B)
+    ang = pos[:, None] * inv[None, :]
+    cos, sin = torch.cat([ang.cos(), ang.cos()], -1), torch.cat([ang.sin(), ang.sin()], -1)
+    x = qkv[:, : (nh + nkv) * d].float().view(B * S, nh + nkv, d)
+    rot = torch.cat([-x[..., d // 2:], x[..., : d // 2]], -1)
+    ref = (x * cos[:, None, :] + rot * sin[:, None, :]).reshape(B * S, -1)
+    _report("rope q|k", out[:, : (nh + nkv) * d], ref, 2e-3, 2e-3)
+    assert torch.equal(out[:, (nh + nkv) * d:], qkv[:, (nh + nkv) * d:])     # V untouched
+
+
+@pytest.mark.parametrize("M,I,K", [(300, 1536, 512), (4096, 8960, 1536), (100, 64, 128)])
+def test_gemm_swiglu(pkg, dev, M, I, K):
+    """SwiGLU GEMM epilogue (act = 3): gate / up rows interleaved in blocks of 32, output [M, I] = silu(gate) * up"""
+    g = torch.Generator().manual_seed(M + I)
+    A = (torch.randn(M, K, generator=g) * 0.5).to(torch.float16).to(dev)
+    Wg = (torch.randn(I, K, generator=g) / math.sqrt(K)).to(torch.float16).to(dev)
+    Wu = (torch.randn(I, K, generator=g) / math.sqrt(K)).to(torch.float16).to(dev)
+    Wi = torch.stack([Wg.view(I // 32, 32, K), Wu.view(I // 32, 32, K)], 1).reshape(2 * I, K).contiguous()
+    C = torch.full((M, I), float("nan"), dtype=torch.float16, device=dev)
+    rc = pkg.lib().glc_op_gemm(_ptr(A), K, _ptr(Wi), K, None, _ptr(C), I, M, 2 * I, K, 3, 0, None)
+    _sync_check(pkg, rc, "glc_op_gemm(swiglu)")
+    gate, up = A.float() @ Wg.float().t(), A.float() @ Wu.float().t()
+    _report(f"gemm swiglu M{M} I{I} K{K}", C, torch.nn.functional.silu(gate) * up, 3e-3, 3e-3)
+
+
+FLASH_CASES = [
+    # B, S, heads, kv_heads, lens
+    (1, 64, 2, 1, [64]),
+    (1, 192, 2, 2, [192]),
+    (2, 320, 4, 2, [320, 111]),
+    (1, 1024, 6, 1, [1000]),
+    (3, 700, 12, 2, [700, 1, 450]),
+]
+
+
+@pytest.mark.parametrize("B,S,heads,kvh,lens", FLASH_CASES)
+def test_attention_flash128(pkg, dev, B, S, heads, kvh, lens):
+    d = 128
+    W = (heads + 2 * kvh) * d
+    g = torch.Generator().manual_seed(S + heads)
+    qkv = torch.randn(B, S, W, generator=g)
+    qkv[..., : (heads + kvh) * d] *= 1.5
+    qkv = qkv.to(torch.float16).to(dev)
+    mask = torch.zeros(B, S, dtype=torch.long)
+    for b, L in enumerate(lens):
+        mask[b, :L] = 1
+    mask = mask.to(dev)
+    bits = torch.zeros(B, (S + 31) // 32, dtype=torch.int32, device=dev)
+    kv = torch.zeros(B, dtype=torch.int32, device=dev)
+    L_ = pkg.lib()
+    _sync_check(pkg, L_.glc_op_mask_prep(_ptr(mask), _ptr(bits), _ptr(kv), B, S, None), "mask_prep")
+    ctx = torch.full((B, S, heads * d), float("nan"), dtype=torch.float16, device=dev)
+    _sync_check(pkg, L_.glc_op_attention_flash128(_ptr(qkv), _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, kvh, None), "flash128")
+    q = qkv[..., : heads * d].float().view(B, S, heads, d).permute(0, 2, 1, 3)
+    k = qkv[..., heads * d: (heads + kvh) * d].float().view(B, S, kvh, d).permute(0, 2, 1, 3).repeat_interleave(heads // kvh, 1)
+    v = qkv[..., (heads + kvh) * d:].float().view(B, S, kvh, d).permute(0, 2, 1, 3).repeat_interleave(heads // kvh, 1)
+    s = q @ k.transpose(-1, -2) / math.sqrt(d)
+    s = s.masked_fill(~mask[:, None, None, :].bool(), float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).permute(0, 2, 1, 3).reshape(B, S, heads * d)
+    vm = mask.bool()
+    _report(f"flash128 B{B} S{S} h{heads}/{kvh}", ctx[vm], ref[vm], 5e-3, 5e-3)

@@ -37,6 +37,21 @@ def test_restated_matches_hf_beyond_512(orc):
     assert (lg - ref).abs().max().item() < 5e-5
 
 
+def test_qwen2_restated_matches_hf_module(orc):
+    """decoder-backbone oracle pinned against transformers.Qwen2Model (eager attention) with the causal mask replaced by a
+    key-padding mask, on a ragged batch with mixed label counts"""
+    cfg = orc.make_config("qwen-mini")
+    w = orc.init_weights(cfg, 0)
+    m = orc.build_hf_module(cfg, w)
+    ids, mask = orc.synth_inputs(cfg, 3, 150, [4, 2, 3], seed=5, ragged=True)
+    with torch.no_grad():
+        ref = m(ids, mask)
+    lg = orc.forward_restated(w, cfg, ids, mask)
+    assert lg.shape == ref.shape == (3, 4)
+    assert (lg - ref).abs().max().item() < 2e-5
+    assert lg.std().item() > 0.3 and (lg > 0).any() and (lg < 0).any()
+
+
 def test_golden_fixture_reproducible(orc, golden):
     cfg = orc.make_config("tiny")
     w = orc.init_weights(cfg, 0)
