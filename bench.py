@@ -59,6 +59,8 @@ def workload_config(world: int, arch=ARCH, B=BATCH, S=SEQ, NL=LABELS) -> dict:
 def model_path(arch: str) -> str:
     d = os.environ.get("GLC_MODEL_CACHE", "/tmp/glc_models")
     os.makedirs(d, exist_ok=True)
+    if arch.startswith("qwen"):   # > 2 GB: external-data files next to model.onnx, so one directory per model
+        return os.path.join(d, arch, "model.onnx")
     return os.path.join(d, f"{arch}.onnx")
 
 
@@ -396,15 +398,22 @@ def main():
                 else "fallback 1.4 PFLOP/s sustained, 6.65 TB/s (B200_PROFILING.md), 'of fallback'")
     H, I, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_layers
     M = B * S
-    gemm_flops_step = L * (2.0 * M * H * 3 * H + 2.0 * M * H * H + 2 * 2.0 * M * H * I)
+    decoder = cfg.backbone == "qwen2"
+    if decoder:
+        Wq, Wkv = cfg.num_heads * cfg.head_dim, cfg.num_kv_heads * cfg.head_dim
+        gemm_flops_step = L * (2.0 * M * H * (Wq + 2 * Wkv) + 2.0 * M * Wq * H + 3 * 2.0 * M * H * I)
+    else:
+        gemm_flops_step = L * (2.0 * M * H * 3 * H + 2.0 * M * H * H + 2 * 2.0 * M * H * I)
     gemm_keys = ("gemm_qkv", "gemm_out", "gemm_ffn1", "gemm_ffn2")
     gemm_ms = sum(prof[k][0] for k in gemm_keys)
     gemm_n = sum(prof[k][1] for k in gemm_keys)
     achieved = gemm_flops_step * args.steps / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-    att_flops_step = L * (4.0 * B * S * S * H + 4.0 * B * S * 2 * cfg.position_buckets * H)
+    att_flops_step = (L * 4.0 * B * S * S * cfg.num_heads * cfg.head_dim if decoder else
+                      L * (4.0 * B * S * S * H + 4.0 * B * S * 2 * cfg.position_buckets * H))
     att_ms, att_n = prof["attention"]
     att_tf = att_flops_step * args.steps / (att_ms * 1e-3) / 1e12 if att_ms else 0.0
-    ln_bytes_step = L * 2 * 3.0 * M * H * 2
+    # DeBERTa: read x, r, write y (fp16); decoder: read h (fp32) + delta, write h + y
+    ln_bytes_step = (2 * L + 1) * 12.0 * M * H if decoder else L * 2 * 3.0 * M * H * 2
     ln_ms, ln_n = prof["residual_ln"]
     ln_gbs = ln_bytes_step * args.steps / (ln_ms * 1e-3) / 1e9 if ln_ms else 0.0
     F_text = SM.flops_per_text(cfg, S, C)
@@ -436,17 +445,18 @@ def main():
                                          "how": "same steps through glc_submit / glc_collect with two requests in flight"}},
         "settled": settled,
         "gpu_launches": int(launches),
-        "roofline": {"bound": "tensor", "kernel": "gemm_f16_2cta_kernel (QKV, out-proj, FFN1+GELU, FFN2)", "achieved": achieved,
+        "roofline": {"bound": "tensor", "kernel": "gemm_f16_2cta_kernel (QKV, out-proj, gate|up+SwiGLU, down)" if decoder else "gemm_f16_2cta_kernel (QKV, out-proj, FFN1+GELU, FFN2)", "achieved": achieved,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf if peak_tf else None,
                      "traffic": tr.get("gemm"), "traffic_note": tr_note,
                      "peak_source": peak_src, "launches_timed": int(gemm_n),
                      "share_of_step": gemm_ms / ms_prof if ms_prof else None,
                      "timed_over": f"{args.steps} steps re-run with CUDA events around every launch ({ms_prof / args.steps:.3f} ms/step)"},
-        "roofline_attention": {"bound": "tensor", "kernel": "attention_persist_kernel (QK^T, c2p, p2c, PV: 4 S^2 H + 4 S R H per text per layer)",
+        "roofline_attention": {"bound": "tensor", "kernel": ("attention_flash128_kernel (QK^T, PV: 4 S^2 heads*128 per text per layer)" if decoder else
+                                          "attention_persist_kernel (QK^T, c2p, p2c, PV: 4 S^2 H + 4 S R H per text per layer)"),
                                "achieved": att_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": att_tf / peak_tf if peak_tf else None,
                                "us_per_launch": 1e3 * att_ms / att_n if att_n else None, "launches_timed": int(att_n),
                                "traffic": tr.get("attention"), "share_of_step": att_ms / ms_prof if ms_prof else None},
-        "roofline_ln": {"bound": "hbm", "kernel": "residual_ln_bulk_kernel (read x, r; write y)", "achieved": ln_gbs, "peak": peak_bw,
+        "roofline_ln": {"bound": "hbm", "kernel": "add_rmsnorm_kernel (fp32 stream)" if decoder else "residual_ln_bulk_kernel (read x, r; write y)", "achieved": ln_gbs, "peak": peak_bw,
                         "unit": "GB/s", "frac": ln_gbs / peak_bw if peak_bw else None, "launches_timed": int(ln_n),
                         "traffic": tr.get("residual_ln"), "share_of_step": ln_ms / ms_prof if ms_prof else None},
         "kernels": kernels,

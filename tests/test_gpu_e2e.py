@@ -590,10 +590,32 @@ def test_qwen2_backbone_mini_parity(pkg, orc, model_cache):
         sess.close()
 
 
-def test_qwen2_1p5b_arch_sample_row(pkg, orc, model_cache):
-    """BASELINE.json configs[4]: gliclass-qwen-1.5B architecture (Qwen2 28L/1536, 12q/2kv x 128, SwiGLU 8960), batch 32 x
-    seq 1024 x 20 labels on the GPU (weights > 2 GB: the ONNX file uses external-data tensors); the CPU oracle checks one
-    sampled row (2.9 TFLOP per text in fp32 on the host)."""
+def test_qwen2_1p5b_layer_geometry(pkg, orc, model_cache):
+    """The gliclass-qwen-1.5B layer geometry (hidden 1536, 12q/2kv x 128, SwiGLU 8960) at 4 layers, batch 32 x seq 1024 x 20
+    labels on the GPU, four sampled rows against the oracle.  The full 28-layer / 151k-vocabulary model (6.2 GB of fp32
+    ONNX external data, minutes to export) runs in test_qwen2_1p5b_full below when GLC_TEST_FULL=1 and in
+    scripts/gpu_qwen_full.sh, whose log is committed under profiles/."""
+    path = os.path.join(model_cache, "qwen1.5b-4l.onnx")
+    cfg, w = orc.make_model_file("qwen1.5b-4l", path, seed=0)
+    sess = pkg.Session(path)
+    try:
+        assert (sess.info["layers"], sess.info["hidden"], sess.info["heads"], sess.info["kv_heads"], sess.info["inter"]) == (4, 1536, 12, 2, 8960)
+        ids, mask = orc.synth_inputs(cfg, 32, 1024, 20, seed=1239, ragged=True, min_frac=0.6)
+        out = sess.run_inference(ids.numpy(), mask.numpy())
+        assert out.shape == (32, 20) and np.isfinite(out).all()
+        rows = [0, 9, 21, 31]
+        ref = orc.forward_restated(w, cfg, ids[rows], mask[rows]).numpy()
+        print(f"qwen1.5b-4l ref logits std {ref.std():.3f} range [{ref.min():.2f},{ref.max():.2f}]")
+        _check_logits("qwen1.5b-4l/B32S1024/20 labels rows 0,9,21,31", out[rows], ref, orc)
+    finally:
+        sess.close()
+
+
+@pytest.mark.skipif(os.environ.get("GLC_TEST_FULL") != "1", reason="full 28-layer model: set GLC_TEST_FULL=1 (scripts/gpu_qwen_full.sh)")
+def test_qwen2_1p5b_full(pkg, orc, model_cache):
+    """BASELINE.json configs[4]: gliclass-qwen-1.5B architecture (Qwen2 28L/1536, 12q/2kv x 128, SwiGLU 8960, vocabulary
+    151938), batch 32 x seq 1024 x 20 labels on the GPU (weights > 2 GB: the ONNX file uses external-data tensors); the CPU
+    oracle checks sampled rows."""
     path = os.path.join(model_cache, "qwen1.5b", "model.onnx")
     cfg, w = orc.make_model_file("qwen1.5b", path, seed=0)
     sess = pkg.Session(path)
@@ -602,9 +624,9 @@ def test_qwen2_1p5b_arch_sample_row(pkg, orc, model_cache):
         ids, mask = orc.synth_inputs(cfg, 32, 1024, 20, seed=1239, ragged=True, min_frac=0.6)
         out = sess.run_inference(ids.numpy(), mask.numpy())
         assert out.shape == (32, 20) and np.isfinite(out).all()
-        rows = [21]
+        rows = [3, 21]
         ref = orc.forward_restated(w, cfg, ids[rows], mask[rows]).numpy()
         print(f"qwen1.5b ref logits std {ref.std():.3f} range [{ref.min():.2f},{ref.max():.2f}]")
-        _check_logits("qwen1.5b/B32S1024/20 labels row 21", out[rows], ref, orc, tol=4e-2)
+        _check_logits("qwen1.5b/B32S1024/20 labels rows 3,21", out[rows], ref, orc)
     finally:
         sess.close()

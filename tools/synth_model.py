@@ -76,6 +76,9 @@ ARCHS = {
     # decoder backbones: Qwen2 (RMSNorm, RoPE theta 1e6, GQA, SwiGLU, QKV bias), bidirectional attention (LLM2Vec style)
     "qwen-mini": dict(backbone="qwen2", vocab_size=2051, hidden_size=512, num_layers=3, num_heads=4, num_kv_heads=2,
                       kv_head_dim=128, intermediate_size=1536, class_token_index=2049, sep_token_index=2050),
+    # the 1.5B layer geometry at 4 layers and a small vocabulary (< 2 GB: inline weights, quick to export) for the default suite
+    "qwen1.5b-4l": dict(backbone="qwen2", vocab_size=32003, hidden_size=1536, num_layers=4, num_heads=12, num_kv_heads=2,
+                        kv_head_dim=128, intermediate_size=8960, class_token_index=32001, sep_token_index=32002),
     "qwen1.5b": dict(backbone="qwen2", vocab_size=151938, hidden_size=1536, num_layers=28, num_heads=12, num_kv_heads=2,
                      kv_head_dim=128, intermediate_size=8960, class_token_index=151936, sep_token_index=151937),
 }
