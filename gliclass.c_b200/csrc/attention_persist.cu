@@ -39,6 +39,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_desc.h"
 
@@ -215,6 +216,8 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  ptx::pdl_wait();                 // everything above overlapped the previous kernel's tail (launch.h)
+  ptx::pdl_launch_dependents();
 
   if (warp < 4) {
     setmaxnreg_dec<UTIL_REGS>();
@@ -736,10 +739,8 @@ cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* ex
   const int grid = p.n_items < num_sms ? p.n_items : num_sms;
   static const int force_mode = [] { const char* e = getenv("GLC_ATTN_MODE"); return e ? atoi(e) : -1; }();   // developer switch
   if (force_mode != 0 && (S + KT - 1) / KT <= TMAX_RES)
-    attention_persist_kernel<2><<<grid, PTHREADS, Smem<2>::BYTES, stream>>>(tm_qkv, tm_ek, tm_eq, p);
-  else
-    attention_persist_kernel<0><<<grid, PTHREADS, Smem<0>::BYTES, stream>>>(tm_qkv, tm_ek, tm_eq, p);
-  return cudaGetLastError();
+    return launch_pdl(attention_persist_kernel<2>, dim3(grid), dim3(PTHREADS), Smem<2>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
+  return launch_pdl(attention_persist_kernel<0>, dim3(grid), dim3(PTHREADS), Smem<0>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
 }
 
 }  // namespace glc

@@ -12,6 +12,7 @@
 #include <type_traits>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 
 namespace glc {
@@ -131,6 +132,8 @@ embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mas
                 const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H, int vocab) {
   const int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   if (row >= M) return;
   int64_t id = ids[row];
   if (id < 0 || id >= vocab) id = 0;   // ORT's Gather would fail; clamp to [PAD] instead of reading out of bounds
@@ -161,6 +164,8 @@ residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * ROWS_PER_BLOCK;
   int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   if (row >= M) return;
   uint4 xa[NC], ra[NC];
   auto fetch = [&](int rw) {
@@ -270,6 +275,8 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
     ptx::fence_barrier_init();
   }
   __syncwarp();
+  ptx::pdl_wait();                 // barrier set-up overlapped the previous kernel's tail (launch.h)
+  ptx::pdl_launch_dependents();
   auto issue = [&](int rw, int s) {
     if (lane == 0) {
       uint8_t* dst = ring + (size_t)s * st_bytes;
@@ -343,6 +350,8 @@ __global__ void mask_prep_kernel(const int64_t* __restrict__ mask, uint32_t* __r
                                  int32_t* __restrict__ kv_len, int B, int S) {
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   if (b >= B) return;
   const int words = (S + 31) / 32;
   int last = 0;
@@ -364,6 +373,8 @@ head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids
   extern __shared__ int pos_s[];   // [C] per block (one batch row per block)
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   if (warp == 0) {
     int count = 0;
     for (int j0 = 0; j0 < S; j0 += 32) {
@@ -454,6 +465,8 @@ head_score_ex_kernel(const float* __restrict__ t, int64_t t_stride, const float*
                      int normalize, float eps, float scale, float bias) {
   const int idx = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   if (idx >= B * C) return;
   const int b = idx / C;
   const float4* tv = reinterpret_cast<const float4*>(t + (int64_t)b * t_stride);
@@ -588,9 +601,8 @@ cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, c
   if (M <= 0) return cudaSuccess;
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
-    embed_ln_kernel<NC><<<(M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK, ROWS_PER_BLOCK * 32, 0, stream>>>(
-        ids, mask, (const __half*)emb, gamma, beta, eps, (__half*)y, M, H, vocab);
-    return cudaGetLastError();
+    return launch_pdl(embed_ln_kernel<NC>, dim3((M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK), dim3(ROWS_PER_BLOCK * 32), 0, stream, ids,
+                      mask, (const __half*)emb, gamma, beta, eps, (__half*)y, M, H, vocab);
   });
 }
 
@@ -626,16 +638,14 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
       int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
       const int per_sm = (int)((224 * 1024) / (ring_bytes + 1024));
       if (blocks > sms * per_sm) blocks = sms * per_sm;
-      residual_ln_bulk_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, ring_bytes, stream>>>(
-          (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages, overflow_flag);
-      return cudaGetLastError();
+      return launch_pdl(residual_ln_bulk_kernel<NC>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), ring_bytes, stream, (const __half*)x,
+                        (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages, overflow_flag);
     }
     int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
     const int cap = ln_grid_cap();   // a few resident blocks per SM, each warp walking several rows
     if (blocks > cap) blocks = cap;
-    residual_ln_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, 0, stream>>>(
-        (const __half*)x, (const __half*)r, gamma, beta, eps, (__half*)y, M, H, overflow_flag);
-    return cudaGetLastError();
+    return launch_pdl(residual_ln_kernel<NC>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, stream, (const __half*)x, (const __half*)r,
+                      gamma, beta, eps, (__half*)y, M, H, overflow_flag);
   });
 }
 
@@ -652,8 +662,7 @@ cudaError_t ln_f32_to_f16(const float* x, const float* gamma, const float* beta,
 
 cudaError_t mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_len, int B, int S, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  mask_prep_kernel<<<(B + 3) / 4, 128, 0, stream>>>(mask, bits, kv_len, B, S);
-  return cudaGetLastError();
+  return launch_pdl(mask_prep_kernel, dim3((B + 3) / 4), dim3(128), 0, stream, mask, bits, kv_len, B, S);
 }
 
 cudaError_t head_gather(const void* h, const int64_t* ids, int64_t class_token, void* pooled, void* cls, int B, int S,
@@ -665,9 +674,8 @@ cudaError_t head_gather_pool(const void* h, const int64_t* ids, const int64_t* m
                              void* pooled, void* cls, int B, int S, int H, int C, cudaStream_t stream, int class_pos_offset) {
   if (B <= 0) return cudaSuccess;
   if (H % 8 != 0 || pool_mode < 0 || pool_mode > 3 || (pool_mode >= 2 && !mask) || class_pos_offset < 0) return cudaErrorInvalidValue;
-  head_gather_kernel<<<B, 128, (size_t)(C > 0 ? C : 1) * sizeof(int), stream>>>(
-      (const __half*)h, ids, mask, class_token, pool_mode, (__half*)pooled, (__half*)cls, B, S, H, C, class_pos_offset);
-  return cudaGetLastError();
+  return launch_pdl(head_gather_kernel, dim3(B), dim3(128), (size_t)(C > 0 ? C : 1) * sizeof(int), stream, (const __half*)h, ids, mask,
+                    class_token, pool_mode, (__half*)pooled, (__half*)cls, B, S, H, C, class_pos_offset);
 }
 
 cudaError_t pad_rows_mean_v(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int H, cudaStream_t stream) {
@@ -682,9 +690,8 @@ cudaError_t head_score_ex(const float* t, int64_t t_stride, const float* k, floa
                           cudaStream_t stream) {
   if (B * C <= 0) return cudaSuccess;
   if (K % 4 != 0 || (t_stride % 4) != 0) return cudaErrorInvalidValue;
-  head_score_ex_kernel<<<(B * C + 7) / 8, 256, 0, stream>>>(t, t_stride, k, logits, probs, decisions, threshold, B, C, K,
-                                                            normalize ? 1 : 0, eps, scale, bias);
-  return cudaGetLastError();
+  return launch_pdl(head_score_ex_kernel, dim3((B * C + 7) / 8), dim3(256), 0, stream, t, t_stride, k, logits, probs, decisions,
+                    threshold, B, C, K, normalize ? 1 : 0, eps, scale, bias);
 }
 
 cudaError_t head_rows16(const float* src, int K, int rep, void* dst_f16, int64_t ld_dst, int col0, int rows, bool normalize,

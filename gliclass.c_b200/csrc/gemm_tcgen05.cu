@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "launch.h"
 #include "ptx.cuh"
 #include "tma_desc.h"
 
@@ -353,6 +354,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();                 // everything above overlapped the previous kernel's tail (launch.h)
+  ptx::pdl_launch_dependents();
 
   const int num_m = (M + BM - 1) / BM;
   const int num_n = (N + BN - 1) / BN;
@@ -507,6 +510,8 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
   ptx::cluster_sync();   // barrier inits and the TMEM allocation of both CTAs are visible
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();                 // everything above overlapped the previous kernel's tail (launch.h)
+  ptx::pdl_launch_dependents();
 
   const int num_m = (M + 2 * BM - 1) / (2 * BM);
   const int num_n = (N + BN - 1) / BN;
@@ -635,8 +640,8 @@ cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t 
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + Cfg::BN - 1) / Cfg::BN);
   const int max_cl = num_sms / 2;
   const int ncl = tiles < max_cl ? tiles : max_cl;
-  kern<<<2 * ncl, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, tm_c, bias, C, ldc, M, N, K, (const __half*)resid, ldr);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(2 * ncl), dim3(EpiCfg<ACT>::THREADS), Cfg::SMEM_BYTES, stream, tm_a, tm_w, tm_c, bias, C, ldc, M, N, K,
+                    (const __half*)resid, ldr);
 }
 
 template <int BN, int ACT, bool OUT_F32>
@@ -662,8 +667,8 @@ cudaError_t launch_gemm(const void* A, int64_t lda, const void* W, int64_t ldw, 
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  kern<<<grid, EpiCfg<ACT>::THREADS, Cfg::SMEM_BYTES, stream>>>(tm_a, tm_w, bias, C, ldc, M, N, K, (const __half*)resid, ldr);
-  return cudaGetLastError();
+  return launch_pdl(kern, dim3(grid), dim3(EpiCfg<ACT>::THREADS), Cfg::SMEM_BYTES, stream, tm_a, tm_w, bias, C, ldc, M, N, K,
+                    (const __half*)resid, ldr);
 }
 
 }  // namespace

@@ -21,6 +21,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// programmatic dependent launch (launch.h): wait for the predecessor grid's completion + memory flush; allow the
+// successor grid to start its prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
