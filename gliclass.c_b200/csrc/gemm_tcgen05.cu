@@ -19,6 +19,8 @@
 // Ragged M/N/K are handled by TMA out-of-bounds zero fill on loads and predication on stores.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+#include <cstdint>
 #include <cstdlib>
 
 #include "kernels.h"
@@ -686,9 +688,6 @@ cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ld
   if ((lda % 8) || (ldw % 8) || (K % 8) || (N % 8) || (ldc % (out_f32 ? 4 : 8))) return cudaErrorInvalidValue;
   if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15)
     return cudaErrorInvalidValue;
-  // 128x256 tiles when that still fills the machine; otherwise 128x128 (more tiles, less tail)
-  const int tiles256 = ((M + BM - 1) / BM) * ((N + 255) / 256);
-  const bool wide = (N % 256 == 0) && tiles256 >= num_sms;
   if (act < 0 || act > 3) return cudaErrorInvalidValue;
   if (act == 3) {
     // SwiGLU: gate / up rows interleaved in blocks of 32 (see silu_mul); output [M, N/2]
@@ -702,23 +701,27 @@ cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ld
     if (act == 1) return launch_gemm<128, 1, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
     return launch_gemm<128, 2, true>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   }
-  // CTA pairs (256 x 256 cluster tiles) whenever they fill the machine
-  const int tiles2 = ((M + 255) / 256) * ((N + 255) / 256);
+  // Tile configuration by a wave model: every candidate keeps 128 output rows per SM, so its time is (rounds of tiles over
+  // the SMs / clusters) x (tile columns); single-CTA tiles pay ~10 % for fetching whole W tiles per SM (see the CTA-pair
+  // kernel's header), the 192-wide pair tile 2 % for re-reading A more often.  Examples on 148 SMs: M = 32768, N = 768 ->
+  // 256 x 192 pairs in 7 rounds (6 rounds of 256 cost 14 % more); M = 4096 (one batch-8 request), N = 768 -> 64 pair
+  // tiles of 256 x 192 in ONE round instead of two rounds of 128 x 128 (-25 % on the K = 3072 FFN2).
   static const bool no_pairs = getenv("GLC_GEMM_NO_PAIRS") != nullptr;
-  if (!no_pairs && tiles2 >= num_sms / 2 && N >= 256) {
-    // 256 x 192 cluster tiles when they quantise into clearly fewer column-rounds (N = 768: 7 rounds of 192 instead of
-    // 6 of 256 per cluster, -12.5 %); a narrower tile re-reads A more often, so it has to win by > 5 %
-    static const bool no_192 = getenv("GLC_GEMM_NO_192") != nullptr;
-    const int ncl = num_sms / 2, mt = (M + 255) / 256;
-    const int64_t cost256 = (int64_t)((mt * ((N + 255) / 256) + ncl - 1) / ncl) * 256;
-    const int64_t cost192 = (int64_t)((mt * ((N + 191) / 192) + ncl - 1) / ncl) * 192;
-    if (!no_192 && act == 0 && N % 192 == 0 && cost192 * 100 < cost256 * 95)
-      return launch_gemm_2cta<192, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+  static const bool no_192 = getenv("GLC_GEMM_NO_192") != nullptr;
+  const int ncl = num_sms / 2, mt1 = (M + BM - 1) / BM, mt2 = (M + 2 * BM - 1) / (2 * BM);
+  auto rounds = [](int tiles, int slots) { return (int64_t)((tiles + slots - 1) / slots); };
+  const int64_t c128 = rounds(mt1 * ((N + 127) / 128), num_sms) * 128 * 110;
+  const int64_t c256 = (N % 256 == 0) ? rounds(mt1 * (N / 256), num_sms) * 256 * 110 : INT64_MAX;
+  const int64_t p256 = (!no_pairs && N >= 256 && ncl > 0) ? rounds(mt2 * ((N + 255) / 256), ncl) * 256 * 100 : INT64_MAX;
+  const int64_t p192 = (!no_pairs && !no_192 && act == 0 && N % 192 == 0 && ncl > 0) ? rounds(mt2 * (N / 192), ncl) * 192 * 102 : INT64_MAX;
+  const int64_t best = std::min(std::min(c128, c256), std::min(p256, p192));
+  if (best == p256) {
     if (act == 0) return launch_gemm_2cta<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
     if (act == 1) return launch_gemm_2cta<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
     return launch_gemm_2cta<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   }
-  if (wide) {
+  if (best == p192) return launch_gemm_2cta<192, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+  if (best == c256) {
     if (act == 0) return launch_gemm<256, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
     if (act == 1) return launch_gemm<256, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
     return launch_gemm<256, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);

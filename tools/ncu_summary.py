@@ -1,6 +1,7 @@
 """Summarise ncu artefacts into markdown for profiles/ (run here, no GPU needed).
     python tools/ncu_summary.py launches gpurun_out/p_launches.csv
-    python tools/ncu_summary.py report gpurun_out/p_gemm.ncu-rep [...]"""
+    python tools/ncu_summary.py report gpurun_out/p_gemm.ncu-rep [...]
+    python tools/ncu_summary.py traffic gemm=gpurun_out/p_gemm.ncu-rep attention=... residual_ln=...  > profiles/ncu_traffic.json"""
 import collections
 import csv
 import io
@@ -69,7 +70,40 @@ def report(path):
                 print(f"| {label} (`{k}`) | {v} {u} |")
 
 
+def traffic(specs):
+    """dram__bytes_read.sum + dram__bytes_write.sum averaged over the launches captured in each report -> the JSON
+    bench.py reads (profiles/ncu_traffic.json)"""
+    import json
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    res, detail = {}, {}
+    for spec in specs:
+        fam, path = spec.split("=", 1)
+        out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        hdr, units = rows[0], rows[1]
+        tot, per = 0.0, []
+        for r in rows[2:]:
+            d = dict(zip(hdr, zip(units, r)))
+            b = 0.0
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                u, v = d[k]
+                b += float(v.replace(",", "")) * mult[u]
+            name = re.sub(r"[(].*", "", d["Kernel Name"][1]).replace("glc::<unnamed>::", "").replace("void ", "")
+            per.append({"kernel": name[:80], "dram_bytes": b, "duration_us_under_ncu": float(d["gpu__time_duration.sum"][1].replace(",", "")) *
+                        {"ns": 1e-3, "us": 1.0, "ms": 1e3, "nsecond": 1e-3, "usecond": 1.0, "msecond": 1e3}[d["gpu__time_duration.sum"][0]]})
+            tot += b
+        res[fam] = tot / max(1, len(per))
+        detail[fam] = per
+    print(json.dumps({"bytes_per_launch": res, "launches": detail,
+                      "note": "dram__bytes_read.sum + dram__bytes_write.sum from `ncu --set full --clock-control none` captures of the "
+                              "bench.py workload (scripts/gpu_profiles.sh), averaged over the captured launches of each family; "
+                              "cold-cache and serialised, so an upper bound on the in-step DRAM traffic"}, indent=1))
+
+
 if __name__ == "__main__":
     mode, paths = sys.argv[1], sys.argv[2:]
-    for p in paths:
-        (launches if mode == "launches" else report)(p)
+    if mode == "traffic":
+        traffic(paths)
+    else:
+        for p in paths:
+            (launches if mode == "launches" else report)(p)
