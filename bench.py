@@ -175,6 +175,8 @@ def main():
     ap.add_argument("--seq", type=int, default=SEQ)
     ap.add_argument("--labels", type=int, default=LABELS)
     ap.add_argument("--arch", default=ARCH)
+    ap.add_argument("--weights", default="fp16", choices=["fp16", "fp8"],
+                    help="fp8 = the opt-in GLC_DTYPE_FP8_E4M3 mode (FFN GEMMs on e4m3 operands); NOT the headline configuration")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -221,7 +223,7 @@ def main():
         SM.make_model_file(args.arch, path, seed=0)
     if dist is not None:
         dist.barrier()
-    sess = pkg.Session(path, devices=[local_rank])
+    sess = pkg.Session(path, devices=[local_rank], weight_dtype=args.weights)
     ids, mask = SM.synth_inputs(cfg, B, S, NL, seed=1235 + rank)
     C = sess.num_classes(ids.numpy())
     d_ids, d_mask = ids.to(dev), mask.to(dev)
@@ -428,7 +430,7 @@ def main():
     line = {
         "metric": METRIC, "value": value, "unit": "texts/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f16", "data": "synthetic",
+        "dtype": "f16" if args.weights == "fp16" else "f16 (FFN1/FFN2 operands e4m3, fp32 accumulate)", "data": "synthetic",
         "config": workload_config(world, args.arch, B, S, NL),
         "forward": {"flops_per_text": F_text, "whole_forward_frac_of_tensor_peak": value / world * F_text / (peak_tf * 1e12),
                     "peak_tflops": peak_tf, "peak_source": peak_src},

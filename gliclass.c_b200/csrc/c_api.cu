@@ -78,10 +78,11 @@ glc_model* glc_load(const char* onnx_path, const glc_opts* opts) {
       preln_f32 = opts->preln_f32 != 0;
       if (opts->weight_dtype != GLC_DTYPE_DEFAULT) dtype = opts->weight_dtype;
     }
-    if (dtype != GLC_DTYPE_FP16) {
+    if (dtype != GLC_DTYPE_FP16 && dtype != GLC_DTYPE_FP8_E4M3) {
       fail(GLC_ERR_ARG,
-           "glc_load: only GLC_DTYPE_FP16 storage is implemented (bf16 cannot meet the 2e-2 parity bar and tcgen05 "
-           "kind::f16 rejects fp16 x bf16 operands; FP8 block-scaled weights are future work)");
+           "glc_load: weight_dtype must be GLC_DTYPE_FP16 (default) or GLC_DTYPE_FP8_E4M3 (opt-in: FFN weights and FFN "
+           "activations in e4m3, everything else fp16); bf16 storage is not implemented (it cannot meet the 2e-2 parity bar "
+           "and tcgen05 kind::f16 rejects fp16 x bf16 operands)");
       return nullptr;
     }
     if (devices.empty()) {
@@ -129,7 +130,7 @@ glc_model* glc_load(const char* onnx_path, const glc_opts* opts) {
     glc_model* h = new glc_model;
     h->m = nullptr;
     try {
-      h->m = new glc::Model(onnx_path, devices, max_tokens, preln_f32);
+      h->m = new glc::Model(onnx_path, devices, max_tokens, preln_f32, dtype == GLC_DTYPE_FP8_E4M3);
       if (want_heads > 0 && want_heads != h->m->cfg().heads)
         throw std::runtime_error("glc_opts.num_heads = " + std::to_string(want_heads) + " but the graph has " +
                                  std::to_string(h->m->cfg().heads) + " attention heads");
@@ -422,6 +423,19 @@ int glc_op_gemm_resid(const void* A, int64_t lda, const void* W, int64_t ldw, co
                       void* C, int64_t ldc, int M, int N, int K, int act, int out_f32, void* stream) {
   GLC_TRY("glc_op_gemm_resid", glc::gemm_f16_resid(A, lda, W, ldw, bias, resid, ldr, C, ldc, M, N, K, act, out_f32 != 0,
                                                    num_sms_current(), (cudaStream_t)stream));
+}
+int glc_op_gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, const float* a_scale, float a_const,
+                     const float* w_scale, const float* bias, void* C, int64_t ldc, int M, int N, int K, int act, int out_e4m3,
+                     float out_mult, void* stream) {
+  GLC_TRY("glc_op_gemm_e4m3", glc::gemm_e4m3(A8, lda, W8, ldw, a_scale, a_const, w_scale, bias, C, ldc, M, N, K, act, out_e4m3 != 0,
+                                             out_mult, num_sms_current(), (cudaStream_t)stream));
+}
+int glc_op_quantize_rows_e4m3(const void* x_f16, int64_t ldx, void* q8, int64_t ldq, float* scale, int M, int K, void* stream) {
+  GLC_TRY("glc_op_quantize_rows_e4m3", glc::quantize_rows_e4m3(x_f16, ldx, q8, ldq, scale, M, K, (cudaStream_t)stream));
+}
+int glc_op_residual_ln_e4m3(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y, void* y8,
+                            float* y8_scale, int M, int H, void* stream) {
+  GLC_TRY("glc_op_residual_ln_e4m3", glc::residual_ln(x, r, gamma, beta, eps, y, M, H, (cudaStream_t)stream, nullptr, false, y8, y8_scale));
 }
 int glc_op_embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, const float* gamma, const float* beta, float eps,
                     void* y, int M, int H, int vocab, void* stream) {

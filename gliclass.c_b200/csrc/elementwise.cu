@@ -85,10 +85,13 @@ struct LnParams {
   }
 };
 
-// LN over a row held as NC chunks of 8 floats per lane; writes fp16, scaled by `post`.
+// LN over a row held as NC chunks of 8 floats per lane; writes fp16, scaled by `post`.  With out8 != nullptr the row is
+// ALSO written as e4m3 under its own dynamic scale (y * 448 / amax_row; *scale_out = amax_row / 448): the A operand of the
+// opt-in FP8 FFN1 GEMM (gemm_e4m3), produced here so no separate quantiser pass re-reads the activations.
 template <int NC>
 __device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, const LnParams<NC>& gb, float eps, float post,
-                                         __half* __restrict__ out) {
+                                         __half* __restrict__ out, uint8_t* __restrict__ out8 = nullptr,
+                                         float* __restrict__ scale_out = nullptr) {
   float s = 0.f;
 #pragma unroll
   for (int c = 0; c < NC; ++c)
@@ -108,19 +111,38 @@ __device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, con
       }
     }
   const float rstd = rsqrtf(warp_sum(q) / (float)H + eps);
+  float amax = 0.f;
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     const int e0 = (lane + 32 * c) * 8;
     if (e0 < H) {
-      float y[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) y[i] = ((v[c][i] - mean) * rstd * gb.g[c][i] + gb.b[c][i]) * post;
+      for (int i = 0; i < 8; ++i) {
+        v[c][i] = ((v[c][i] - mean) * rstd * gb.g[c][i] + gb.b[c][i]) * post;
+        amax = fmaxf(amax, fabsf(v[c][i]));
+      }
       uint4 o;
-      o.x = ptx::pack_f16(y[0], y[1]);
-      o.y = ptx::pack_f16(y[2], y[3]);
-      o.z = ptx::pack_f16(y[4], y[5]);
-      o.w = ptx::pack_f16(y[6], y[7]);
+      o.x = ptx::pack_f16(v[c][0], v[c][1]);
+      o.y = ptx::pack_f16(v[c][2], v[c][3]);
+      o.z = ptx::pack_f16(v[c][4], v[c][5]);
+      o.w = ptx::pack_f16(v[c][6], v[c][7]);
       *reinterpret_cast<uint4*>(out + e0) = o;
+    }
+  }
+  if (out8 != nullptr) {   // warp-uniform
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float inv = amax > 0.f ? 448.0f / amax : 1.0f;
+    if (lane == 0) *scale_out = amax > 0.f ? amax / 448.0f : 1.0f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int e0 = (lane + 32 * c) * 8;
+      if (e0 < H) {
+        uint2 o;
+        o.x = ptx::pack_e4m3x4(v[c][0] * inv, v[c][1] * inv, v[c][2] * inv, v[c][3] * inv);
+        o.y = ptx::pack_e4m3x4(v[c][4] * inv, v[c][5] * inv, v[c][6] * inv, v[c][7] * inv);
+        *reinterpret_cast<uint2*>(out8 + e0) = o;
+      }
     }
   }
 }
@@ -160,7 +182,8 @@ template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                   __half* __restrict__ y, int M, int H, int* __restrict__ flag) {
+                   __half* __restrict__ y, int M, int H, int* __restrict__ flag, uint8_t* __restrict__ y8,
+                   float* __restrict__ y8_scale) {
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * ROWS_PER_BLOCK;
   int row = blockIdx.x * ROWS_PER_BLOCK + (threadIdx.x >> 5);
@@ -202,7 +225,7 @@ residual_ln_kernel(const __half* __restrict__ x, const __half* __restrict__ r,
     const bool more = row < M;   // warp-uniform
     if (more) fetch(row);
     sat_probe<NC>(v, lane, H, flag);
-    ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)cur * H);
+    ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)cur * H, y8 ? y8 + (int64_t)cur * H : nullptr, y8_scale + cur);
     if (!more) break;
   }
 }
@@ -259,7 +282,7 @@ template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__ r, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H, int stages,
-                        int* __restrict__ flag) {
+                        int* __restrict__ flag, uint8_t* __restrict__ y8, float* __restrict__ y8_scale) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t row_bytes = (uint32_t)H * 2u;
@@ -316,7 +339,7 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
     const int nxt = rw + stages * nwarps;
     if (nxt < M) issue(nxt, s);
     sat_probe<NC>(v, lane, H, flag);
-    ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)rw * H);
+    ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)rw * H, y8 ? y8 + (int64_t)rw * H : nullptr, y8_scale + rw);
     if (++s == stages) { s = 0; parity ^= 1u; }
   }
 }
@@ -607,8 +630,9 @@ cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* emb, c
 }
 
 cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const float* beta, float eps, void* y, int M,
-                        int H, cudaStream_t stream, int* overflow_flag, bool x_is_f32) {
+                        int H, cudaStream_t stream, int* overflow_flag, bool x_is_f32, void* y8, float* y8_scale) {
   if (M <= 0) return cudaSuccess;
+  if ((y8 != nullptr) != (y8_scale != nullptr) || (y8 != nullptr && x_is_f32)) return cudaErrorInvalidValue;
   return dispatch_nc(H, [&](auto nc) {
     constexpr int NC = decltype(nc)::value;
     if (x_is_f32) {
@@ -639,14 +663,42 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
       const int per_sm = (int)((224 * 1024) / (ring_bytes + 1024));
       if (blocks > sms * per_sm) blocks = sms * per_sm;
       return launch_pdl(residual_ln_bulk_kernel<NC>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), ring_bytes, stream, (const __half*)x,
-                        (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages, overflow_flag);
+                        (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages, overflow_flag, (uint8_t*)y8, y8_scale);
     }
     int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
     const int cap = ln_grid_cap();   // a few resident blocks per SM, each warp walking several rows
     if (blocks > cap) blocks = cap;
     return launch_pdl(residual_ln_kernel<NC>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), 0, stream, (const __half*)x, (const __half*)r,
-                      gamma, beta, eps, (__half*)y, M, H, overflow_flag);
+                      gamma, beta, eps, (__half*)y, M, H, overflow_flag, (uint8_t*)y8, y8_scale);
   });
+}
+
+// one warp per row: amax, then e4m3 under the row's scale (tests and the load-time weight quantiser use it)
+__global__ void __launch_bounds__(256)
+quantize_rows_e4m3_kernel(const __half* __restrict__ x, int64_t ldx, uint8_t* __restrict__ q, int64_t ldq, float* __restrict__ scale,
+                          int M, int K) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const __half* xr = x + (int64_t)row * ldx;
+  float amax = 0.f;
+  for (int k = lane; k < K; k += 32) amax = fmaxf(amax, fabsf(__half2float(xr[k])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  const float inv = amax > 0.f ? 448.0f / amax : 1.0f;
+  if (lane == 0) scale[row] = amax > 0.f ? amax / 448.0f : 1.0f;
+  uint8_t* qr = q + (int64_t)row * ldq;
+  for (int k = 2 * lane; k < K; k += 64) {
+    const float a = __half2float(xr[k]) * inv, b = (k + 1 < K) ? __half2float(xr[k + 1]) * inv : 0.f;
+    const uint32_t p = ptx::pack_e4m3x2(a, b);
+    qr[k] = (uint8_t)(p & 0xff);
+    if (k + 1 < K) qr[k + 1] = (uint8_t)(p >> 8);
+  }
+}
+
+cudaError_t quantize_rows_e4m3(const void* x_f16, int64_t ldx, void* q8, int64_t ldq, float* scale, int M, int K, cudaStream_t stream) {
+  if (M <= 0 || K <= 0) return cudaSuccess;
+  quantize_rows_e4m3_kernel<<<(M + 7) / 8, 256, 0, stream>>>((const __half*)x_f16, ldx, (uint8_t*)q8, ldq, scale, M, K);
+  return cudaGetLastError();
 }
 
 cudaError_t ln_f32_to_f16(const float* x, const float* gamma, const float* beta, float eps, void* y, int M, int H,

@@ -102,7 +102,7 @@ void DeviceModel::upload_w16(void** dst, const float* src, size_t n) {
   GLC_CUDA(cudaMemcpy(*dst, h.data(), n * 2, cudaMemcpyHostToDevice));
 }
 
-DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool preln_f32) : device_(device), cfg_(w.cfg) {
+DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool preln_f32, bool fp8_ffn) : device_(device), cfg_(w.cfg) {
   GLC_CUDA(cudaSetDevice(device_));
   cudaDeviceProp prop;
   GLC_CUDA(cudaGetDeviceProperties(&prop, device_));
@@ -139,6 +139,18 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
     const char* pf = getenv("GLC_PRELN_F32");
     preln_f32_ = preln_f32 || (pf && pf[0] == '1');
     if (preln_f32_) fuse_resid_ = false;
+  }
+  {
+    const char* f8 = getenv("GLC_FP8_FFN");
+    fp8_ffn_ = fp8_ffn || (f8 && f8[0] == '1');
+    if (const char* fm = getenv("GLC_FP8_MULT")) fp8_mult_ = (float)atof(fm);
+    if (fp8_ffn_) {
+      if (cfg_.backbone == BACKBONE_QWEN2) throw std::runtime_error("FP8 FFN weights are implemented for the DeBERTa encoder stack only");
+      if (preln_f32_) throw std::runtime_error("FP8 FFN weights and preln_f32 cannot be combined");
+      if (cfg_.hidden % 16 || cfg_.inter % 16) throw std::runtime_error("FP8 FFN weights need hidden and intermediate sizes divisible by 16");
+      if (!(fp8_mult_ > 0.f)) throw std::runtime_error("GLC_FP8_MULT must be positive");
+      fuse_resid_ = false;
+    }
   }
   GLC_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   d_overflow_ = (int*)dalloc(sizeof(int));
@@ -248,6 +260,15 @@ void DeviceModel::init_deberta(const ModelWeights& w) {
     upload_f32(&d.b1, w.at(r + ".ffn1.b"));
     upload_w16(&d.w2, w.at(r + ".ffn2.w").data.data(), (size_t)H * I);
     upload_f32(&d.b2, w.at(r + ".ffn2.b"));
+    if (fp8_ffn_) {
+      // load-time quantiser: per-output-channel (row of W) symmetric e4m3, scale = amax / 448
+      d.w1_8 = dalloc((size_t)I * H); perm_allocs_.push_back(d.w1_8);
+      d.w2_8 = dalloc((size_t)H * I); perm_allocs_.push_back(d.w2_8);
+      d.w1_s = (float*)dalloc((size_t)I * 4); perm_allocs_.push_back(d.w1_s);
+      d.w2_s = (float*)dalloc((size_t)H * 4); perm_allocs_.push_back(d.w2_s);
+      GLC_CUDA(quantize_rows_e4m3(d.w1, H, d.w1_8, H, d.w1_s, I, H, stream_));
+      GLC_CUDA(quantize_rows_e4m3(d.w2, I, d.w2_8, I, d.w2_s, H, I, stream_));
+    }
     upload_f32(&d.ln2g, w.at(r + ".ln2.g"));
     upload_f32(&d.ln2b, w.at(r + ".ln2.b"));
     // position projections with the shared content weights (T:296-302, share_att_key), hoisted
@@ -366,7 +387,11 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   qkv_ = A(M * Wqkv * 2);
   ctx_ = A(M * Wq * 2);
   tmp_ = A(M * H * (preln_f32_ ? 4 : 2));
-  ffn_ = A(M * I * 2);
+  ffn_ = A(M * I * 2);   // fp16 [M, I]; the FP8 path stores e4m3 [M, I] in its first half
+  if (fp8_ffn_) {
+    x1_8_ = A(M * H);
+    x1_s_ = (float*)A(M * 4);
+  }
   mask_bits_ = (uint32_t*)A(((M + 31) / 32 + (size_t)ws_B_) * 4);
   kv_len_ = (int32_t*)A((size_t)ws_B_ * 4);
   pooled_ = A((size_t)ws_B_ * H * 2);
@@ -588,7 +613,18 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
       GLC_LAUNCH(KC_LN, residual_ln(tmp_, nullptr, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st, d_overflow_));
     } else {
       GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, H, d.wo, H, d.bo, tmp_, H, M, H, H, 0, preln_f32_, num_sms_, st));
-      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st, d_overflow_, preln_f32_));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x_, d.ln1g, d.ln1b, cfg_.ln_eps, x1_, M, H, st, d_overflow_, preln_f32_,
+                                    fp8_ffn_ ? x1_8_ : nullptr, fp8_ffn_ ? x1_s_ : nullptr));
+    }
+    if (fp8_ffn_) {
+      // e4m3 FFN: LN1 wrote the rows as e4m3 under per-row scales; GELU output stays e4m3 (x fp8_mult_) for FFN2
+      GLC_LAUNCH(KC_GEMM_FFN1, gemm_e4m3(x1_8_, H, d.w1_8, H, x1_s_, 1.0f, d.w1_s, d.b1, ffn_, I, M, I, H, 1, true, fp8_mult_,
+                                         num_sms_, st));
+      GLC_LAUNCH(KC_GEMM_FFN2, gemm_e4m3(ffn_, I, d.w2_8, I, nullptr, 1.0f / fp8_mult_, d.w2_s, d.b2, tmp_, H, M, H, I, 0, false,
+                                         1.0f, num_sms_, st));
+      GLC_LAUNCH(KC_LN, residual_ln(tmp_, x1_, d.ln2g, d.ln2b, cfg_.ln_eps, x_, M, H, st, d_overflow_));
+      if (debug_keep_) keep(("h" + std::to_string(l)).c_str(), x_, (size_t)M * H);
+      continue;
     }
     GLC_LAUNCH(KC_GEMM_FFN1, gemm_f16(x1_, H, d.w1, H, d.b1, ffn_, I, M, I, H, 1, false, num_sms_, st));
     if (fuse_resid_) {
@@ -930,12 +966,12 @@ void TaskQueue::loop() {
   }
 }
 
-Model::Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens, bool preln_f32) {
+Model::Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens, bool preln_f32, bool fp8_ffn) {
   ModelWeights w;
   load_model_weights(onnx_path, &w);
   cfg_ = w.cfg;
   if (devices.empty()) throw std::runtime_error("no CUDA device selected");
-  for (int d : devices) devs_.emplace_back(new DeviceModel(d, w, max_tokens, preln_f32));
+  for (int d : devices) devs_.emplace_back(new DeviceModel(d, w, max_tokens, preln_f32, fp8_ffn));
   if (devs_.size() > 1)
     for (size_t i = 0; i < devs_.size(); ++i) workers_.emplace_back(new TaskQueue(1));
   const char* co = getenv("GLC_COALESCE");

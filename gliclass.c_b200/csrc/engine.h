@@ -34,6 +34,9 @@ struct DeviceLayer {
   void* w2 = nullptr;     // fp16 [H,I]
   float* b2 = nullptr;
   float *ln2g = nullptr, *ln2b = nullptr;
+  // opt-in FP8 FFN (glc_opts.weight_dtype = GLC_DTYPE_FP8_E4M3): e4m3 copies of w1 / w2 with one scale per output channel
+  void *w1_8 = nullptr, *w2_8 = nullptr;
+  float *w1_s = nullptr, *w2_s = nullptr;
   void* pos_qk = nullptr; // fp16 [2*buckets, 2H]: cols [0,H) = query_proj(rel), [H,2H) = key_proj(rel)
   void* pos_exp = nullptr; // fp16 [expanded_pos_rows(), 2H]: pos_qk expanded to one row per delta (row rho = pos_qk[idx(2047 - rho)]; in shift mode the posQ half [0,H) is stored in the opposite order, row sigma = idx(sigma - 2047))
 };
@@ -52,7 +55,7 @@ enum KernelCat { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTN, KC_GEMM_OUT, KC_LN, KC_GEMM
 
 class DeviceModel {
  public:
-  DeviceModel(int device, const ModelWeights& w, int max_tokens, bool preln_f32 = false);
+  DeviceModel(int device, const ModelWeights& w, int max_tokens, bool preln_f32 = false, bool fp8_ffn = false);
   ~DeviceModel();
   DeviceModel(const DeviceModel&) = delete;
 
@@ -118,6 +121,10 @@ class DeviceModel {
   int max_tokens_ = 65536;
   bool debug_keep_ = false;
   bool fuse_resid_ = false;    // GLC_FUSE_RESID=1: residual add in the out-proj / FFN2 GEMM epilogues instead of the LN kernel
+  bool fp8_ffn_ = false;       // FFN1 / FFN2 on e4m3 operands (kind::f8f6f4), everything else fp16; off by default (DESIGN.md "FP8")
+  float fp8_mult_ = 4.0f;      // static multiplier the e4m3 GELU output is stored with (saturates at 448 / mult; GLC_FP8_MULT)
+  void* x1_8_ = nullptr;       // e4m3 [tokens, H]: LN1 output under per-row scales x1_s_
+  float* x1_s_ = nullptr;
   bool preln_f32_ = false;     // GLC_PRELN_F32=1 / glc_opts.preln_f32: out-proj and FFN2 outputs (the pre-LN sums) stay fp32
   int* d_overflow_ = nullptr;  // set by the LN kernels when a pre-LN sum hit the fp16 saturation value
   int* h_overflow_ = nullptr;  // pinned ring of per-request copies of the flag
@@ -220,7 +227,7 @@ class TaskQueue {
 
 class Model {
  public:
-  Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens, bool preln_f32 = false);
+  Model(const std::string& onnx_path, const std::vector<int>& devices, int max_tokens, bool preln_f32 = false, bool fp8_ffn = false);
   ~Model();
   TaskQueue& submit_queue();
   int num_classes(const int64_t* ids, int B, int S) const;

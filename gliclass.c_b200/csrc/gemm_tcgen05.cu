@@ -66,6 +66,20 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(hx, t, hx);
 }
 
+// The same fit evaluated on two values in packed fp16 (HFMA2 / MUFU.TANH.F16x2): half the instructions per element.  Only
+// for the e4m3-output epilogue, whose 3-bit result mantissa hides fp16's 2^-11 (the FP8 FFN1 tile is paced by its
+// epilogue, not by the e4m3 MMA, which runs at twice the fp16 rate).
+__device__ __forceinline__ __half2 gelu_erf_h2(__half2 x) {
+  const __half2 x2 = __hmin2(__hmul2(x, x), __float2half2_rn(49.0f));
+  __half2 q = __hfma2(__float2half2_rn(-3.5785683e-4f), x2, __float2half2_rn(3.7043383e-2f));
+  q = __hfma2(q, x2, __float2half2_rn(7.9746913e-1f));
+  const __half2 p = __hmul2(q, x);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&p)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  return __hfma2(hx, *reinterpret_cast<const __half2*>(&t), hx);
+}
+
 // SwiGLU (ACT = 3; Qwen2 / Llama MLP, transformers modeling_qwen2.py:46-48): the weight rows are interleaved in blocks
 // of 32 — rows [64 j, 64 j + 32) = gate_proj rows [32 j, 32 j + 32), rows [64 j + 32, 64 j + 64) = the matching up_proj
 // rows — so an epilogue warp holds a gate chunk and its up chunk and writes silu(gate) * up: the output has N / 2 columns.
@@ -250,14 +264,101 @@ __device__ __forceinline__ void epilogue_tile_tma_swiglu(uint32_t t_row, int grp
   }
 }
 
+// FP8 (e4m3) operands: the accumulator is sum(a8 * w8); the real product is that times the activation scale of the row
+// (per-row dynamic scale from the LN kernel, or one constant for a statically scaled activation) times the weight
+// scale of the output channel (per-row-of-W scale from the load-time quantiser).  out_mult: the static multiplier an
+// e4m3 OUTPUT is stored with (its consumer passes 1 / out_mult as `k`).
+struct Fp8Scales {
+  const float* row;   // [M] or nullptr
+  const float* col;   // [N]
+  float k;            // constant factor (1 when `row` carries everything)
+  float out_mult;
+};
+
+template <bool SCALED>
+__device__ __forceinline__ void apply_scales(float (&v)[32], const Fp8Scales& sc, int row, int n, int M, int N) {
+  if (!SCALED) return;
+  const float rs = (sc.row != nullptr && row < M) ? __ldg(sc.row + row) * sc.k : sc.k;
+  if (n + 32 <= N) {
+    const float4* c4 = reinterpret_cast<const float4*>(sc.col + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 cc = __ldg(c4 + j);
+      v[4 * j + 0] *= rs * cc.x; v[4 * j + 1] *= rs * cc.y; v[4 * j + 2] *= rs * cc.z; v[4 * j + 3] *= rs * cc.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) if (n + j < N) v[j] *= rs * __ldg(sc.col + n + j);
+  }
+}
+
+// e4m3 OUTPUT epilogue (FFN1 of the FP8 path: scale -> +bias -> erf-GELU -> * out_mult -> saturating e4m3), 32 rows x 32
+// bytes per chunk through an unswizzled staging buffer and one bulk tensor store (tm_c: uint8 [M, N], box 32 x 32).
+template <int BN, int ACT, int NBUF>
+__device__ __forceinline__ void epilogue_tile_tma_f8out(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
+                                                        const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int M, int N,
+                                                        const Fp8Scales& sc) {
+#pragma unroll 1
+  for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
+    const int n = n0 + c * 32;
+    uint32_t r[32];
+    ptx::tmem_ld_x32(t_row + (uint32_t)(c * 32), r);
+    ptx::tmem_ld_wait();
+    if (n >= N) continue;   // warp-uniform
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    apply_scales<true>(v, sc, row0 + lane, n, M, N);
+    if (bias != nullptr) {
+      if (n + 32 <= N) {
+        const float4* b4 = reinterpret_cast<const float4*>(bias + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(bias + n + j);
+      }
+    }
+    // activation and the output multiplier in packed fp16, then f16x2 -> e4m3x2 (saturating)
+    const __half2 om2 = __float2half2_rn(sc.out_mult);
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      uint32_t h01 = ptx::pack_f16(v[4 * j + 0], v[4 * j + 1]), h23 = ptx::pack_f16(v[4 * j + 2], v[4 * j + 3]);
+      __half2 a = *reinterpret_cast<__half2*>(&h01), b = *reinterpret_cast<__half2*>(&h23);
+      if (ACT == 1) { a = gelu_erf_h2(a); b = gelu_erf_h2(b); }
+      if (ACT == 2) { a = __hmax2(a, __float2half2_rn(0.f)); b = __hmax2(b, __float2half2_rn(0.f)); }
+      a = __hmul2(a, om2);
+      b = __hmul2(b, om2);
+      pk[j] = ptx::pack_e4m3x2_h2(*reinterpret_cast<uint32_t*>(&a)) | (ptx::pack_e4m3x2_h2(*reinterpret_cast<uint32_t*>(&b)) << 16);
+    }
+    if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
+    __syncwarp();
+    uint8_t* sb = stage + buf * 2048;
+    uint8_t* srow = sb + lane * 32;
+    *reinterpret_cast<uint4*>(srow) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(srow + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tm_c, sb, n, row0);
+      ptx::bulk_commit_group();
+    }
+    buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+  }
+}
+
 // fp16 epilogue through shared memory + TMA store.  A warp's direct stores put 32 different rows in
 // every STG (32 L1 line visits per instruction: the epilogue then outlasts a K=768 tile's MMAs); here
 // the 32 x 32 chunk is written once to a 64B-swizzled staging buffer and stored by one bulk tensor copy.
 //   stage: this warp's NBUF x 2 KB staging buffers (1024-byte aligned); row0: first tile row of the warp
-template <int BN, int ACT, int NBUF, bool RESID>
+template <int BN, int ACT, int NBUF, bool RESID, bool SCALED = false>
 __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
                                                   const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int M, int N,
-                                                  const __half* __restrict__ resid, int64_t ldr) {
+                                                  const __half* __restrict__ resid, int64_t ldr, const Fp8Scales& sc = Fp8Scales{}) {
 #pragma unroll 1
   for (int c = grp; c < BN / 32; c += EpiCfg<ACT>::GROUPS) {
     const int n = n0 + c * 32;
@@ -270,6 +371,7 @@ __device__ __forceinline__ void epilogue_tile_tma(uint32_t t_row, int grp, int n
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    apply_scales<SCALED>(v, sc, row0 + lane, n, M, N);
     if (bias != nullptr) {
       if (n + 32 <= N) {
         const float4* b4 = reinterpret_cast<const float4*>(bias + n);
@@ -471,11 +573,14 @@ struct Gemm2Cfg {
   static constexpr uint32_t TMEM_COLS = 512;   // two BN-column accumulators
 };
 
-template <int BN_, int ACT, bool OUT_F32, bool RESID>
+// FP8 = true: A and W are e4m3 bytes (tensor maps over uint8, 128 elements per 128-byte stage row, kind::f8f6f4); the
+// epilogue multiplies by the scales in `sc`.  OUT_F8: the output is e4m3 too (see epilogue_tile_tma_f8out).
+template <int BN_, int ACT, bool OUT_F32, bool RESID, bool FP8 = false, bool OUT_F8 = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(EpiCfg<ACT>::THREADS, 1)
 gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
                      const __grid_constant__ CUtensorMap tm_c, const float* __restrict__ bias, void* __restrict__ Cout,
-                     int64_t ldc, int M, int N, int K, const __half* __restrict__ resid, int64_t ldr) {
+                     int64_t ldc, int M, int N, int K, const __half* __restrict__ resid, int64_t ldr, const Fp8Scales sc) {
+  constexpr int BKE = FP8 ? 2 * BK : BK;   // elements per 128-byte stage row
   using Cfg = Gemm2Cfg<BN_>;
   constexpr int BN = Cfg::BN;
   extern __shared__ uint8_t smem_raw[];
@@ -517,7 +622,7 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
   const int num_m = (M + 2 * BM - 1) / (2 * BM);
   const int num_n = (N + BN - 1) / BN;
-  const int num_k = (K + BK - 1) / BK;
+  const int num_k = (K + BKE - 1) / BKE;
   const int tiles = num_m * num_n;
   const int cl = blockIdx.x >> 1, ncl = gridDim.x >> 1;
 
@@ -533,8 +638,8 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
           if (leader) ptx::mbar_arrive_expect_tx(&full[s], 2 * Cfg::STAGE_BYTES);
           const uint32_t fb = ptx::smem_u32(&full[s]) & ptx::PEER_BIT_MASK;   // the leader's barrier
           uint8_t* sa = smem + s * Cfg::STAGE_BYTES;
-          ptx::tma_load_2d_2cta(sa, &tm_a, fb, kb * BK, m0);
-          ptx::tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_w, fb, kb * BK, n0);
+          ptx::tma_load_2d_2cta(sa, &tm_a, fb, kb * BKE, m0);
+          ptx::tma_load_2d_2cta(sa + Cfg::A_BYTES, &tm_w, fb, kb * BKE, n0);
         }
         __syncwarp();
         if (++s == Cfg::STAGES) { s = 0; ph ^= 1; }
@@ -559,8 +664,10 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
             const uint64_t da = desc0 + (uint64_t)(s * (Cfg::STAGE_BYTES >> 4));
             const uint64_t db = da + (Cfg::A_BYTES >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              ptx::mma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 0; k < BK / 16; ++k) {
+              if (FP8) ptx::mma_e4m3_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+              else ptx::mma_f16_ss_2cta(d_tmem, da + 2 * k, db + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            }
             ptx::mma_commit_2cta_mc(&empty[s], 3);
             if (kb == num_k - 1) ptx::mma_commit_2cta_mc(&tfull[acc], 3);
           }
@@ -586,14 +693,16 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      if (ACT == 3 && OUT_F32)
+      if (OUT_F8)
+        epilogue_tile_tma_f8out<BN, ACT, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, sc);
+      else if (ACT == 3 && OUT_F32)
         epilogue_tile_swiglu<BN, true>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
       else if (ACT == 3)
         epilogue_tile_tma_swiglu<BN, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, N);
       else if (OUT_F32)
         epilogue_tile<BN, ACT, OUT_F32, RESID>(t_row, grp, n0, row, bias, Cout, ldc, M, N, resid, ldr);
       else
-        epilogue_tile_tma<BN, ACT, NBUF, RESID>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, resid, ldr);
+        epilogue_tile_tma<BN, ACT, NBUF, RESID, FP8>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, resid, ldr, sc);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::smem_u32(&tempty[acc]) & ptx::PEER_BIT_MASK);
@@ -643,7 +752,46 @@ cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t 
   const int max_cl = num_sms / 2;
   const int ncl = tiles < max_cl ? tiles : max_cl;
   return launch_pdl(kern, dim3(2 * ncl), dim3(EpiCfg<ACT>::THREADS), Cfg::SMEM_BYTES, stream, tm_a, tm_w, tm_c, bias, C, ldc, M, N, K,
-                    (const __half*)resid, ldr);
+                    (const __half*)resid, ldr, Fp8Scales{});
+}
+
+// e4m3 x e4m3 -> fp16 (OUT_F8 = false) or e4m3 (OUT_F8 = true), always on CTA pairs
+template <int BN_, int ACT, bool OUT_F8>
+cudaError_t launch_gemm_e4m3(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                             int M, int N, int K, int num_sms, cudaStream_t stream, const Fp8Scales& sc) {
+  using Cfg = Gemm2Cfg<BN_>;
+  uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t sa[1] = {(uint64_t)lda};
+  uint32_t ba[2] = {2 * BK, BM};
+  uint64_t dw[2] = {(uint64_t)K, (uint64_t)N};
+  uint64_t sw[1] = {(uint64_t)ldw};
+  uint32_t bw[2] = {2 * BK, (uint32_t)(Cfg::BN / 2)};
+  CUtensorMap tm_a = make_tmap_8b(A, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tm_w = make_tmap_8b(W, 2, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B);
+  CUtensorMap tm_c;
+  uint64_t dc[2] = {(uint64_t)N, (uint64_t)M};
+  uint32_t bc[2] = {32, 32};
+  if (OUT_F8) {
+    uint64_t sc1[1] = {(uint64_t)ldc};
+    tm_c = make_tmap_8b(C, 2, dc, sc1, bc, CU_TENSOR_MAP_SWIZZLE_NONE);
+  } else {
+    uint64_t sc1[1] = {(uint64_t)ldc * 2};
+    tm_c = make_tmap_16b(C, 2, dc, sc1, bc, CU_TENSOR_MAP_SWIZZLE_64B);
+  }
+  auto kern = gemm_f16_2cta_kernel<BN_, ACT, false, false, true, OUT_F8>;
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 63] = true;
+  }
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + Cfg::BN - 1) / Cfg::BN);
+  const int max_cl = num_sms / 2;
+  const int ncl = tiles < max_cl ? tiles : max_cl;
+  return launch_pdl(kern, dim3(2 * ncl), dim3(EpiCfg<ACT>::THREADS), Cfg::SMEM_BYTES, stream, tm_a, tm_w, tm_c, bias, C, ldc, M, N, K,
+                    (const __half*)nullptr, (int64_t)0, sc);
 }
 
 template <int BN, int ACT, bool OUT_F32>
@@ -729,6 +877,29 @@ cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ld
   if (act == 0) return launch_gemm<128, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   if (act == 1) return launch_gemm<128, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   return launch_gemm<128, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+}
+
+cudaError_t gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, const float* a_scale, float a_const,
+                      const float* w_scale, const float* bias, void* C, int64_t ldc, int M, int N, int K, int act, bool out_e4m3,
+                      float out_mult, int num_sms, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || w_scale == nullptr) return cudaErrorInvalidValue;
+  if ((lda % 16) || (ldw % 16) || (K % 16) || (N % 16) || (ldc % (out_e4m3 ? 16 : 8))) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(A8) | reinterpret_cast<uintptr_t>(W8) | reinterpret_cast<uintptr_t>(C)) & 15)
+    return cudaErrorInvalidValue;
+  if (num_sms < 2) return cudaErrorInvalidValue;
+  const Fp8Scales sc{a_scale, w_scale, a_const, out_mult};
+  if (out_e4m3) {
+    if (act == 1) return launch_gemm_e4m3<256, 1, true>(A8, lda, W8, ldw, bias, C, ldc, M, N, K, num_sms, stream, sc);
+    if (act == 0) return launch_gemm_e4m3<256, 0, true>(A8, lda, W8, ldw, bias, C, ldc, M, N, K, num_sms, stream, sc);
+    return cudaErrorInvalidValue;
+  }
+  if (act != 0) return cudaErrorInvalidValue;
+  // same wave model as the fp16 pairs: 192-wide tiles when they quantise into clearly fewer column-rounds
+  const int ncl = num_sms / 2, mt2 = (M + 2 * BM - 1) / (2 * BM);
+  const int64_t p256 = (int64_t)((mt2 * ((N + 255) / 256) + ncl - 1) / ncl) * 256 * 100;
+  const int64_t p192 = (N % 192 == 0) ? (int64_t)((mt2 * (N / 192) + ncl - 1) / ncl) * 192 * 102 : INT64_MAX;
+  if (p192 < p256) return launch_gemm_e4m3<192, 0, false>(A8, lda, W8, ldw, bias, C, ldc, M, N, K, num_sms, stream, sc);
+  return launch_gemm_e4m3<256, 0, false>(A8, lda, W8, ldw, bias, C, ldc, M, N, K, num_sms, stream, sc);
 }
 
 }  // namespace glc

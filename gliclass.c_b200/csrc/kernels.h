@@ -20,6 +20,15 @@ cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ld
                            int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act, bool out_f32, int num_sms,
                            cudaStream_t stream);
 
+// K2 on e4m3 operands (the opt-in FP8 FFN path): C = act((A8 W8^T) * a_scale[m] * a_const * w_scale[n] + bias).
+// A8 [M,K], W8 [N,K] e4m3 bytes, K % 16 == 0; a_scale may be null (then a_const alone); C fp16 [M,ldc], or with
+// out_e4m3 the saturating e4m3 of (act(...) * out_mult).  act: 0, or 1 (erf-GELU, e4m3 output only).
+cudaError_t gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, const float* a_scale, float a_const,
+                      const float* w_scale, const float* bias, void* C, int64_t ldc, int M, int N, int K, int act, bool out_e4m3,
+                      float out_mult, int num_sms, cudaStream_t stream);
+// per-row e4m3 quantiser: q[r, :] = e4m3(x[r, :] * 448 / amax_r), scale[r] = amax_r / 448 (1 for an all-zero row)
+cudaError_t quantize_rows_e4m3(const void* x_f16, int64_t ldx, void* q8, int64_t ldq, float* scale, int M, int K, cudaStream_t stream);
+
 // decoder backbone (decoder.cu): fp32 residual stream h, fp16 normalised activations
 cudaError_t embed_rows_f32(const int64_t* ids, const void* emb_f16, float* h, int M, int H, int vocab, cudaStream_t stream);
 // h += delta (fp16 [M,H], may be null); y = rmsnorm(h) * g
@@ -43,7 +52,9 @@ cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* word_e
 // epilogue clamps at +-65504): the engine turns that into a loud Run failure.  x_is_f32: x is the fp32 output of the
 // GEMM's fp32 epilogue (robust mode, GLC_PRELN_F32=1) instead of fp16.
 cudaError_t residual_ln(const void* x, const void* r_f16, const float* gamma, const float* beta, float eps,
-                        void* y_f16, int M, int H, cudaStream_t stream, int* overflow_flag = nullptr, bool x_is_f32 = false);
+                        void* y_f16, int M, int H, cudaStream_t stream, int* overflow_flag = nullptr, bool x_is_f32 = false,
+                        void* y_e4m3 = nullptr, float* y_e4m3_scale = nullptr);
+// (y_e4m3 / y_e4m3_scale: also write each row as e4m3 under its dynamic scale amax/448 — the FP8 FFN1 operand)
 // plain LN on fp32 rows -> fp16 (load-time LN of rel_embeddings, T:597-601)
 cudaError_t ln_f32_to_f16(const float* x, const float* gamma, const float* beta, float eps, void* y_f16, int M, int H,
                            cudaStream_t stream);

@@ -195,6 +195,17 @@ __device__ __forceinline__ void mma_f16_ss_2cta(uint32_t tmem_d, uint64_t desc_a
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same pair MMA on 8-bit operands: kind::f8f6f4 with both formats e4m3 (format code 0, so the instruction descriptor is
+// bit-identical to the fp16 one: cute/arch/mma_sm100_desc.hpp InstrDescriptor), K = 32 per instruction (32 bytes, the same
+// byte geometry as 16 fp16: a 128-byte swizzle row holds 128 elements and the descriptor still advances by 2 per step).
+__device__ __forceinline__ void mma_e4m3_ss_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // commit of cta_group::2 MMAs, arriving on the mbarrier at this offset in every CTA of `cta_mask`
 __device__ __forceinline__ void mma_commit_2cta_mc(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
@@ -375,6 +386,22 @@ __device__ __forceinline__ uint32_t pack_f16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
+}
+
+// two floats -> two e4m3 bytes (round to nearest even, saturating to +-448); lo in bits [0,8)
+__device__ __forceinline__ uint32_t pack_e4m3x2(float lo, float hi) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+  return (uint32_t)r;
+}
+// packed fp16 pair -> two e4m3 bytes (element 0 of the pair in bits [0,8))
+__device__ __forceinline__ uint32_t pack_e4m3x2_h2(uint32_t h2) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+  return (uint32_t)r;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float a, float b, float c, float d) {
+  return pack_e4m3x2(a, b) | (pack_e4m3x2(c, d) << 16);
 }
 
 }  // namespace ptx

@@ -47,4 +47,21 @@ inline CUtensorMap make_tmap_16b(const void* base, int rank, const uint64_t* dim
   return m;
 }
 
+// Byte-element tensor (e4m3 operands and outputs): same conventions, strides in bytes = elements.
+inline CUtensorMap make_tmap_8b(const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                                 const uint32_t* box, CUtensorMapSwizzle swizzle) {
+  CUtensorMap m;
+  cuuint64_t gdims[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bx[5];
+  cuuint32_t es[5];
+  for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = get_encode_tiled()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)rank, const_cast<void*>(base), gdims, gstr,
+                                  bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (uint8) failed, CUresult=" + std::to_string((int)r));
+  return m;
+}
+
 }  // namespace glc

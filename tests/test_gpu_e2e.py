@@ -333,10 +333,52 @@ def test_fp16_overflow_fails_loudly_and_f32_preln_mode_recovers(pkg, orc, tmp_pa
 
 
 def test_unsupported_storage_types_are_rejected(pkg, golden_onnx):
-    """bf16 / fp8 storage is refused loudly rather than silently computing in another type"""
-    for wd in ("bf16", "fp8"):
-        with pytest.raises(pkg.GlcError, match="only GLC_DTYPE_FP16"):
-            pkg.Session(golden_onnx, weight_dtype=wd)
+    """bf16 storage is refused loudly rather than silently computing in another type"""
+    with pytest.raises(pkg.GlcError, match="weight_dtype must be GLC_DTYPE_FP16"):
+        pkg.Session(golden_onnx, weight_dtype="bf16")
+
+
+FP8_BAR = 5e-2   # VERDICT r1 item 7 / SURVEY.md N1: the logit bar an FP8 tier would have to meet to become a default
+
+
+def test_fp8_ffn_mode(pkg, orc, model_cache):
+    """Opt-in GLC_DTYPE_FP8_E4M3 (FFN1 / FFN2 on e4m3 operands): runs BASELINE configs[1] end to end, reports its logit
+    error against the oracle next to the fp16 engine's, and asserts only what the mode promises: finite logits, an error
+    that is bounded (same order as the logit scale's rounding noise, not garbage), and the decisions outside a wider
+    band.  Whether it meets the 5e-2 bar is PRINTED and recorded in DESIGN.md — the mode is off by default."""
+    path = os.path.join(model_cache, "base.onnx")
+    cfg, w = orc.make_model_file("base", path, seed=0)
+    ids, mask = orc.synth_inputs(cfg, 64, 512, 10, seed=1235)
+    rows = list(range(0, 64, 8))
+    ref = orc.forward_restated(w, cfg, ids[rows], mask[rows]).numpy()
+    s16 = pkg.Session(path)
+    out16 = s16.run_inference(ids.numpy(), mask.numpy())
+    s16.close()
+    s8 = pkg.Session(path, weight_dtype="fp8")
+    try:
+        assert s8.info["weight_dtype"] == 3
+        out8 = s8.run_inference(ids.numpy(), mask.numpy())
+        again = s8.run_inference(ids.numpy(), mask.numpy())
+    finally:
+        s8.close()
+    assert np.isfinite(out8).all() and np.array_equal(out8, again)
+    d8, d16 = np.abs(out8[rows] - ref), np.abs(out16[rows] - ref)
+    d816 = np.abs(out8 - out16)
+    print(f"fp8-ffn base/B64S512: max|d| vs oracle {d8.max():.4e} (mean {d8.mean():.4e}); fp16 engine {d16.max():.4e} (mean {d16.mean():.4e}); "
+          f"fp8 vs fp16 engine over all 64 rows max {d816.max():.4e} mean {d816.mean():.4e}; bar {FP8_BAR:g} -> "
+          f"{'MET' if d8.max() <= FP8_BAR else 'MISSED'}")
+    assert d8.max() < 0.5, "FP8 FFN mode is broken, not merely lossy"
+    p_ref = orc.sigmoid32(ref)
+    outside = np.abs(p_ref - THRESHOLD) > 0.1
+    assert np.array_equal(orc.decisions_multilabel(out8[rows], THRESHOLD)[outside], orc.decisions_multilabel(ref, THRESHOLD)[outside])
+
+
+def test_fp8_ffn_mode_rejections(pkg, model_cache, orc):
+    """combinations the FP8 mode does not implement fail at load"""
+    path = os.path.join(model_cache, "mini.onnx")
+    orc.make_model_file("mini", path, seed=0)
+    with pytest.raises(pkg.GlcError, match="cannot be combined"):
+        pkg.Session(path, weight_dtype="fp8", preln_f32=True)
 
 
 def test_unchanged_reference_binary_end_to_end(pkg, orc, tmp_path):

@@ -119,6 +119,106 @@ def test_gemm_fused_residual(pkg, dev, M, N, K, act, out_f32):
     _report(f"gemm+resid {M}x{N}x{K}", C, ref, 3e-3, 3e-3)
 
 
+# ---------------------------------------------------------------------------------------------
+# K2 on e4m3 operands (opt-in FP8 FFN path): the kernel must reproduce, to fp32-accumulation accuracy, the product of the
+# DEQUANTISED operands — quantisation error itself is measured end to end (test_gpu_e2e.py::test_fp8_ffn_mode)
+# ---------------------------------------------------------------------------------------------
+
+
+def _quantize_rows(pkg, dev, x16):
+    M, K = x16.shape
+    q = torch.empty(M, K, dtype=torch.uint8, device=dev)
+    sc = torch.empty(M, dtype=torch.float32, device=dev)
+    rc = pkg.lib().glc_op_quantize_rows_e4m3(_ptr(x16), K, _ptr(q), K, _ptr(sc), M, K, None)
+    _sync_check(pkg, rc, "glc_op_quantize_rows_e4m3")
+    return q, sc
+
+
+def test_quantize_rows_e4m3(pkg, dev):
+    g = torch.Generator().manual_seed(11)
+    x = (torch.randn(300, 784, generator=g) * torch.rand(300, 1, generator=g) * 3).to(torch.float16).to(dev)
+    x[7] = 0
+    q, sc = _quantize_rows(pkg, dev, x)
+    amax = x.float().abs().amax(1)
+    want_sc = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
+    assert torch.allclose(sc, want_sc, rtol=1e-6, atol=0)
+    deq = q.view(torch.float8_e4m3fn).float() * sc[:, None]
+    # round-to-nearest e4m3: relative error <= 2^-4 of the value, or half a subnormal step of the row scale
+    err = (deq - x.float()).abs()
+    bound = torch.maximum(x.float().abs() * 2.0 ** -4, sc[:, None] * 2.0 ** -10) * 1.001
+    assert (err <= bound).all(), float((err - bound).max())
+    want_q = (x.float() / sc[:, None]).to(torch.float8_e4m3fn).view(torch.uint8)
+    assert (q == want_q).float().mean() > 0.999   # ties / fp32 division vs multiplication by the reciprocal
+
+
+@pytest.mark.parametrize("M,N,K", [(32768, 768, 3072), (4096, 768, 3072), (300, 192, 128), (1000, 256, 784), (77, 768, 3072)])
+def test_gemm_e4m3_fp16_out(pkg, dev, M, N, K):
+    """FFN2 shape: static activation scale, per-channel weight scale, fp16 output"""
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(torch.float16).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.float16).to(dev)
+    bias = (torch.randn(N, generator=g) * 0.5).float().to(dev)
+    mult = 16.0
+    a8 = (A.float() * mult).to(torch.float8_e4m3fn)
+    w8, ws = _quantize_rows(pkg, dev, W)
+    C = torch.full((M, N), float("nan"), dtype=torch.float16, device=dev)
+    rc = pkg.lib().glc_op_gemm_e4m3(_ptr(a8), K, _ptr(w8), K, None, 1.0 / mult, _ptr(ws), _ptr(bias), _ptr(C), N, M, N, K, 0, 0,
+                                    1.0, None)
+    _sync_check(pkg, rc, "glc_op_gemm_e4m3")
+    ref = (a8.float() @ w8.view(torch.float8_e4m3fn).float().t()) * (ws[None, :] / mult) + bias
+    _report(f"gemm e4m3 {M}x{N}x{K}", C, ref, 2e-3, 2e-3)
+
+
+@pytest.mark.parametrize("M,N,K", [(32768, 3072, 768), (4096, 3072, 768), (300, 256, 128), (999, 1024, 400)])
+def test_gemm_e4m3_gelu_e4m3_out(pkg, dev, M, N, K):
+    """FFN1 shape: per-row activation scales, per-channel weight scales, erf-GELU, e4m3 output under a static multiplier"""
+    g = torch.Generator().manual_seed(M + N + K + 1)
+    A = (torch.randn(M, K, generator=g) * (0.5 + torch.rand(M, 1, generator=g))).to(torch.float16).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.float16).to(dev)
+    bias = (torch.randn(N, generator=g) * 0.5).float().to(dev)
+    a8, a_s = _quantize_rows(pkg, dev, A)
+    w8, ws = _quantize_rows(pkg, dev, W)
+    mult = 4.0
+    C = torch.full((M, N), 0x7f, dtype=torch.uint8, device=dev)
+    rc = pkg.lib().glc_op_gemm_e4m3(_ptr(a8), K, _ptr(w8), K, _ptr(a_s), 1.0, _ptr(ws), _ptr(bias), _ptr(C), N, M, N, K, 1, 1,
+                                    mult, None)
+    _sync_check(pkg, rc, "glc_op_gemm_e4m3 (e4m3 out)")
+    pre = (a8.view(torch.float8_e4m3fn).float() @ w8.view(torch.float8_e4m3fn).float().t()) * a_s[:, None] * ws[None, :] + bias
+    ref = torch.nn.functional.gelu(pre) * mult
+    got = C.view(torch.float8_e4m3fn).float()
+    assert torch.isfinite(got).all()
+    # one e4m3 step of slack: the result sits within 2^-3 relative (or one subnormal step 2^-9) of the fp32 reference.
+    # The absolute term covers the packed-fp16 GELU of this epilogue: in the negative tail hx * (1 + tanh) cancels against
+    # fp16's 2^-11, an absolute error of up to ~1.5e-3 (x mult) on outputs that are themselves ~1e-3
+    err = (got - ref.clamp(-448, 448)).abs()
+    bound = torch.maximum(ref.abs() * 2.0 ** -3, torch.full_like(ref, 2.0 ** -9)) + 1.5e-3 * mult
+    assert (err <= bound).all(), f"max excess {(err - bound).max().item():.3e}"
+    exact = (C == ref.clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)).float().mean().item()
+    print(f"gemm e4m3->e4m3 {M}x{N}x{K}: {100 * exact:.2f}% of output bytes identical to torch's rounding of the fp32 reference")
+    assert exact > 0.95
+
+
+@pytest.mark.parametrize("H,M", [(768, 5001), (1024, 700), (128, 300)])
+def test_residual_ln_e4m3_output(pkg, dev, H, M):
+    g = torch.Generator().manual_seed(H + M + 5)
+    x = (torch.randn(M, H, generator=g) * 1.7).to(torch.float16).to(dev)
+    r = torch.randn(M, H, generator=g).to(torch.float16).to(dev)
+    gamma = (1 + 0.1 * torch.randn(H, generator=g)).float().to(dev)
+    beta = (0.02 * torch.randn(H, generator=g)).float().to(dev)
+    y = torch.empty(M, H, dtype=torch.float16, device=dev)
+    y8 = torch.empty(M, H, dtype=torch.uint8, device=dev)
+    ys = torch.empty(M, dtype=torch.float32, device=dev)
+    rc = pkg.lib().glc_op_residual_ln_e4m3(_ptr(x), _ptr(r), _ptr(gamma), _ptr(beta), 1e-7, _ptr(y), _ptr(y8), _ptr(ys), M, H, None)
+    _sync_check(pkg, rc, "glc_op_residual_ln_e4m3")
+    ref = torch.nn.functional.layer_norm(x.float() + r.float(), (H,), gamma, beta, 1e-7)
+    _report(f"ln+e4m3 H={H} (fp16 output)", y, ref, 2e-3, 2e-3)
+    assert torch.allclose(ys, ref.abs().amax(1) / 448.0, rtol=2e-3)
+    deq = y8.view(torch.float8_e4m3fn).float() * ys[:, None]
+    err = (deq - ref).abs()
+    bound = torch.maximum(ref.abs() * 2.0 ** -4, ys[:, None] * 2.0 ** -10) * 1.01 + 2e-3
+    assert (err <= bound).all(), float((err - bound).max())
+
+
 @pytest.mark.parametrize("H,M", [(768, 70001), (1024, 40003), (128, 300)])
 def test_ln_without_residual_operand(pkg, dev, H, M):
     g = torch.Generator().manual_seed(H + M)
