@@ -384,6 +384,44 @@ def main():
                "how": "wall clock; 16 host threads x 6 synchronous batch-8 glc_run calls each (the reference's OpenMP loop), "
                       "coalesced inside the engine"}
 
+    # ---- ragged batches (lengths uniform in [S/4, S], what pad-to-longest batches of real texts look like,
+    #      reference tokenizer.c:44-54): the engine compacts them to their real tokens; the same engine with the
+    #      packing turned off is timed beside it
+    ragged = None
+    if rank == 0 and not args.no_extras and cfg.backbone != "qwen2":
+        try:
+            idr, mr = SM.synth_inputs(cfg, B, S, NL, seed=97, ragged=True, min_frac=0.25)
+            p_idr, p_mr = idr.pin_memory(), mr.pin_memory()
+            outr = torch.empty(B, C).pin_memory()
+            os.environ["GLC_VARLEN"] = "0"
+            try:
+                sess_pad = pkg.Session(path, devices=[local_rank], weight_dtype=args.weights)
+            finally:
+                os.environ.pop("GLC_VARLEN")
+
+            def rag(sx, n):
+                for _ in range(3):
+                    sx.run_pinned(p_idr.data_ptr(), p_mr.data_ptr(), B, S, outr.data_ptr(), outr.numel())
+                t0 = time.perf_counter()
+                for _ in range(n):
+                    sx.run_pinned(p_idr.data_ptr(), p_mr.data_ptr(), B, S, outr.data_ptr(), outr.numel())
+                return (time.perf_counter() - t0) / n
+
+            st0 = sess.packed_stats()
+            t_pk = rag(sess, args.steps)
+            st1 = sess.packed_stats()
+            o_pk = outr.clone()
+            t_pad = rag(sess_pad, args.steps)
+            sess_pad.close()
+            ragged = {"value": B / t_pk, "unit": "texts/s", "padded_layout_value": B / t_pad, "speedup": t_pad / t_pk,
+                      "batch": B, "seq_len": S, "mean_len": float(mr.sum(1).float().mean()),
+                      "rows_computed_frac": (st1[1] - st0[1]) / max(1, st1[2] - st0[2]),
+                      "max_abs_diff_vs_padded_layout": float((o_pk - outr).abs().max()),
+                      "how": "wall clock around synchronous glc_run on pinned host buffers (H2D, forward, D2H), lengths uniform in "
+                             "[S/4, S]; 'padded_layout_value' = same engine with GLC_VARLEN=0"}
+        except Exception as e:   # noqa: BLE001
+            ragged = {"error": str(e)[:300]}
+
     total_texts = B * args.steps * world
     value = total_texts / (ms_dev * 1e-3)
     e2e = total_texts / (ms_e2e * 1e-3)
@@ -464,6 +502,7 @@ def main():
         "kernels": kernels,
         "latency_batch8": lat,
         "omp_style_batch8": omp,
+        "ragged_batch": ragged,
         "clocks": sampler.summary(),
     }
     sess.close()

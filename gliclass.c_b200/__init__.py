@@ -70,6 +70,7 @@ _SIGS = {
     "glc_poll": (_i, [_vp]),
     "glc_collect": (_i, [_vp]),
     "glc_coalesce_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "glc_packed_stats": (_i, [_vp, _vp, _vp, _vp]),
     "glc_profile_enable": (_i, [_vp, _i, _i]),
     "glc_profile_collect": (_i, [_vp, _i, _vp, _vp, _i]),
     "glc_debug_fetch": (_i64, [_vp, _i, C.c_char_p, _vp, C.c_size_t]),
@@ -260,6 +261,12 @@ class Session:
         g, r = C.c_uint64(0), C.c_uint64(0)
         _check(lib().glc_coalesce_stats(self._h, C.byref(g), C.byref(r)), "glc_coalesce_stats")
         return int(g.value), int(r.value)
+
+    def packed_stats(self):
+        """(packed launches, rows computed, rows the padded [B,S] layout would have computed) since load"""
+        a, b, c = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        _check(lib().glc_packed_stats(self._h, C.byref(a), C.byref(b), C.byref(c)), "glc_packed_stats")
+        return int(a.value), int(b.value), int(c.value)
 
     def run_pinned(self, ids_ptr: int, mask_ptr: int, B: int, S: int, out_ptr: int, out_capacity: int) -> int:
         """Same call on raw host pointers (pinned buffers in bench.py's e2e leg). Returns C."""

@@ -93,25 +93,54 @@ constexpr uint32_t TM_G0 = 416;    // 32: window rows 0..127,  keys 32..63
 constexpr uint32_t TM_PV = 448;    // 64
 
 struct PersistParams {
-  const uint32_t* mask_bits; // [B][ceil(S/32)]
+  const uint32_t* mask_bits; // [B][ceil(S/32)]; packed layout: one bit per packed row (text b starts at word text_row[b] / 32)
   const int32_t* kv_len;     // [B]
-  __half* ctx;               // [B*S, H]
-  int B, S, heads, H;
+  __half* ctx;               // [B*S, H]; packed layout: [packed rows, H]
+  int B, S, heads, H;        // packed layout: S = the longest text's row count (sizes the resident position tables)
   int nq;                    // query tiles per row = ceil(S / 128)
   int n_items;               // heads * nq * B, ordered (head, query tile, batch row) with the batch row fastest
   float scale_log2;          // log2(e) / sqrt(3*d)
+  // Packed (varlen) layout, engine.cu run_host: text b occupies rows [text_row[b], text_row[b+1]) of qkv / ctx, a multiple
+  // of 128 rows, so no 128-row query tile or 64-row key tile ever spans two texts.  tile_info[t] = (query tile index in
+  // its text) << 24 | text, for the n_tiles query tiles ordered (query tile index, text): items are (head, t) with t
+  // fastest, which keeps the (head, query tile) runs the resident position tables are reused over.  nullptr = [B,S] layout.
+  const int32_t* tile_info;
+  const int32_t* text_row;
+  int n_tiles;
+  const void* qkv_base;      // host-side only (tensor-map construction)
 };
 
 struct Item {
   int head, q0, b, T;        // T = key tiles with at least one valid key (0: padded query tile, zero-filled)
+  int trow, tb;              // TMA coordinates of the text's position 0: (row, batch) = (0, b), or (text_row[b], 0) when packed
+  int grow;                  // row of ctx / qkv holding the text's position 0
+  int rows;                  // rows the text owns (S, or its packed row count)
+  int mword;                 // first mask word of the text
 };
 
 __device__ __forceinline__ Item decode_item(const PersistParams& p, int idx) {
   Item it;
-  it.b = idx % p.B;
-  const int r = idx / p.B;
-  it.q0 = (r % p.nq) * QT;
-  it.head = r / p.nq;
+  if (p.tile_info != nullptr) {
+    const int info = __ldg(p.tile_info + idx % p.n_tiles);
+    it.head = idx / p.n_tiles;
+    it.b = info & 0xffffff;
+    it.q0 = (info >> 24) * QT;
+    it.grow = __ldg(p.text_row + it.b);
+    it.rows = __ldg(p.text_row + it.b + 1) - it.grow;
+    it.trow = it.grow;
+    it.tb = 0;
+    it.mword = it.grow >> 5;
+  } else {
+    it.b = idx % p.B;
+    const int r = idx / p.B;
+    it.q0 = (r % p.nq) * QT;
+    it.head = r / p.nq;
+    it.grow = it.b * p.S;
+    it.rows = p.S;
+    it.trow = 0;
+    it.tb = it.b;
+    it.mword = it.b * ((p.S + 31) >> 5);
+  }
   const int kvlen = __ldg(p.kv_len + it.b);
   it.T = (it.q0 < kvlen) ? (kvlen + KT - 1) / KT : 0;
   return it;
@@ -230,7 +259,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
           const Item it = decode_item(p, idx);
           if (it.T == 0) continue;
           if (MODE == 2) {
-            const int pair = idx / p.B;
+            const int pair = it.head * 32 + it.q0 / QT;   // (head, query tile): what the resident tables depend on
             if (pair != cur_pair) {
               // the tables of another (head, query tile): every MMA that read the old ones must have completed
               if (n_sw > 0) ptx::mbar_wait(tab_free, (uint32_t)((n_sw - 1) & 1));
@@ -251,14 +280,14 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
             ptx::mbar_wait(&a_empty[st], (uint32_t)(((g / AST) & 1) ^ 1));
             if (MODE == 2) {
               ptx::mbar_arrive_expect_tx(&a_full[st], KT * 128);
-              ptx::tma_load_3d(smem + SM::OFF_K + st * 8192, &tm_qkv, &a_full[st], p.H + it.head * D, t * KT, it.b);
+              ptx::tma_load_3d(smem + SM::OFF_K + st * 8192, &tm_qkv, &a_full[st], p.H + it.head * D, it.trow + t * KT, it.tb);
             } else {
               const int k0 = t * KT;
               const int rho0 = EXP_CENTER - (QT - 1) - it.q0 + k0;
               const int sig0 = EXP_CENTER - (KT - 1) + it.q0 - k0;
               // the C window slides by 64 table rows per key tile: only the first tile needs the whole 192-row EK slice
               ptx::mbar_arrive_expect_tx(&a_full[st], (uint32_t)(KT * 128 + SM::POS_BYTES + (t == 0 ? SM::POS_BYTES : 8192)));
-              ptx::tma_load_3d(smem + SM::OFF_K + st * 8192, &tm_qkv, &a_full[st], p.H + it.head * D, k0, it.b);
+              ptx::tma_load_3d(smem + SM::OFF_K + st * 8192, &tm_qkv, &a_full[st], p.H + it.head * D, it.trow + k0, it.tb);
               if (t == 0) {
 #pragma unroll
                 for (int bx = 0; bx < SLICE / 64; ++bx)
@@ -283,13 +312,13 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
           if (it.T == 0) continue;
           if (iq > 0) ptx::mbar_wait(q_empty, (uint32_t)((iq - 1) & 1));   // the previous Q tile has been copied to TMEM
           ptx::mbar_arrive_expect_tx(&q_full[iq % ISLOTS], QT * 128);
-          ptx::tma_load_3d(smem + SM::OFF_Q, &tm_qkv, &q_full[iq % ISLOTS], it.head * D, it.q0, it.b);
-          ptx::tma_load_3d(smem + SM::OFF_Q + 8192, &tm_qkv, &q_full[iq % ISLOTS], it.head * D, it.q0 + 64, it.b);
+          ptx::tma_load_3d(smem + SM::OFF_Q, &tm_qkv, &q_full[iq % ISLOTS], it.head * D, it.trow + it.q0, it.tb);
+          ptx::tma_load_3d(smem + SM::OFF_Q + 8192, &tm_qkv, &q_full[iq % ISLOTS], it.head * D, it.trow + it.q0 + 64, it.tb);
           for (int t = 0; t < it.T; ++t, ++g) {
             const int st = g & 1;
             ptx::mbar_wait(&b_empty[st], (uint32_t)(((g >> 1) & 1) ^ 1));
             ptx::mbar_arrive_expect_tx(&b_full[st], KT * 128);
-            ptx::tma_load_3d(smem + SM::OFF_V + st * 8192, &tm_qkv, &b_full[st], 2 * p.H + it.head * D, t * KT, it.b);
+            ptx::tma_load_3d(smem + SM::OFF_V + st * 8192, &tm_qkv, &b_full[st], 2 * p.H + it.head * D, it.trow + t * KT, it.tb);
           }
           ++iq;
         }
@@ -307,7 +336,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         const Item it = decode_item(p, idx);
         if (it.T == 0) continue;
         if (MODE == 2) {
-          const int pair = idx / p.B;
+          const int pair = it.head * 32 + it.q0 / QT;   // (head, query tile): what the resident tables depend on
           if (pair != cur_pair) {
             cur_pair = pair;
             // every MMA issued so far read the old tables: tell the producer when they have all completed
@@ -404,7 +433,6 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
     const int i = qd * 32 + lane;     // row in the query tile
     const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
     const float sc = p.scale_log2;
-    const int words = (p.S + 31) >> 5;
 
     // tile-independent shift controls (both 32-key halves of a tile use the same ones: their first key is 0 mod 32)
     const int sh = 31 - lane;                  // c2p: element shift inside the window
@@ -420,8 +448,8 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         // padded queries only: their outputs are never read by valid rows
         for (int e = threadIdx.x - 128; e < QT * 8; e += 128 * NWG) {
           const int r = it.q0 + (e >> 3);
-          if (r < p.S)
-            *reinterpret_cast<uint4*>(p.ctx + ((int64_t)it.b * p.S + r) * p.H + it.head * D + (e & 7) * 8) = make_uint4(0, 0, 0, 0);
+          if (r < it.rows)
+            *reinterpret_cast<uint4*>(p.ctx + ((int64_t)it.grow + r) * p.H + it.head * D + (e & 7) * 8) = make_uint4(0, 0, 0, 0);
         }
         continue;
       }
@@ -465,8 +493,9 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         const int k0 = t * KT;
         float s[KT];
         // key-validity words of this tile (warp-uniform broadcast loads; consumed after the skew stages)
-        const uint32_t kb0 = __ldg(p.mask_bits + (int64_t)it.b * words + (k0 >> 5));
-        const uint32_t kb1 = ((k0 >> 5) + 1 < words) ? __ldg(p.mask_bits + (int64_t)it.b * words + (k0 >> 5) + 1) : 0u;
+        const int words = (it.rows + 31) >> 5;
+        const uint32_t kb0 = __ldg(p.mask_bits + it.mword + (k0 >> 5));
+        const uint32_t kb1 = ((k0 >> 5) + 1 < words) ? __ldg(p.mask_bits + it.mword + (k0 >> 5) + 1) : 0u;
 
         // ---- drain S and this warp's two 64-column windows of C in one go, then hand the accumulators back: the next
         //      tile's S | C MMA waits for exactly this
@@ -665,8 +694,8 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(o_free);   // the next item's first PV may overwrite O
         const int row = it.q0 + i;
-        if (row < p.S) {
-          __half* dst = p.ctx + ((int64_t)it.b * p.S + row) * p.H + it.head * D;
+        if (row < it.rows) {
+          __half* dst = p.ctx + ((int64_t)it.grow + row) * p.H + it.head * D;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             uint4 o4;
@@ -702,30 +731,20 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
 
 }  // namespace
 
-cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
-                              const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
-                              int num_sms, cudaStream_t stream) {
-  if (B <= 0 || S <= 0) return cudaSuccess;
-  if (S > 2048) return cudaErrorInvalidValue;   // reference MAX_LENGTH (include/configs.h:5)
-  const int H = heads * D;
-  // qkv viewed as [B][S][3H]; box 64 cols x 64 rows
-  uint64_t dq[3] = {(uint64_t)(3 * H), (uint64_t)S, (uint64_t)B};
-  uint64_t sq[2] = {(uint64_t)(3 * H) * 2, (uint64_t)S * 3 * H * 2};
+static cudaError_t launch_persist(const void* exp_k, const void* exp_qr, int64_t ld_exp, PersistParams p,
+                                  uint64_t tm_rows, uint64_t tm_batch, int num_sms, cudaStream_t stream) {
+  const int H = p.H, S = p.S;
+  // qkv viewed as [batch][rows][3H]; box 64 cols x 64 rows
+  uint64_t dq[3] = {(uint64_t)(3 * H), tm_rows, tm_batch};
+  uint64_t sq[2] = {(uint64_t)(3 * H) * 2, tm_rows * 3 * H * 2};
   uint32_t bq[3] = {64, 64, 1};
   // expanded tables are [EXP_ROWS][ld_exp] row-major (head h = columns h*64..): dims (d, row, head)
-  uint64_t dp[3] = {64, (uint64_t)EXP_ROWS, (uint64_t)heads};
+  uint64_t dp[3] = {64, (uint64_t)EXP_ROWS, (uint64_t)p.heads};
   uint64_t sp[2] = {(uint64_t)ld_exp * 2, 128};
   uint32_t bp[3] = {64, 64, 1};
-  CUtensorMap tm_qkv = make_tmap_16b(qkv, 3, dq, sq, bq);
+  CUtensorMap tm_qkv = make_tmap_16b(p.qkv_base, 3, dq, sq, bq);
   CUtensorMap tm_ek = make_tmap_16b(exp_k, 3, dp, sp, bp);
   CUtensorMap tm_eq = make_tmap_16b(exp_qr, 3, dp, sp, bp);
-  PersistParams p;
-  p.mask_bits = mask_bits;
-  p.kv_len = kv_len;
-  p.ctx = (__half*)ctx;
-  p.B = B; p.S = S; p.heads = heads; p.H = H;
-  p.nq = (S + QT - 1) / QT;
-  p.n_items = heads * p.nq * B;
   p.scale_log2 = 1.4426950408889634f / sqrtf(3.0f * D);
   static bool attr_set[64] = {};
   int dev = 0;
@@ -741,6 +760,42 @@ cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* ex
   if (force_mode != 0 && (S + KT - 1) / KT <= TMAX_RES)
     return launch_pdl(attention_persist_kernel<2>, dim3(grid), dim3(PTHREADS), Smem<2>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
   return launch_pdl(attention_persist_kernel<0>, dim3(grid), dim3(PTHREADS), Smem<0>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
+}
+
+cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                              const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
+                              int num_sms, cudaStream_t stream) {
+  if (B <= 0 || S <= 0) return cudaSuccess;
+  if (S > 2048) return cudaErrorInvalidValue;   // reference MAX_LENGTH (include/configs.h:5)
+  PersistParams p{};
+  p.qkv_base = qkv;
+  p.mask_bits = mask_bits;
+  p.kv_len = kv_len;
+  p.ctx = (__half*)ctx;
+  p.B = B; p.S = S; p.heads = heads; p.H = heads * D;
+  p.nq = (S + QT - 1) / QT;
+  p.n_items = heads * p.nq * B;
+  return launch_persist(exp_k, exp_qr, ld_exp, p, (uint64_t)S, (uint64_t)B, num_sms, stream);
+}
+
+cudaError_t attention_persist_packed(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                                     const uint32_t* row_bits, const int32_t* kv_len, const int32_t* text_row,
+                                     const int32_t* tile_info, void* ctx, int B, int rows, int max_text_rows, int n_tiles,
+                                     int heads, int num_sms, cudaStream_t stream) {
+  if (B <= 0 || rows <= 0 || n_tiles <= 0) return cudaSuccess;
+  if (max_text_rows > 2048 || (rows % QT) || (max_text_rows % QT) || n_tiles != rows / QT || B >= (1 << 24)) return cudaErrorInvalidValue;
+  PersistParams p{};
+  p.qkv_base = qkv;
+  p.mask_bits = row_bits;
+  p.kv_len = kv_len;
+  p.ctx = (__half*)ctx;
+  p.B = B; p.S = max_text_rows; p.heads = heads; p.H = heads * D;
+  p.nq = max_text_rows / QT;
+  p.tile_info = tile_info;
+  p.text_row = text_row;
+  p.n_tiles = n_tiles;
+  p.n_items = heads * n_tiles;
+  return launch_persist(exp_k, exp_qr, ld_exp, p, (uint64_t)rows, 1, num_sms, stream);
 }
 
 }  // namespace glc

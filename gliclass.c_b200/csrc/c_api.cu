@@ -306,6 +306,20 @@ int glc_coalesce_stats(const glc_model* m, uint64_t* groups, uint64_t* requests)
   return GLC_OK;
 }
 
+int glc_packed_stats(const glc_model* m, uint64_t* launches, uint64_t* rows, uint64_t* rows_padded) {
+  if (!m) return fail(GLC_ERR_ARG, "glc_packed_stats: null model");
+  uint64_t a = 0, b = 0, c = 0;
+  for (int i = 0; i < m->m->num_devices(); ++i) {
+    uint64_t x, y, z;
+    m->m->dev(i).packed_stats(&x, &y, &z);
+    a += x; b += y; c += z;
+  }
+  if (launches) *launches = a;
+  if (rows) *rows = b;
+  if (rows_padded) *rows_padded = c;
+  return GLC_OK;
+}
+
 int glc_profile_enable(glc_model* m, int slot, int on) {
   if (!m || slot < 0 || slot >= m->m->num_devices()) return fail(GLC_ERR_ARG, "glc_profile_enable: bad argument");
   m->m->dev(slot).profile_enable(on != 0);

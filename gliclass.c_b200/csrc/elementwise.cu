@@ -391,10 +391,16 @@ __global__ void mask_prep_kernel(const int64_t* __restrict__ mask, uint32_t* __r
 // one warp per batch row scans for <<LABEL>> tokens; then every lane copies rows with 128-bit loads
 __global__ void __launch_bounds__(128)
 head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
-                   int64_t class_token, int pool_mode, __half* __restrict__ pooled, __half* __restrict__ cls, int B, int S,
-                   int H, int C, int pos_offset) {
+                   int64_t class_token, int pool_mode, __half* __restrict__ pooled, __half* __restrict__ cls, int B, int S_in,
+                   int H, int C, int pos_offset, const int32_t* __restrict__ text_row) {
   extern __shared__ int pos_s[];   // [C] per block (one batch row per block)
   const int b = blockIdx.x;
+  // packed (varlen) layout: the text's rows are [text_row[b], text_row[b+1]) of the flat ids / mask / h arrays
+  const int64_t base = text_row ? (int64_t)text_row[b] : (int64_t)b * S_in;
+  const int S = text_row ? text_row[b + 1] - text_row[b] : S_in;
+  ids += base;
+  if (mask) mask += base;
+  h += base * H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ptx::pdl_wait();
   ptx::pdl_launch_dependents();
@@ -402,7 +408,7 @@ head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids
     int count = 0;
     for (int j0 = 0; j0 < S; j0 += 32) {
       const int j = j0 + lane;
-      const bool hit = (j < S) && (ids[(int64_t)b * S + j] == class_token);
+      const bool hit = (j < S) && (ids[j] == class_token);
       const uint32_t m = __ballot_sync(0xffffffffu, hit);
       if (hit) {
         const int c = count + __popc(m & ((1u << lane) - 1u));
@@ -422,9 +428,9 @@ head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids
       for (int e = 0; e < 8; ++e) acc[e] = (pool_mode == 2) ? 0.f : -3.4028234663852886e38f;
       int cnt = 0;
       for (int j = 0; j < S; ++j) {
-        if (mask[(int64_t)b * S + j] == 0) continue;   // block-uniform
+        if (mask[j] == 0) continue;   // block-uniform
         ++cnt;
-        const uint4 u = *reinterpret_cast<const uint4*>(h + ((int64_t)b * S + j) * H + i * 8);
+        const uint4 u = *reinterpret_cast<const uint4*>(h + (int64_t)j * H + i * 8);
         const __half2* hp = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
@@ -445,7 +451,7 @@ head_gather_kernel(const __half* __restrict__ h, const int64_t* __restrict__ ids
   for (int r = (pool_mode >= 2 ? warp + 1 : warp); r <= C; r += (blockDim.x >> 5)) {
     const int p = (r == 0) ? (pool_mode == 1 ? S - 1 : 0) : pos_s[r - 1];
     __half* dst = (r == 0) ? pooled + (int64_t)b * H : cls + ((int64_t)b * C + (r - 1)) * H;
-    const __half* src = h + ((int64_t)b * S + (p < 0 ? 0 : p)) * H;
+    const __half* src = h + (int64_t)(p < 0 ? 0 : p) * H;
     for (int i = lane; i < vec; i += 32) {
       uint4 u = make_uint4(0u, 0u, 0u, 0u);
       if (p >= 0) u = *reinterpret_cast<const uint4*>(src + i * 8);
@@ -723,11 +729,12 @@ cudaError_t head_gather(const void* h, const int64_t* ids, int64_t class_token, 
 }
 
 cudaError_t head_gather_pool(const void* h, const int64_t* ids, const int64_t* mask, int64_t class_token, int pool_mode,
-                             void* pooled, void* cls, int B, int S, int H, int C, cudaStream_t stream, int class_pos_offset) {
+                             void* pooled, void* cls, int B, int S, int H, int C, cudaStream_t stream, int class_pos_offset,
+                             const int32_t* text_row) {
   if (B <= 0) return cudaSuccess;
   if (H % 8 != 0 || pool_mode < 0 || pool_mode > 3 || (pool_mode >= 2 && !mask) || class_pos_offset < 0) return cudaErrorInvalidValue;
   return launch_pdl(head_gather_kernel, dim3(B), dim3(128), (size_t)(C > 0 ? C : 1) * sizeof(int), stream, (const __half*)h, ids, mask,
-                    class_token, pool_mode, (__half*)pooled, (__half*)cls, B, S, H, C, class_pos_offset);
+                    class_token, pool_mode, (__half*)pooled, (__half*)cls, B, S, H, C, class_pos_offset, text_row);
 }
 
 cudaError_t pad_rows_mean_v(const void* qkv, const int64_t* mask, void* ctx, int B, int S, int H, cudaStream_t stream) {

@@ -141,6 +141,10 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
     if (preln_f32_) fuse_resid_ = false;
   }
   {
+    const char* vl = getenv("GLC_VARLEN");
+    varlen_ = !(vl && vl[0] == '0');
+  }
+  {
     const char* f8 = getenv("GLC_FP8_FFN");
     fp8_ffn_ = fp8_ffn || (f8 && f8[0] == '1');
     if (const char* fm = getenv("GLC_FP8_MULT")) fp8_mult_ = (float)atof(fm);
@@ -394,6 +398,8 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   }
   mask_bits_ = (uint32_t*)A(((M + 31) / 32 + (size_t)ws_B_) * 4);
   kv_len_ = (int32_t*)A((size_t)ws_B_ * 4);
+  pk_ints_ = (int32_t*)A(((size_t)2 * ws_B_ + 2 + M / 128 + 1) * 4);
+  pk_scratch_ = (int32_t*)A((M / 128 + 1) * 4);
   pooled_ = A((size_t)ws_B_ * H * 2);
   cls_ = A((size_t)ws_rows_ * H * 2);
   tmid_ = A((size_t)ws_B_ * Hh * 2);
@@ -565,11 +571,17 @@ void DeviceModel::forward(const int64_t* d_ids, const int64_t* d_mask, int B, in
 void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits,
                                 float* d_probs, uint8_t* d_decisions, float threshold) {
   const int H = cfg_.hidden, I = cfg_.inter, Hh = cfg_.head_hidden;
-  const int M = B * S;
+  const PackedCtx* pk = pk_;   // packed (varlen) micro-batch: d_ids / d_mask are flat [rows], see engine.h
+  const int M = pk ? pk->rows : B * S;
   cudaStream_t st = stream_;
   uint64_t n = 0;
 
-  GLC_LAUNCH(KC_EMBED, mask_prep(d_mask, mask_bits_, kv_len_, B, S, st));
+  if (pk) {
+    // one validity bit per packed row (rows / 128 pseudo-rows of 128); the per-text key lengths came from the host
+    GLC_LAUNCH(KC_EMBED, mask_prep(d_mask, mask_bits_, pk_scratch_, pk->n_tiles, 128, st));
+  } else {
+    GLC_LAUNCH(KC_EMBED, mask_prep(d_mask, mask_bits_, kv_len_, B, S, st));
+  }
   if (cfg_.backbone == BACKBONE_QWEN2) {
     // decoder backbone (transformers modeling_qwen2.py Q:353-410, bidirectional): pre-norm residual stream in fp32
     const int d = cfg_.head_dim, nh = cfg_.heads, nkv = cfg_.kv_heads;
@@ -598,7 +610,10 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, d.wqkv, H, d.bqkv, qkv_, 3 * H, M, 3 * H, H, 0, false, num_sms_, st));
     if (l == 0) keep("qkv0", qkv_, (size_t)M * 3 * H);
     const __half* pe = (const __half*)d.pos_exp;
-    if (attn_mode_ == 2) {
+    if (pk) {
+      GLC_LAUNCH(KC_ATTN, attention_persist_packed(qkv_, pe + H, pe, 2 * H, mask_bits_, pk->kv_len, pk->text_row, pk->tile_info, ctx_,
+                                                   B, pk->rows, pk->max_rows, pk->n_tiles, cfg_.heads, num_sms_, st));
+    } else if (attn_mode_ == 2) {
       GLC_LAUNCH(KC_ATTN, attention_persist(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, num_sms_, st));
     } else if (attn_mode_ == 0) {
       GLC_LAUNCH(KC_ATTN, attention_rows(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
@@ -640,7 +655,7 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
   if (C > 0) {
     const int pa = cfg_.proj_act;
     GLC_LAUNCH(KC_HEAD_MISC, head_gather_pool(x_, d_ids, d_mask, cfg_.class_token, cfg_.pooling, pooled_, cls_, B, S, H, C, st,
-                                              cfg_.class_pos_offset));
+                                              cfg_.class_pos_offset, pk ? pk->text_row : nullptr));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(pooled_, H, t1w_, H, t1b_, tmid_, Hh, B, Hh, H, pa, false, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(tmid_, Hh, t2w_, Hh, t2b_, tvec_, Hh, B, Hh, Hh, 0, true, num_sms_, st));
     GLC_LAUNCH(KC_HEAD_GEMM, gemm_f16(cls_, H, c1w_, H, c1b_, cmid_, Hh, B * C, Hh, H, pa, false, num_sms_, st));
@@ -708,9 +723,48 @@ void DeviceModel::check_overflow_sync() {
   if (v) throw std::runtime_error(kOverflowMsg);
 }
 
+bool DeviceModel::plan_pack(const int64_t* ids, const int64_t* mask, int B, int S, PackPlan& pl) const {
+  if (!varlen_ || cfg_.backbone == BACKBONE_QWEN2 || attn_mode_ != 2 || cfg_.pooling == POOL_LAST || S < 256 || S > 2048) return false;
+  if ((int64_t)B * S < 8192) return false;   // small requests replay a captured graph of the [B,S] layout: latency first
+  pl.len.resize(B);
+  pl.prow.resize(B);
+  int64_t total = 0;
+  for (int b = 0; b < B; ++b) {
+    const int64_t* m = mask + (size_t)b * S;
+    int L = S;
+    while (L > 0 && m[L - 1] == 0) --L;
+    // every class token (and the neighbour embed_class_token=false reads) must lie inside the kept positions
+    const int64_t* id = ids + (size_t)b * S;
+    int j0 = L - cfg_.class_pos_offset;
+    for (int j = j0 < 0 ? 0 : j0; j < S; ++j)
+      if (id[j] == cfg_.class_token) return false;
+    pl.len[b] = L;
+    pl.prow[b] = L <= 128 ? 128 : round_up(L, 128);
+    total += pl.prow[b];
+  }
+  if (total * 10 > (int64_t)B * S * 9) return false;   // under 10 % of the rows are padding: not worth leaving the graph path
+  PackPlan::MB cur{0, 0, 0, 0};
+  auto close = [&](int b1) {
+    cur.b1 = b1;
+    pl.mbs.push_back(cur);
+    if (cur.rows > pl.max_mb_rows) pl.max_mb_rows = cur.rows;
+    if (b1 - cur.b0 > pl.max_mb_texts) pl.max_mb_texts = b1 - cur.b0;
+    cur = PackPlan::MB{b1, b1, 0, 0};
+  };
+  for (int b = 0; b < B; ++b) {
+    if (cur.rows + pl.prow[b] > max_tokens_ && b > cur.b0) close(b);
+    cur.rows += pl.prow[b];
+    if (pl.prow[b] > cur.max_rows) cur.max_rows = pl.prow[b];
+  }
+  close(B);
+  return true;
+}
+
 void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,
                            const DecisionOut* dec, bool cacheable) {
   if (B <= 0 || S <= 0) return;
+  PackPlan plan;
+  const bool packed = plan_pack(ids, mask, B, S, plan);
   static const bool timing = getenv("GLC_TIMING") != nullptr;
   auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   const double t0 = timing ? now() : 0;
@@ -740,14 +794,82 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
     int rows_mb = max_tokens_ / S;
     if (rows_mb < 1) rows_mb = 1;
     if (rows_mb > B) rows_mb = B;
-    ensure_workspace(rows_mb * S, rows_mb, C);
+    if (packed) ensure_workspace(plan.max_mb_rows, plan.max_mb_texts, C);
+    else ensure_workspace(rows_mb * S, rows_mb, C);
     if (!out_pinned && nout > 0) {
       ob = take_out_block(nout * 9);
       o_logits = logits ? (float*)ob.p : nullptr;
       o_probs = want_p ? (float*)ob.p + nout : nullptr;
       o_dec = want_d ? (uint8_t*)((float*)ob.p + 2 * nout) : nullptr;
     }
-    for (int r0 = 0; r0 < B; r0 += rows_mb) {
+    for (size_t mi = 0; packed && mi < plan.mbs.size(); ++mi) {
+      // ---- packed micro-batch: compact the texts into a pinned slot (ids | mask | text_row | kv_len | tile_info), one
+      //      H2D each, then the same forward on rows = sum of the texts' 128-aligned lengths
+      const PackPlan::MB& mb = plan.mbs[mi];
+      const int nb = mb.b1 - mb.b0, rows = mb.rows, nt = rows / 128;
+      const size_t idb = (size_t)rows * 8, nints = (size_t)2 * nb + 1 + nt;
+      const int k = h_in_next_;
+      h_in_next_ ^= 1;
+      PinnedBlock& hb = h_in_[k];
+      if (hb.bytes < 2 * idb + nints * 4) {
+        if (hb.p) { GLC_CUDA(cudaStreamSynchronize(stream_)); cudaFreeHost(hb.p); hb.p = nullptr; }
+        hb.bytes = 2 * (size_t)plan.max_mb_rows * 8 + ((size_t)2 * plan.max_mb_texts + 2 + plan.max_mb_rows / 128) * 4;
+        if (hb.bytes < 2 * idb + nints * 4) hb.bytes = 2 * idb + nints * 4;
+        GLC_CUDA(cudaMallocHost(&hb.p, hb.bytes));
+      }
+      if (!h_in_ev_[k]) GLC_CUDA(cudaEventCreateWithFlags(&h_in_ev_[k], cudaEventDisableTiming));
+      else GLC_CUDA(cudaEventSynchronize(h_in_ev_[k]));
+      int64_t* pi = (int64_t*)hb.p;
+      int64_t* pm = pi + rows;
+      int32_t* text_row = (int32_t*)(pm + rows);
+      int32_t* kvl = text_row + nb + 1;
+      int32_t* tinfo = kvl + nb;
+      int row = 0;
+      for (int i = 0; i < nb; ++i) {
+        const int b = mb.b0 + i, L = plan.len[b], P = plan.prow[b];
+        text_row[i] = row;
+        kvl[i] = L;
+        memcpy(pi + row, ids + (size_t)b * S, (size_t)L * 8);
+        memcpy(pm + row, mask + (size_t)b * S, (size_t)L * 8);
+        memset(pi + row + L, 0, (size_t)(P - L) * 8);   // id 0 / mask 0, what the reference pads with (tokenizer.c:78-82)
+        memset(pm + row + L, 0, (size_t)(P - L) * 8);
+        row += P;
+      }
+      text_row[nb] = row;
+      int n_t = 0;
+      for (int q = 0; q * 128 < mb.max_rows; ++q)
+        for (int i = 0; i < nb; ++i)
+          if (q * 128 < plan.prow[mb.b0 + i]) tinfo[n_t++] = (q << 24) | i;
+      GLC_CUDA(cudaMemcpyAsync(ids_, pi, idb, cudaMemcpyHostToDevice, stream_));
+      GLC_CUDA(cudaMemcpyAsync(mask_, pm, idb, cudaMemcpyHostToDevice, stream_));
+      GLC_CUDA(cudaMemcpyAsync(pk_ints_, text_row, nints * 4, cudaMemcpyHostToDevice, stream_));
+      GLC_CUDA(cudaEventRecord(h_in_ev_[k], stream_));
+      PackedCtx pc;
+      pc.rows = rows; pc.max_rows = mb.max_rows; pc.n_tiles = nt;
+      pc.text_row = pk_ints_; pc.kv_len = pk_ints_ + nb + 1; pc.tile_info = pk_ints_ + 2 * nb + 1;
+      pk_ = &pc;
+      try {
+        forward_eager(ids_, mask_, nb, S, C, logits_, want_p ? probs_ : nullptr, want_d ? decisions_ : nullptr,
+                      dec ? dec->threshold : 0.5f);
+      } catch (...) {
+        pk_ = nullptr;
+        throw;
+      }
+      pk_ = nullptr;
+      packed_runs_ += 1;
+      packed_rows_ += (uint64_t)rows;
+      packed_rows_padded_ += (uint64_t)nb * S;
+      if (C > 0) {
+        const int r0 = mb.b0;
+        if (o_logits)
+          GLC_CUDA(cudaMemcpyAsync(o_logits + (size_t)r0 * C, logits_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+        if (o_probs)
+          GLC_CUDA(cudaMemcpyAsync(o_probs + (size_t)r0 * C, probs_, (size_t)nb * C * 4, cudaMemcpyDeviceToHost, stream_));
+        if (o_dec)
+          GLC_CUDA(cudaMemcpyAsync(o_dec + (size_t)r0 * C, decisions_, (size_t)nb * C, cudaMemcpyDeviceToHost, stream_));
+      }
+    }
+    for (int r0 = 0; !packed && r0 < B; r0 += rows_mb) {
       const int nb = (B - r0 < rows_mb) ? (B - r0) : rows_mb;
       const size_t bytes = (size_t)nb * S * 8;
       const int64_t* src_i = ids + (size_t)r0 * S;

@@ -85,6 +85,10 @@ class DeviceModel {
   void run_host_coalesced(HostReq& r);
   uint64_t merged_groups() const { return merged_groups_.load(); }
   uint64_t merged_requests() const { return merged_requests_.load(); }
+  // packed (varlen) launches so far: count, rows computed, rows the padded [B,S] layout would have computed
+  void packed_stats(uint64_t* runs, uint64_t* rows, uint64_t* rows_padded) const {
+    *runs = packed_runs_.load(); *rows = packed_rows_.load(); *rows_padded = packed_rows_padded_.load();
+  }
 
   int device() const { return device_; }
   cudaStream_t stream() const { return stream_; }
@@ -106,6 +110,28 @@ class DeviceModel {
   const void* rope_table_for(int S);
   void ensure_workspace(int tokens, int B, int C);
   void run_group(std::vector<HostReq*>& group);
+  // ---- packed (varlen) layout of one host request: padding rows are dropped before the forward --------------------------
+  // A text keeps positions [0, len) (len = 1 + last non-zero mask entry) rounded up to whole 128-row query tiles; GEMM, LN
+  // and embedding rows then scale with the real tokens instead of B * S (the reference pads to the longest text of the
+  // batch, tokenizer.c:44-54, and ORT computes every padded row).  Nothing a valid row reads changes: padded keys are
+  // masked in both layouts and padded query rows are never read by the head.  Used by run_host when it removes >= 10 % of
+  // the rows; needs the persistent attention kernel, a pooling other than 'last' (which reads padded position S-1) and
+  // every class token inside the kept rows.  GLC_VARLEN=0 turns it off.
+  struct PackPlan {
+    std::vector<int> len, prow;           // per text: kv length, packed rows (multiple of 128)
+    struct MB { int b0, b1, rows, max_rows; };
+    std::vector<MB> mbs;                  // micro-batches of at most max_tokens_ packed rows
+    int max_mb_rows = 0, max_mb_texts = 0;
+  };
+  struct PackedCtx {                      // device-side description of the micro-batch being run
+    int rows = 0, max_rows = 0, n_tiles = 0;
+    const int32_t *text_row = nullptr, *kv_len = nullptr, *tile_info = nullptr;
+  };
+  bool plan_pack(const int64_t* ids, const int64_t* mask, int B, int S, PackPlan& pl) const;
+  bool varlen_ = true;
+  const PackedCtx* pk_ = nullptr;         // set (under mu) around forward_eager for a packed micro-batch
+  int32_t* pk_ints_ = nullptr;            // device: text_row[nb+1] | kv_len[nb] | tile_info[n_tiles]
+  int32_t* pk_scratch_ = nullptr;
   void forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
                      uint8_t* d_decisions, float threshold);
   const int32_t* rel_table(int S);
@@ -198,7 +224,9 @@ class DeviceModel {
   float *h_logits_ = nullptr, *h_probs_ = nullptr;
   uint8_t* h_dec_ = nullptr;
   size_t h_tok_ = 0, h_rows_ = 0;
+  std::atomic<uint64_t> packed_runs_{0}, packed_rows_{0}, packed_rows_padded_{0};
   std::atomic<uint64_t> merged_groups_{0}, merged_requests_{0};
+
   // profiler state
   struct ProfRec { int cat; cudaEvent_t a, b; };
   bool prof_on_ = false;

@@ -83,6 +83,13 @@ cudaError_t attention_rows(const void* qkv, const void* exp_k, const void* exp_q
 cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
                               const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                               int num_sms, cudaStream_t stream);
+// The same kernel on the PACKED (varlen) layout: text b owns rows [text_row[b], text_row[b+1]) of qkv / ctx (multiples of
+// 128), row_bits holds one validity bit per packed row, tile_info[t] = (query tile index within its text) << 24 | text for
+// the rows / 128 query tiles ordered (query tile index, text); max_text_rows = the longest text's row count.
+cudaError_t attention_persist_packed(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
+                                     const uint32_t* row_bits, const int32_t* kv_len, const int32_t* text_row,
+                                     const int32_t* tile_info, void* ctx, int B, int rows, int max_text_rows, int n_tiles,
+                                     int heads, int num_sms, cudaStream_t stream);
 // previous production kernel (attention_shift.cu): both biases skewed in registers (barrel shifter for c2p, lane rotation for
 // p2c); the two warps that share a query row split the 64 keys of a tile and exchange the row maximum.
 cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
@@ -106,7 +113,8 @@ cudaError_t head_gather(const void* h_f16, const int64_t* ids, int64_t class_tok
 // class_pos_offset = 1 reads each class row one position after its <<LABEL>> token (gliclass embed_class_token=false)
 cudaError_t head_gather_pool(const void* h_f16, const int64_t* ids, const int64_t* mask, int64_t class_token, int pool_mode,
                              void* pooled_f16, void* cls_f16, int B, int S, int H, int C, cudaStream_t stream,
-                             int class_pos_offset = 0);
+                             int class_pos_offset = 0, const int32_t* text_row = nullptr);
+// (text_row != nullptr: packed layout, text b = rows [text_row[b], text_row[b+1]) of the flat h / ids / mask arrays)
 // K5b generalised: logits[b,c] = scale * <t[b*t_stride..], k[b,c,:]> / ((|t|+eps)(|k|+eps) if normalize) + bias, then the
 // sigmoid / strict-threshold epilogue.  t_stride = 0: shared weight row (last Linear(K->1) of the MLP scorers).
 cudaError_t head_score_ex(const float* t, int64_t t_stride, const float* k, float* logits, float* probs, uint8_t* decisions,

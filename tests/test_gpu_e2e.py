@@ -338,6 +338,88 @@ def test_unsupported_storage_types_are_rejected(pkg, golden_onnx):
         pkg.Session(golden_onnx, weight_dtype="bf16")
 
 
+def _ragged_quarter_to_full(orc, cfg, B, S, labels, seed):
+    """lengths uniform in [S/4, S] (VERDICT r1 item 9's ragged workload)"""
+    return orc.synth_inputs(cfg, B, S, labels, seed=seed, ragged=True, min_frac=0.25)
+
+
+def test_varlen_packing_matches_padded_layout(pkg, orc, model_cache):
+    """f2 / reference tokenizer.c:44-54: a ragged batch is compacted to its real tokens (128-row aligned per text) before
+    the forward.  The logits must be those of the padded layout — compared against the same engine with GLC_VARLEN=0 and
+    against the oracle — and the row count must actually drop."""
+    path = os.path.join(model_cache, "base.onnx")
+    cfg, w = orc.make_model_file("base", path, seed=0)
+    ids, mask = _ragged_quarter_to_full(orc, cfg, 48, 512, 10, seed=777)
+    lens = mask.sum(1)
+    assert int(lens.min()) < 256 and int(lens.max()) > 400
+    os.environ["GLC_VARLEN"] = "0"
+    try:
+        s_pad = pkg.Session(path)
+    finally:
+        os.environ.pop("GLC_VARLEN")
+    s_pk = pkg.Session(path)
+    try:
+        out_pad = s_pad.run_inference(ids.numpy(), mask.numpy())
+        assert s_pad.packed_stats()[0] == 0
+        out_pk = s_pk.run_inference(ids.numpy(), mask.numpy())
+        runs, rows, rows_padded = s_pk.packed_stats()
+        assert runs == 1 and rows_padded == 48 * 512 and rows % 128 == 0
+        want_rows = int(sum(max(128, -(-int(l) // 128) * 128) for l in lens))
+        assert rows == want_rows and rows < 0.8 * rows_padded, (rows, want_rows, rows_padded)
+        d = np.abs(out_pk - out_pad)
+        print(f"varlen base/B48S512 ragged: rows {rows} of {rows_padded} ({100 * rows / rows_padded:.0f}%), "
+              f"packed vs padded max|d|={d.max():.3e} ({'bit-identical' if d.max() == 0 else 'not bit-identical'})")
+        assert d.max() <= 2e-3
+        rows_chk = [0, 7, 19, 33, 47]
+        ref = orc.forward_restated(w, cfg, ids[rows_chk], mask[rows_chk]).numpy()
+        _check_logits("varlen base/B48S512 rows 0,7,19,33,47", out_pk[rows_chk], ref, orc)
+        # the same request again (staging slots, workspace reuse) and a batch that does not qualify (< 10 % padding)
+        assert np.array_equal(s_pk.run_inference(ids.numpy(), mask.numpy()), out_pk)
+        ids2, mask2 = orc.synth_inputs(cfg, 16, 512, 10, seed=3)
+        s_pk.run_inference(ids2.numpy(), mask2.numpy())
+        assert s_pk.packed_stats()[0] == 2
+    finally:
+        s_pad.close()
+        s_pk.close()
+
+
+def test_varlen_packing_edge_cases(pkg, orc, model_cache):
+    """masks with interior holes keep their positions; a class token in the padded tail disables packing for the request;
+    several micro-batches of packed texts (max_tokens smaller than the packed batch) give the same logits"""
+    path = os.path.join(model_cache, "mini.onnx")
+    cfg, w = orc.make_model_file("mini", path, seed=0)
+    B, S = 40, 384
+    ids, mask = orc.synth_inputs(cfg, B, S, 5, seed=99, ragged=True, min_frac=0.2)
+    mask = mask.clone()
+    for b in range(0, B, 3):   # interior holes: masked keys inside the kept region
+        L = int(mask[b].sum())
+        mask[b, L // 2: L // 2 + 3] = 0
+    ref = orc.forward_restated(w, cfg, ids, mask).numpy()
+    s = pkg.Session(path)
+    s_small = pkg.Session(path, max_tokens=4096)
+    try:
+        out = s.run_inference(ids.numpy(), mask.numpy())
+        assert s.packed_stats()[0] == 1
+        _check_logits("varlen mini holes", out, ref, orc)
+        out_s = s_small.run_inference(ids.numpy(), mask.numpy())
+        assert s_small.packed_stats()[0] >= 2
+        assert np.abs(out_s - out).max() <= 2e-3
+        # a <<LABEL>> id in the padded tail of one text: the padded layout would count it, so the request is not packed
+        ids3 = ids.clone()
+        short = int(mask.sum(1).argmin())
+        ids3[short, S - 1] = cfg.class_token_index
+        before = s.packed_stats()[0]
+        out3 = s.run_inference(ids3.numpy(), mask.numpy())
+        assert s.packed_stats()[0] == before
+        # (the extra class row itself sits on a padded position, whose hidden state is outside the parity contract —
+        #  SURVEY.md App. A.7 — so only its presence and the other columns are checked)
+        assert out3.shape == (B, 6) and np.isfinite(out3).all()
+        assert np.abs(out3[:, :5] - out).max() <= 2e-3
+    finally:
+        s.close()
+        s_small.close()
+
+
 FP8_BAR = 5e-2   # VERDICT r1 item 7 / SURVEY.md N1: the logit bar an FP8 tier would have to meet to become a default
 
 
