@@ -165,7 +165,7 @@ __device__ __forceinline__ void setmaxnreg_inc() { asm volatile("setmaxnreg.inc.
 template <uint32_t N>
 __device__ __forceinline__ void setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <int MODE>
+template <int MODE, bool POLY>
 __global__ void __launch_bounds__(PTHREADS, 1)
 attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_ek,
                          const __grid_constant__ CUtensorMap tm_eq, const PersistParams p) {
@@ -627,7 +627,7 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         for (int jj = 0; jj < KT; jj += 2) {
           const float x0 = fmaf(s[jj], sc, neg_ms), x1 = fmaf(s[jj + 1], sc, neg_ms);
           const float e0 = ptx::ex2(x0);
-          const float e1 = ((jj & 3) == 2) ? exp2_poly(x1) : ptx::ex2(x1);
+          const float e1 = (POLY && (jj & 3) == 2) ? exp2_poly(x1) : ptx::ex2(x1);
           ps[jj & 3] += e0;
           ps[(jj + 1) & 3] += e1;
           pk[jj >> 1] = ptx::pack_f16(e0, e1);
@@ -750,16 +750,22 @@ static cudaError_t launch_persist(const void* exp_k, const void* exp_qr, int64_t
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_persist_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_persist_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<0>::BYTES);
+    cudaError_t e = cudaFuncSetAttribute(attention_persist_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_persist_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_persist_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<0>::BYTES);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
   const int grid = p.n_items < num_sms ? p.n_items : num_sms;
   static const int force_mode = [] { const char* e = getenv("GLC_ATTN_MODE"); return e ? atoi(e) : -1; }();   // developer switch
-  if (force_mode != 0 && (S + KT - 1) / KT <= TMAX_RES)
-    return launch_pdl(attention_persist_kernel<2>, dim3(grid), dim3(PTHREADS), Smem<2>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
-  return launch_pdl(attention_persist_kernel<0>, dim3(grid), dim3(PTHREADS), Smem<0>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
+  // every exponential on the MUFU unit by default: routing every 4th through the FMA-pipe polynomial (GLC_ATTN_POLY=1, what
+  // the two-warps-per-row kernels needed) costs 112 more instructions per tile here — 229.7 vs 218.8 us per launch
+  static const bool poly = [] { const char* e = getenv("GLC_ATTN_POLY"); return e && e[0] == '1'; }();   // developer switch
+  if (force_mode != 0 && (S + KT - 1) / KT <= TMAX_RES) {
+    if (!poly) return launch_pdl(attention_persist_kernel<2, false>, dim3(grid), dim3(PTHREADS), Smem<2>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
+    return launch_pdl(attention_persist_kernel<2, true>, dim3(grid), dim3(PTHREADS), Smem<2>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
+  }
+  return launch_pdl(attention_persist_kernel<0, true>, dim3(grid), dim3(PTHREADS), Smem<0>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
 }
 
 cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,

@@ -178,6 +178,8 @@ int glc_run(glc_model* m, const int64_t* input_ids, const int64_t* attention_mas
     if (!logits_out) return fail(GLC_ERR_ARG, "glc_run: null output");
     m->m->run(input_ids, attention_mask, B, S, C, logits_out);
     return GLC_OK;
+  } catch (const std::invalid_argument& e) {
+    return fail(GLC_ERR_ARG, std::string("glc_run: ") + e.what());
   } catch (const std::exception& e) {
     return fail(GLC_ERR_CUDA, std::string("glc_run: ") + e.what());
   }

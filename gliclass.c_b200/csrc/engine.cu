@@ -1124,14 +1124,44 @@ void Model::coalesce_stats(uint64_t* groups, uint64_t* requests) const {
   if (requests) *requests = r;
 }
 
-int Model::num_classes(const int64_t* ids, int B, int S) const {
+static int count_classes_rows(const int64_t* ids, int B, int S, int64_t class_token) {
   int C = 0;
   for (int b = 0; b < B; ++b) {
     int n = 0;
     const int64_t* row = ids + (size_t)b * S;
-    for (int j = 0; j < S; ++j) n += (row[j] == cfg_.class_token);
+    for (int j = 0; j < S; ++j) n += (row[j] == class_token);
     if (n > C) C = n;
   }
+  return C;
+}
+
+int Model::num_classes(const int64_t* ids, int B, int S) const {
+  const int G = (int)workers_.size();
+  if (G < 2 || (int64_t)B * S < (1 << 20)) return count_classes_rows(ids, B, S, cfg_.class_token);
+  // a reranker-sized batch (4096 x 1024 ids = 33 MB): the scan is the only serial host work in front of a sharded run,
+  // so the per-device workers do it
+  const int per = (B + G - 1) / G;
+  std::vector<int> part(G, 0);
+  std::mutex lmu;
+  std::condition_variable lcv;
+  int pending = 0;
+  for (int g = 0; g < G; ++g) {
+    const int r0 = g * per, nb = (r0 >= B) ? 0 : ((B - r0 < per) ? B - r0 : per);
+    if (nb == 0) continue;
+    {
+      std::lock_guard<std::mutex> lk(lmu);
+      ++pending;
+    }
+    workers_[g]->post([&, g, r0, nb]() {
+      part[g] = count_classes_rows(ids + (size_t)r0 * S, nb, S, cfg_.class_token);
+      std::lock_guard<std::mutex> lk(lmu);
+      if (--pending == 0) lcv.notify_all();
+    });
+  }
+  std::unique_lock<std::mutex> lk(lmu);
+  lcv.wait(lk, [&] { return pending == 0; });
+  int C = 0;
+  for (int v : part) C = v > C ? v : C;
   return C;
 }
 
@@ -1141,9 +1171,22 @@ uint64_t Model::launches() const {
   return n;
 }
 
+// ORT's Gather fails on an index outside the embedding table; so does this Run — checked before the request can be merged with
+// other callers' (the kernel itself clamps, which only the device-pointer entry point relies on)
+static void validate_ids(const int64_t* ids, int row0, int B, int S, int vocab) {
+  const uint64_t V = (uint64_t)vocab;
+  const size_t n = (size_t)B * S;
+  for (size_t i = 0; i < n; ++i)
+    if ((uint64_t)ids[i] >= V)
+      throw std::invalid_argument("input_ids[" + std::to_string(row0 + (int)(i / S)) + "][" + std::to_string(i % S) + "] = " +
+                                  std::to_string((long long)ids[i]) + " is outside the embedding table [0, " +
+                                  std::to_string(vocab) + ")");
+}
+
 void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits, const DecisionOut* dec) {
   const int G = (int)devs_.size();
   if (G == 1 || B < 2 * G) {
+    validate_ids(ids, 0, B, S, cfg_.vocab);
     // small call (the reference's BATCH_SIZE=8 Run): whole batch on one device, round robin
     // across concurrent callers (the OpenMP loop of main.c:141-150)
     const int slot = (int)(rr_.fetch_add(1) % (uint32_t)G);
@@ -1178,6 +1221,7 @@ void Model::run(const int64_t* ids, const int64_t* mask, int B, int S, int C, fl
           sub.probs = dec->probs ? dec->probs + (size_t)r0 * C : nullptr;
           sub.decisions = dec->decisions ? dec->decisions + (size_t)r0 * C : nullptr;
         }
+        validate_ids(ids + (size_t)r0 * S, r0, nb, S, cfg_.vocab);   // each worker checks its own shard
         devs_[g]->run_host(ids + (size_t)r0 * S, mask + (size_t)r0 * S, nb, S, C, logits ? logits + (size_t)r0 * C : nullptr,
                            dec ? &sub : nullptr);
       } catch (...) {

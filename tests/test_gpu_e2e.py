@@ -332,6 +332,21 @@ def test_fp16_overflow_fails_loudly_and_f32_preln_mode_recovers(pkg, orc, tmp_pa
         s.close()
 
 
+def test_out_of_vocabulary_ids_fail_the_run(pkg, golden, tiny_session):
+    """ORT's Gather fails on an index outside the embedding table (what the reference would see); so does glc_run, with a
+    message naming the position, instead of classifying a clamped token"""
+    ids, mask = golden["full.input_ids"].copy(), golden["full.attention_mask"]
+    ids[1, 3] = tiny_session.info["vocab"]
+    with pytest.raises(pkg.GlcError, match=r"input_ids\[1\]\[3\]"):
+        tiny_session.run_inference(ids, mask)
+    ids[1, 3] = -5
+    with pytest.raises(pkg.GlcError, match="outside the embedding table"):
+        tiny_session.run_inference(ids, mask)
+    # the session is still usable
+    out = tiny_session.run_inference(golden["full.input_ids"], mask)
+    assert np.abs(out - golden["full.logits"]).max() <= TOL
+
+
 def test_unsupported_storage_types_are_rejected(pkg, golden_onnx):
     """bf16 storage is refused loudly rather than silently computing in another type"""
     with pytest.raises(pkg.GlcError, match="weight_dtype must be GLC_DTYPE_FP16"):
