@@ -753,18 +753,24 @@ static cudaError_t launch_persist(const void* exp_k, const void* exp_qr, int64_t
     cudaError_t e = cudaFuncSetAttribute(attention_persist_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_persist_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2>::BYTES);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_persist_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<0>::BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_persist_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<0>::BYTES);
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
   const int grid = p.n_items < num_sms ? p.n_items : num_sms;
   static const int force_mode = [] { const char* e = getenv("GLC_ATTN_MODE"); return e ? atoi(e) : -1; }();   // developer switch
-  // every exponential on the MUFU unit by default: routing every 4th through the FMA-pipe polynomial (GLC_ATTN_POLY=1, what
-  // the two-warps-per-row kernels needed) costs 112 more instructions per tile here — 229.7 vs 218.8 us per launch
-  static const bool poly = [] { const char* e = getenv("GLC_ATTN_POLY"); return e && e[0] == '1'; }();   // developer switch
+  // Every 4th exponential goes through the FMA-pipe polynomial (exp2_poly) by default.  GLC_ATTN_POLY=0 puts them all on the
+  // MUFU unit: 112 fewer instructions per tile, 218.8 instead of 229.7 us per launch in isolation, but no change of the
+  // power-capped step time (8.43 ms either way), and the logits move by their noise level — which on the deep random
+  // fixtures sits AT the 2e-2 bar (S=1024 / 100 labels: 1.58e-2 with the polynomial, 2.04e-2 without; C2: 1.74e-2 / 1.67e-2;
+  // profiles/r2h_precision_probe.txt).  The default is the variant the whole parity suite was validated with.
+  static const bool poly = [] { const char* e = getenv("GLC_ATTN_POLY"); return !(e && e[0] == '0'); }();   // developer switch
   if (force_mode != 0 && (S + KT - 1) / KT <= TMAX_RES) {
     if (!poly) return launch_pdl(attention_persist_kernel<2, false>, dim3(grid), dim3(PTHREADS), Smem<2>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
     return launch_pdl(attention_persist_kernel<2, true>, dim3(grid), dim3(PTHREADS), Smem<2>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
   }
+  // (both table modes use the same exponential: a text's logits must not depend on the padded length of its launch)
+  if (!poly) return launch_pdl(attention_persist_kernel<0, false>, dim3(grid), dim3(PTHREADS), Smem<0>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
   return launch_pdl(attention_persist_kernel<0, true>, dim3(grid), dim3(PTHREADS), Smem<0>::BYTES, stream, tm_qkv, tm_ek, tm_eq, p);
 }
 
