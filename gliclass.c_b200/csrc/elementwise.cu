@@ -147,6 +147,61 @@ __device__ __forceinline__ void ln_store(float (&v)[NC][8], int lane, int H, con
   }
 }
 
+// ln_store for rows of exactly NC * 256 elements (every lane owns NC full chunks: no guards) — the hot case (H = 768 /
+// 1024).  Same arithmetic and summation ORDER per lane as ln_store would not be needed for parity, but batch-composition
+// invariance needs one order everywhere, so this is the only LN the bulk kernel uses for such rows.  Four independent
+// partial sums per statistic (the single chain of ln_store is 24 dependent FADDs), d = x - mean kept in place and reused
+// by the normalisation: 120 FP32 instructions per lane and row instead of 168.
+template <int NC>
+__device__ __forceinline__ void ln_store_full(float (&v)[NC][8], int lane, const LnParams<NC>& gb, float eps,
+                                              __half* __restrict__ out, uint8_t* __restrict__ out8, float* __restrict__ scale_out) {
+  constexpr float inv_h = 1.0f / (float)(NC * 256);
+  float s4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s4[i & 3] += v[c][i];
+  const float mean = warp_sum((s4[0] + s4[1]) + (s4[2] + s4[3])) * inv_h;
+  float q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      v[c][i] -= mean;
+      q4[i & 3] = fmaf(v[c][i], v[c][i], q4[i & 3]);
+    }
+  const float rstd = rsqrtf(warp_sum((q4[0] + q4[1]) + (q4[2] + q4[3])) * inv_h + eps);
+  float amax = 0.f;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[c][i] = fmaf(v[c][i] * rstd, gb.g[c][i], gb.b[c][i]);
+    uint4 o;
+    o.x = ptx::pack_f16(v[c][0], v[c][1]);
+    o.y = ptx::pack_f16(v[c][2], v[c][3]);
+    o.z = ptx::pack_f16(v[c][4], v[c][5]);
+    o.w = ptx::pack_f16(v[c][6], v[c][7]);
+    *reinterpret_cast<uint4*>(out + (lane + 32 * c) * 8) = o;
+  }
+  if (out8 != nullptr) {   // warp-uniform
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) amax = fmaxf(amax, fabsf(v[c][i]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    const float inv = amax > 0.f ? 448.0f / amax : 1.0f;
+    if (lane == 0) *scale_out = amax > 0.f ? amax / 448.0f : 1.0f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      uint2 o;
+      o.x = ptx::pack_e4m3x4(v[c][0] * inv, v[c][1] * inv, v[c][2] * inv, v[c][3] * inv);
+      o.y = ptx::pack_e4m3x4(v[c][4] * inv, v[c][5] * inv, v[c][6] * inv, v[c][7] * inv);
+      *reinterpret_cast<uint2*>(out8 + (lane + 32 * c) * 8) = o;
+    }
+  }
+}
+
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 embed_ln_kernel(const int64_t* __restrict__ ids, const int64_t* __restrict__ mask,
@@ -278,7 +333,9 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                : "memory");
 }
 
-template <int NC>
+// FAST: H == NC * 256 and a residual operand (every layer LN of the base / large stacks): unguarded chunk loops and
+// ln_store_full.  The generic instantiation handles ragged widths and the no-residual form.
+template <int NC, bool FAST>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__ r, const float* __restrict__ gamma,
                         const float* __restrict__ beta, float eps, __half* __restrict__ y, int M, int H, int stages,
@@ -320,6 +377,27 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
     ptx::mbar_wait(&bars[s], parity);
     const uint8_t* xs = ring + (size_t)s * st_bytes;
     float v[NC][8];
+    if (FAST) {
+      uint4 xa[NC], ra[NC];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        xa[c] = *reinterpret_cast<const uint4*>(xs + (lane + 32 * c) * 16);
+        ra[c] = *reinterpret_cast<const uint4*>(xs + row_bytes + (lane + 32 * c) * 16);
+      }
+      __syncwarp();   // every lane has read the stage: refill it
+      const int nxt = rw + stages * nwarps;
+      if (nxt < M) issue(nxt, s);
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        float t[8];
+        unpack8(xa[c], v[c]);
+        unpack8(ra[c], t);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[c][i] += t[i];
+      }
+      sat_probe<NC>(v, lane, NC * 256, flag);
+      ln_store_full<NC>(v, lane, gb, eps, y + (int64_t)rw * H, y8 ? y8 + (int64_t)rw * H : nullptr, y8_scale + rw);
+    } else {
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int e0 = (lane + 32 * c) * 8;
@@ -340,6 +418,7 @@ residual_ln_bulk_kernel(const __half* __restrict__ x, const __half* __restrict__
     if (nxt < M) issue(nxt, s);
     sat_probe<NC>(v, lane, H, flag);
     ln_store<NC>(v, lane, H, gb, eps, 1.0f, y + (int64_t)rw * H, y8 ? y8 + (int64_t)rw * H : nullptr, y8_scale + rw);
+    }
     if (++s == stages) { s = 0; parity ^= 1u; }
   }
 }
@@ -660,7 +739,8 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
       int dev = 0, sms = 148;
       cudaGetDevice(&dev);
       if (!attr_set[dev & 63][NC]) {
-        cudaError_t e = cudaFuncSetAttribute(residual_ln_bulk_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(residual_ln_bulk_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(residual_ln_bulk_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev & 63][NC] = true;
       }
@@ -668,7 +748,10 @@ cudaError_t residual_ln(const void* x, const void* r, const float* gamma, const 
       int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
       const int per_sm = (int)((224 * 1024) / (ring_bytes + 1024));
       if (blocks > sms * per_sm) blocks = sms * per_sm;
-      return launch_pdl(residual_ln_bulk_kernel<NC>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), ring_bytes, stream, (const __half*)x,
+      if (r != nullptr && H == NC * 256)
+        return launch_pdl(residual_ln_bulk_kernel<NC, true>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), ring_bytes, stream, (const __half*)x,
+                          (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages, overflow_flag, (uint8_t*)y8, y8_scale);
+      return launch_pdl(residual_ln_bulk_kernel<NC, false>, dim3(blocks), dim3(ROWS_PER_BLOCK * 32), ring_bytes, stream, (const __half*)x,
                         (const __half*)r, gamma, beta, eps, (__half*)y, M, H, stages, overflow_flag, (uint8_t*)y8, y8_scale);
     }
     int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
