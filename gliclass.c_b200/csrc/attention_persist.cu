@@ -550,7 +550,14 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
         // ---- p2c, both halves: lane rotation by 31 - (b mod 32), the source lane picks the copy
         ptx::mbar_wait(&g_full[slot], par);
         ptx::tc_fence_after();
-        auto p2c_half = [&](auto half_tag) {
+        // both halves are fetched and reduced to the selected copy FIRST (16 registers per half), so the G accumulators go
+        // back to the tensor core after two load round trips instead of after half of the rotations (228.5 -> 222.5 us).
+        // Tried on top and rejected: issuing S|C one tile ahead of G (340 us: G(g) is delayed, its K stage is released
+        // late and the TMA latency of K(g+2) is exposed — shared memory has no room for a third K stage), and issuing
+        // S|C / G in readiness order with non-blocking mbarrier probes (291 us: all three groups run concurrently and the
+        // group that holds G finishes later)
+        uint32_t gv[2][16];
+        auto p2c_fetch = [&](auto half_tag) {
           constexpr int HF = decltype(half_tag)::value;
           // keys 0..31: copies G32 (lower) / G64 (upper); keys 32..63: copies G0 (lower) / G32 (upper)
           const uint32_t a_lo = t_lane + (HF == 0 ? TM_G32 : TM_G0);
@@ -571,16 +578,23 @@ attention_persist_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __gri
 #pragma unroll
             for (int mm = 0; mm < 4; ++mm) {
               const int m = 4 * m4 + mm;
-              const uint32_t v = (hi[m] & hmv[mm]) | (lo[m] & ~hmv[mm]);
-              const uint32_t x0 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m);        // low half = key 2m
-              const uint32_t x1 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m - 1);    // high half = key 2m + 1
-              ptx::add_f16_lo_to_f32(s[32 * HF + 2 * m], x0);
-              ptx::add_f16_hi_to_f32(s[32 * HF + 2 * m + 1], x1);
+              gv[HF][m] = (hi[m] & hmv[mm]) | (lo[m] & ~hmv[mm]);
             }
           }
         };
-        p2c_half(std::integral_constant<int, 0>{});
-        p2c_half(std::integral_constant<int, 1>{});
+        p2c_fetch(std::integral_constant<int, 0>{});
+        p2c_fetch(std::integral_constant<int, 1>{});
+#pragma unroll
+        for (int HF = 0; HF < 2; ++HF) {
+#pragma unroll
+          for (int m = 0; m < 16; ++m) {
+            const uint32_t v = gv[HF][m];
+            const uint32_t x0 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m);        // low half = key 2m
+            const uint32_t x1 = __shfl_sync(0xffffffffu, v, rot0 - 2 * m - 1);    // high half = key 2m + 1
+            ptx::add_f16_lo_to_f32(s[32 * HF + 2 * m], x0);
+            ptx::add_f16_hi_to_f32(s[32 * HF + 2 * m + 1], x1);
+          }
+        }
 
         // ---- key validity, local row maximum (four independent chains of 3-input maxima)
         if ((kb0 & kb1) != 0xffffffffu) {
