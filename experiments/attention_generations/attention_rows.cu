@@ -1,4 +1,4 @@
-// K3 (production) — fused DeBERTa disentangled attention for sm_100a, head dim 64:
+// K3 (superseded generation, kept for reference; not part of libgliclass_b200.so) — fused DeBERTa disentangled attention for sm_100a, head dim 64:
 //
 //   ctx[b,i,h,:] = softmax_j( (Q_i.K_j + Q_i.posK[idx(i-j)] + K_j.posQ[idx(i-j)]) / sqrt(3d) + mask_j ) . V_j
 //
@@ -48,6 +48,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "kernels_exp.h"
 #include "ptx.cuh"
 #include "tma_desc.h"
 

@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "kernels.h"
+#include "kernels_exp.h"
 #include "model_weights.h"
 #include "ptx.cuh"
 #include "tma_desc.h"

@@ -91,12 +91,10 @@ _SIGS = {
     "glc_op_residual_ln": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
     "glc_op_mask_prep": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "glc_op_attention_naive": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
-    "glc_op_attention_rows": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_op_attention_persist": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_expanded_pos_rows": (_i, []),
     "glc_op_expand_pos": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
     "glc_op_expand_pos_rev": (_i, [_vp, _i64, _i, _i, _vp, _i64, _i, _vp]),
-    "glc_op_attention_shift": (_i, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "glc_op_add_rmsnorm": (_i, [_vp, _vp, _vp, _f, _vp, _i, _i, _vp]),
     "glc_op_rope": (_i, [_vp, _i64, _vp, _i, _i, _i, _i, _vp]),
     "glc_op_attention_flash128": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),

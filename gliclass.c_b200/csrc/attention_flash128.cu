@@ -7,7 +7,7 @@
 // (transformers modeling_qwen2.py: repeat_kv Q:150-158, eager_attention_forward Q:160-185, with the causal mask of Q:378-393
 // replaced by the key-padding mask.)  Q and K arrive already rotated (rope_inplace).
 //
-// Same skeleton as the DeBERTa kernel (attention_rows.cu) without the position-bias machinery: one CTA per (128-query
+// Same skeleton as the DeBERTa kernel (attention_persist.cu, in its one-CTA-per-item form) without the position-bias machinery: one CTA per (128-query
 // tile, q head, batch row); 64-key tiles; S = Q.K_t^T double-buffered in TMEM (fp32), P as fp16 pairs in TMEM, O (128
 // fp32 columns) resident in TMEM with a sticky row maximum; one softmax thread per query row of a tile; three softmax
 // warpgroups rotate over the key tiles and chain the maximum (tile t -> group t % 3).

@@ -6,13 +6,30 @@
 // softmax T:256-259, context T:262-271; idx(delta) = clamp(bucket(delta)+span, 0, 2*span-1))
 // Replaces the attention sub-graph ORT executes inside the reference's session Run (src/model.c:173-182).
 //
-// Arithmetic and register skews are those of attention_rows.cu (see there): expanded position tables EK / EQr make both
-// biases Toeplitz inside a (128-query, 64-key) tile, c2p is un-skewed by a barrel shifter on the packed fp16 window of
-// C = Q.EK^T (a ring of three 64-column blocks in TMEM, one new block per tile), p2c by lane rotations of three
-// row-shifted copies of G = EQr.K^T; one softmax thread owns a whole query row of a tile; three softmax warpgroups rotate
-// over the key tiles and chain a sticky row maximum; O accumulates in TMEM.
+// Tensor-core side: the position tables are expanded at load to one row per DELTA
+//     EK [rho]   = posK[idx(2047 - rho)]          EQr[sigma] = posQ[idx(sigma - 2047)]
+// so that inside a (128-query, 64-key) tile (a = query row, b = key column) both biases are Toeplitz,
+//     c2p[a,b] = C[a, 127 - a + b]     C = Q_tile . EK[rho0 .. rho0+191]^T          rho0   = 1920 - q0 + k0
+//     p2c[a,b] = G[a + 63 - b, b]      G = EQr[sigma0 .. sigma0+191] . K_tile^T     sigma0 = 1984 + q0 - k0
+// and the skews are undone in registers, where the accumulators already are: c2p by a 5-stage barrel shifter on the packed
+// fp16 window of C (tcgen05.ld.pack::16b), p2c by a lane rotation — the tensor core computes G three times, with the A
+// window starting at slice rows 0 / 32 / 64, so that row a + s of the skew sits in lane (a + s) mod 32 of one of two copies:
+// one select (precomputed lane masks) + one SHFL per score.  C and G use fp16 accumulators.
+// Softmax side:
+//   * a softmax thread owns a WHOLE row of a tile (64 keys: two 32-key halves through the same register-skew code): no
+//     cross-warp exchange, one straight-line code path for every softmax warp;
+//   * NWG = 3 warpgroups (12 softmax warps, three per scheduler) ROTATE over the key tiles: tile g belongs to group g mod 3.
+//     S | C | G stay single-buffered in TMEM (all 512 columns are used): the tensor core computes the next tile as soon as
+//     the group of the current one has drained it into registers;
+//   * O stays in TMEM and accumulates over all tiles with a STICKY row maximum (raised only when the row maximum grew by
+//     more than 2^8).  The maximum is chained from tile to tile through shared memory + one mbarrier per (group, lane
+//     quarter); the (rare) rescale of O is done by the group that raises the maximum; each group keeps a partial row sum
+//     relative to the maximum it last saw, merged by the group of the item's last tile in tile-residue order;
+//   * the C window SLIDES: consecutive key tiles use slices shifted by 64 table rows, so C lives in a ring of three
+//     64-column blocks and the tensor core computes only the new block per tile (the first tile computes all three).
 //
-// What the per-tile clock traces of attention_rows showed (profiles/r2_attention_trace.md): a CTA spends ~3000 cycles in
+// What the per-tile clock traces of the one-CTA-per-item form of this kernel showed (experiments/attention_generations/
+// attention_rows.cu, profiles/r2_attention_trace.md): a CTA spends ~3000 cycles in
 // its prologue (barrier init, TMEM allocation, first TMA round trip) and ~1500 in its tail for 8 tiles of work, and the
 // tile period (1750 cycles) is set by the L2 -> SM fabric: 48 KB per tile, of which 32 KB are position-table slices that
 // every CTA of the same (head, query tile) fetches again.  Hence this kernel:
@@ -20,7 +37,7 @@
 //     the list ordered with the batch row fastest, so a CTA stays on one (head, query tile) for all but one switch;
 //   * for S <= 512 both expanded table windows of that (head, query tile) — (Tmax + 2) * 64 rows each, 80 KB + 80 KB —
 //     stay RESIDENT in shared memory; a tile then costs 16 KB of L2 traffic (K_t, V_t).  Longer sequences stream the
-//     slices per tile as attention_rows does (MODE 0);
+//     slices per tile (MODE 0);
 //   * tiles of consecutive items form one stream g = 0, 1, 2, ...: group g % 3 owns tile g, the S | C | G accumulators,
 //     the P buffer and the operand rings are handed over by the same barriers across item boundaries, so the pipeline never
 //     drains.  Per item only the Q tile (copied to TMEM by the group that owns the item's first tile), the O accumulator

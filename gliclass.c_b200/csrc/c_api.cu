@@ -505,16 +505,6 @@ int glc_op_expand_pos_rev(const void* pos_f16, int64_t ld_src, int buckets, int 
     return fail(GLC_ERR_CUDA, std::string("glc_op_expand_pos_rev: ") + e.what());
   }
 }
-int glc_op_attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
-                           const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
-  GLC_TRY("glc_op_attention_shift",
-          glc::attention_shift(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
-}
-int glc_op_attention_rows(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
-                          const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
-  GLC_TRY("glc_op_attention_rows",
-          glc::attention_rows(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads, (cudaStream_t)stream));
-}
 int glc_op_attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp, const uint32_t* mask_bits,
                              const int32_t* kv_len, void* ctx, int B, int S, int heads, void* stream) {
   GLC_TRY("glc_op_attention_persist", glc::attention_persist(qkv, exp_k, exp_qr, ld_exp, mask_bits, kv_len, ctx, B, S, heads,

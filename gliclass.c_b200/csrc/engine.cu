@@ -120,17 +120,8 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
   const char* dk = getenv("GLC_DEBUG_KEEP");
   debug_keep_ = dk && dk[0] == '1';
   graphs_on_ = getenv("GLC_NO_GRAPHS") == nullptr;
-  // production attention = attention_persist.cu (persistent CTAs, row-owner warpgroups rotating over key tiles, position
-  // tables resident in shared memory for S <= 512); GLC_ATTN=rows | shift select the two previous production kernels for
-  // A/B comparisons.  The three earlier generations live under experiments/attention_generations/.
-  attn_mode_ = 2;
-  if (const char* am = getenv("GLC_ATTN")) {
-    const std::string m(am);
-    if (m == "rows") attn_mode_ = 0;
-    else if (m == "shift") attn_mode_ = 1;
-    else if (m == "persist") attn_mode_ = 2;
-    else throw std::runtime_error("GLC_ATTN must be persist, rows or shift (got '" + m + "')");
-  }
+  // attention = attention_persist.cu (persistent CTAs, row-owner warpgroups rotating over key tiles, position tables
+  // resident in shared memory for S <= 512); the generations it supersedes live under experiments/attention_generations/
   {
     const char* fr = getenv("GLC_FUSE_RESID");
     fuse_resid_ = fr && fr[0] == '1';   // measured: LN -0.1 ms, but the out-proj / FFN2 epilogues +0.28 ms per step -> off
@@ -613,12 +604,8 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     if (pk) {
       GLC_LAUNCH(KC_ATTN, attention_persist_packed(qkv_, pe + H, pe, 2 * H, mask_bits_, pk->kv_len, pk->text_row, pk->tile_info, ctx_,
                                                    B, pk->rows, pk->max_rows, pk->n_tiles, cfg_.heads, num_sms_, st));
-    } else if (attn_mode_ == 2) {
-      GLC_LAUNCH(KC_ATTN, attention_persist(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, num_sms_, st));
-    } else if (attn_mode_ == 0) {
-      GLC_LAUNCH(KC_ATTN, attention_rows(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
     } else {
-      GLC_LAUNCH(KC_ATTN, attention_shift(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, st));
+      GLC_LAUNCH(KC_ATTN, attention_persist(qkv_, pe + H, pe, 2 * H, mask_bits_, kv_len_, ctx_, B, S, cfg_.heads, num_sms_, st));
     }
     if (cfg_.pooling == POOL_LAST) GLC_LAUNCH(KC_ATTN, pad_rows_mean_v(qkv_, d_mask, ctx_, B, S, H, st));
     if (l == 0) keep("ctx0", ctx_, (size_t)M * H);
@@ -724,7 +711,7 @@ void DeviceModel::check_overflow_sync() {
 }
 
 bool DeviceModel::plan_pack(const int64_t* ids, const int64_t* mask, int B, int S, PackPlan& pl) const {
-  if (!varlen_ || cfg_.backbone == BACKBONE_QWEN2 || attn_mode_ != 2 || cfg_.pooling == POOL_LAST || S < 256 || S > 2048) return false;
+  if (!varlen_ || cfg_.backbone == BACKBONE_QWEN2 || cfg_.pooling == POOL_LAST || S < 256 || S > 2048) return false;
   if ((int64_t)B * S < 8192) return false;   // small requests replay a captured graph of the [B,S] layout: latency first
   pl.len.resize(B);
   pl.prow.resize(B);

@@ -115,7 +115,7 @@ class DeviceModel {
   // and embedding rows then scale with the real tokens instead of B * S (the reference pads to the longest text of the
   // batch, tokenizer.c:44-54, and ORT computes every padded row).  Nothing a valid row reads changes: padded keys are
   // masked in both layouts and padded query rows are never read by the head.  Used by run_host when it removes >= 10 % of
-  // the rows; needs the persistent attention kernel, a pooling other than 'last' (which reads padded position S-1) and
+  // the rows; needs a pooling other than 'last' (which reads padded position S-1) and
   // every class token inside the kept rows.  GLC_VARLEN=0 turns it off.
   struct PackPlan {
     std::vector<int> len, prow;           // per text: kv length, packed rows (multiple of 128)
@@ -164,7 +164,6 @@ class DeviceModel {
   int h_in_next_ = 0;
   std::vector<PinnedBlock> out_pool_;
   PinnedBlock take_out_block(size_t bytes);
-  int attn_mode_ = 2;          // 2 attention_persist.cu (production), 0 attention_rows.cu, 1 attention_shift.cu (env GLC_ATTN=persist|rows|shift)
   std::atomic<uint64_t> launches_{0};
 
   // weights

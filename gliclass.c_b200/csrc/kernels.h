@@ -71,15 +71,11 @@ void expanded_pos_index(int buckets, int max_pos, int32_t* out /* host, [expande
 void expanded_pos_index_rev(int buckets, int max_pos, int32_t* out /* host, [expanded_pos_rows()] */);
 cudaError_t expand_pos_table(const void* pos_f16, int64_t ld_src, const int32_t* d_exp_index, void* out_f16, int64_t ld_dst,
                              int cols, cudaStream_t stream);
-// production kernel (attention_rows.cu): same register skews, but a softmax thread owns a whole query row of a 64-key
-// tile and three warpgroups rotate over the key tiles (tile t -> group t mod 3), chaining the sticky row maximum from
-// tile to tile: no lock-step exchange, three warps per scheduler in different phases of their tiles.
-cudaError_t attention_rows(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
-                           const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
-                           cudaStream_t stream);
-// persistent form of attention_rows (attention_persist.cu): one CTA per SM for the whole launch, work items dealt out in
+// production kernel (attention_persist.cu): both biases un-skewed in registers, a softmax thread owns a whole query row of
+// a 64-key tile, three warpgroups rotate over the key tiles; one CTA per SM for the whole launch, work items dealt out in
 // contiguous chunks ordered (head, query tile, batch row); for S <= 512 the expanded table windows of the CTA's
-// (head, query tile) stay resident in shared memory, so a tile costs 16 KB of L2 traffic instead of 48 KB.
+// (head, query tile) stay resident in shared memory, so a tile costs 16 KB of L2 traffic instead of 48 KB.  (The two
+// generations it supersedes are experiments/attention_generations/attention_{shift,rows}.cu.)
 cudaError_t attention_persist(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
                               const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
                               int num_sms, cudaStream_t stream);
@@ -90,11 +86,6 @@ cudaError_t attention_persist_packed(const void* qkv, const void* exp_k, const v
                                      const uint32_t* row_bits, const int32_t* kv_len, const int32_t* text_row,
                                      const int32_t* tile_info, void* ctx, int B, int rows, int max_text_rows, int n_tiles,
                                      int heads, int num_sms, cudaStream_t stream);
-// previous production kernel (attention_shift.cu): both biases skewed in registers (barrel shifter for c2p, lane rotation for
-// p2c); the two warps that share a query row split the 64 keys of a tile and exchange the row maximum.
-cudaError_t attention_shift(const void* qkv, const void* exp_k, const void* exp_qr, int64_t ld_exp,
-                            const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S, int heads,
-                            cudaStream_t stream);
 // slow CUDA-core restatement of the same op on the UNEXPANDED tables (pos_k / pos_q fp16 [2*buckets][ld_pos], rel_idx
 // int32 [2*Spad-1] with Spad = S rounded up to 128), used only by tests to localise bugs on the GPU
 cudaError_t attention_naive(const void* qkv, const void* pos_k, const void* pos_q, int64_t ld_pos, const int32_t* rel_idx,

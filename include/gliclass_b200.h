@@ -201,11 +201,9 @@ GLC_API int glc_op_mask_prep(const int64_t* mask, uint32_t* bits, int32_t* kv_le
  *   glc_op_expand_pos_rev  out[sigma][0:cols) = pos[idx(sigma - 2047)][0:cols)  (posQ half)
  * for rho, sigma in [0, glc_expanded_pos_rows()); idx = glc_rel_index_table, the last row is zero; both synchronise
  * `stream`.  exp_k / exp_qr: fp16 [glc_expanded_pos_rows()][ld_exp], head h at columns h*64...
- *   glc_op_attention_persist  persistent form of the rows kernel (csrc/attention_persist.cu): one CTA per SM, position
- *                           tables resident in shared memory for S <= 512.
- *   glc_op_attention_rows   production kernel (csrc/attention_rows.cu): register skews of both biases, one softmax
- *                           thread per query row of a 64-key tile, three warpgroups rotating over the key tiles.
- *   glc_op_attention_shift  previous production kernel (csrc/attention_shift.cu), kept for A/B runs (GLC_ATTN=shift).
+ *   glc_op_attention_persist  production kernel (csrc/attention_persist.cu): register skews of both biases, one softmax
+ *                           thread per query row of a 64-key tile, three warpgroups rotating over the key tiles, one
+ *                           persistent CTA per SM, position tables resident in shared memory for S <= 512.
  *   glc_op_attention_naive  slow CUDA-core restatement on the UNEXPANDED tables (pos_k / pos_q fp16 [2*buckets][ld_pos],
  *                           rel_idx int32 [2*Spad-1] from glc_rel_index_table(Spad), Spad = S rounded up to 128): the
  *                           on-GPU debugging oracle of the tests. */
@@ -214,15 +212,9 @@ GLC_API int glc_op_expand_pos(const void* pos_f16, int64_t ld_src, int buckets, 
                               int cols, void* stream);
 GLC_API int glc_op_expand_pos_rev(const void* pos_f16, int64_t ld_src, int buckets, int max_pos, void* out_f16, int64_t ld_dst,
                                   int cols, void* stream);
-GLC_API int glc_op_attention_rows(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
-                                  const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
-                                  void* stream);
 GLC_API int glc_op_attention_persist(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
                                      const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
                                      void* stream);
-GLC_API int glc_op_attention_shift(const void* qkv_f16, const void* exp_k_f16, const void* exp_qr_f16, int64_t ld_exp,
-                                   const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S, int heads,
-                                   void* stream);
 GLC_API int glc_op_attention_naive(const void* qkv_f16, const void* pos_k_f16, const void* pos_q_f16, int64_t ld_pos,
                                    const int32_t* rel_idx, const uint32_t* mask_bits, void* ctx_f16, int B, int S, int heads,
                                    int buckets, void* stream);

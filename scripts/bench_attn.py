@@ -1,6 +1,6 @@
 """Attention-kernel micro benchmark on the bench shape (base arch: B=64, S=512, 12 heads) through the C ABI
-(glc_op_attention_rows / glc_op_attention_shift), plus a parity check against the slow CUDA-core restatement on the
-same inputs.  Usage: python scripts/bench_attn.py [B S heads iters]      (GLC_ATTN=rows|shift|both, default both)"""
+(glc_op_attention_persist), plus a parity check against the slow CUDA-core restatement on the
+same inputs.  Usage: python scripts/bench_attn.py [B S heads iters]"""
 import os
 import sys
 
@@ -38,9 +38,8 @@ rc = L.glc_op_attention_naive(qkv.data_ptr(), pos_k.data_ptr(), pos_q.data_ptr()
 assert rc == 0, pkg.last_error()
 torch.cuda.synchronize()
 fl = 4.0 * B * S * S * H + 4.0 * B * S * 512 * H
-mode = os.environ.get("GLC_ATTN", "both")
-for name in (("persist", "rows", "shift") if mode == "both" else (mode,)):
-    op = {"rows": L.glc_op_attention_rows, "shift": L.glc_op_attention_shift, "persist": L.glc_op_attention_persist}[name]
+for name in ("persist",):
+    op = L.glc_op_attention_persist
     ctx = torch.zeros(B, S, H, dtype=torch.float16, device=dev)
 
     def run():

@@ -348,7 +348,7 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, kernel, qk_std=1.8):
     _sync_check(pkg, L.glc_op_mask_prep(_ptr(mask), _ptr(bits), _ptr(kv), B, S, None), "mask_prep")
     ctx = torch.full((B, S, H), float("nan"), dtype=torch.float16, device=dev)
     pos_q, pos_k = pos[:, :H], pos[:, H:]
-    if kernel in ("rows", "shift", "persist"):
+    if kernel == "persist":
         # posK half expanded in rho order, posQ half in the opposite (sigma) order, one row per relative distance
         ER = L.glc_expanded_pos_rows()
         exp = torch.full((ER, 2 * H), float("nan"), dtype=torch.float16, device=dev)
@@ -358,8 +358,7 @@ def _run_attention(pkg, dev, B, S, heads, lens, seed, kernel, qk_std=1.8):
         full = torch.from_numpy(pkg.rel_index_table(2048, 256, 512)).long().to(dev)    # idx[delta + 2047]
         assert torch.equal(exp[:ER - 1, H:], pos[full.flip(0)][:, H:]) and (exp[ER - 1] == 0).all()   # row rho = posK[idx(2047 - rho)]
         assert torch.equal(exp[:ER - 1, :H], pos[full][:, :H])                                        # row sigma = posQ[idx(sigma - 2047)]
-        op = {"rows": L.glc_op_attention_rows, "shift": L.glc_op_attention_shift, "persist": L.glc_op_attention_persist}[kernel]
-        rc = op(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
+        rc = L.glc_op_attention_persist(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
         _sync_check(pkg, rc, "glc_op_attention_" + kernel)
     else:
         rc = L.glc_op_attention_naive(_ptr(qkv), pos_k.data_ptr(), pos_q.data_ptr(), 2 * H, _ptr(rel), _ptr(bits),
@@ -375,7 +374,7 @@ ATT_CASES = [
     # B, S, heads, lens
     (1, 64, 1, [64]),              # one key tile, one (partial) query tile
     (1, 128, 2, [128]),            # two key tiles
-    (1, 192, 1, [192]),            # three key tiles: every softmax group of attention_rows gets exactly one
+    (1, 192, 1, [192]),            # three key tiles: every softmax group gets exactly one
     (2, 256, 2, [256, 256]),       # 2 q tiles x 4 k tiles: off-diagonal slices
     (2, 512, 2, [512, 300]),       # log-bucket region + ragged
     (3, 200, 2, [200, 37, 129]),   # S not a multiple of 64/128
@@ -395,10 +394,10 @@ def test_attention_naive_kernel(pkg, dev, B, S, heads, lens):
     _report(f"attn-naive B{B} S{S} h{heads}", ctx[v], ref[v], 3e-3, 3e-3)
 
 
-@pytest.mark.parametrize("kernel", ["persist", "rows", "shift"])
+@pytest.mark.parametrize("kernel", ["persist"])
 @pytest.mark.parametrize("B,S,heads,lens", ATT_CASES + [(1, 2048, 1, [2048]), (2, 1500, 2, [1500, 1]), (70, 384, 3, [384] * 35 + list(range(1, 36)))])
 def test_attention(pkg, dev, B, S, heads, lens, kernel):
-    """attention kernels (csrc/attention_rows.cu = production, csrc/attention_shift.cu) against the fp32 restatement"""
+    """the attention kernel (csrc/attention_persist.cu) against the fp32 restatement"""
     ctx, ref, mask = _run_attention(pkg, dev, B, S, heads, lens, seed=S + B, kernel=kernel)
     v = mask.bool()
     got, want = ctx[v], ref[v]
@@ -414,7 +413,7 @@ def test_attention(pkg, dev, B, S, heads, lens, kernel):
     _report(f"attn-{kernel} B{B} S{S} h{heads}", got, want, 1e-2, 1e-2)
 
 
-@pytest.mark.parametrize("kernel", ["persist", "rows", "shift"])
+@pytest.mark.parametrize("kernel", ["persist"])
 def test_attention_softmax_peaked(pkg, dev, kernel):
     # large score magnitudes: the row maximum keeps growing across key tiles (exercises the sticky-maximum chain and the
     # rescale of the TMEM-resident output accumulator)
@@ -422,8 +421,8 @@ def test_attention_softmax_peaked(pkg, dev, kernel):
     _report(f"attn-{kernel} peaked", ctx[mask.bool()], ref[mask.bool()], 2e-2, 2e-2)
 
 
-def test_attention_rows_growing_maximum(pkg, dev):
-    """keys sorted so that every tile raises the row maximum by far more than 2^8: every group of attention_rows rescales
+def test_attention_growing_maximum(pkg, dev):
+    """keys sorted so that every tile raises the row maximum by far more than 2^8: every softmax group rescales
     O in turn and the partial row sums of the other groups must follow the chained maximum"""
     B, S, heads = 1, 512, 1
     H = 64
@@ -447,13 +446,13 @@ def test_attention_rows_growing_maximum(pkg, dev):
     _sync_check(pkg, L.glc_op_expand_pos_rev(_ptr(pos), 2 * H, 256, 512, _ptr(exp), 2 * H, H, None), "expand_pos_rev")
     _sync_check(pkg, L.glc_op_expand_pos(pos[:, H:].data_ptr(), 2 * H, 256, 512, exp[:, H:].data_ptr(), 2 * H, H, None), "expand_pos")
     ctx = torch.full((B, S, H), float("nan"), dtype=torch.float16, device=dev)
-    rc = L.glc_op_attention_rows(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
-    _sync_check(pkg, rc, "glc_op_attention_rows")
+    rc = L.glc_op_attention_persist(_ptr(qkv), exp[:, H:].data_ptr(), exp.data_ptr(), 2 * H, _ptr(bits), _ptr(kv), _ptr(ctx), B, S, heads, None)
+    _sync_check(pkg, rc, "glc_op_attention_persist")
     rel = torch.from_numpy(pkg.rel_index_table(S, 256, 512)).to(dev)
     ii = torch.arange(S, device=dev)
     idx = rel.long()[(ii[:, None] - ii[None, :]) + (S - 1)]
     ref = _attention_ref(qkv, pos[:, H:].contiguous(), pos[:, :H].contiguous(), idx, mask, heads)
-    _report("attn-rows growing maximum", ctx[0], ref[0], 2e-2, 2e-2)
+    _report("attn-persist growing maximum", ctx[0], ref[0], 2e-2, 2e-2)
 
 
 # ---------------------------------------------------------------------------------------------
