@@ -930,6 +930,7 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
 void DeviceModel::run_host_coalesced(HostReq& r) {
   std::unique_lock<std::mutex> lk(qmu_);
   queue_.push_back(&r);
+  if (leader_) qcv_.notify_all();   // a leader inside its batching window re-checks the queue length
   while (!r.done) {
     if (leader_) {
       qcv_.wait(lk);
@@ -937,6 +938,14 @@ void DeviceModel::run_host_coalesced(HostReq& r) {
     }
     // device idle: lead.  Take requests from the front while the padded group fits one launch.
     leader_ = true;
+    // The caller that led the previous group is usually back first with its next request and would lead ALONE (the
+    // reference's OpenMP loop, main.c:141-150: launches of 15 requests alternated with launches of 1) — when the last
+    // group was a merged one, give the other callers a moment to enqueue: at most 150 us, or until half of that group's
+    // size has arrived.  A lone caller (last group of size 1) never waits.
+    if (last_group_size_ > 1) {
+      const size_t want = (size_t)(last_group_size_ + 1) / 2;
+      qcv_.wait_for(lk, std::chrono::microseconds(150), [&] { return queue_.size() >= want; });
+    }
     std::vector<HostReq*> group;
     int rows = 0, smax = 0;
     while (!queue_.empty()) {
@@ -964,6 +973,7 @@ void DeviceModel::run_host_coalesced(HostReq& r) {
     }
     lk.lock();
     for (HostReq* q : group) { q->err = err; q->done = true; }
+    last_group_size_ = (int)group.size();
     leader_ = false;
     qcv_.notify_all();
   }

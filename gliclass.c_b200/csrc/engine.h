@@ -225,6 +225,7 @@ class DeviceModel {
   size_t h_tok_ = 0, h_rows_ = 0;
   std::atomic<uint64_t> packed_runs_{0}, packed_rows_{0}, packed_rows_padded_{0};
   std::atomic<uint64_t> merged_groups_{0}, merged_requests_{0};
+  int last_group_size_ = 1;    // under qmu_: size of the previous coalesced group (sizes the leader's batching window)
 
   // profiler state
   struct ProfRec { int cat; cudaEvent_t a, b; };
