@@ -60,6 +60,10 @@ struct FlashParams {
   __half* ctx;               // [B*S, heads*128]
   int B, S, heads, kv_heads;
   float scale_log2;          // log2(e) / sqrt(128)
+  // packed (varlen) layout, same conventions as attention_persist.cu: text b owns rows [text_row[b], text_row[b+1]) (a
+  // multiple of 128), grid.x runs over the 128-row query tiles, tile_info[t] = (query tile within its text) << 24 | text
+  const int32_t* tile_info;
+  const int32_t* text_row;
 };
 
 __device__ __forceinline__ float exp2_poly(float x) {
@@ -98,9 +102,26 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * QT;
   const int head = blockIdx.y;
-  const int b = blockIdx.z;
+  int q0, b, grow, rows, trow, tb, mword;   // query offset in the text, text, first row of the text in ctx / qkv, rows it owns,
+  if (p.tile_info != nullptr) {              // TMA (row, batch) coordinates of its position 0, its first mask word
+    const int info = __ldg(p.tile_info + blockIdx.x);
+    b = info & 0xffffff;
+    q0 = (info >> 24) * QT;
+    grow = __ldg(p.text_row + b);
+    rows = __ldg(p.text_row + b + 1) - grow;
+    trow = grow;
+    tb = 0;
+    mword = grow >> 5;
+  } else {
+    q0 = blockIdx.x * QT;
+    b = blockIdx.z;
+    grow = b * p.S;
+    rows = p.S;
+    trow = 0;
+    tb = b;
+    mword = b * ((p.S + 31) >> 5);
+  }
   const int kvh = head / (p.heads / p.kv_heads);
   const int H = p.heads * D;
   const int kvlen = p.kv_len[b];
@@ -110,7 +131,7 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
     // padded queries only: never read by valid rows
     for (int e = threadIdx.x; e < QT * 16; e += FTHREADS) {
       const int r = q0 + (e >> 4);
-      if (r < p.S) *reinterpret_cast<uint4*>(p.ctx + ((int64_t)b * p.S + r) * H + head * D + (e & 15) * 8) = make_uint4(0, 0, 0, 0);
+      if (r < rows) *reinterpret_cast<uint4*>(p.ctx + ((int64_t)grow + r) * H + head * D + (e & 15) * 8) = make_uint4(0, 0, 0, 0);
     }
     return;
   }
@@ -147,15 +168,15 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
         for (int a = 0; a < 2; ++a)
 #pragma unroll
           for (int r = 0; r < 2; ++r)
-            ptx::tma_load_3d(smem + OFF_Q + a * 16384 + r * 8192, &tm_qkv, q_full, qcol + a * 64, q0 + r * 64, b);
+            ptx::tma_load_3d(smem + OFF_Q + a * 16384 + r * 8192, &tm_qkv, q_full, qcol + a * 64, trow + q0 + r * 64, tb);
         for (int t = 0; t < T; ++t) {
           const int st = t % KVSTAGES;
           ptx::mbar_wait(&kv_empty[st], (uint32_t)(((t / KVSTAGES) & 1) ^ 1));
           ptx::mbar_arrive_expect_tx(&kv_full[st], 2 * KT * D * 2);
 #pragma unroll
           for (int a = 0; a < 2; ++a) {
-            ptx::tma_load_3d(smem + OFF_K + st * 16384 + a * 8192, &tm_qkv, &kv_full[st], kcol + a * 64, t * KT, b);
-            ptx::tma_load_3d(smem + OFF_V + st * 16384 + a * 8192, &tm_qkv, &kv_full[st], vcol + a * 64, t * KT, b);
+            ptx::tma_load_3d(smem + OFF_K + st * 16384 + a * 8192, &tm_qkv, &kv_full[st], kcol + a * 64, trow + t * KT, tb);
+            ptx::tma_load_3d(smem + OFF_V + st * 16384 + a * 8192, &tm_qkv, &kv_full[st], vcol + a * 64, trow + t * KT, tb);
           }
         }
       }
@@ -212,7 +233,7 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
     const int i = qd * 32 + lane;
     const uint32_t t_lane = tmem + ((uint32_t)(qd * 32) << 16);
     const float sc = p.scale_log2;
-    const int words = (p.S + 31) >> 5;
+    const int words = (rows + 31) >> 5;
 
     if (wg == 0) {
       // Q tile -> TMEM: this thread's row, 2 atoms x 8 16-byte chunks of the swizzled 128-byte rows
@@ -238,8 +259,8 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
     for (int t = wg; t < T; t += NWG) {
       const int k0 = t * KT;
       const uint32_t par = (uint32_t)((t / NWG) & 1);
-      const uint32_t kb0 = __ldg(p.mask_bits + (int64_t)b * words + (k0 >> 5));
-      const uint32_t kb1 = ((k0 >> 5) + 1 < words) ? __ldg(p.mask_bits + (int64_t)b * words + (k0 >> 5) + 1) : 0u;
+      const uint32_t kb0 = __ldg(p.mask_bits + mword + (k0 >> 5));
+      const uint32_t kb1 = ((k0 >> 5) + 1 < words) ? __ldg(p.mask_bits + mword + (k0 >> 5) + 1) : 0u;
       float s[KT];
       ptx::mbar_wait(&s_full[t % NWG], par);
       ptx::tc_fence_after();
@@ -350,8 +371,8 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
         uint32_t r[32];
         ptx::tmem_ld_x32(t_lane + TM_O + (uint32_t)(32 * q4), r);
         ptx::tmem_ld_wait();
-        if (row < p.S) {
-          __half* dst = p.ctx + ((int64_t)b * p.S + row) * H + head * D + 32 * q4;
+        if (row < rows) {
+          __half* dst = p.ctx + ((int64_t)grow + row) * H + head * D + 32 * q4;
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
             uint4 o4;
@@ -376,20 +397,12 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
 
 }  // namespace
 
-cudaError_t attention_flash128(const void* qkv, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S,
-                               int heads, int kv_heads, cudaStream_t stream) {
-  if (B <= 0 || S <= 0) return cudaSuccess;
-  if (heads <= 0 || kv_heads <= 0 || heads % kv_heads) return cudaErrorInvalidValue;
-  const int W = (heads + 2 * kv_heads) * D;
-  uint64_t dq[3] = {(uint64_t)W, (uint64_t)S, (uint64_t)B};
-  uint64_t sq[2] = {(uint64_t)W * 2, (uint64_t)S * W * 2};
+static cudaError_t launch_flash128(const void* qkv, FlashParams p, uint64_t tm_rows, uint64_t tm_batch, dim3 grid, cudaStream_t stream) {
+  const int W = (p.heads + 2 * p.kv_heads) * D;
+  uint64_t dq[3] = {(uint64_t)W, tm_rows, tm_batch};
+  uint64_t sq[2] = {(uint64_t)W * 2, tm_rows * W * 2};
   uint32_t bq[3] = {64, 64, 1};
   CUtensorMap tm_qkv = make_tmap_16b(qkv, 3, dq, sq, bq);
-  FlashParams p;
-  p.mask_bits = mask_bits;
-  p.kv_len = kv_len;
-  p.ctx = (__half*)ctx;
-  p.B = B; p.S = S; p.heads = heads; p.kv_heads = kv_heads;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)D);
   static bool attr_set[64] = {};
   int dev = 0;
@@ -399,9 +412,35 @@ cudaError_t attention_flash128(const void* qkv, const uint32_t* mask_bits, const
     if (e != cudaSuccess) return e;
     attr_set[dev & 63] = true;
   }
-  dim3 grid((S + QT - 1) / QT, heads, B);
   attention_flash128_kernel<<<grid, FTHREADS, FLASH_SMEM, stream>>>(tm_qkv, p);
   return cudaGetLastError();
+}
+
+cudaError_t attention_flash128(const void* qkv, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx, int B, int S,
+                               int heads, int kv_heads, cudaStream_t stream) {
+  if (B <= 0 || S <= 0) return cudaSuccess;
+  if (heads <= 0 || kv_heads <= 0 || heads % kv_heads) return cudaErrorInvalidValue;
+  FlashParams p{};
+  p.mask_bits = mask_bits;
+  p.kv_len = kv_len;
+  p.ctx = (__half*)ctx;
+  p.B = B; p.S = S; p.heads = heads; p.kv_heads = kv_heads;
+  return launch_flash128(qkv, p, (uint64_t)S, (uint64_t)B, dim3((S + QT - 1) / QT, heads, B), stream);
+}
+
+cudaError_t attention_flash128_packed(const void* qkv, const uint32_t* row_bits, const int32_t* kv_len, const int32_t* text_row,
+                                      const int32_t* tile_info, void* ctx, int B, int rows, int n_tiles, int heads, int kv_heads,
+                                      cudaStream_t stream) {
+  if (B <= 0 || rows <= 0 || n_tiles <= 0) return cudaSuccess;
+  if (heads <= 0 || kv_heads <= 0 || heads % kv_heads || (rows % QT) || n_tiles != rows / QT || B >= (1 << 24)) return cudaErrorInvalidValue;
+  FlashParams p{};
+  p.mask_bits = row_bits;
+  p.kv_len = kv_len;
+  p.ctx = (__half*)ctx;
+  p.B = B; p.S = rows; p.heads = heads; p.kv_heads = kv_heads;
+  p.tile_info = tile_info;
+  p.text_row = text_row;
+  return launch_flash128(qkv, p, (uint64_t)rows, 1, dim3(n_tiles, heads, 1), stream);
 }
 
 }  // namespace glc

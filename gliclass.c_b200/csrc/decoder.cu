@@ -112,14 +112,16 @@ add_rmsnorm_kernel(float* __restrict__ h, const __half* __restrict__ delta, cons
 // n_rot_heads (q heads then kv heads); pair (p, p + d/2) of a head at position s = m % S is rotated by s * inv_freq[p].
 // cs: float2 [S, d/2] = (cos, sin).  One thread per (row, head, 8 consecutive p).
 __global__ void __launch_bounds__(256)
-rope_kernel(__half* __restrict__ qkv, int64_t ld, const float2* __restrict__ cs, int M, int S, int n_rot_heads, int d) {
+rope_kernel(__half* __restrict__ qkv, int64_t ld, const float2* __restrict__ cs, int M, int S, int n_rot_heads, int d,
+            const int32_t* __restrict__ tile_pos) {
   const int half = d >> 1, chunks = half >> 3;
   const int64_t total = (int64_t)M * n_rot_heads * chunks;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(e % chunks);
     const int hd = (int)((e / chunks) % n_rot_heads);
     const int64_t m = e / ((int64_t)chunks * n_rot_heads);
-    const int s = (int)(m % S);
+    // packed (varlen) layout: tile_pos[m / 128] = position of the first row of that 128-row tile within its text
+    const int s = tile_pos ? __ldg(tile_pos + (m >> 7)) + (int)(m & 127) : (int)(m % S);
     __half* base = qkv + m * ld + (int64_t)hd * d + c * 8;
     uint4 lo = *reinterpret_cast<const uint4*>(base), hi = *reinterpret_cast<const uint4*>(base + half);
     __half2* l2 = reinterpret_cast<__half2*>(&lo);
@@ -194,13 +196,14 @@ cudaError_t rope_table(const float* inv_freq, void* cs_f32x2, int S, int head_di
   return cudaGetLastError();
 }
 
-cudaError_t rope_inplace(void* qkv_f16, int64_t ld, const void* cs_f32x2, int M, int S, int n_rot_heads, int head_dim, cudaStream_t stream) {
+cudaError_t rope_inplace(void* qkv_f16, int64_t ld, const void* cs_f32x2, int M, int S, int n_rot_heads, int head_dim, cudaStream_t stream,
+                         const int32_t* tile_pos) {
   if (M <= 0) return cudaSuccess;
   if (head_dim % 16 != 0 || ld % 8 != 0) return cudaErrorInvalidValue;
   const int64_t total = (int64_t)M * n_rot_heads * (head_dim / 16);
   int64_t blocks = (total + 255) / 256;
   if (blocks > grid_cap() * 4) blocks = grid_cap() * 4;
-  rope_kernel<<<(int)blocks, 256, 0, stream>>>((__half*)qkv_f16, ld, (const float2*)cs_f32x2, M, S, n_rot_heads, head_dim);
+  rope_kernel<<<(int)blocks, 256, 0, stream>>>((__half*)qkv_f16, ld, (const float2*)cs_f32x2, M, S, n_rot_heads, head_dim, tile_pos);
   return cudaGetLastError();
 }
 

@@ -389,7 +389,7 @@ void DeviceModel::ensure_workspace(int tokens, int B, int C) {
   }
   mask_bits_ = (uint32_t*)A(((M + 31) / 32 + (size_t)ws_B_) * 4);
   kv_len_ = (int32_t*)A((size_t)ws_B_ * 4);
-  pk_ints_ = (int32_t*)A(((size_t)2 * ws_B_ + 2 + M / 128 + 1) * 4);
+  pk_ints_ = (int32_t*)A(((size_t)2 * ws_B_ + 2 + 2 * (M / 128 + 1)) * 4);
   pk_scratch_ = (int32_t*)A((M / 128 + 1) * 4);
   pooled_ = A((size_t)ws_B_ * H * 2);
   cls_ = A((size_t)ws_rows_ * H * 2);
@@ -577,14 +577,19 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     // decoder backbone (transformers modeling_qwen2.py Q:353-410, bidirectional): pre-norm residual stream in fp32
     const int d = cfg_.head_dim, nh = cfg_.heads, nkv = cfg_.kv_heads;
     const int Wq = nh * d, Wqkv = Wq + 2 * nkv * d;
-    const void* cs = rope_table_for(S);
+    const void* cs = rope_table_for(pk ? round_up(S, 128) : S);   // packed texts own whole 128-row tiles
     GLC_LAUNCH(KC_EMBED, embed_rows_f32(d_ids, word_emb_, h32_, M, H, cfg_.vocab, st));
     for (int l = 0; l < cfg_.layers; ++l) {
       const DeviceLayer& dl = layers_[l];
       GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, l == 0 ? nullptr : tmp_, dl.ln1g, cfg_.rms_eps, x_, M, H, st));
       GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, dl.wqkv, H, dl.bqkv, qkv_, Wqkv, M, Wqkv, H, 0, false, num_sms_, st));
-      GLC_LAUNCH(KC_EMBED, rope_inplace(qkv_, Wqkv, cs, M, S, nh + nkv, d, st));
-      GLC_LAUNCH(KC_ATTN, attention_flash128(qkv_, mask_bits_, kv_len_, ctx_, B, S, nh, nkv, st));
+      GLC_LAUNCH(KC_EMBED, rope_inplace(qkv_, Wqkv, cs, M, S, nh + nkv, d, st, pk ? pk->tile_pos : nullptr));
+      if (pk) {
+        GLC_LAUNCH(KC_ATTN, attention_flash128_packed(qkv_, mask_bits_, pk->kv_len, pk->text_row, pk->tile_info, ctx_, B, pk->rows,
+                                                      pk->n_tiles, nh, nkv, st));
+      } else {
+        GLC_LAUNCH(KC_ATTN, attention_flash128(qkv_, mask_bits_, kv_len_, ctx_, B, S, nh, nkv, st));
+      }
       if (l == 0) keep("ctx0", ctx_, (size_t)M * Wq);
       GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, Wq, dl.wo, Wq, nullptr, tmp_, H, M, H, Wq, 0, false, num_sms_, st));
       GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, tmp_, dl.ln2g, cfg_.rms_eps, x_, M, H, st));
@@ -711,7 +716,7 @@ void DeviceModel::check_overflow_sync() {
 }
 
 bool DeviceModel::plan_pack(const int64_t* ids, const int64_t* mask, int B, int S, PackPlan& pl) const {
-  if (!varlen_ || cfg_.backbone == BACKBONE_QWEN2 || cfg_.pooling == POOL_LAST || S < 256 || S > 2048) return false;
+  if (!varlen_ || cfg_.pooling == POOL_LAST || S < 256 || S > 2048) return false;
   if ((int64_t)B * S < 8192) return false;   // small requests replay a captured graph of the [B,S] layout: latency first
   pl.len.resize(B);
   pl.prow.resize(B);
@@ -794,13 +799,13 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
       //      H2D each, then the same forward on rows = sum of the texts' 128-aligned lengths
       const PackPlan::MB& mb = plan.mbs[mi];
       const int nb = mb.b1 - mb.b0, rows = mb.rows, nt = rows / 128;
-      const size_t idb = (size_t)rows * 8, nints = (size_t)2 * nb + 1 + nt;
+      const size_t idb = (size_t)rows * 8, nints = (size_t)2 * nb + 1 + 2 * nt;
       const int k = h_in_next_;
       h_in_next_ ^= 1;
       PinnedBlock& hb = h_in_[k];
       if (hb.bytes < 2 * idb + nints * 4) {
         if (hb.p) { GLC_CUDA(cudaStreamSynchronize(stream_)); cudaFreeHost(hb.p); hb.p = nullptr; }
-        hb.bytes = 2 * (size_t)plan.max_mb_rows * 8 + ((size_t)2 * plan.max_mb_texts + 2 + plan.max_mb_rows / 128) * 4;
+        hb.bytes = 2 * (size_t)plan.max_mb_rows * 8 + ((size_t)2 * plan.max_mb_texts + 2 + 2 * (plan.max_mb_rows / 128)) * 4;
         if (hb.bytes < 2 * idb + nints * 4) hb.bytes = 2 * idb + nints * 4;
         GLC_CUDA(cudaMallocHost(&hb.p, hb.bytes));
       }
@@ -811,11 +816,13 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
       int32_t* text_row = (int32_t*)(pm + rows);
       int32_t* kvl = text_row + nb + 1;
       int32_t* tinfo = kvl + nb;
+      int32_t* tpos = tinfo + nt;   // position of each 128-row tile's first row within its text (rotary embedding)
       int row = 0;
       for (int i = 0; i < nb; ++i) {
         const int b = mb.b0 + i, L = plan.len[b], P = plan.prow[b];
         text_row[i] = row;
         kvl[i] = L;
+        for (int q = 0; q * 128 < P; ++q) tpos[row / 128 + q] = q * 128;
         memcpy(pi + row, ids + (size_t)b * S, (size_t)L * 8);
         memcpy(pm + row, mask + (size_t)b * S, (size_t)L * 8);
         memset(pi + row + L, 0, (size_t)(P - L) * 8);   // id 0 / mask 0, what the reference pads with (tokenizer.c:78-82)
@@ -833,7 +840,7 @@ void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S
       GLC_CUDA(cudaEventRecord(h_in_ev_[k], stream_));
       PackedCtx pc;
       pc.rows = rows; pc.max_rows = mb.max_rows; pc.n_tiles = nt;
-      pc.text_row = pk_ints_; pc.kv_len = pk_ints_ + nb + 1; pc.tile_info = pk_ints_ + 2 * nb + 1;
+      pc.text_row = pk_ints_; pc.kv_len = pk_ints_ + nb + 1; pc.tile_info = pk_ints_ + 2 * nb + 1; pc.tile_pos = pc.tile_info + nt;
       pk_ = &pc;
       try {
         forward_eager(ids_, mask_, nb, S, C, logits_, want_p ? probs_ : nullptr, want_d ? decisions_ : nullptr,

@@ -125,12 +125,12 @@ class DeviceModel {
   };
   struct PackedCtx {                      // device-side description of the micro-batch being run
     int rows = 0, max_rows = 0, n_tiles = 0;
-    const int32_t *text_row = nullptr, *kv_len = nullptr, *tile_info = nullptr;
+    const int32_t *text_row = nullptr, *kv_len = nullptr, *tile_info = nullptr, *tile_pos = nullptr;
   };
   bool plan_pack(const int64_t* ids, const int64_t* mask, int B, int S, PackPlan& pl) const;
   bool varlen_ = true;
   const PackedCtx* pk_ = nullptr;         // set (under mu) around forward_eager for a packed micro-batch
-  int32_t* pk_ints_ = nullptr;            // device: text_row[nb+1] | kv_len[nb] | tile_info[n_tiles]
+  int32_t* pk_ints_ = nullptr;            // device: text_row[nb+1] | kv_len[nb] | tile_info[n_tiles] | tile_pos[n_tiles]
   int32_t* pk_scratch_ = nullptr;
   void forward_eager(const int64_t* d_ids, const int64_t* d_mask, int B, int S, int C, float* d_logits, float* d_probs,
                      uint8_t* d_decisions, float threshold);

@@ -37,11 +37,16 @@ cudaError_t add_rmsnorm(float* h, const void* delta_f16, const float* g, float e
 cudaError_t rope_table(const float* inv_freq, void* cs_f32x2, int S, int head_dim, cudaStream_t stream);
 // rotary embedding in place on the first n_rot_heads heads (q heads, then kv heads) of qkv fp16 [M, ld]
 cudaError_t rope_inplace(void* qkv_f16, int64_t ld, const void* cs_f32x2, int M, int S, int n_rot_heads, int head_dim,
-                         cudaStream_t stream);
+                         cudaStream_t stream, const int32_t* tile_pos = nullptr);
+// (tile_pos != nullptr: packed layout, position of row m = tile_pos[m / 128] + m % 128 instead of m % S)
 // plain (bias-free) flash attention for head dim 128 with grouped-query heads, bidirectional, key padding mask:
 // qkv fp16 [B*S, (heads + 2 kv_heads) * 128] (Q heads | K heads | V heads), ctx fp16 [B*S, heads * 128]
 cudaError_t attention_flash128(const void* qkv_f16, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S,
                                int heads, int kv_heads, cudaStream_t stream);
+// the same kernel on the packed (varlen) layout (conventions of attention_persist_packed)
+cudaError_t attention_flash128_packed(const void* qkv, const uint32_t* row_bits, const int32_t* kv_len, const int32_t* text_row,
+                                      const int32_t* tile_info, void* ctx, int B, int rows, int n_tiles, int heads, int kv_heads,
+                                      cudaStream_t stream);
 
 // K1: y[m,:] = LN(word_emb[ids[m],:]) * gamma + beta, times mask[m]   (T:520-564)
 cudaError_t embed_ln(const int64_t* ids, const int64_t* mask, const void* word_emb_f16, const float* gamma,

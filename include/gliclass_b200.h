@@ -115,7 +115,7 @@ GLC_API int glc_coalesce_stats(const glc_model* m, uint64_t* merged_launches, ui
  * request whose attention masks leave >= 10 % of the B*S positions as trailing padding is compacted before the forward —
  * every text keeps positions [0, 1 + last unmasked) rounded up to 128 rows — so embedding, GEMM, LayerNorm and attention
  * rows scale with the real tokens.  Logits are those of the padded layout (padded keys are masked either way, padded
- * query rows are never read).  Applies to glc_run / glc_submit / the ORT-named Run on the DeBERTa stack for requests of
+ * query rows are never read).  Applies to glc_run / glc_submit / the ORT-named Run on both backbones for requests of
  * >= 8192 positions; GLC_VARLEN=0 disables it.  glc_packed_stats: packed launches so far, rows they computed, rows the
  * padded layout would have computed. */
 GLC_API int glc_packed_stats(const glc_model* m, uint64_t* launches, uint64_t* rows, uint64_t* rows_padded);

@@ -729,6 +729,34 @@ def test_qwen2_backbone_mini_parity(pkg, orc, model_cache):
         sess.close()
 
 
+def test_qwen2_varlen_packing_matches_padded_layout(pkg, orc, model_cache):
+    """the packed (varlen) layout on the decoder backbone: flash attention and the rotary positions follow the per-text row
+    offsets; logits must equal the padded layout's and the oracle's"""
+    path = os.path.join(model_cache, "qwen-mini.onnx")
+    cfg, w = orc.make_model_file("qwen-mini", path, seed=0)
+    ids, mask = orc.synth_inputs(cfg, 40, 500, 5, seed=41, ragged=True, min_frac=0.2)   # S not a multiple of 128
+    os.environ["GLC_VARLEN"] = "0"
+    try:
+        s_pad = pkg.Session(path)
+    finally:
+        os.environ.pop("GLC_VARLEN")
+    s_pk = pkg.Session(path)
+    try:
+        out_pad = s_pad.run_inference(ids.numpy(), mask.numpy())
+        out_pk = s_pk.run_inference(ids.numpy(), mask.numpy())
+        runs, rows, rows_padded = s_pk.packed_stats()
+        assert runs == 1 and rows < 0.85 * rows_padded and s_pad.packed_stats()[0] == 0
+        d = np.abs(out_pk - out_pad)
+        print(f"varlen qwen-mini/B40S500: rows {rows} of {rows_padded}, packed vs padded max|d|={d.max():.3e}")
+        assert d.max() <= 2e-3
+        chk = [0, 9, 21, 39]
+        ref = orc.forward_restated(w, cfg, ids[chk], mask[chk]).numpy()
+        _check_logits("varlen qwen-mini rows 0,9,21,39", out_pk[chk], ref, orc)
+    finally:
+        s_pad.close()
+        s_pk.close()
+
+
 def test_qwen2_1p5b_layer_geometry(pkg, orc, model_cache):
     """The gliclass-qwen-1.5B layer geometry (hidden 1536, 12q/2kv x 128, SwiGLU 8960) at 4 layers, batch 32 x seq 1024 x 20
     labels on the GPU, four sampled rows against the oracle.  The full 28-layer / 151k-vocabulary model (6.2 GB of fp32
