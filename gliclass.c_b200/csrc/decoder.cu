@@ -52,7 +52,7 @@ embed_rows_f32_kernel(const int64_t* __restrict__ ids, const __half* __restrict_
 template <int NC>
 __global__ void __launch_bounds__(ROWS_PER_BLOCK * 32)
 add_rmsnorm_kernel(float* __restrict__ h, const __half* __restrict__ delta, const float* __restrict__ g, float eps,
-                   __half* __restrict__ y, int M, int H) {
+                   __half* __restrict__ y, int M, int H, uint8_t* __restrict__ y8, float* __restrict__ y8_scale) {
   const int lane = threadIdx.x & 31;
   const int stride = gridDim.x * ROWS_PER_BLOCK;
   float gw[NC][8];
@@ -93,16 +93,38 @@ add_rmsnorm_kernel(float* __restrict__ h, const __half* __restrict__ delta, cons
       }
     }
     const float r = rsqrtf(warp_sum(q) / (float)H + eps);
+    float amax = 0.f;
 #pragma unroll
     for (int c = 0; c < NC; ++c) {
       const int e0 = (lane + 32 * c) * 8;
       if (e0 < H) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          v[c][k] = v[c][k] * r * gw[c][k];
+          amax = fmaxf(amax, fabsf(v[c][k]));
+        }
         uint4 o;
-        o.x = ptx::pack_f16(v[c][0] * r * gw[c][0], v[c][1] * r * gw[c][1]);
-        o.y = ptx::pack_f16(v[c][2] * r * gw[c][2], v[c][3] * r * gw[c][3]);
-        o.z = ptx::pack_f16(v[c][4] * r * gw[c][4], v[c][5] * r * gw[c][5]);
-        o.w = ptx::pack_f16(v[c][6] * r * gw[c][6], v[c][7] * r * gw[c][7]);
+        o.x = ptx::pack_f16(v[c][0], v[c][1]);
+        o.y = ptx::pack_f16(v[c][2], v[c][3]);
+        o.z = ptx::pack_f16(v[c][4], v[c][5]);
+        o.w = ptx::pack_f16(v[c][6], v[c][7]);
         *reinterpret_cast<uint4*>(y + (int64_t)row * H + e0) = o;
+      }
+    }
+    if (y8 != nullptr) {   // warp-uniform: the row again as e4m3 under its own scale (operand of the FP8 gate|up GEMM)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+      const float inv = amax > 0.f ? 448.0f / amax : 1.0f;
+      if (lane == 0) y8_scale[row] = amax > 0.f ? amax / 448.0f : 1.0f;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const int e0 = (lane + 32 * c) * 8;
+        if (e0 < H) {
+          uint2 o;
+          o.x = ptx::pack_e4m3x4(v[c][0] * inv, v[c][1] * inv, v[c][2] * inv, v[c][3] * inv);
+          o.y = ptx::pack_e4m3x4(v[c][4] * inv, v[c][5] * inv, v[c][6] * inv, v[c][7] * inv);
+          *reinterpret_cast<uint2*>(y8 + (int64_t)row * H + e0) = o;
+        }
       }
     }
   }
@@ -168,7 +190,9 @@ cudaError_t embed_rows_f32(const int64_t* ids, const void* emb_f16, float* h, in
   return cudaGetLastError();
 }
 
-cudaError_t add_rmsnorm(float* h, const void* delta_f16, const float* g, float eps, void* y_f16, int M, int H, cudaStream_t stream) {
+cudaError_t add_rmsnorm(float* h, const void* delta_f16, const float* g, float eps, void* y_f16, int M, int H,
+                        cudaStream_t stream, void* y8, float* y8_scale) {
+  if ((y8 != nullptr) != (y8_scale != nullptr)) return cudaErrorInvalidValue;
   if (M <= 0) return cudaSuccess;
   if (H % 8 != 0 || H > 256 * 8) return cudaErrorInvalidValue;
   int blocks = (M + ROWS_PER_BLOCK - 1) / ROWS_PER_BLOCK;
@@ -176,7 +200,8 @@ cudaError_t add_rmsnorm(float* h, const void* delta_f16, const float* g, float e
   const int nc = (H + 255) / 256;
   auto launch = [&](auto tag) {
     constexpr int NC = decltype(tag)::value;
-    add_rmsnorm_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, 0, stream>>>(h, (const __half*)delta_f16, g, eps, (__half*)y_f16, M, H);
+    add_rmsnorm_kernel<NC><<<blocks, ROWS_PER_BLOCK * 32, 0, stream>>>(h, (const __half*)delta_f16, g, eps, (__half*)y_f16, M, H,
+                                                                       (uint8_t*)y8, y8_scale);
     return cudaGetLastError();
   };
   switch (nc) {

@@ -140,7 +140,6 @@ DeviceModel::DeviceModel(int device, const ModelWeights& w, int max_tokens, bool
     fp8_ffn_ = fp8_ffn || (f8 && f8[0] == '1');
     if (const char* fm = getenv("GLC_FP8_MULT")) fp8_mult_ = (float)atof(fm);
     if (fp8_ffn_) {
-      if (cfg_.backbone == BACKBONE_QWEN2) throw std::runtime_error("FP8 FFN weights are implemented for the DeBERTa encoder stack only");
       if (preln_f32_) throw std::runtime_error("FP8 FFN weights and preln_f32 cannot be combined");
       if (cfg_.hidden % 16 || cfg_.inter % 16) throw std::runtime_error("FP8 FFN weights need hidden and intermediate sizes divisible by 16");
       if (!(fp8_mult_ > 0.f)) throw std::runtime_error("GLC_FP8_MULT must be positive");
@@ -195,6 +194,15 @@ void DeviceModel::init_qwen2(const ModelWeights& w) {
     }
     upload_w16(&dl.w1, gu.data(), gu.size());
     upload_w16(&dl.w2, w.at(r + ".down.w").data.data(), (size_t)H * I);
+    if (fp8_ffn_) {
+      // load-time quantiser (see init_deberta): the interleaved gate|up matrix and the down projection, one scale per row
+      dl.w1_8 = dalloc((size_t)2 * I * H); perm_allocs_.push_back(dl.w1_8);
+      dl.w2_8 = dalloc((size_t)H * I); perm_allocs_.push_back(dl.w2_8);
+      dl.w1_s = (float*)dalloc((size_t)2 * I * 4); perm_allocs_.push_back(dl.w1_s);
+      dl.w2_s = (float*)dalloc((size_t)H * 4); perm_allocs_.push_back(dl.w2_s);
+      GLC_CUDA(quantize_rows_e4m3(dl.w1, H, dl.w1_8, H, dl.w1_s, 2 * I, H, stream_));
+      GLC_CUDA(quantize_rows_e4m3(dl.w2, I, dl.w2_8, I, dl.w2_s, H, I, stream_));
+    }
     upload_f32(&dl.ln1g, w.at(r + ".ln1.g"));
     upload_f32(&dl.ln2g, w.at(r + ".ln2.g"));
   }
@@ -592,7 +600,16 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
       }
       if (l == 0) keep("ctx0", ctx_, (size_t)M * Wq);
       GLC_LAUNCH(KC_GEMM_OUT, gemm_f16(ctx_, Wq, dl.wo, Wq, nullptr, tmp_, H, M, H, Wq, 0, false, num_sms_, st));
-      GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, tmp_, dl.ln2g, cfg_.rms_eps, x_, M, H, st));
+      GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, tmp_, dl.ln2g, cfg_.rms_eps, x_, M, H, st, fp8_ffn_ ? x1_8_ : nullptr,
+                                    fp8_ffn_ ? x1_s_ : nullptr));
+      if (fp8_ffn_) {
+        // e4m3 MLP: the post-attention RMSNorm wrote the rows as e4m3 under per-row scales; silu(gate) * up stays e4m3
+        GLC_LAUNCH(KC_GEMM_FFN1, gemm_e4m3(x1_8_, H, dl.w1_8, H, x1_s_, 1.0f, dl.w1_s, nullptr, ffn_, I, M, 2 * I, H, 3, true,
+                                           fp8_mult_, num_sms_, st));
+        GLC_LAUNCH(KC_GEMM_FFN2, gemm_e4m3(ffn_, I, dl.w2_8, I, nullptr, 1.0f / fp8_mult_, dl.w2_s, nullptr, tmp_, H, M, H, I, 0,
+                                           false, 1.0f, num_sms_, st));
+        continue;
+      }
       GLC_LAUNCH(KC_GEMM_FFN1, gemm_f16(x_, H, dl.w1, H, nullptr, ffn_, I, M, 2 * I, H, 3, false, num_sms_, st));
       GLC_LAUNCH(KC_GEMM_FFN2, gemm_f16(ffn_, I, dl.w2, I, nullptr, tmp_, H, M, H, I, 0, false, num_sms_, st));
     }

@@ -351,6 +351,65 @@ __device__ __forceinline__ void epilogue_tile_tma_f8out(uint32_t t_row, int grp,
   }
 }
 
+// SwiGLU with e4m3 operands AND e4m3 output (the decoder MLP of the FP8 tier): gate / up chunks scaled by the row scale and
+// their own channel scales, silu(gate) * up * out_mult in packed fp16, saturating e4m3; tm_c: uint8 [M, N/2], box 32 x 32.
+__device__ __forceinline__ __half2 silu_mul_h2(__half2 g, __half2 u) {
+  const __half2 hg = __hmul2(g, __float2half2_rn(0.5f));
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&hg)));
+  return __hmul2(__hfma2(hg, *reinterpret_cast<const __half2*>(&t), hg), u);
+}
+
+template <int BN, int NBUF>
+__device__ __forceinline__ void epilogue_tile_tma_swiglu_f8(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
+                                                            const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int M, int N,
+                                                            const Fp8Scales& sc) {
+#pragma unroll 1
+  for (int pc = grp; pc < BN / 64; pc += EpiCfg<3>::GROUPS) {
+    const int n = n0 + pc * 64;
+    uint32_t rg[32], ru[32];
+    ptx::tmem_ld_x32(t_row + (uint32_t)(pc * 64), rg);
+    ptx::tmem_ld_x32(t_row + (uint32_t)(pc * 64 + 32), ru);
+    ptx::tmem_ld_wait();
+    if (n + 64 > N) continue;   // warp-uniform (N is a multiple of 64 for this activation)
+    const int row = row0 + lane;
+    const float rs = (sc.row != nullptr && row < M) ? __ldg(sc.row + row) * sc.k : sc.k;
+    const __half2 om2 = __float2half2_rn(sc.out_mult);
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 cg = __ldg(reinterpret_cast<const float4*>(sc.col + n) + j);
+      const float4 cu = __ldg(reinterpret_cast<const float4*>(sc.col + n + 32) + j);
+      float g[4] = {__uint_as_float(rg[4 * j]) * rs * cg.x, __uint_as_float(rg[4 * j + 1]) * rs * cg.y,
+                    __uint_as_float(rg[4 * j + 2]) * rs * cg.z, __uint_as_float(rg[4 * j + 3]) * rs * cg.w};
+      float u[4] = {__uint_as_float(ru[4 * j]) * rs * cu.x, __uint_as_float(ru[4 * j + 1]) * rs * cu.y,
+                    __uint_as_float(ru[4 * j + 2]) * rs * cu.z, __uint_as_float(ru[4 * j + 3]) * rs * cu.w};
+      if (bias != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { g[k] += __ldg(bias + n + 4 * j + k); u[k] += __ldg(bias + n + 32 + 4 * j + k); }
+      }
+      uint32_t g01 = ptx::pack_f16(g[0], g[1]), g23 = ptx::pack_f16(g[2], g[3]);
+      uint32_t u01 = ptx::pack_f16(u[0], u[1]), u23 = ptx::pack_f16(u[2], u[3]);
+      __half2 a = __hmul2(silu_mul_h2(*reinterpret_cast<__half2*>(&g01), *reinterpret_cast<__half2*>(&u01)), om2);
+      __half2 b = __hmul2(silu_mul_h2(*reinterpret_cast<__half2*>(&g23), *reinterpret_cast<__half2*>(&u23)), om2);
+      pk[j] = ptx::pack_e4m3x2_h2(*reinterpret_cast<uint32_t*>(&a)) | (ptx::pack_e4m3x2_h2(*reinterpret_cast<uint32_t*>(&b)) << 16);
+    }
+    if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
+    __syncwarp();
+    uint8_t* sb = stage + buf * 2048;
+    uint8_t* srow = sb + lane * 32;
+    *reinterpret_cast<uint4*>(srow) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    *reinterpret_cast<uint4*>(srow + 16) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_2d(tm_c, sb, n / 2, row0);
+      ptx::bulk_commit_group();
+    }
+    buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+  }
+}
+
 // fp16 epilogue through shared memory + TMA store.  A warp's direct stores put 32 different rows in
 // every STG (32 L1 line visits per instruction: the epilogue then outlasts a K=768 tile's MMAs); here
 // the 32 x 32 chunk is written once to a 64B-swizzled staging buffer and stored by one bulk tensor copy.
@@ -693,7 +752,9 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      if (OUT_F8)
+      if (OUT_F8 && ACT == 3)
+        epilogue_tile_tma_swiglu_f8<BN, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, sc);
+      else if (OUT_F8)
         epilogue_tile_tma_f8out<BN, ACT, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, sc);
       else if (ACT == 3 && OUT_F32)
         epilogue_tile_swiglu<BN, true>(t_row, grp, n0, row, bias, Cout, ldc, M, N);
@@ -769,7 +830,7 @@ cudaError_t launch_gemm_e4m3(const void* A, int64_t lda, const void* W, int64_t 
   CUtensorMap tm_a = make_tmap_8b(A, 2, da, sa, ba, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap tm_w = make_tmap_8b(W, 2, dw, sw, bw, CU_TENSOR_MAP_SWIZZLE_128B);
   CUtensorMap tm_c;
-  uint64_t dc[2] = {(uint64_t)N, (uint64_t)M};
+  uint64_t dc[2] = {(uint64_t)(ACT == 3 ? N / 2 : N), (uint64_t)M};
   uint32_t bc[2] = {32, 32};
   if (OUT_F8) {
     uint64_t sc1[1] = {(uint64_t)ldc};
@@ -889,6 +950,10 @@ cudaError_t gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, 
   if (num_sms < 2) return cudaErrorInvalidValue;
   const Fp8Scales sc{a_scale, w_scale, a_const, out_mult};
   if (out_e4m3) {
+    if (act == 3) {   // SwiGLU: gate / up rows interleaved in blocks of 32, output [M, N/2]
+      if (N % 64 != 0) return cudaErrorInvalidValue;
+      return launch_gemm_e4m3<256, 3, true>(A8, lda, W8, ldw, bias, C, ldc, M, N, K, num_sms, stream, sc);
+    }
     if (act == 1) return launch_gemm_e4m3<256, 1, true>(A8, lda, W8, ldw, bias, C, ldc, M, N, K, num_sms, stream, sc);
     if (act == 0) return launch_gemm_e4m3<256, 0, true>(A8, lda, W8, ldw, bias, C, ldc, M, N, K, num_sms, stream, sc);
     return cudaErrorInvalidValue;

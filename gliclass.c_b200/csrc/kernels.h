@@ -32,7 +32,8 @@ cudaError_t quantize_rows_e4m3(const void* x_f16, int64_t ldx, void* q8, int64_t
 // decoder backbone (decoder.cu): fp32 residual stream h, fp16 normalised activations
 cudaError_t embed_rows_f32(const int64_t* ids, const void* emb_f16, float* h, int M, int H, int vocab, cudaStream_t stream);
 // h += delta (fp16 [M,H], may be null); y = rmsnorm(h) * g
-cudaError_t add_rmsnorm(float* h, const void* delta_f16, const float* g, float eps, void* y_f16, int M, int H, cudaStream_t stream);
+cudaError_t add_rmsnorm(float* h, const void* delta_f16, const float* g, float eps, void* y_f16, int M, int H, cudaStream_t stream,
+                        void* y_e4m3 = nullptr, float* y_e4m3_scale = nullptr);   // optional: the row also as e4m3 + per-row scale
 // (cos, sin) float2 table [S, head_dim / 2] from the rotary inverse frequencies
 cudaError_t rope_table(const float* inv_freq, void* cs_f32x2, int S, int head_dim, cudaStream_t stream);
 // rotary embedding in place on the first n_rot_heads heads (q heads, then kv heads) of qkv fp16 [M, ld]

@@ -28,10 +28,10 @@ typedef struct glc_onnx glc_onnx;     /* host-only parse of a model.onnx (no GPU
 
 enum { GLC_OK = 0, GLC_ERR = -1, GLC_ERR_ARG = -2, GLC_ERR_CUDA = -3, GLC_ERR_CAPACITY = -4 };
 /* storage type of weights and activations (every accumulation / statistic is fp32).  FP16 is the default and the only
- * mode that meets the 2e-2 logit parity bar.  GLC_DTYPE_FP8_E4M3 is an OPT-IN throughput mode for the DeBERTa stack
+ * mode that meets the 2e-2 logit parity bar.  GLC_DTYPE_FP8_E4M3 is an OPT-IN throughput mode for both backbones
  * (the B200 analogue of the reference's int8 quantize_dynamic export, ONNX_CONVERTING/convert_to_onnx.py:81-89): the two
- * FFN GEMMs of every layer run on e4m3 operands (weights quantised at load, one scale per output channel; LN output
- * under per-row dynamic scales; GELU output under a static multiplier), everything else stays fp16.  Its measured
+ * FFN / MLP GEMMs of every layer run on e4m3 operands (weights quantised at load, one scale per output channel; LN /
+ * RMSNorm output under per-row dynamic scales; GELU or SwiGLU output under a static multiplier), everything else stays fp16.  Its measured
  * logit error is in DESIGN.md "FP8"; bf16 storage is rejected. */
 enum { GLC_DTYPE_DEFAULT = 0, GLC_DTYPE_FP16 = 1, GLC_DTYPE_BF16 = 2 /* rejected */, GLC_DTYPE_FP8_E4M3 = 3 };
 

@@ -470,6 +470,23 @@ def test_fp8_ffn_mode(pkg, orc, model_cache):
     assert np.array_equal(orc.decisions_multilabel(out8[rows], THRESHOLD)[outside], orc.decisions_multilabel(ref, THRESHOLD)[outside])
 
 
+def test_fp8_ffn_mode_decoder_backbone(pkg, orc, model_cache):
+    """the same opt-in tier on the decoder stack (e4m3 gate|up and down projections, SwiGLU in the epilogue)"""
+    path = os.path.join(model_cache, "qwen-mini.onnx")
+    cfg, w = orc.make_model_file("qwen-mini", path, seed=0)
+    ids, mask = orc.synth_inputs(cfg, 16, 512, 6, seed=55)
+    ref = orc.forward_restated(w, cfg, ids[:6], mask[:6]).numpy()
+    s8 = pkg.Session(path, weight_dtype="fp8")
+    try:
+        out8 = s8.run_inference(ids.numpy(), mask.numpy())
+    finally:
+        s8.close()
+    d8 = np.abs(out8[:6] - ref)
+    print(f"fp8-ffn qwen-mini/B16S512: max|d| vs oracle {d8.max():.4e} (mean {d8.mean():.4e}); bar {FP8_BAR:g} -> "
+          f"{'MET' if d8.max() <= FP8_BAR else 'MISSED'}")
+    assert np.isfinite(out8).all() and d8.max() < 0.5
+
+
 def test_fp8_ffn_mode_rejections(pkg, model_cache, orc):
     """combinations the FP8 mode does not implement fail at load"""
     path = os.path.join(model_cache, "mini.onnx")

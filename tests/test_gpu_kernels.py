@@ -198,6 +198,33 @@ def test_gemm_e4m3_gelu_e4m3_out(pkg, dev, M, N, K):
     assert exact > 0.95
 
 
+@pytest.mark.parametrize("M,I,K", [(4096, 8960, 1536), (300, 128, 128), (1000, 1024, 512)])
+def test_gemm_e4m3_swiglu_e4m3_out(pkg, dev, M, I, K):
+    """decoder MLP of the FP8 tier: gate / up rows interleaved in blocks of 32, e4m3 operands, silu(gate) * up as e4m3"""
+    g = torch.Generator().manual_seed(M + I + K)
+    A = (torch.randn(M, K, generator=g) * (0.5 + torch.rand(M, 1, generator=g))).to(torch.float16).to(dev)
+    Wg = (torch.randn(I, K, generator=g) / math.sqrt(K)).to(torch.float16)
+    Wu = (torch.randn(I, K, generator=g) / math.sqrt(K)).to(torch.float16)
+    W = torch.stack([Wg.view(I // 32, 32, K), Wu.view(I // 32, 32, K)], 1).reshape(2 * I, K).contiguous().to(dev)
+    a8, a_s = _quantize_rows(pkg, dev, A)
+    w8, ws = _quantize_rows(pkg, dev, W)
+    mult = 4.0
+    C = torch.full((M, I), 0x7f, dtype=torch.uint8, device=dev)
+    rc = pkg.lib().glc_op_gemm_e4m3(_ptr(a8), K, _ptr(w8), K, _ptr(a_s), 1.0, _ptr(ws), None, _ptr(C), I, M, 2 * I, K, 3, 1, mult, None)
+    _sync_check(pkg, rc, "glc_op_gemm_e4m3 (swiglu)")
+    pre = (a8.view(torch.float8_e4m3fn).float() @ w8.view(torch.float8_e4m3fn).float().t()) * a_s[:, None] * ws[None, :]
+    pre = pre.view(M, I // 32, 2, 32)
+    ref = (torch.nn.functional.silu(pre[:, :, 0]) * pre[:, :, 1]).reshape(M, I) * mult
+    got = C.view(torch.float8_e4m3fn).float()
+    assert torch.isfinite(got).all()
+    err = (got - ref.clamp(-448, 448)).abs()
+    bound = torch.maximum(ref.abs() * 2.0 ** -3, torch.full_like(ref, 2.0 ** -9)) + 1.5e-3 * mult
+    assert (err <= bound).all(), f"max excess {(err - bound).max().item():.3e}"
+    exact = (C == ref.clamp(-448, 448).to(torch.float8_e4m3fn).view(torch.uint8)).float().mean().item()
+    print(f"gemm e4m3 swiglu {M}x{2 * I}x{K}: {100 * exact:.2f}% of output bytes identical to torch's rounding of the fp32 reference")
+    assert exact > 0.93
+
+
 @pytest.mark.parametrize("H,M", [(768, 5001), (1024, 700), (128, 300)])
 def test_residual_ln_e4m3_output(pkg, dev, H, M):
     g = torch.Generator().manual_seed(H + M + 5)
