@@ -36,7 +36,8 @@ constexpr int NWG = 3;
 constexpr int FTHREADS = 128 + 128 * NWG;
 constexpr int UTIL_REGS = 40;
 constexpr int SMX_REGS = 152;
-constexpr int KVSTAGES = 3;
+constexpr int KVSTAGES = 5;   // a stage is refilled only after the PV MMA of its tile retired, and a TMA round trip is ~2 tiles long:
+                              // with 3 stages the softmax groups slept on s_full for 31 % of the ncu samples
 
 constexpr int OFF_Q = 0;                              // [2 atoms][128 rows][128 B]
 constexpr int OFF_K = OFF_Q + 32768;                  // KVSTAGES x [2 atoms][64 rows][128 B]
@@ -89,13 +90,14 @@ attention_flash128_kernel(const __grid_constant__ CUtensorMap tm_qkv, const Flas
   uint64_t* q_full = bars + 0;
   uint64_t* qt_full = bars + 1;      // Q copied to TMEM (4 warps)
   uint64_t* kv_full = bars + 2;      // [KVSTAGES]
-  uint64_t* kv_empty = bars + 5;     // [KVSTAGES] the PV MMA of the tile retired
-  uint64_t* s_free = bars + 8;       // [2] S buffer drained (4 warps)
-  uint64_t* p_full = bars + 10;      // P written (4 warps)
-  uint64_t* l_bar = bars + 11;       // partial sums published (4 * NWG warps)
-  uint64_t* s_full = bars + 12;      // [NWG] S of tile t ready (index t % NWG)
-  uint64_t* pv_full = bars + 15;     // [NWG]
-  uint64_t* m_bar = bars + 18;       // [NWG][4]
+  uint64_t* kv_empty = kv_full + KVSTAGES;   // [KVSTAGES] the PV MMA of the tile retired
+  uint64_t* s_free = kv_empty + KVSTAGES;    // [2] S buffer drained (4 warps)
+  uint64_t* p_full = s_free + 2;     // P written (4 warps)
+  uint64_t* l_bar = p_full + 1;      // partial sums published (4 * NWG warps)
+  uint64_t* s_full = l_bar + 1;      // [NWG] S of tile t ready (index t % NWG)
+  uint64_t* pv_full = s_full + NWG;  // [NWG]
+  uint64_t* m_bar = pv_full + NWG;   // [NWG][4]
+  static_assert(2 + 2 * KVSTAGES + 4 + 2 * NWG + 4 * NWG <= NUM_BARS, "barrier slots");
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
   float* mrow = reinterpret_cast<float*>(smem + OFF_MROW);
   float* lsum = reinterpret_cast<float*>(smem + OFF_LSUM);
