@@ -71,6 +71,7 @@ _SIGS = {
     "glc_collect": (_i, [_vp]),
     "glc_coalesce_stats": (_i, [_vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "glc_packed_stats": (_i, [_vp, _vp, _vp, _vp]),
+    "glc_pack_plan": (_i64, [_vp, _vp, _i, _i, _i64, _i, _i, _vp, _vp, _vp]),
     "glc_profile_enable": (_i, [_vp, _i, _i]),
     "glc_profile_collect": (_i, [_vp, _i, _vp, _vp, _i]),
     "glc_debug_fetch": (_i64, [_vp, _i, C.c_char_p, _vp, C.c_size_t]),

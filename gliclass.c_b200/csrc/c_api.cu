@@ -308,6 +308,27 @@ int glc_coalesce_stats(const glc_model* m, uint64_t* groups, uint64_t* requests)
   return GLC_OK;
 }
 
+int64_t glc_pack_plan(const int64_t* input_ids, const int64_t* attention_mask, int B, int S, int64_t class_token, int class_pos_offset,
+                      int max_rows_per_launch, int32_t* kv_len, int32_t* text_rows, int32_t* launch_of) {
+  if (!input_ids || !attention_mask || B <= 0 || S <= 0 || class_pos_offset < 0 || max_rows_per_launch <= 0) {
+    fail(GLC_ERR_ARG, "glc_pack_plan: bad argument");
+    return -1;
+  }
+  glc::PackPlan pl;
+  const bool ok = glc::make_pack_plan(input_ids, attention_mask, B, S, class_token, class_pos_offset, max_rows_per_launch, pl);
+  if ((int)pl.len.size() == B) {   // (a class token in the padded tail stops the scan early: nothing to report then)
+    for (int b = 0; b < B; ++b) {
+      if (kv_len) kv_len[b] = pl.len[b];
+      if (text_rows) text_rows[b] = pl.prow[b];
+    }
+  }
+  if (!ok) return 0;
+  if (launch_of)
+    for (size_t i = 0; i < pl.mbs.size(); ++i)
+      for (int b = pl.mbs[i].b0; b < pl.mbs[i].b1; ++b) launch_of[b] = (int)i;
+  return pl.total_rows;
+}
+
 int glc_packed_stats(const glc_model* m, uint64_t* launches, uint64_t* rows, uint64_t* rows_padded) {
   if (!m) return fail(GLC_ERR_ARG, "glc_packed_stats: null model");
   uint64_t a = 0, b = 0, c = 0;

@@ -732,9 +732,10 @@ void DeviceModel::check_overflow_sync() {
   if (v) throw std::runtime_error(kOverflowMsg);
 }
 
-bool DeviceModel::plan_pack(const int64_t* ids, const int64_t* mask, int B, int S, PackPlan& pl) const {
-  if (!varlen_ || cfg_.pooling == POOL_LAST || S < 256 || S > 2048) return false;
-  if ((int64_t)B * S < 8192) return false;   // small requests replay a captured graph of the [B,S] layout: latency first
+bool make_pack_plan(const int64_t* ids, const int64_t* mask, int B, int S, int64_t class_token, int class_pos_offset, int max_rows,
+                    PackPlan& pl) {
+  pl = PackPlan{};
+  if (B <= 0 || S <= 0) return false;
   pl.len.resize(B);
   pl.prow.resize(B);
   int64_t total = 0;
@@ -744,13 +745,14 @@ bool DeviceModel::plan_pack(const int64_t* ids, const int64_t* mask, int B, int 
     while (L > 0 && m[L - 1] == 0) --L;
     // every class token (and the neighbour embed_class_token=false reads) must lie inside the kept positions
     const int64_t* id = ids + (size_t)b * S;
-    int j0 = L - cfg_.class_pos_offset;
+    int j0 = L - class_pos_offset;
     for (int j = j0 < 0 ? 0 : j0; j < S; ++j)
-      if (id[j] == cfg_.class_token) return false;
+      if (id[j] == class_token) return false;
     pl.len[b] = L;
     pl.prow[b] = L <= 128 ? 128 : round_up(L, 128);
     total += pl.prow[b];
   }
+  pl.total_rows = total;
   if (total * 10 > (int64_t)B * S * 9) return false;   // under 10 % of the rows are padding: not worth leaving the graph path
   PackPlan::MB cur{0, 0, 0, 0};
   auto close = [&](int b1) {
@@ -761,12 +763,18 @@ bool DeviceModel::plan_pack(const int64_t* ids, const int64_t* mask, int B, int 
     cur = PackPlan::MB{b1, b1, 0, 0};
   };
   for (int b = 0; b < B; ++b) {
-    if (cur.rows + pl.prow[b] > max_tokens_ && b > cur.b0) close(b);
+    if (cur.rows + pl.prow[b] > max_rows && b > cur.b0) close(b);
     cur.rows += pl.prow[b];
     if (pl.prow[b] > cur.max_rows) cur.max_rows = pl.prow[b];
   }
   close(B);
   return true;
+}
+
+bool DeviceModel::plan_pack(const int64_t* ids, const int64_t* mask, int B, int S, PackPlan& pl) const {
+  if (!varlen_ || cfg_.pooling == POOL_LAST || S < 256 || S > 2048) return false;
+  if ((int64_t)B * S < 8192) return false;   // small requests replay a captured graph of the [B,S] layout: latency first
+  return make_pack_plan(ids, mask, B, S, cfg_.class_token, cfg_.class_pos_offset, max_tokens_, pl);
 }
 
 void DeviceModel::run_host(const int64_t* ids, const int64_t* mask, int B, int S, int C, float* logits,

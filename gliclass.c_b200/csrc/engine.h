@@ -53,6 +53,21 @@ struct DecisionOut {
 // kernel categories for the in-stream profiler (CUDA events around every launch)
 enum KernelCat { KC_EMBED = 0, KC_GEMM_QKV, KC_ATTN, KC_GEMM_OUT, KC_LN, KC_GEMM_FFN1, KC_GEMM_FFN2, KC_HEAD_GEMM, KC_HEAD_MISC, KC_COUNT };
 
+// Packed (varlen) layout of one host request (see DeviceModel::run_host): per text the key length (1 + last unmasked
+// position) and the rows it owns (rounded up to whole 128-row query tiles), grouped into micro-batches of at most
+// `max_rows` packed rows.  Pure host logic, also exported as glc_pack_plan for the CPU tests.
+struct PackPlan {
+  std::vector<int> len, prow;           // per text: kv length, packed rows (multiple of 128)
+  struct MB { int b0, b1, rows, max_rows; };
+  std::vector<MB> mbs;                  // micro-batches of at most max_rows packed rows
+  int max_mb_rows = 0, max_mb_texts = 0;
+  int64_t total_rows = 0;
+};
+// false when the request does not qualify: a class token (or the neighbour embed_class_token=false reads) outside the kept
+// positions, or less than 10 % of the B*S positions saved
+bool make_pack_plan(const int64_t* ids, const int64_t* mask, int B, int S, int64_t class_token, int class_pos_offset, int max_rows,
+                    PackPlan& pl);
+
 class DeviceModel {
  public:
   DeviceModel(int device, const ModelWeights& w, int max_tokens, bool preln_f32 = false, bool fp8_ffn = false);
@@ -117,12 +132,6 @@ class DeviceModel {
   // masked in both layouts and padded query rows are never read by the head.  Used by run_host when it removes >= 10 % of
   // the rows; needs a pooling other than 'last' (which reads padded position S-1) and
   // every class token inside the kept rows.  GLC_VARLEN=0 turns it off.
-  struct PackPlan {
-    std::vector<int> len, prow;           // per text: kv length, packed rows (multiple of 128)
-    struct MB { int b0, b1, rows, max_rows; };
-    std::vector<MB> mbs;                  // micro-batches of at most max_tokens_ packed rows
-    int max_mb_rows = 0, max_mb_texts = 0;
-  };
   struct PackedCtx {                      // device-side description of the micro-batch being run
     int rows = 0, max_rows = 0, n_tiles = 0;
     const int32_t *text_row = nullptr, *kv_len = nullptr, *tile_info = nullptr, *tile_pos = nullptr;

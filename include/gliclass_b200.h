@@ -119,6 +119,15 @@ GLC_API int glc_coalesce_stats(const glc_model* m, uint64_t* merged_launches, ui
  * >= 8192 positions; GLC_VARLEN=0 disables it.  glc_packed_stats: packed launches so far, rows they computed, rows the
  * padded layout would have computed. */
 GLC_API int glc_packed_stats(const glc_model* m, uint64_t* launches, uint64_t* rows, uint64_t* rows_padded);
+/* The host-side plan of that compaction, without a model or a GPU (what the CPU tests check): per text the key length
+ * kv_len[b] = 1 + last unmasked position and the rows it would own, text_rows[b] = max(128, kv_len rounded up to 128);
+ * launch_of[b] = index of the device launch (at most max_rows_per_launch packed rows each) the text falls into.  Returns
+ * the total packed rows, 0 when the request would stay in the padded layout (a class token — or with class_pos_offset = 1
+ * the token after it — outside the kept positions, or less than 10 % of the B*S positions saved), -1 on a bad argument.
+ * Any output pointer may be NULL. */
+GLC_API int64_t glc_pack_plan(const int64_t* input_ids, const int64_t* attention_mask, int B, int S, int64_t class_token,
+                              int class_pos_offset, int max_rows_per_launch, int32_t* kv_len, int32_t* text_rows,
+                              int32_t* launch_of);
 
 /* Same forward with inputs/outputs already resident on `device` (kernel-only timing, parity
  * tests).  d_logits fp32 [B,C] device memory with C = num_classes (caller computes it with

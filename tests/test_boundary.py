@@ -288,3 +288,43 @@ def test_onnx_reader_qwen2_backbone(pkg, orc, model_cache):
     inv = 1.0 / (cfg.rope_theta ** (np.arange(0, 128, 2, dtype=np.float32) / 128))
     assert np.allclose(f.tensor("rope.inv_freq"), inv, rtol=1e-6)
     f.close()
+
+
+def test_pack_plan_host_logic(pkg):
+    """Host side of the varlen packing (f2; replaces the pad-to-longest batches of reference src/tokenizer.c:44-54): per text
+    the kept length, its 128-aligned row count, the split into device launches, and the cases that keep the padded layout."""
+    import ctypes as C
+    L = pkg.lib()
+    rng = np.random.default_rng(7)
+    B, S, CLS = 40, 512, 900
+    lens = rng.integers(40, S + 1, size=B)
+    lens[3], lens[4], lens[5] = 128, 129, S
+    ids = np.zeros((B, S), dtype=np.int64)
+    mask = np.zeros((B, S), dtype=np.int64)
+    for b, n in enumerate(lens):
+        ids[b, :n] = rng.integers(3, 800, size=n)
+        ids[b, n - 8], ids[b, n - 5] = CLS, CLS
+        mask[b, :n] = 1
+    mask[7, lens[7] // 2] = 0                      # an interior hole does not shorten the text
+    kv = np.zeros(B, dtype=np.int32); rows = np.zeros(B, dtype=np.int32); launch = np.full(B, -1, dtype=np.int32)
+    def plan(i, m, max_rows=65536, off=0):
+        return L.glc_pack_plan(i.ctypes.data, m.ctypes.data, B, S, CLS, off, max_rows, kv.ctypes.data, rows.ctypes.data, launch.ctypes.data)
+    total = plan(ids, mask)
+    want_rows = np.maximum(128, (lens + 127) // 128 * 128)
+    assert total == int(want_rows.sum()) and np.array_equal(kv, lens) and np.array_equal(rows, want_rows)
+    assert (launch == 0).all()
+    # launches of at most 4096 packed rows: contiguous, in order, never above the cap (a text larger than the cap goes alone)
+    assert plan(ids, mask, max_rows=4096) == total
+    assert launch[0] == 0 and (np.diff(launch) >= 0).all() and (np.diff(launch) <= 1).all() and launch[-1] >= 2
+    for k in range(launch[-1] + 1):
+        assert rows[launch == k].sum() <= 4096
+    # a <<LABEL>> id in the padded tail: the padded layout would count it as a class, so the request is not packed
+    ids2 = ids.copy(); ids2[11, S - 1] = CLS
+    assert plan(ids2, mask) == 0
+    # embed_class_token=false reads the token AFTER the class token: a class token on the last kept position disqualifies
+    ids3 = ids.copy(); ids3[12, lens[12] - 1] = CLS
+    assert plan(ids3, mask, off=0) == total and plan(ids3, mask, off=1) == 0
+    # full-length batches save nothing: padded layout
+    full = np.ones((B, S), dtype=np.int64)
+    assert plan(ids, full) == 0
+    assert L.glc_pack_plan(None, None, B, S, CLS, 0, 65536, None, None, None) == -1
