@@ -85,6 +85,7 @@ _SIGS = {
     "glc_rel_index_table": (_i, [_i, _i, _i, _vp]),
     "glc_op_gemm": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
     "glc_op_gemm_resid": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _vp]),
+    "glc_op_gemm_rope": (_i, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _vp, _i, _i, _vp]),
     "glc_op_gemm_e4m3": (_i, [_vp, _i64, _vp, _i64, _vp, _f, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _f, _vp]),
     "glc_op_quantize_rows_e4m3": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp]),
     "glc_op_residual_ln_e4m3": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _i, _vp]),

@@ -548,6 +548,20 @@ int glc_op_rope(void* qkv_f16, int64_t ld, const float* inv_freq, int M, int S, 
     return fail(GLC_ERR_CUDA, std::string("glc_op_rope: ") + e.what());
   }
 }
+int glc_op_gemm_rope(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N, int K,
+                     const float* inv_freq, int S, int rope_cols, void* stream) {
+  try {
+    void* cs = nullptr;
+    cudaError_t e = cudaMalloc(&cs, (size_t)S * 64 * 8);
+    if (e == cudaSuccess) e = glc::rope_table(inv_freq, cs, S, 128, (cudaStream_t)stream);
+    if (e == cudaSuccess) e = glc::gemm_f16_rope(A, lda, W, ldw, bias, C, ldc, M, N, K, cs, S, nullptr, rope_cols, num_sms_current(), (cudaStream_t)stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (cs) cudaFree(cs);
+    return wrap("glc_op_gemm_rope", e);
+  } catch (const std::exception& e) {
+    return fail(GLC_ERR_CUDA, std::string("glc_op_gemm_rope: ") + e.what());
+  }
+}
 int glc_op_attention_flash128(const void* qkv_f16, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16, int B, int S,
                               int heads, int kv_heads, void* stream) {
   GLC_TRY("glc_op_attention_flash128",

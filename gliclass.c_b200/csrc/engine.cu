@@ -590,8 +590,14 @@ void DeviceModel::forward_eager(const int64_t* d_ids, const int64_t* d_mask, int
     for (int l = 0; l < cfg_.layers; ++l) {
       const DeviceLayer& dl = layers_[l];
       GLC_LAUNCH(KC_LN, add_rmsnorm(h32_, l == 0 ? nullptr : tmp_, dl.ln1g, cfg_.rms_eps, x_, M, H, st));
-      GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, dl.wqkv, H, dl.bqkv, qkv_, Wqkv, M, Wqkv, H, 0, false, num_sms_, st));
-      GLC_LAUNCH(KC_EMBED, rope_inplace(qkv_, Wqkv, cs, M, S, nh + nkv, d, st, pk ? pk->tile_pos : nullptr));
+      if (d == 128) {
+        // rotary embedding in the GEMM epilogue (fp32 accumulators, one rounding): no separate pass over the q | k slab
+        GLC_LAUNCH(KC_GEMM_QKV, gemm_f16_rope(x_, H, dl.wqkv, H, dl.bqkv, qkv_, Wqkv, M, Wqkv, H, cs, pk ? round_up(S, 128) : S,
+                                              pk ? pk->tile_pos : nullptr, (nh + nkv) * d, num_sms_, st));
+      } else {
+        GLC_LAUNCH(KC_GEMM_QKV, gemm_f16(x_, H, dl.wqkv, H, dl.bqkv, qkv_, Wqkv, M, Wqkv, H, 0, false, num_sms_, st));
+        GLC_LAUNCH(KC_EMBED, rope_inplace(qkv_, Wqkv, cs, M, S, nh + nkv, d, st, pk ? pk->tile_pos : nullptr));
+      }
       if (pk) {
         GLC_LAUNCH(KC_ATTN, attention_flash128_packed(qkv_, mask_bits_, pk->kv_len, pk->text_row, pk->tile_info, ctx_, B, pk->rows,
                                                       pk->n_tiles, nh, nkv, st));

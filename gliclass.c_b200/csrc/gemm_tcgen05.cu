@@ -273,6 +273,12 @@ struct Fp8Scales {
   const float* col;   // [N]
   float k;            // constant factor (1 when `row` carries everything)
   float out_mult;
+  // ACT = 4 (rotary embedding fused into the QKV projection of the decoder stack, head dim 128): columns < rope_cols are
+  // rotated in pairs (p, p + 64) of their head by the angle of the row's position; cs = (cos, sin) [positions][64],
+  // position = rope_tile_pos[row / 128] + row % 128 (packed layout) or row % rope_S
+  const float2* rope_cs;
+  const int32_t* rope_tile_pos;
+  int rope_S, rope_cols;
 };
 
 template <bool SCALED>
@@ -416,6 +422,81 @@ __device__ __forceinline__ void epilogue_tile_tma_swiglu_f8(uint32_t t_row, int 
       ptx::bulk_commit_group();
     }
     buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+  }
+}
+
+// QKV projection of the decoder stack with the rotary embedding applied to the fp32 accumulators (transformers
+// modeling_qwen2.py Q:60-80 rotate_half / apply_rotary_pos_emb): a head is 128 columns = four 32-column chunks, the pair
+// (p, p + 64) sits in chunks c and c + 2 of the same row, and with two epilogue groups one warp owns both.  One rounding to
+// fp16 instead of two (GEMM output, then the rotation), and no separate pass over the [M, (q + kv heads) * 128] slab.
+template <int BN, int NBUF>
+__device__ __forceinline__ void epilogue_tile_tma_rope(uint32_t t_row, int grp, int n0, int row0, const float* __restrict__ bias,
+                                                       const CUtensorMap* tm_c, uint8_t* stage, int& buf, int lane, int M, int N,
+                                                       const Fp8Scales& sc) {
+  static_assert(EpiCfg<4>::GROUPS == 2 && BN % 128 == 0, "chunk pairing of the rotary epilogue");
+  const int row = row0 + lane;
+  int pos = 0;
+  if (row < M) pos = sc.rope_tile_pos ? __ldg(sc.rope_tile_pos + (row >> 7)) + (row & 127) : row % sc.rope_S;
+#pragma unroll 1
+  for (int hd = 0; hd < BN / 128; ++hd) {
+    const int c_lo = 4 * hd + grp, c_hi = c_lo + 2;
+    const int n_lo = n0 + 32 * c_lo, n_hi = n0 + 32 * c_hi;
+    uint32_t r_lo[32], r_hi[32];
+    ptx::tmem_ld_x32(t_row + (uint32_t)(32 * c_lo), r_lo);
+    ptx::tmem_ld_x32(t_row + (uint32_t)(32 * c_hi), r_hi);
+    ptx::tmem_ld_wait();
+    if (n_lo >= N) continue;   // warp-uniform (N is a multiple of 128 here)
+    float lo[32], hi[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      lo[j] = __uint_as_float(r_lo[j]);
+      hi[j] = __uint_as_float(r_hi[j]);
+    }
+    if (bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(bias + n_lo) + j), b = __ldg(reinterpret_cast<const float4*>(bias + n_hi) + j);
+        lo[4 * j] += a.x; lo[4 * j + 1] += a.y; lo[4 * j + 2] += a.z; lo[4 * j + 3] += a.w;
+        hi[4 * j] += b.x; hi[4 * j + 1] += b.y; hi[4 * j + 2] += b.z; hi[4 * j + 3] += b.w;
+      }
+    }
+    if (n_lo < sc.rope_cols) {   // warp-uniform: a Q or K head (V heads pass through)
+      const float4* t4 = reinterpret_cast<const float4*>(sc.rope_cs + (int64_t)pos * 64 + 32 * grp);   // two (cos, sin) per float4
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float4 t = __ldg(t4 + j);
+        const float a0 = lo[2 * j], b0 = hi[2 * j], a1 = lo[2 * j + 1], b1 = hi[2 * j + 1];
+        lo[2 * j] = a0 * t.x - b0 * t.y;          // x1' = x1 cos - x2 sin
+        hi[2 * j] = b0 * t.x + a0 * t.y;          // x2' = x2 cos + x1 sin
+        lo[2 * j + 1] = a1 * t.z - b1 * t.w;
+        hi[2 * j + 1] = b1 * t.z + a1 * t.w;
+      }
+    }
+#pragma unroll
+    for (int part = 0; part < 2; ++part) {
+      const float* v = part == 0 ? lo : hi;
+      if (lane == 0) ptx::bulk_wait_group_read<NBUF - 1>();
+      __syncwarp();
+      uint8_t* sb = stage + buf * 2048;
+      uint8_t* srow = sb + lane * 64;
+      const int sw = (lane >> 1) & 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 o;
+        o.x = ptx::pack_f16(v[8 * j + 0], v[8 * j + 1]);
+        o.y = ptx::pack_f16(v[8 * j + 2], v[8 * j + 3]);
+        o.z = ptx::pack_f16(v[8 * j + 4], v[8 * j + 5]);
+        o.w = ptx::pack_f16(v[8 * j + 6], v[8 * j + 7]);
+        *reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4)) = o;
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::tma_store_2d(tm_c, sb, part == 0 ? n_lo : n_hi, row0);
+        ptx::bulk_commit_group();
+      }
+      buf = (buf + 1 == NBUF) ? 0 : buf + 1;
+    }
   }
 }
 
@@ -761,7 +842,9 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
       ptx::mbar_wait(&tfull[acc], acc_ph);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(q * 32) << 16);
-      if (OUT_F8 && ACT == 3)
+      if constexpr (ACT == 4)
+        epilogue_tile_tma_rope<BN, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, sc);
+      else if (OUT_F8 && ACT == 3)
         epilogue_tile_tma_swiglu_f8<BN, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, sc);
       else if (OUT_F8)
         epilogue_tile_tma_f8out<BN, ACT, NBUF>(t_row, grp, n0, m0 + q * 32, bias, &tm_c, my_stage, sbuf, lane, M, N, sc);
@@ -792,7 +875,8 @@ gemm_f16_2cta_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_cons
 
 template <int BN_, int ACT, bool OUT_F32>
 cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
-                             int M, int N, int K, int num_sms, cudaStream_t stream, const void* resid, int64_t ldr) {
+                             int M, int N, int K, int num_sms, cudaStream_t stream, const void* resid, int64_t ldr,
+                             const Fp8Scales& extra = Fp8Scales{}) {
   using Cfg = Gemm2Cfg<BN_>;
   uint64_t da[2] = {(uint64_t)K, (uint64_t)M};
   uint64_t sa[1] = {(uint64_t)lda * 2};
@@ -822,7 +906,7 @@ cudaError_t launch_gemm_2cta(const void* A, int64_t lda, const void* W, int64_t 
   const int max_cl = num_sms / 2;
   const int ncl = tiles < max_cl ? tiles : max_cl;
   return launch_pdl(kern, dim3(2 * ncl), dim3(EpiCfg<ACT>::THREADS), Cfg::SMEM_BYTES, stream, tm_a, tm_w, tm_c, bias, C, ldc, M, N, K,
-                    (const __half*)resid, ldr, Fp8Scales{});
+                    (const __half*)resid, ldr, extra);
 }
 
 // e4m3 x e4m3 -> fp16 (OUT_F8 = false) or e4m3 (OUT_F8 = true), always on CTA pairs
@@ -947,6 +1031,20 @@ cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ld
   if (act == 0) return launch_gemm<128, 0, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   if (act == 1) return launch_gemm<128, 1, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
   return launch_gemm<128, 2, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, resid, ldr);
+}
+
+cudaError_t gemm_f16_rope(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N,
+                          int K, const void* rope_cs_f32x2, int rope_S, const int32_t* rope_tile_pos, int rope_cols, int num_sms,
+                          cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || rope_cs_f32x2 == nullptr || rope_S <= 0) return cudaErrorInvalidValue;
+  if ((lda % 8) || (ldw % 8) || (K % 8) || (N % 128) || (rope_cols % 128) || rope_cols > N || (ldc % 8) || num_sms < 2) return cudaErrorInvalidValue;
+  if ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(C)) & 15) return cudaErrorInvalidValue;
+  Fp8Scales ex{};
+  ex.rope_cs = (const float2*)rope_cs_f32x2;
+  ex.rope_tile_pos = rope_tile_pos;
+  ex.rope_S = rope_S;
+  ex.rope_cols = rope_cols;
+  return launch_gemm_2cta<256, 4, false>(A, lda, W, ldw, bias, C, ldc, M, N, K, num_sms, stream, nullptr, 0, ex);
 }
 
 cudaError_t gemm_e4m3(const void* A8, int64_t lda, const void* W8, int64_t ldw, const float* a_scale, float a_const,

@@ -20,6 +20,13 @@ cudaError_t gemm_f16_resid(const void* A, int64_t lda, const void* W, int64_t ld
                            int64_t ldr, void* C, int64_t ldc, int M, int N, int K, int act, bool out_f32, int num_sms,
                            cudaStream_t stream);
 
+// K2 with the rotary embedding fused into the epilogue (QKV projection of the decoder stack, head dim 128): columns
+// [0, rope_cols) — the q and kv heads, 128 columns each — are rotated in pairs (p, p + 64) by the angle of the row's position
+// (rope_tile_pos[row / 128] + row % 128 in the packed layout, else row % rope_S); rope_cs from rope_table; N % 128 == 0.
+cudaError_t gemm_f16_rope(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc, int M, int N,
+                          int K, const void* rope_cs_f32x2, int rope_S, const int32_t* rope_tile_pos, int rope_cols, int num_sms,
+                          cudaStream_t stream);
+
 // K2 on e4m3 operands (the opt-in FP8 FFN path): C = act((A8 W8^T) * a_scale[m] * a_const * w_scale[n] + bias).
 // A8 [M,K], W8 [N,K] e4m3 bytes, K % 16 == 0; a_scale may be null (then a_const alone); C fp16 [M,ldc], or with
 // out_e4m3 the saturating e4m3 of (act(...) * out_mult).  act: 0, or 1 (erf-GELU, e4m3 output only).

@@ -239,6 +239,10 @@ GLC_API int glc_op_add_rmsnorm(float* h_f32, const void* delta_f16, const float*
                                void* stream);
 GLC_API int glc_op_rope(void* qkv_f16, int64_t ld, const float* inv_freq, int M, int S, int n_rot_heads, int head_dim,
                         void* stream);
+/* glc_op_gemm (act 0) with glc_op_rope applied to columns [0, rope_cols) in the epilogue, head dim 128 (what the engine
+ * runs for the decoder's QKV projection): position = row % S; N and rope_cols multiples of 128; synchronises `stream` */
+GLC_API int glc_op_gemm_rope(const void* A, int64_t lda, const void* W, int64_t ldw, const float* bias, void* C, int64_t ldc,
+                             int M, int N, int K, const float* inv_freq, int S, int rope_cols, void* stream);
 GLC_API int glc_op_attention_flash128(const void* qkv_f16, const uint32_t* mask_bits, const int32_t* kv_len, void* ctx_f16,
                                       int B, int S, int heads, int kv_heads, void* stream);
 /* K5a: pooled[b,:] = h[b,0,:]; cls[b,c,:] = h[b,pos_c(b),:] for the c-th <<LABEL>> token, else 0 */

@@ -560,6 +560,30 @@ def test_rope(pkg, dev):
     assert torch.equal(out[:, (nh + nkv) * d:], qkv[:, (nh + nkv) * d:])     # V untouched
 
 
+@pytest.mark.parametrize("B,S,nh,nkv,K", [(32, 1024, 12, 2, 1536), (3, 333, 4, 2, 512), (1, 100, 3, 1, 256)])
+def test_gemm_rope(pkg, dev, B, S, nh, nkv, K):
+    """QKV projection with the rotary embedding fused into the epilogue (what the decoder stack runs): q and k heads rotated
+    by the row position, v heads untouched, one rounding of the fp32 result"""
+    d = 128
+    N, M = (nh + 2 * nkv) * d, B * S
+    g = torch.Generator().manual_seed(B + S + nh)
+    A = torch.randn(M, K, generator=g).to(torch.float16).to(dev)
+    W = (torch.randn(N, K, generator=g) / math.sqrt(K)).to(torch.float16).to(dev)
+    bias = (torch.randn(N, generator=g) * 0.5).float().to(dev)
+    inv = (1.0 / (1.0e6 ** (torch.arange(0, d, 2).float() / d))).to(dev)
+    C = torch.full((M, N), float("nan"), dtype=torch.float16, device=dev)
+    rc = pkg.lib().glc_op_gemm_rope(_ptr(A), K, _ptr(W), K, _ptr(bias), _ptr(C), N, M, N, K, _ptr(inv), S, (nh + nkv) * d, None)
+    _sync_check(pkg, rc, "glc_op_gemm_rope")
+    y = A.float() @ W.float().t() + bias
+    pos = torch.arange(S, device=dev).float().repeat(B)
+    ang = pos[:, None] * inv[None, :]
+    cos, sin = torch.cat([ang.cos(), ang.cos()], -1), torch.cat([ang.sin(), ang.sin()], -1)
+    x = y[:, : (nh + nkv) * d].view(M, nh + nkv, d)
+    rot = torch.cat([-x[..., d // 2:], x[..., : d // 2]], -1)
+    ref = torch.cat([(x * cos[:, None, :] + rot * sin[:, None, :]).reshape(M, -1), y[:, (nh + nkv) * d:]], -1)
+    _report(f"gemm+rope M{M} N{N} K{K}", C, ref, 3e-3, 3e-3)
+
+
 @pytest.mark.parametrize("M,I,K", [(300, 1536, 512), (4096, 8960, 1536), (100, 64, 128)])
 def test_gemm_swiglu(pkg, dev, M, I, K):
     """SwiGLU GEMM epilogue (act = 3): gate / up rows interleaved in blocks of 32, output [M, I] = silu(gate) * up"""
